@@ -1,0 +1,458 @@
+// G1 = E(Fp): y^2 = x^3 + 4 and G2 = E'(Fp2): y^2 = x^3 + 4(1+u), Jacobian coordinates (x = X/Z^2, y = Y/Z^3, Z = 0 is
+// the identity), generic over the field through the f* vocabulary of fp2.cuh.
+// Replaces the group operations blsful takes from its curve crate: `+=` / `*` / `is_identity` / neg
+// (reference src/traits/sig_core.rs:42-57,126-139; src/secure_aggregation.rs:150-153,201-204), point decoding incl.
+// the subgroup check (`from_compressed`, reference src/impls/legacy.rs:107,117,151,161; src/public_key.rs:71) and
+// encoding (`to_compressed`, src/impls/legacy.rs:88,132).
+#pragma once
+#include "fp2.cuh"
+
+namespace bls {
+
+template <class F>
+struct Aff {
+  F x, y;
+  uint32_t inf;
+};
+template <class F>
+struct Jac {
+  F X, Y, Z;
+};
+typedef Aff<Fp> G1Aff;
+typedef Aff<Fp2> G2Aff;
+typedef Jac<Fp> G1Jac;
+typedef Jac<Fp2> G2Jac;
+
+template <class F>
+BLS_HD void jac_set_inf(Jac<F>& r) {
+  fone(r.X);
+  fone(r.Y);
+  fzero(r.Z);
+}
+template <class F>
+BLS_HD bool jac_is_inf(const Jac<F>& p) {
+  return fis_zero(p.Z);
+}
+template <class F>
+BLS_HD void jac_from_aff(Jac<F>& r, const Aff<F>& p) {
+  if (p.inf) {
+    jac_set_inf(r);
+  } else {
+    r.X = p.x;
+    r.Y = p.y;
+    fone(r.Z);
+  }
+}
+template <class F>
+BLS_HD void jac_neg(Jac<F>& r, const Jac<F>& p) {
+  r.X = p.X;
+  fneg(r.Y, p.Y);
+  r.Z = p.Z;
+}
+template <class F>
+BLS_HD void aff_neg(Aff<F>& r, const Aff<F>& p) {
+  r.x = p.x;
+  fneg(r.y, p.y);
+  r.inf = p.inf;
+}
+
+// dbl-2009-l (a = 0): 2M + 5S
+template <class F>
+BLS_HD void jac_dbl_impl(Jac<F>& r, const Jac<F>& p) {
+  F A, B, C, D, E, Fq, t;
+  fsqr(A, p.X);
+  fsqr(B, p.Y);
+  fsqr(C, B);
+  fadd(t, p.X, B);
+  fsqr(t, t);
+  fsub(t, t, A);
+  fsub(t, t, C);
+  fdbl(D, t);
+  fdbl(E, A);
+  fadd(E, E, A);
+  fsqr(Fq, E);
+  fmul(t, p.Y, p.Z);  // before X/Y are overwritten (r may alias p)
+  F X3, Y3;
+  fsub(X3, Fq, D);
+  fsub(X3, X3, D);
+  fsub(Y3, D, X3);
+  fmul(Y3, E, Y3);
+  fdbl(C, C);
+  fdbl(C, C);
+  fdbl(C, C);
+  fsub(r.Y, Y3, C);
+  r.X = X3;
+  fdbl(r.Z, t);
+}
+
+// madd-2007-bl: 7M + 4S, with the exceptional cases handled (public data, variable time)
+template <class F>
+BLS_HD void jac_add_mixed_impl(Jac<F>& r, const Jac<F>& p, const Aff<F>& q) {
+  if (q.inf) {
+    r = p;
+    return;
+  }
+  if (jac_is_inf(p)) {
+    jac_from_aff(r, q);
+    return;
+  }
+  F Z1Z1, U2, S2, H, HH, I, J, rr, V, t;
+  fsqr(Z1Z1, p.Z);
+  fmul(U2, q.x, Z1Z1);
+  fmul(S2, q.y, p.Z);
+  fmul(S2, S2, Z1Z1);
+  fsub(H, U2, p.X);
+  fsub(rr, S2, p.Y);
+  if (fis_zero(H)) {
+    if (fis_zero(rr)) {
+      jac_dbl_impl(r, p);
+    } else {
+      jac_set_inf(r);
+    }
+    return;
+  }
+  fdbl(rr, rr);
+  fsqr(HH, H);
+  fdbl(I, HH);
+  fdbl(I, I);
+  fmul(J, H, I);
+  fmul(V, p.X, I);
+  F X3, Y3, Z3;
+  fsqr(X3, rr);
+  fsub(X3, X3, J);
+  fsub(X3, X3, V);
+  fsub(X3, X3, V);
+  fsub(Y3, V, X3);
+  fmul(Y3, rr, Y3);
+  fmul(t, p.Y, J);
+  fdbl(t, t);
+  fsub(Y3, Y3, t);
+  fadd(Z3, p.Z, H);
+  fsqr(Z3, Z3);
+  fsub(Z3, Z3, Z1Z1);
+  fsub(Z3, Z3, HH);
+  r.X = X3;
+  r.Y = Y3;
+  r.Z = Z3;
+}
+
+// add-2007-bl: 11M + 5S
+template <class F>
+BLS_HD void jac_add_impl(Jac<F>& r, const Jac<F>& p, const Jac<F>& q) {
+  if (jac_is_inf(q)) {
+    r = p;
+    return;
+  }
+  if (jac_is_inf(p)) {
+    r = q;
+    return;
+  }
+  F Z1Z1, Z2Z2, U1, U2, S1, S2, H, I, J, rr, V, t;
+  fsqr(Z1Z1, p.Z);
+  fsqr(Z2Z2, q.Z);
+  fmul(U1, p.X, Z2Z2);
+  fmul(U2, q.X, Z1Z1);
+  fmul(S1, p.Y, q.Z);
+  fmul(S1, S1, Z2Z2);
+  fmul(S2, q.Y, p.Z);
+  fmul(S2, S2, Z1Z1);
+  fsub(H, U2, U1);
+  fsub(rr, S2, S1);
+  if (fis_zero(H)) {
+    if (fis_zero(rr)) {
+      jac_dbl_impl(r, p);
+    } else {
+      jac_set_inf(r);
+    }
+    return;
+  }
+  fdbl(rr, rr);
+  fdbl(I, H);
+  fsqr(I, I);
+  fmul(J, H, I);
+  fmul(V, U1, I);
+  F X3, Y3, Z3;
+  fsqr(X3, rr);
+  fsub(X3, X3, J);
+  fsub(X3, X3, V);
+  fsub(X3, X3, V);
+  fsub(Y3, V, X3);
+  fmul(Y3, rr, Y3);
+  fmul(t, S1, J);
+  fdbl(t, t);
+  fsub(Y3, Y3, t);
+  fadd(Z3, p.Z, q.Z);
+  fsqr(Z3, Z3);
+  fsub(Z3, Z3, Z1Z1);
+  fsub(Z3, Z3, Z2Z2);
+  fmul(Z3, Z3, H);
+  r.X = X3;
+  r.Y = Y3;
+  r.Z = Z3;
+}
+
+// out-of-line instances (code size: one copy of each per group)
+BLS_FN void jac_dbl(G1Jac& r, const G1Jac& p) { jac_dbl_impl(r, p); }
+BLS_FN void jac_dbl(G2Jac& r, const G2Jac& p) { jac_dbl_impl(r, p); }
+BLS_FN void jac_add_mixed(G1Jac& r, const G1Jac& p, const G1Aff& q) { jac_add_mixed_impl(r, p, q); }
+BLS_FN void jac_add_mixed(G2Jac& r, const G2Jac& p, const G2Aff& q) { jac_add_mixed_impl(r, p, q); }
+BLS_FN void jac_add(G1Jac& r, const G1Jac& p, const G1Jac& q) { jac_add_impl(r, p, q); }
+BLS_FN void jac_add(G2Jac& r, const G2Jac& p, const G2Jac& q) { jac_add_impl(r, p, q); }
+
+template <class F>
+BLS_HD void jac_to_aff(Aff<F>& r, const Jac<F>& p) {
+  if (jac_is_inf(p)) {
+    fzero(r.x);
+    fzero(r.y);
+    r.inf = 1;
+    return;
+  }
+  F zi, zi2;
+  finv(zi, p.Z);
+  fsqr(zi2, zi);
+  fmul(r.x, p.X, zi2);
+  fmul(zi2, zi2, zi);
+  fmul(r.y, p.Y, zi2);
+  r.inf = 0;
+}
+
+// projective equality
+template <class F>
+BLS_HD bool jac_eq(const Jac<F>& a, const Jac<F>& b) {
+  bool ia = jac_is_inf(a), ib = jac_is_inf(b);
+  if (ia || ib) return ia && ib;
+  F za2, zb2, t0, t1;
+  fsqr(za2, a.Z);
+  fsqr(zb2, b.Z);
+  fmul(t0, a.X, zb2);
+  fmul(t1, b.X, za2);
+  if (!feq(t0, t1)) return false;
+  fmul(za2, za2, a.Z);
+  fmul(zb2, zb2, b.Z);
+  fmul(t0, a.Y, zb2);
+  fmul(t1, b.Y, za2);
+  return feq(t0, t1);
+}
+
+// [k]P for an affine base point, k given as little-endian 32-bit limbs (public scalars: plain double-and-add)
+template <class F>
+BLS_HD void jac_mul_aff(Jac<F>& r, const Aff<F>& p, const uint32_t* k, int nlimbs) {
+  Jac<F> acc;
+  jac_set_inf(acc);
+  bool started = false;
+  for (int i = nlimbs - 1; i >= 0; i--) {
+    uint32_t w = k[i];
+    for (int b = 31; b >= 0; b--) {
+      if (started) jac_dbl(acc, acc);
+      if ((w >> b) & 1u) {
+        jac_add_mixed(acc, acc, p);
+        started = true;
+      }
+    }
+  }
+  r = acc;
+}
+// [|x|]P, |x| = 0xd201000000010000 (Hamming weight 6), Jacobian base
+template <class F>
+BLS_HD void jac_mul_xabs(Jac<F>& r, const Jac<F>& p) {
+  Jac<F> acc = p;
+  const uint64_t e = K_X_ABS;
+  for (int i = 62; i >= 0; i--) {
+    jac_dbl(acc, acc);
+    if ((e >> i) & 1) jac_add(acc, acc, p);
+  }
+  r = acc;
+}
+template <class F>
+BLS_HD void jac_mul_xabs_aff(Jac<F>& r, const Aff<F>& p) {
+  Jac<F> acc;
+  jac_from_aff(acc, p);
+  const uint64_t e = K_X_ABS;
+  for (int i = 62; i >= 0; i--) {
+    jac_dbl(acc, acc);
+    if ((e >> i) & 1) jac_add_mixed(acc, acc, p);
+  }
+  r = acc;
+}
+
+// ---- endomorphisms and subgroup checks -----------------------------------------------------------------
+// G1: phi(x,y) = (beta x, y) acts as [-x^2] on G1; P in G1  <=>  phi(P) + [x^2]P = O   (Scott, eprint 2021/1130)
+BLS_FN bool g1_in_subgroup(const G1Aff& p) {
+  if (p.inf) return true;
+  G1Jac t;
+  jac_mul_xabs_aff(t, p);
+  jac_mul_xabs(t, t);  // [x^2]P  (sign of x cancels)
+  G1Aff phi;
+  Fp beta;
+  fp_set(beta, K_BETA);
+  fp_mul(phi.x, p.x, beta);
+  phi.y = p.y;
+  phi.inf = 0;
+  jac_add_mixed(t, t, phi);
+  return jac_is_inf(t);
+}
+// psi on E'(Fp2): (X,Y,Z) -> (conj(X) cx, conj(Y) cy, conj(Z))
+BLS_HD void g2_psi(G2Jac& r, const G2Jac& p) {
+  Fp2 cx, cy, t;
+  fp2_set(cx, K_PSI_CX);
+  fp2_set(cy, K_PSI_CY);
+  fp2_conj(t, p.X);
+  fp2_mul(r.X, t, cx);
+  fp2_conj(t, p.Y);
+  fp2_mul(r.Y, t, cy);
+  fp2_conj(r.Z, p.Z);
+}
+// psi^2: (x,y) -> (x * K_PSI2_CX, -y)
+BLS_HD void g2_psi2(G2Jac& r, const G2Jac& p) {
+  Fp c;
+  fp_set(c, K_PSI2_CX);
+  fp2_mul_fp(r.X, p.X, c);
+  fneg(r.Y, p.Y);
+  r.Z = p.Z;
+}
+// G2: P in G2  <=>  psi(P) = [x]P  (Scott), x = -|x|
+BLS_FN bool g2_in_subgroup(const G2Aff& p) {
+  if (p.inf) return true;
+  G2Jac t, pj, ps;
+  jac_mul_xabs_aff(t, p);
+  jac_neg(t, t);
+  jac_from_aff(pj, p);
+  g2_psi(ps, pj);
+  return jac_eq(t, ps);
+}
+
+// ---- compressed encodings (ZCash/IETF "Modern" flags; the Legacy header rewrite is in codec.cuh) --------------
+// status codes shared with include/blsgpu.h
+enum : uint8_t {
+  ST_OK = 0,
+  ST_INVALID_SIGNATURE = 1,
+  ST_SIG_IDENTITY = 2,
+  ST_PK_IDENTITY = 3,
+  ST_DESERIALIZE = 4,
+  ST_LEGACY_FORMAT = 5,
+  ST_INVALID_LENGTH = 6,
+  ST_INVALID_COEFFICIENT = 7,
+  ST_DUPLICATE_MESSAGES = 8,
+  ST_SCHEME = 9,
+  ST_MISMATCHED_LENGTHS = 10
+};
+
+BLS_HD bool bytes_all_zero(const uint8_t* b, int n) {
+  uint32_t t = 0;
+  for (int i = 0; i < n; i++) t |= b[i];
+  return t == 0;
+}
+
+// 48 Modern bytes -> G1 affine (Montgomery).  `check_subgroup` false is used by tests only.
+BLS_FN uint8_t g1_decompress(G1Aff& r, const uint8_t* in, bool check_subgroup) {
+  uint8_t b[48];
+  for (int i = 0; i < 48; i++) b[i] = in[i];
+  uint8_t h = b[0];
+  b[0] &= 0x1f;
+  if (!(h & 0x80)) return ST_DESERIALIZE;
+  if (h & 0x40) {
+    if ((h & 0x20) || !bytes_all_zero(b, 48)) return ST_DESERIALIZE;
+    fzero(r.x);
+    fzero(r.y);
+    r.inf = 1;
+    return ST_OK;
+  }
+  Fp raw, x, y2, y, b4;
+  if (!fp_from_be48_raw(raw.l, b)) return ST_DESERIALIZE;
+  fp_to_mont(x, raw);
+  fp_sqr(y2, x);
+  fp_mul(y2, y2, x);
+  fp_set(b4, K_B1);
+  fp_add(y2, y2, b4);
+  if (!fp_sqrt(y, y2)) return ST_DESERIALIZE;
+  if (fp_lex_largest(y) != ((h & 0x20) != 0)) fp_neg(y, y);
+  r.x = x;
+  r.y = y;
+  r.inf = 0;
+  if (check_subgroup && !g1_in_subgroup(r)) return ST_DESERIALIZE;
+  return ST_OK;
+}
+
+// 96 Modern bytes (x.c1 || x.c0) -> G2 affine
+BLS_FN uint8_t g2_decompress(G2Aff& r, const uint8_t* in, bool check_subgroup) {
+  uint8_t b[96];
+  for (int i = 0; i < 96; i++) b[i] = in[i];
+  uint8_t h = b[0];
+  b[0] &= 0x1f;
+  if (!(h & 0x80)) return ST_DESERIALIZE;
+  if (h & 0x40) {
+    if ((h & 0x20) || !bytes_all_zero(b, 96)) return ST_DESERIALIZE;
+    fzero(r.x);
+    fzero(r.y);
+    r.inf = 1;
+    return ST_OK;
+  }
+  Fp raw0, raw1;
+  if (!fp_from_be48_raw(raw1.l, b)) return ST_DESERIALIZE;
+  if (!fp_from_be48_raw(raw0.l, b + 48)) return ST_DESERIALIZE;
+  Fp2 x, y2, y, b2, one;
+  fp_to_mont(x.c0, raw0);
+  fp_to_mont(x.c1, raw1);
+  fp2_sqr(y2, x);
+  fp2_mul(y2, y2, x);
+  fp2_set(b2, K_B2);
+  fadd(y2, y2, b2);
+  fone(one);
+  if (!fp2_sqrt_ratio(y, y2, one)) return ST_DESERIALIZE;
+  if (fp2_lex_largest(y) != ((h & 0x20) != 0)) fneg(y, y);
+  r.x = x;
+  r.y = y;
+  r.inf = 0;
+  if (check_subgroup && !g2_in_subgroup(r)) return ST_DESERIALIZE;
+  return ST_OK;
+}
+
+BLS_HD void g1_compress(uint8_t* out, const G1Aff& p) {
+  if (p.inf) {
+    out[0] = 0xc0;
+    for (int i = 1; i < 48; i++) out[i] = 0;
+    return;
+  }
+  Fp raw;
+  fp_from_mont(raw, p.x);
+  fp_to_be48_raw(out, raw.l);
+  out[0] |= 0x80 | (fp_lex_largest(p.y) ? 0x20 : 0);
+}
+BLS_HD void g2_compress(uint8_t* out, const G2Aff& p) {
+  if (p.inf) {
+    out[0] = 0xc0;
+    for (int i = 1; i < 96; i++) out[i] = 0;
+    return;
+  }
+  Fp raw;
+  fp_from_mont(raw, p.x.c1);
+  fp_to_be48_raw(out, raw.l);
+  fp_from_mont(raw, p.x.c0);
+  fp_to_be48_raw(out + 48, raw.l);
+  out[0] |= 0x80 | (fp2_lex_largest(p.y) ? 0x20 : 0);
+}
+
+// Header handling of the two serialisation formats (reference src/impls/legacy.rs:19-82):
+// rewrites byte 0 into the Modern form or reports the reference's error.  format: 0 = Legacy, 1 = Modern.
+BLS_HD uint8_t header_to_modern(uint8_t& b0, int format) {
+  if (format == 1) {
+    if (b0 != 0xc0 && (b0 & 0xc0) != 0x80) return ST_DESERIALIZE;  // validate_modern_format
+    return ST_OK;
+  }
+  if (b0 == 0xc0) return ST_OK;
+  uint8_t y_sign = b0 & 0x80;
+  uint8_t v = b0 & 0x7f;
+  if (v & 0xe0) return ST_LEGACY_FORMAT;
+  v |= 0x80;
+  if (y_sign) v |= 0x20;
+  b0 = v;
+  return ST_OK;
+}
+BLS_HD void header_from_modern(uint8_t& b0, int format) {
+  if (format == 1 || b0 == 0xc0) return;
+  uint8_t y_sign = b0 & 0x20;
+  b0 &= 0x1f;
+  if (y_sign) b0 |= 0x80;
+}
+
+}  // namespace bls

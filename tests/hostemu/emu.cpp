@@ -1,0 +1,146 @@
+// TEST INFRASTRUCTURE ONLY: compiles the engine's device headers for the host (g++) so that the CPU-only test suite can
+// check the field/curve/pairing logic against the oracle without a GPU.  Nothing in the product links or loads this;
+// the C-ABI library (csrc/blsgpu.cu) has no CPU path and fails loudly without a CUDA device.
+#include <cstring>
+#include "../../agora-blsful_b200/csrc/pairing.cuh"
+#include "../../agora-blsful_b200/csrc/h2c.cuh"
+
+using namespace bls;
+
+static void fp_in(Fp& r, const uint8_t* b) {
+  Fp raw;
+  fp_from_be48_raw(raw.l, b);
+  fp_to_mont(r, raw);
+}
+static void fp_out(uint8_t* b, const Fp& a) {
+  Fp raw;
+  fp_from_mont(raw, a);
+  fp_to_be48_raw(b, raw.l);
+}
+static void fp2_in(Fp2& r, const uint8_t* b) { fp_in(r.c0, b); fp_in(r.c1, b + 48); }
+static void fp2_out(uint8_t* b, const Fp2& a) { fp_out(b, a.c0); fp_out(b + 48, a.c1); }
+static void fp12_out(uint8_t* b, const Fp12& f) {
+  // order w^0..w^5 (oracle layout): a0, b0, a1, b1, a2, b2
+  fp2_out(b, f.c0.c0); fp2_out(b + 96, f.c1.c0); fp2_out(b + 192, f.c0.c1);
+  fp2_out(b + 288, f.c1.c1); fp2_out(b + 384, f.c0.c2); fp2_out(b + 480, f.c1.c2);
+}
+static void fp12_in(Fp12& f, const uint8_t* b) {
+  fp2_in(f.c0.c0, b); fp2_in(f.c1.c0, b + 96); fp2_in(f.c0.c1, b + 192);
+  fp2_in(f.c1.c1, b + 288); fp2_in(f.c0.c2, b + 384); fp2_in(f.c1.c2, b + 480);
+}
+
+extern "C" {
+void emu_fp_mul(const uint8_t* a, const uint8_t* b, uint8_t* out, int which) {
+  Fp x, y, z;
+  fp_in(x, a); fp_in(y, b);
+  if (which == 0) fp_mul(z, x, y); else fp_mul_cios(z, x, y);
+  fp_out(out, z);
+}
+void emu_fp_addsub(const uint8_t* a, const uint8_t* b, uint8_t* out_add, uint8_t* out_sub, uint8_t* out_neg) {
+  Fp x, y, z;
+  fp_in(x, a); fp_in(y, b);
+  fp_add(z, x, y); fp_out(out_add, z);
+  fp_sub(z, x, y); fp_out(out_sub, z);
+  fp_neg(z, x); fp_out(out_neg, z);
+}
+void emu_fp_inv(const uint8_t* a, uint8_t* out) { Fp x, z; fp_in(x, a); fp_inv(z, x); fp_out(out, z); }
+int emu_fp_sqrt(const uint8_t* a, uint8_t* out) { Fp x, z; fp_in(x, a); bool ok = fp_sqrt(z, x); fp_out(out, z); return ok; }
+int emu_fp2_sqrt_ratio(const uint8_t* n, const uint8_t* d, uint8_t* out) {
+  Fp2 x, y, z; fp2_in(x, n); fp2_in(y, d);
+  bool ok = fp2_sqrt_ratio(z, x, y); fp2_out(out, z); return ok;
+}
+void emu_fp2_mul(const uint8_t* a, const uint8_t* b, uint8_t* out_mul, uint8_t* out_sqr, uint8_t* out_inv) {
+  Fp2 x, y, z; fp2_in(x, a); fp2_in(y, b);
+  fp2_mul(z, x, y); fp2_out(out_mul, z);
+  fp2_sqr(z, x); fp2_out(out_sqr, z);
+  fp2_inv(z, x); fp2_out(out_inv, z);
+}
+void emu_fp12_ops(const uint8_t* a, const uint8_t* b, uint8_t* mul, uint8_t* sqr, uint8_t* inv, uint8_t* fr1, uint8_t* fr2) {
+  Fp12 x, y, z; fp12_in(x, a); fp12_in(y, b);
+  fp12_mul(z, x, y); fp12_out(mul, z);
+  fp12_sqr(z, x); fp12_out(sqr, z);
+  fp12_inv(z, x); fp12_out(inv, z);
+  fp12_frob1(z, x); fp12_out(fr1, z);
+  fp12_frob2(z, x); fp12_out(fr2, z);
+}
+// returns 1 if cyclotomic squaring agrees with the generic squaring on easy_part(a)
+int emu_cyclo_check(const uint8_t* a) {
+  Fp12 x, t0, t1, m, s0, s1;
+  fp12_in(x, a);
+  fp12_conj(t0, x); fp12_inv(t1, x); fp12_mul(t0, t0, t1); fp12_frob2(t1, t0); fp12_mul(m, t1, t0);
+  fp12_cyclo_sqr(s0, m); fp12_sqr(s1, m);
+  return fp12_eq(s0, s1);
+}
+void emu_final_exp(const uint8_t* a, uint8_t* out) { Fp12 x, z; fp12_in(x, a); final_exponentiation(z, x); fp12_out(out, z); }
+
+int emu_g1_decompress(const uint8_t* in, int format, uint8_t* xy, int* inf) {
+  uint8_t b[48]; memcpy(b, in, 48);
+  uint8_t st = header_to_modern(b[0], format);
+  if (st) return st;
+  G1Aff p; st = g1_decompress(p, b, true);
+  if (st) return st;
+  *inf = p.inf; fp_out(xy, p.x); fp_out(xy + 48, p.y);
+  return 0;
+}
+int emu_g2_decompress(const uint8_t* in, int format, uint8_t* xy, int* inf) {
+  uint8_t b[96]; memcpy(b, in, 96);
+  uint8_t st = header_to_modern(b[0], format);
+  if (st) return st;
+  G2Aff p; st = g2_decompress(p, b, true);
+  if (st) return st;
+  *inf = p.inf; fp2_out(xy, p.x); fp2_out(xy + 96, p.y);
+  return 0;
+}
+// decode (no subgroup check), multiply by a scalar (little-endian 32-bit limbs), re-encode in `format`
+int emu_g1_mul(const uint8_t* in, const uint32_t* k, int nl, int format, uint8_t* out) {
+  G1Aff p, q; if (g1_decompress(p, in, false)) return -1;
+  G1Jac r; jac_mul_aff(r, p, k, nl); jac_to_aff(q, r); g1_compress(out, q); header_from_modern(out[0], format); return 0;
+}
+int emu_g2_mul(const uint8_t* in, const uint32_t* k, int nl, int format, uint8_t* out) {
+  G2Aff p, q; if (g2_decompress(p, in, false)) return -1;
+  G2Jac r; jac_mul_aff(r, p, k, nl); jac_to_aff(q, r); g2_compress(out, q); header_from_modern(out[0], format); return 0;
+}
+int emu_g1_add(const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  G1Aff p, q, s; if (g1_decompress(p, a, false) || g1_decompress(q, b, false)) return -1;
+  G1Jac x, y, r; jac_from_aff(x, p); jac_from_aff(y, q); jac_add(r, x, y);
+  G1Jac r2; jac_add_mixed(r2, x, q); if (!jac_eq(r, r2)) return -2;
+  jac_to_aff(s, r); g1_compress(out, s); return 0;
+}
+int emu_g2_add(const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  G2Aff p, q, s; if (g2_decompress(p, a, false) || g2_decompress(q, b, false)) return -1;
+  G2Jac x, y, r; jac_from_aff(x, p); jac_from_aff(y, q); jac_add(r, x, y);
+  G2Jac r2; jac_add_mixed(r2, x, q); if (!jac_eq(r, r2)) return -2;
+  jac_to_aff(s, r); g2_compress(out, s); return 0;
+}
+int emu_subgroup(const uint8_t* in, int g2) {
+  if (g2) { G2Aff p; if (g2_decompress(p, in, false)) return -1; return g2_in_subgroup(p); }
+  G1Aff p; if (g1_decompress(p, in, false)) return -1; return g1_in_subgroup(p);
+}
+void emu_hash_to_g2(const uint8_t* prefix, int plen, const uint8_t* msg, int mlen, const uint8_t* dst, int dlen, uint8_t* out) {
+  G2Jac r; hash_to_g2(r, prefix, plen, msg, mlen, dst, dlen);
+  G2Aff a; jac_to_aff(a, r); g2_compress(out, a);
+}
+void emu_hash_to_g1(const uint8_t* prefix, int plen, const uint8_t* msg, int mlen, const uint8_t* dst, int dlen, uint8_t* out) {
+  G1Jac r; hash_to_g1(r, prefix, plen, msg, mlen, dst, dlen);
+  G1Aff a; jac_to_aff(a, r); g1_compress(out, a);
+}
+void emu_sha256(const uint8_t* m, int n, uint8_t* out) { Sha256 s; sha256_init(s); sha256_update(s, m, n); sha256_final(s, out); }
+// Miller loop of (P in G1 scaled by k to exercise the Jacobian path, Q in G2), raw and after the final exponentiation
+int emu_pairing(const uint8_t* p48, const uint8_t* q96, const uint32_t* k, int nl, uint8_t* ml_out, uint8_t* fe_out) {
+  G1Aff p; G2Aff q;
+  if (g1_decompress(p, p48, false) || g2_decompress(q, q96, false)) return -1;
+  MillerG1 mp;
+  if (nl) { G1Jac pj; jac_mul_aff(pj, p, k, nl); miller_prepare(mp, pj); } else miller_prepare(mp, p);
+  Fp12 f, g; miller_loop(f, mp, q); fp12_out(ml_out, f);
+  final_exponentiation(g, f); fp12_out(fe_out, g);
+  return 0;
+}
+// e(p1,q1) e(p2,q2) == 1 ?
+int emu_pairing_check2(const uint8_t* p1, const uint8_t* q1, const uint8_t* p2, const uint8_t* q2) {
+  G1Aff a, c; G2Aff b, d;
+  if (g1_decompress(a, p1, true) || g2_decompress(b, q1, true) || g1_decompress(c, p2, true) || g2_decompress(d, q2, true)) return -1;
+  MillerG1 m1, m2; miller_prepare(m1, a); miller_prepare(m2, c);
+  Fp12 f, g; miller_loop(f, m1, b); miller_loop(g, m2, d); fp12_mul(f, f, g); final_exponentiation(g, f);
+  return fp12_is_one(g);
+}
+}
