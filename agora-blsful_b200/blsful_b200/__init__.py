@@ -1,0 +1,393 @@
+"""Host-side mirror of blsful's verification API over the blsgpu C ABI (include/blsgpu.h).
+
+The reference is a Rust crate; this image has no Rust toolchain, so the slice-taking batch entry points the Rust
+crate would gain are mirrored here in Python over the same C ABI, with the reference's names,
+argument meaning and error behaviour:
+
+  Signature::verify            -> verify_batch            (reference src/signature.rs:130-138)
+  ProofOfPossession::verify    -> pop_verify_batch        (src/proof_of_possession.rs:77-81)
+  AggregateSignature::verify   -> aggregate_verify        (src/aggregate_signature.rs:230-239)
+  MultiSignature / AggregateSignature::from_signatures, MultiPublicKey::from_public_keys
+                               -> sum_signatures / sum_public_keys (src/multi_signature.rs:80-107, multi_public_key.rs:79-83)
+  Signature::verify_secure[_with_mode] -> verify_secure_batch   (src/signature.rs:177-197,256-276)
+  aggregate_secure[_with_mode] -> aggregate_secure_batch  (src/secure_aggregation.rs:159-169,338-352)
+
+There is no CPU fallback: importing works anywhere, but creating an Engine without the CUDA library or a GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+# impls.rs:102-109 / sig_types.rs:8-12 / serialization.rs:10-17
+Bls12381G1Impl, Bls12381G2Impl = 1, 2
+class SignatureSchemes:
+    Basic, MessageAugmentation, ProofOfPossession = 0, 1, 2
+class SerializationFormat:
+    Legacy, Modern = 0, 1
+
+ST_OK, ST_INVALID_SIGNATURE, ST_SIG_IDENTITY, ST_PK_IDENTITY, ST_DESERIALIZE, ST_LEGACY_FORMAT = 0, 1, 2, 3, 4, 5
+ST_INVALID_LENGTH, ST_INVALID_COEFFICIENT, ST_DUPLICATE_MESSAGES, ST_SCHEME, ST_MISMATCHED_LENGTHS = 6, 7, 8, 9, 10
+
+_STATUS_TEXT = {
+    ST_INVALID_SIGNATURE: "invalid signature",
+    ST_SIG_IDENTITY: "invalid inputs: signature is the identity point",
+    ST_PK_IDENTITY: "invalid inputs: public key is the identity point",
+    ST_DESERIALIZE: "deserialization error: invalid point",
+    ST_LEGACY_FORMAT: "legacy format error: unexpected bits in byte[0]",
+    ST_INVALID_LENGTH: "invalid length",
+    ST_INVALID_COEFFICIENT: "invalid coefficient: zero coefficient generated",
+    ST_DUPLICATE_MESSAGES: "invalid inputs: duplicate messages detected",
+    ST_SCHEME: "Invalid signature scheme",
+    ST_MISMATCHED_LENGTHS: "invalid inputs: Mismatched array lengths",
+}
+
+STAGES = ["decode_pk", "decode_sig", "hash_to_curve", "miller", "scale_sig", "reduce", "final", "bisect"]
+
+
+class BlsError(Exception):
+    """Mirror of blsful::BlsError (reference src/error.rs:5-55); `.status` is the C-ABI status code."""
+
+    def __init__(self, status: int, detail: str = ""):
+        self.status = status
+        super().__init__(_STATUS_TEXT.get(status, f"status {status}") + (f" ({detail})" if detail else ""))
+
+
+class EngineError(RuntimeError):
+    """Engine-level failure (CUDA, allocation, argument). There is no CPU path to fall back to."""
+
+
+def pk_len(impl_id: int) -> int:
+    return 48 if impl_id == Bls12381G2Impl else 96
+
+
+def sig_len(impl_id: int) -> int:
+    return 96 if impl_id == Bls12381G2Impl else 48
+
+
+_LIB_NAME = "libblsgpu.so"
+
+
+def lib_path() -> str:
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), _LIB_NAME)
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise EngineError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(no CPU fallback exists)")
+    lib = ctypes.CDLL(path)
+    c = ctypes
+    u8p, u64p, i64p, vp = c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p
+    sigs = {
+        "blsgpu_ctx_create": (c.c_int, [c.POINTER(c.c_int), c.c_int, c.POINTER(vp)]),
+        "blsgpu_ctx_destroy": (None, [vp]),
+        "blsgpu_last_error": (c.c_char_p, [vp]),
+        "blsgpu_ctx_set_rlc_salt": (c.c_int, [vp, u8p]),
+        "blsgpu_verify_batch": (c.c_int, [vp, c.c_int, c.c_int, c.c_int, c.c_size_t, u8p, u8p, u8p, u64p, u8p]),
+        "blsgpu_verify_batch_dev": (c.c_int, [vp, c.c_int, c.c_int, c.c_int, c.c_size_t, u8p, u8p, u8p, u64p, u8p]),
+        "blsgpu_pop_verify_batch": (c.c_int, [vp, c.c_int, c.c_int, c.c_size_t, u8p, u8p, u8p]),
+        "blsgpu_aggregate_verify": (c.c_int, [vp, c.c_int, c.c_int, c.c_int, c.c_size_t, u8p, u8p, u64p, u8p, u8p, i64p]),
+        "blsgpu_sum_points": (c.c_int, [vp, c.c_int, c.c_int, c.c_size_t, u8p, u8p, u8p, i64p]),
+        "blsgpu_verify_secure_batch": (c.c_int, [vp, c.c_int, c.c_int, c.c_int, c.c_size_t, u64p, u8p, u8p, u8p, u64p, u8p]),
+        "blsgpu_aggregate_secure_batch": (c.c_int, [vp, c.c_int, c.c_int, c.c_size_t, u64p, u8p, u8p, u8p, u8p]),
+        "blsgpu_hash_to_curve_batch": (c.c_int, [vp, c.c_int, c.c_size_t, u8p, u64p, u8p, c.c_size_t, u8p]),
+        "blsgpu_recode_points": (c.c_int, [vp, c.c_int, c.c_int, c.c_int, c.c_size_t, u8p, u8p, u8p]),
+        "blsgpu_fp_mul_batch": (c.c_int, [vp, c.c_int, c.c_size_t, u8p, u8p, u8p]),
+        "blsgpu_pairing_product_is_one": (c.c_int, [vp, c.c_size_t, u8p, u8p, c.POINTER(c.c_int)]),
+        "blsgpu_testdata_sign": (c.c_int, [vp, c.c_int, c.c_int, c.c_size_t, u8p, u8p, u64p, u8p, u8p]),
+        "blsgpu_imad_peak": (c.c_int, [vp, c.POINTER(c.c_double)]),
+        "blsgpu_last_stage_ms": (c.c_int, [vp, c.POINTER(c.c_float)]),
+        "blsgpu_launch_count": (c.c_uint64, [vp]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)  # AttributeError here means the library does not export what include/blsgpu.h declares
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = [
+    "blsgpu_ctx_create", "blsgpu_ctx_destroy", "blsgpu_last_error", "blsgpu_ctx_set_rlc_salt", "blsgpu_verify_batch",
+    "blsgpu_verify_batch_dev", "blsgpu_pop_verify_batch", "blsgpu_aggregate_verify", "blsgpu_sum_points",
+    "blsgpu_verify_secure_batch", "blsgpu_aggregate_secure_batch", "blsgpu_hash_to_curve_batch", "blsgpu_recode_points",
+    "blsgpu_fp_mul_batch", "blsgpu_pairing_product_is_one", "blsgpu_testdata_sign", "blsgpu_imad_peak",
+    "blsgpu_last_stage_ms", "blsgpu_launch_count",
+]
+
+
+def _u8(buf) -> np.ndarray:
+    if isinstance(buf, np.ndarray):
+        a = buf
+        if a.dtype != np.uint8:
+            a = a.view(np.uint8)
+        return np.ascontiguousarray(a).reshape(-1)
+    return np.frombuffer(bytes(buf), dtype=np.uint8)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None or a.size == 0 else a.ctypes.data
+
+
+def pack_messages(msgs: Sequence[bytes]) -> Tuple[np.ndarray, np.ndarray]:
+    off = np.zeros(len(msgs) + 1, dtype=np.uint64)
+    if len(msgs):
+        off[1:] = np.cumsum([len(m) for m in msgs], dtype=np.uint64)
+    data = np.frombuffer(b"".join(bytes(m) for m in msgs), dtype=np.uint8)
+    return data, off
+
+
+def _pack_points(points, length: int, what: str) -> np.ndarray:
+    """Accepts a list of byte strings or one flat uint8 array; enforces the reference's length rule."""
+    if isinstance(points, np.ndarray):
+        a = _u8(points)
+        if a.size % length:
+            raise BlsError(ST_INVALID_LENGTH, f"{what}: expected multiples of {length} bytes")
+        return a
+    for p in points:
+        if len(p) != length:
+            raise BlsError(ST_INVALID_LENGTH, f"{what}: expected {length} bytes, got {len(p)}")
+    return np.frombuffer(b"".join(bytes(p) for p in points), dtype=np.uint8)
+
+
+class Engine:
+    """One blsgpu context (one host thread at a time)."""
+
+    def __init__(self, devices: Sequence[int] = (0,)):
+        self._lib = load_library()
+        self._ctx = ctypes.c_void_p()
+        devs = (ctypes.c_int * len(devices))(*devices)
+        rc = self._lib.blsgpu_ctx_create(devs, len(devices), ctypes.byref(self._ctx))
+        if rc != 0:
+            msg = self._lib.blsgpu_last_error(None)
+            raise EngineError(f"blsgpu_ctx_create failed ({rc}): {msg.decode() if msg else ''}")
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.blsgpu_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self._lib.blsgpu_last_error(self._ctx)
+            raise EngineError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    # ---- Signature::verify over slices --------------------------------------------------------------------------
+    def verify_batch(self, impl_id: int, scheme: int, pks, sigs, msgs: Sequence[bytes],
+                     fmt: int = SerializationFormat.Modern) -> np.ndarray:
+        """status[i] == 0  <=>  Signature::verify(&pk_i, msg_i).is_ok(); other values name the reference's error."""
+        pk = _pack_points(pks, pk_len(impl_id), "public key")
+        sg = _pack_points(sigs, sig_len(impl_id), "signature")
+        n = pk.size // pk_len(impl_id)
+        if sg.size // sig_len(impl_id) != n or len(msgs) != n:
+            raise BlsError(ST_MISMATCHED_LENGTHS)
+        data, off = pack_messages(msgs)
+        return self.verify_batch_packed(impl_id, scheme, pk, sg, data, off, fmt)
+
+    def verify_batch_packed(self, impl_id, scheme, pk: np.ndarray, sg: np.ndarray, data: np.ndarray, off: np.ndarray,
+                            fmt: int = SerializationFormat.Modern) -> np.ndarray:
+        n = off.size - 1
+        status = np.empty(n, dtype=np.uint8)
+        rc = self._lib.blsgpu_verify_batch(self._ctx, impl_id, scheme, fmt, n, _ptr(pk), _ptr(sg), _ptr(data), _ptr(off),
+                                           _ptr(status))
+        self._check(rc, "blsgpu_verify_batch")
+        return status
+
+    def verify_batch_dev(self, impl_id, scheme, n, pk_ptr: int, sig_ptr: int, msg_ptr: int, off_ptr: int, status_ptr: int,
+                         fmt: int = SerializationFormat.Modern) -> None:
+        rc = self._lib.blsgpu_verify_batch_dev(self._ctx, impl_id, scheme, fmt, n, pk_ptr, sig_ptr, msg_ptr, off_ptr, status_ptr)
+        self._check(rc, "blsgpu_verify_batch_dev")
+
+    def pop_verify_batch(self, impl_id: int, pks, sigs, fmt: int = SerializationFormat.Modern) -> np.ndarray:
+        pk = _pack_points(pks, pk_len(impl_id), "public key")
+        sg = _pack_points(sigs, sig_len(impl_id), "proof of possession")
+        n = pk.size // pk_len(impl_id)
+        if sg.size // sig_len(impl_id) != n:
+            raise BlsError(ST_MISMATCHED_LENGTHS)
+        status = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.blsgpu_pop_verify_batch(self._ctx, impl_id, fmt, n, _ptr(pk), _ptr(sg), _ptr(status)),
+                    "blsgpu_pop_verify_batch")
+        return status
+
+    # ---- AggregateSignature::verify -------------------------------------------------------------------------------
+    def aggregate_verify(self, impl_id: int, scheme: int, pks, msgs: Sequence[bytes], sig: bytes,
+                         fmt: int = SerializationFormat.Modern) -> None:
+        """Returns None on success, raises BlsError like AggregateSignature::verify (aggregate_signature.rs:230-239)."""
+        st, idx = self.aggregate_verify_status(impl_id, scheme, pks, msgs, sig, fmt)
+        if st != ST_OK:
+            detail = ""
+            if st == ST_DUPLICATE_MESSAGES:
+                detail = f"at {idx[0]} and {idx[1]}"
+            elif st == ST_PK_IDENTITY:
+                detail = f"public key at {idx[0]}"
+            raise BlsError(st, detail)
+
+    def aggregate_verify_status(self, impl_id, scheme, pks, msgs, sig, fmt=SerializationFormat.Modern):
+        pk = _pack_points(pks, pk_len(impl_id), "public key")
+        n = pk.size // pk_len(impl_id)
+        if len(msgs) != n:
+            raise BlsError(ST_MISMATCHED_LENGTHS)
+        if len(sig) != sig_len(impl_id):
+            raise BlsError(ST_INVALID_LENGTH, "signature")
+        data, off = pack_messages(msgs)
+        sg = _u8(sig)
+        status = np.zeros(1, dtype=np.uint8)
+        idx = np.full(2, -1, dtype=np.int64)
+        rc = self._lib.blsgpu_aggregate_verify(self._ctx, impl_id, scheme, fmt, n, _ptr(pk), _ptr(data), _ptr(off), _ptr(sg),
+                                               _ptr(status), _ptr(idx))
+        self._check(rc, "blsgpu_aggregate_verify")
+        return int(status[0]), (int(idx[0]), int(idx[1]))
+
+    # ---- point sums -------------------------------------------------------------------------------------------------
+    def sum_points(self, group: int, points, fmt: int = SerializationFormat.Modern) -> bytes:
+        length = 48 if group == 1 else 96
+        pts = _pack_points(points, length, "point")
+        n = pts.size // length
+        out = np.zeros(length, dtype=np.uint8)
+        status = np.zeros(1, dtype=np.uint8)
+        bad = np.full(1, -1, dtype=np.int64)
+        rc = self._lib.blsgpu_sum_points(self._ctx, group, fmt, n, _ptr(pts), _ptr(out), _ptr(status), _ptr(bad))
+        self._check(rc, "blsgpu_sum_points")
+        if status[0] != ST_OK:
+            raise BlsError(int(status[0]), f"element {int(bad[0])}")
+        return out.tobytes()
+
+    def sum_signatures(self, impl_id: int, sigs, fmt: int = SerializationFormat.Modern, multi: bool = False,
+                       schemes: Optional[Sequence[int]] = None) -> bytes:
+        """AggregateSignature/MultiSignature::from_signatures (aggregate_signature.rs:123-148, multi_signature.rs:80-107):
+        fewer than 2 signatures -> InvalidSignature; mixed schemes -> InvalidSignatureScheme; MultiSignature rejects
+        MessageAugmentation elements at positions >= 1."""
+        n = len(sigs) if not isinstance(sigs, np.ndarray) else sigs.size // sig_len(impl_id)
+        if n < 2:
+            raise BlsError(ST_INVALID_SIGNATURE)
+        if schemes is not None:
+            for s in schemes[1:]:
+                if s != schemes[0] or (multi and s == SignatureSchemes.MessageAugmentation):
+                    raise BlsError(ST_SCHEME)
+        return self.sum_points(1 if impl_id == Bls12381G1Impl else 2, sigs, fmt)
+
+    def sum_public_keys(self, impl_id: int, pks, fmt: int = SerializationFormat.Modern) -> bytes:
+        """MultiPublicKey::from_public_keys (multi_public_key.rs:79-83)."""
+        return self.sum_points(2 if impl_id == Bls12381G1Impl else 1, pks, fmt)
+
+    # ---- secure aggregation -------------------------------------------------------------------------------------------
+    def verify_secure_batch(self, impl_id: int, scheme: int, key_sets: Sequence[Sequence[bytes]], sigs, msgs: Sequence[bytes],
+                            fmt: int = SerializationFormat.Modern) -> np.ndarray:
+        q = len(key_sets)
+        koff = np.zeros(q + 1, dtype=np.uint64)
+        if q:
+            koff[1:] = np.cumsum([len(k) for k in key_sets], dtype=np.uint64)
+        flat = [k for ks in key_sets for k in ks]
+        pk = _pack_points(flat, pk_len(impl_id), "public key")
+        sg = _pack_points(sigs, sig_len(impl_id), "signature")
+        if sg.size // sig_len(impl_id) != q or len(msgs) != q:
+            raise BlsError(ST_MISMATCHED_LENGTHS)
+        data, off = pack_messages(msgs)
+        return self.verify_secure_batch_packed(impl_id, scheme, koff, pk, sg, data, off, fmt)
+
+    def verify_secure_batch_packed(self, impl_id, scheme, koff, pk, sg, data, off, fmt=SerializationFormat.Modern):
+        q = koff.size - 1
+        status = np.empty(q, dtype=np.uint8)
+        rc = self._lib.blsgpu_verify_secure_batch(self._ctx, impl_id, scheme, fmt, q, _ptr(koff), _ptr(pk), _ptr(sg), _ptr(data),
+                                                  _ptr(off), _ptr(status))
+        self._check(rc, "blsgpu_verify_secure_batch")
+        return status
+
+    def aggregate_secure_batch(self, impl_id: int, key_sets: Sequence[Sequence[bytes]], sig_sets: Sequence[Sequence[bytes]],
+                               fmt: int = SerializationFormat.Modern) -> Tuple[np.ndarray, List[bytes]]:
+        q = len(key_sets)
+        status_pre = np.zeros(q, dtype=np.uint8)
+        for j in range(q):
+            if len(key_sets[j]) != len(sig_sets[j]):
+                status_pre[j] = ST_MISMATCHED_LENGTHS
+        if status_pre.any():
+            raise BlsError(ST_MISMATCHED_LENGTHS)
+        koff = np.zeros(q + 1, dtype=np.uint64)
+        if q:
+            koff[1:] = np.cumsum([len(k) for k in key_sets], dtype=np.uint64)
+        pk = _pack_points([k for ks in key_sets for k in ks], pk_len(impl_id), "public key")
+        sg = _pack_points([s for ss in sig_sets for s in ss], sig_len(impl_id), "signature")
+        out = np.zeros(q * sig_len(impl_id), dtype=np.uint8)
+        status = np.empty(q, dtype=np.uint8)
+        rc = self._lib.blsgpu_aggregate_secure_batch(self._ctx, impl_id, fmt, q, _ptr(koff), _ptr(pk), _ptr(sg), _ptr(out),
+                                                     _ptr(status))
+        self._check(rc, "blsgpu_aggregate_secure_batch")
+        L = sig_len(impl_id)
+        return status, [out[j * L:(j + 1) * L].tobytes() for j in range(q)]
+
+    # ---- building blocks ------------------------------------------------------------------------------------------------
+    def hash_to_curve_batch(self, group: int, msgs: Sequence[bytes], dst: bytes) -> List[bytes]:
+        data, off = pack_messages(msgs)
+        n = len(msgs)
+        L = 48 if group == 1 else 96
+        out = np.zeros(n * L, dtype=np.uint8)
+        d = _u8(dst)
+        rc = self._lib.blsgpu_hash_to_curve_batch(self._ctx, group, n, _ptr(data), _ptr(off), _ptr(d), len(dst), _ptr(out))
+        self._check(rc, "blsgpu_hash_to_curve_batch")
+        return [out[i * L:(i + 1) * L].tobytes() for i in range(n)]
+
+    def recode_points(self, group: int, points, fmt_in: int, fmt_out: int) -> Tuple[np.ndarray, List[bytes]]:
+        L = 48 if group == 1 else 96
+        pts = _pack_points(points, L, "point")
+        n = pts.size // L
+        out = np.zeros(n * L, dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        rc = self._lib.blsgpu_recode_points(self._ctx, group, fmt_in, fmt_out, n, _ptr(pts), _ptr(out), _ptr(status))
+        self._check(rc, "blsgpu_recode_points")
+        return status, [out[i * L:(i + 1) * L].tobytes() for i in range(n)]
+
+    def fp_mul_batch(self, a: np.ndarray, b: np.ndarray, variant: int = 0) -> np.ndarray:
+        a, b = _u8(a), _u8(b)
+        n = a.size // 48
+        out = np.zeros(n * 48, dtype=np.uint8)
+        self._check(self._lib.blsgpu_fp_mul_batch(self._ctx, variant, n, _ptr(a), _ptr(b), _ptr(out)), "blsgpu_fp_mul_batch")
+        return out
+
+    def pairing_product_is_one(self, g1_points, g2_points) -> bool:
+        a = _pack_points(g1_points, 48, "G1 point")
+        b = _pack_points(g2_points, 96, "G2 point")
+        n = a.size // 48
+        res = ctypes.c_int(0)
+        self._check(self._lib.blsgpu_pairing_product_is_one(self._ctx, n, _ptr(a), _ptr(b), ctypes.byref(res)),
+                    "blsgpu_pairing_product_is_one")
+        return bool(res.value)
+
+    def testdata_sign(self, impl_id: int, scheme: int, scalars: np.ndarray, msgs_data: np.ndarray, msg_off: np.ndarray):
+        """Synthetic data only (see include/blsgpu.h): returns (pks, sigs) flat uint8 arrays."""
+        n = msg_off.size - 1
+        k = _u8(scalars)
+        pks = np.zeros(n * pk_len(impl_id), dtype=np.uint8)
+        sigs = np.zeros(n * sig_len(impl_id), dtype=np.uint8)
+        rc = self._lib.blsgpu_testdata_sign(self._ctx, impl_id, scheme, n, _ptr(k), _ptr(msgs_data), _ptr(msg_off), _ptr(pks),
+                                            _ptr(sigs))
+        self._check(rc, "blsgpu_testdata_sign")
+        return pks, sigs
+
+    def imad_peak(self) -> float:
+        v = ctypes.c_double(0)
+        self._check(self._lib.blsgpu_imad_peak(self._ctx, ctypes.byref(v)), "blsgpu_imad_peak")
+        return v.value
+
+    def last_stage_ms(self) -> dict:
+        arr = (ctypes.c_float * len(STAGES))()
+        self._check(self._lib.blsgpu_last_stage_ms(self._ctx, arr), "blsgpu_last_stage_ms")
+        return {name: float(arr[i]) for i, name in enumerate(STAGES)}
+
+    def launch_count(self) -> int:
+        return int(self._lib.blsgpu_launch_count(self._ctx))

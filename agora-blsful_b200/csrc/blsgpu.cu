@@ -1,0 +1,782 @@
+// C ABI of the engine (include/blsgpu.h): host orchestration of the kernels in kernels.cuh.
+// No CPU arithmetic lives here: every field/curve/pairing operation runs on the device; the host only stages buffers,
+// launches kernels, walks the bisection tree and applies the reference's host-side rules (duplicate messages, sorting).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/blsgpu.h"
+#include "kernels.cuh"
+
+using namespace bls;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+#define CK(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      ctx->err = std::string(#expr) + ": " + cudaGetErrorString(e_);                               \
+      return (e_ == cudaErrorMemoryAllocation) ? BLSGPU_E_ALLOC : BLSGPU_E_CUDA;                   \
+    }                                                                                              \
+  } while (0)
+#define CKR(expr)                         \
+  do {                                    \
+    int r_ = (expr);                      \
+    if (r_ != BLSGPU_OK) return r_;       \
+  } while (0)
+
+constexpr int TPB = 128;
+inline unsigned blocks_for(size_t n, int tpb = TPB) { return (unsigned)((n + tpb - 1) / tpb); }
+
+// bump allocator over one device buffer, regrown between calls
+struct Arena {
+  uint8_t* base = nullptr;
+  size_t cap = 0, off = 0;
+  template <class T>
+  T* take(size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+    T* p = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return p;
+  }
+};
+
+struct Level {
+  size_t off, cnt;
+};
+
+}  // namespace
+
+struct blsgpu_ctx {
+  std::vector<int> devices;
+  cudaStream_t stream = nullptr;
+  Arena arena;
+  std::string err;
+  uint8_t salt[32];
+  cudaEvent_t ev[BLSGPU_STAGE_COUNT + 1];
+  bool ev_valid[BLSGPU_STAGE_COUNT + 1];
+  float stage_ms[BLSGPU_STAGE_COUNT];
+  uint64_t launches = 0;
+};
+
+namespace {
+
+int ensure_arena(blsgpu_ctx* ctx, size_t bytes) {
+  ctx->arena.off = 0;
+  if (ctx->arena.cap >= bytes) return BLSGPU_OK;
+  if (ctx->arena.base) CK(cudaFree(ctx->arena.base));
+  ctx->arena.base = nullptr;
+  ctx->arena.cap = 0;
+  size_t want = bytes + (bytes >> 3) + (1 << 20);
+  CK(cudaMalloc(&ctx->arena.base, want));
+  ctx->arena.cap = want;
+  return BLSGPU_OK;
+}
+
+int check_launch(blsgpu_ctx* ctx, const char* what) {
+  ctx->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    ctx->err = std::string(what) + " launch: " + cudaGetErrorString(e);
+    return BLSGPU_E_CUDA;
+  }
+  return BLSGPU_OK;
+}
+#define LAUNCH(name, grid, block, ...)                          \
+  do {                                                          \
+    name<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__);     \
+    CKR(check_launch(ctx, #name));                              \
+  } while (0)
+
+void stage_mark(blsgpu_ctx* ctx, int idx) {
+  cudaEventRecord(ctx->ev[idx], ctx->stream);
+  ctx->ev_valid[idx] = true;
+}
+void stage_reset(blsgpu_ctx* ctx) {
+  for (int i = 0; i <= BLSGPU_STAGE_COUNT; i++) ctx->ev_valid[i] = false;
+  for (int i = 0; i < BLSGPU_STAGE_COUNT; i++) ctx->stage_ms[i] = 0.f;
+}
+void stage_collect(blsgpu_ctx* ctx) {
+  if (ctx->ev_valid[BLSGPU_STAGE_COUNT]) cudaEventSynchronize(ctx->ev[BLSGPU_STAGE_COUNT]);
+  for (int i = 0; i < BLSGPU_STAGE_COUNT; i++) {
+    if (ctx->ev_valid[i] && ctx->ev_valid[i + 1]) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]) == cudaSuccess) ctx->stage_ms[i] = ms;
+    }
+  }
+}
+
+bool make_dst(DstParam& d, int impl_id, int scheme, bool pop_proof) {
+  // reference src/impls/g2.rs:107-118, src/impls/g1.rs:109-120
+  const char* g = impl_id == 2 ? "G2" : "G1";
+  const char* tag = scheme == 0 ? "NUL_" : scheme == 1 ? "AUG_" : "POP_";
+  char buf[64];
+  int n = snprintf(buf, sizeof buf, "BLS_%s_BLS12381%s_XMD:SHA-256_SSWU_RO_%s", pop_proof ? "POP" : "SIG", g, tag);
+  if (n <= 0 || n > 63) return false;
+  memset(d.b, 0, sizeof d.b);
+  memcpy(d.b, buf, n);
+  d.len = (uint32_t)n;
+  return true;
+}
+
+std::vector<Level> make_levels(size_t n) {
+  std::vector<Level> lv;
+  size_t off = 0, cnt = n;
+  lv.push_back({off, cnt});
+  while (cnt > 1) {
+    off += cnt;
+    cnt = (cnt + 15) / 16;
+    lv.push_back({off, cnt});
+  }
+  return lv;
+}
+size_t levels_total(const std::vector<Level>& lv) { return lv.back().off + lv.back().cnt; }
+
+// -----------------------------------------------------------------------------------------------------------------
+// The batch pipeline on decoded points.  PkA/SigA are the affine types of the impl.
+//   pre[i]   : status before pairing work (non-OK items are excluded from the batch equation)
+//   use_rlc  : true  -> per-item check  e(pk_i,H_i) e(-g,sig_i) == 1 for all i, decided by one random linear combination
+//                       and bisection on failure (writes INVALID_SIGNATURE into status[i] for the exact failures);
+//              false -> aggregate check prod e(pk_i,H_i) * e(-g, sig_0) == 1 (sig has ONE element), *agg_ok receives it
+// -----------------------------------------------------------------------------------------------------------------
+template <class PkA, class SigA>
+int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA* d_sig, const SigA* d_h, uint8_t* d_status,
+                         bool use_rlc, int* agg_ok) {
+  typedef typename PtInfo<SigA>::Jac SigJ;
+  std::vector<Level> lv = make_levels(n);
+  size_t total = levels_total(lv);
+  Fp12* d_F = ctx->arena.take<Fp12>(total);
+  SigJ* d_S = ctx->arena.take<SigJ>(use_rlc ? total : 1);
+  Digest* d_dig = ctx->arena.take<Digest>(total + 2);
+  Digest* d_root = d_dig + total;  // [root, salt]
+  uint8_t* d_ok = ctx->arena.take<uint8_t>(std::max<size_t>(n, 16));
+  uint32_t* d_idx = ctx->arena.take<uint32_t>(std::max<size_t>(n, 16));
+
+  if (use_rlc) {
+    LAUNCH((k_leaf_digest<PkA, SigA>), blocks_for(n), TPB, n, d_pk, d_sig, d_h, d_dig);
+    for (size_t k = 0; k + 1 < lv.size(); k++)
+      LAUNCH(k_digest_reduce, blocks_for(lv[k + 1].cnt), TPB, lv[k].cnt, d_dig + lv[k].off, lv[k + 1].cnt, d_dig + lv[k + 1].off);
+    CK(cudaMemcpyAsync(d_root, d_dig + lv.back().off, sizeof(Digest), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_root + 1, ctx->salt, 32, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  stage_mark(ctx, BLSGPU_STAGE_MILLER);
+  LAUNCH((k_miller<PkA, SigA>), blocks_for(n), TPB, n, d_pk, d_h, d_status, d_root, use_rlc ? 1 : 0, d_F);
+  stage_mark(ctx, BLSGPU_STAGE_SCALE_SIG);
+  if (use_rlc) LAUNCH((k_scale_sig<SigA>), blocks_for(n), TPB, n, d_sig, d_status, d_root, d_S);
+  stage_mark(ctx, BLSGPU_STAGE_REDUCE);
+  for (size_t k = 0; k + 1 < lv.size(); k++) {
+    LAUNCH(k_reduce_fp12, blocks_for(lv[k + 1].cnt), TPB, lv[k].cnt, d_F + lv[k].off, lv[k + 1].cnt, d_F + lv[k + 1].off);
+    if (use_rlc)
+      LAUNCH((k_reduce_jac<SigJ>), blocks_for(lv[k + 1].cnt), TPB, lv[k].cnt, d_S + lv[k].off, lv[k + 1].cnt, d_S + lv[k + 1].off);
+  }
+  stage_mark(ctx, BLSGPU_STAGE_FINAL);
+  if (!use_rlc) {
+    // S = the single aggregate signature
+    typedef typename PtInfo<SigA>::Jac J;
+    LAUNCH((k_reduce_aff<SigA>), 1, 32, (size_t)1, d_sig, (size_t)1, d_S);
+    (void)sizeof(J);
+  }
+  const Fp12* rootF = d_F + lv.back().off;
+  const SigJ* rootS = use_rlc ? d_S + lv.back().off : d_S;
+  LAUNCH((k_probe<SigJ>), 1, 64, (size_t)1, (const uint32_t*)nullptr, rootF, rootS, d_ok);
+  uint8_t ok = 0;
+  CK(cudaMemcpyAsync(&ok, d_ok, 1, cudaMemcpyDeviceToHost, ctx->stream));
+  stage_mark(ctx, BLSGPU_STAGE_BISECT);
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (!use_rlc) {
+    *agg_ok = ok;
+    stage_mark(ctx, BLSGPU_STAGE_COUNT);
+    return BLSGPU_OK;
+  }
+  if (!ok) {
+    // walk down the 16-ary tree: children of node j at level k+1 are {j + m * cnt(k+1)} at level k
+    std::vector<uint32_t> bad{0};
+    for (size_t k = lv.size() - 1; k-- > 0;) {
+      std::vector<uint32_t> cand;
+      size_t cn = lv[k + 1].cnt;
+      for (uint32_t j : bad)
+        for (int m = 0; m < 16; m++) {
+          size_t idx = (size_t)j + (size_t)m * cn;
+          if (idx < lv[k].cnt) cand.push_back((uint32_t)idx);
+        }
+      if (cand.empty()) break;
+      CK(cudaMemcpyAsync(d_idx, cand.data(), cand.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+      LAUNCH((k_probe<SigJ>), blocks_for(cand.size(), 64), 64, cand.size(), (const uint32_t*)d_idx, d_F + lv[k].off, d_S + lv[k].off,
+             d_ok);
+      if (k == 0) LAUNCH(k_mark_invalid, blocks_for(cand.size()), TPB, cand.size(), (const uint32_t*)d_idx, (const uint8_t*)d_ok, d_status);
+      std::vector<uint8_t> res(cand.size());
+      CK(cudaMemcpyAsync(res.data(), d_ok, cand.size(), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      bad.clear();
+      for (size_t c = 0; c < cand.size(); c++)
+        if (!res[c]) bad.push_back(cand[c]);
+      if (bad.empty()) break;  // cannot happen for a failing parent; defensive
+    }
+  }
+  stage_mark(ctx, BLSGPU_STAGE_COUNT);
+  return BLSGPU_OK;
+}
+
+template <class PkA, class SigA>
+size_t pipeline_bytes(size_t n) {
+  typedef typename PtInfo<SigA>::Jac SigJ;
+  size_t total = levels_total(make_levels(std::max<size_t>(n, 1)));
+  return total * (sizeof(Fp12) + sizeof(SigJ) + sizeof(Digest)) + (n + 64) * 8 + 16 * 256 + 4096;
+}
+
+// verify over device-resident compressed inputs.  msg_mode: 0 msg, 1 pk||msg, 2 pk bytes (PoP)
+template <int IMPL>
+int verify_dev(blsgpu_ctx* ctx, int msg_mode, const DstParam& dst, int format, size_t n, const uint8_t* d_pks, const uint8_t* d_sigs,
+               const uint8_t* d_msgs, const uint64_t* d_moff, uint8_t* d_status_out, size_t arena_reserved) {
+  typedef typename ImplT<IMPL>::PkAff PkA;
+  typedef typename ImplT<IMPL>::SigAff SigA;
+  (void)arena_reserved;
+  PkA* d_pk = ctx->arena.take<PkA>(n);
+  SigA* d_sig = ctx->arena.take<SigA>(n);
+  SigA* d_h = ctx->arena.take<SigA>(n);
+  uint8_t* d_stpk = ctx->arena.take<uint8_t>(n);
+  uint8_t* d_stsig = ctx->arena.take<uint8_t>(n);
+  stage_reset(ctx);
+  stage_mark(ctx, BLSGPU_STAGE_DECODE_PK);
+  LAUNCH((k_decode<PkA>), blocks_for(n), TPB, n, d_pks, format, d_pk, d_stpk);
+  stage_mark(ctx, BLSGPU_STAGE_DECODE_SIG);
+  LAUNCH((k_decode<SigA>), blocks_for(n), TPB, n, d_sigs, format, d_sig, d_stsig);
+  LAUNCH((k_prestatus<PkA, SigA>), blocks_for(n), TPB, n, d_stpk, d_stsig, d_pk, d_sig, d_status_out);
+  stage_mark(ctx, BLSGPU_STAGE_HASH);
+  LAUNCH((k_hash<SigA, PkA>), blocks_for(n), TPB, n, d_msgs, d_moff, msg_mode, (const PkA*)d_pk, (const uint8_t*)d_status_out, dst, d_h);
+  CKR((run_pairing_pipeline<PkA, SigA>(ctx, n, d_pk, d_sig, d_h, d_status_out, true, nullptr)));
+  stage_collect(ctx);
+  return BLSGPU_OK;
+}
+template <int IMPL>
+size_t verify_bytes(size_t n) {
+  typedef typename ImplT<IMPL>::PkAff PkA;
+  typedef typename ImplT<IMPL>::SigAff SigA;
+  return n * (sizeof(PkA) + 2 * sizeof(SigA) + 2) + 8 * 256 + pipeline_bytes<PkA, SigA>(n);
+}
+
+bool args_ok(int impl_id, int scheme, int format) {
+  return (impl_id == 1 || impl_id == 2) && scheme >= 0 && scheme <= 2 && (format == 0 || format == 1);
+}
+
+template <class T>
+int upload(blsgpu_ctx* ctx, T*& d, const T* h, size_t count) {
+  d = ctx->arena.take<T>(std::max<size_t>(count, 1));
+  if (count) CK(cudaMemcpyAsync(d, h, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  return BLSGPU_OK;
+}
+
+int set_device(blsgpu_ctx* ctx) {
+  CK(cudaSetDevice(ctx->devices[0]));
+  return BLSGPU_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+// (C linkage comes from the declarations in include/blsgpu.h)
+
+int blsgpu_ctx_create(const int* devices, int ndev, blsgpu_ctx** out) {
+  if (!out || ndev < 1 || !devices) {
+    g_create_error = "blsgpu_ctx_create: bad arguments";
+    return BLSGPU_E_ARG;
+  }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this engine has no CPU fallback)";
+    return BLSGPU_E_CUDA;
+  }
+  for (int i = 0; i < ndev; i++)
+    if (devices[i] < 0 || devices[i] >= count) {
+      g_create_error = "device index out of range";
+      return BLSGPU_E_ARG;
+    }
+  blsgpu_ctx* ctx = new blsgpu_ctx();
+  ctx->devices.assign(devices, devices + ndev);
+  memset(ctx->salt, 0, 32);
+  memcpy(ctx->salt, "blsgpu-rlc-v1", 13);
+  e = cudaSetDevice(devices[0]);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  for (int i = 0; e == cudaSuccess && i <= BLSGPU_STAGE_COUNT; i++) e = cudaEventCreate(&ctx->ev[i]);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("context setup: ") + cudaGetErrorString(e);
+    delete ctx;
+    return BLSGPU_E_CUDA;
+  }
+  stage_reset(ctx);
+  *out = ctx;
+  return BLSGPU_OK;
+}
+
+void blsgpu_ctx_destroy(blsgpu_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->devices[0]);
+  if (ctx->arena.base) cudaFree(ctx->arena.base);
+  for (int i = 0; i <= BLSGPU_STAGE_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* blsgpu_last_error(const blsgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int blsgpu_ctx_set_rlc_salt(blsgpu_ctx* ctx, const uint8_t salt[32]) {
+  if (!ctx || !salt) return BLSGPU_E_ARG;
+  memcpy(ctx->salt, salt, 32);
+  return BLSGPU_OK;
+}
+
+int blsgpu_last_stage_ms(const blsgpu_ctx* ctx, float ms_out[BLSGPU_STAGE_COUNT]) {
+  if (!ctx || !ms_out) return BLSGPU_E_ARG;
+  for (int i = 0; i < BLSGPU_STAGE_COUNT; i++) ms_out[i] = ctx->stage_ms[i];
+  return BLSGPU_OK;
+}
+uint64_t blsgpu_launch_count(const blsgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int blsgpu_verify_batch_dev(blsgpu_ctx* ctx, int impl_id, int scheme, int format, size_t n, const uint8_t* pks_dev,
+                            const uint8_t* sigs_dev, const uint8_t* msgs_dev, const uint64_t* msg_off_dev, uint8_t* status_out_dev) {
+  if (!ctx) return BLSGPU_E_ARG;
+  if (!args_ok(impl_id, scheme, format) || (n && (!pks_dev || !sigs_dev || !msg_off_dev || !status_out_dev))) {
+    ctx->err = "blsgpu_verify_batch_dev: bad arguments";
+    return BLSGPU_E_ARG;
+  }
+  if (n == 0) return BLSGPU_OK;
+  CKR(set_device(ctx));
+  DstParam dst;
+  make_dst(dst, impl_id, scheme, false);
+  int mode = scheme == 1 ? 1 : 0;
+  if (impl_id == 2) {
+    CKR(ensure_arena(ctx, verify_bytes<2>(n)));
+    return verify_dev<2>(ctx, mode, dst, format, n, pks_dev, sigs_dev, msgs_dev, msg_off_dev, status_out_dev, 0);
+  }
+  CKR(ensure_arena(ctx, verify_bytes<1>(n)));
+  return verify_dev<1>(ctx, mode, dst, format, n, pks_dev, sigs_dev, msgs_dev, msg_off_dev, status_out_dev, 0);
+}
+
+static int verify_host_common(blsgpu_ctx* ctx, int impl_id, int msg_mode, const DstParam& dst, int format, size_t n, const uint8_t* pks,
+                              const uint8_t* sigs, const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out) {
+  CKR(set_device(ctx));
+  size_t pk_len = impl_id == 2 ? 48 : 96, sig_len = impl_id == 2 ? 96 : 48;
+  size_t msg_bytes = msg_off ? (size_t)msg_off[n] : 0;
+  size_t in_bytes = n * (pk_len + sig_len + 1) + msg_bytes + (n + 1) * 8 + 8 * 256;
+  CKR(ensure_arena(ctx, in_bytes + (impl_id == 2 ? verify_bytes<2>(n) : verify_bytes<1>(n))));
+  uint8_t *d_pks, *d_sigs, *d_msgs, *d_st;
+  uint64_t* d_off;
+  CKR(upload(ctx, d_pks, pks, n * pk_len));
+  CKR(upload(ctx, d_sigs, sigs, n * sig_len));
+  CKR(upload(ctx, d_msgs, msgs, msg_bytes));
+  std::vector<uint64_t> zero_off;
+  if (!msg_off) {
+    zero_off.assign(n + 1, 0);
+    msg_off = zero_off.data();
+  }
+  CKR(upload(ctx, d_off, msg_off, n + 1));
+  d_st = ctx->arena.take<uint8_t>(n);
+  int r = impl_id == 2 ? verify_dev<2>(ctx, msg_mode, dst, format, n, d_pks, d_sigs, d_msgs, d_off, d_st, 0)
+                       : verify_dev<1>(ctx, msg_mode, dst, format, n, d_pks, d_sigs, d_msgs, d_off, d_st, 0);
+  CKR(r);
+  CK(cudaMemcpyAsync(status_out, d_st, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return BLSGPU_OK;
+}
+
+int blsgpu_verify_batch(blsgpu_ctx* ctx, int impl_id, int scheme, int format, size_t n, const uint8_t* pks, const uint8_t* sigs,
+                        const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out) {
+  if (!ctx) return BLSGPU_E_ARG;
+  if (!args_ok(impl_id, scheme, format) || (n && (!pks || !sigs || !msg_off || !status_out))) {
+    ctx->err = "blsgpu_verify_batch: bad arguments";
+    return BLSGPU_E_ARG;
+  }
+  if (n == 0) return BLSGPU_OK;
+  DstParam dst;
+  make_dst(dst, impl_id, scheme, false);
+  return verify_host_common(ctx, impl_id, scheme == 1 ? 1 : 0, dst, format, n, pks, sigs, msgs, msg_off, status_out);
+}
+
+int blsgpu_pop_verify_batch(blsgpu_ctx* ctx, int impl_id, int format, size_t n, const uint8_t* pks, const uint8_t* sigs,
+                            uint8_t* status_out) {
+  if (!ctx) return BLSGPU_E_ARG;
+  if (!args_ok(impl_id, 2, format) || (n && (!pks || !sigs || !status_out))) {
+    ctx->err = "blsgpu_pop_verify_batch: bad arguments";
+    return BLSGPU_E_ARG;
+  }
+  if (n == 0) return BLSGPU_OK;
+  DstParam dst;
+  make_dst(dst, impl_id, 2, true);
+  return verify_host_common(ctx, impl_id, 2, dst, format, n, pks, sigs, nullptr, nullptr, status_out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+template <int IMPL>
+static int aggregate_verify_impl(blsgpu_ctx* ctx, int scheme, int format, size_t n, const uint8_t* pks, const uint8_t* msgs,
+                                 const uint64_t* msg_off, const uint8_t* sig, uint8_t* status_out, int64_t index_out[2]) {
+  typedef typename ImplT<IMPL>::PkAff PkA;
+  typedef typename ImplT<IMPL>::SigAff SigA;
+  const size_t pk_len = PtInfo<PkA>::LEN, sig_len = PtInfo<SigA>::LEN;
+  size_t msg_bytes = (size_t)msg_off[n];
+  size_t need = n * (pk_len + sizeof(PkA) + sizeof(SigA) + 2) + msg_bytes + (n + 1) * 8 + sig_len + sizeof(SigA) + 16 * 256 +
+                pipeline_bytes<PkA, SigA>(std::max<size_t>(n, 1));
+  CKR(ensure_arena(ctx, need));
+  uint8_t *d_pks, *d_msgs, *d_sigb;
+  uint64_t* d_off;
+  CKR(upload(ctx, d_pks, pks, n * pk_len));
+  CKR(upload(ctx, d_msgs, msgs, msg_bytes));
+  CKR(upload(ctx, d_off, msg_off, n + 1));
+  CKR(upload(ctx, d_sigb, sig, sig_len));
+  PkA* d_pk = ctx->arena.take<PkA>(std::max<size_t>(n, 1));
+  SigA* d_sig = ctx->arena.take<SigA>(1);
+  SigA* d_h = ctx->arena.take<SigA>(std::max<size_t>(n, 1));
+  uint8_t* d_stpk = ctx->arena.take<uint8_t>(n + 1);
+  uint8_t* d_stsig = d_stpk + n;
+  stage_reset(ctx);
+  if (n) LAUNCH((k_decode<PkA>), blocks_for(n), TPB, n, (const uint8_t*)d_pks, format, d_pk, d_stpk);
+  LAUNCH((k_decode<SigA>), 1, 32, (size_t)1, (const uint8_t*)d_sigb, format, d_sig, d_stsig);
+  std::vector<uint8_t> st(n + 1);
+  CK(cudaMemcpyAsync(st.data(), d_stpk, n + 1, cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<uint32_t> inf(n + 1, 0);
+  // identity flags: read the `inf` words back (strided copy)
+  if (n) CK(cudaMemcpy2DAsync(inf.data(), 4, reinterpret_cast<const uint8_t*>(d_pk) + offsetof(PkA, inf), sizeof(PkA), 4, n,
+                              cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(&inf[n], reinterpret_cast<const uint8_t*>(d_sig) + offsetof(SigA, inf), 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  index_out[0] = index_out[1] = -1;
+  for (size_t i = 0; i < n; i++)
+    if (st[i] != BLSGPU_ST_OK) {
+      *status_out = st[i];
+      index_out[0] = (int64_t)i;
+      return BLSGPU_OK;
+    }
+  if (st[n] != BLSGPU_ST_OK) {
+    *status_out = st[n];
+    return BLSGPU_OK;
+  }
+  if (scheme == 0) {
+    // Basic: duplicate messages are rejected before any curve work (reference src/traits/sig_basic.rs:46-58)
+    std::unordered_map<std::string, size_t> seen;
+    seen.reserve(n * 2);
+    for (size_t i = 0; i < n; i++) {
+      std::string m(reinterpret_cast<const char*>(msgs + msg_off[i]), (size_t)(msg_off[i + 1] - msg_off[i]));
+      auto it = seen.find(m);
+      if (it != seen.end()) {
+        *status_out = BLSGPU_ST_DUPLICATE_MESSAGES;
+        index_out[0] = (int64_t)it->second;
+        index_out[1] = (int64_t)i;
+        return BLSGPU_OK;
+      }
+      seen.emplace(std::move(m), i);
+    }
+  }
+  if (inf[n]) {
+    *status_out = BLSGPU_ST_SIG_IDENTITY;
+    return BLSGPU_OK;
+  }
+  for (size_t i = 0; i < n; i++)
+    if (inf[i]) {
+      *status_out = BLSGPU_ST_PK_IDENTITY;
+      index_out[0] = (int64_t)i + 1;  // the reference reports i+1 (sig_core.rs:162-167)
+      return BLSGPU_OK;
+    }
+  int ok = 0;
+  if (n == 0) {
+    // only the (sig, -g) pair remains and sig != identity: never the Gt identity
+    *status_out = BLSGPU_ST_INVALID_SIGNATURE;
+    return BLSGPU_OK;
+  }
+  DstParam dst;
+  make_dst(dst, IMPL, scheme, false);
+  uint8_t* d_status = ctx->arena.take<uint8_t>(n);
+  CK(cudaMemsetAsync(d_status, 0, n, ctx->stream));
+  LAUNCH((k_hash<SigA, PkA>), blocks_for(n), TPB, n, (const uint8_t*)d_msgs, (const uint64_t*)d_off, scheme == 1 ? 1 : 0, (const PkA*)d_pk,
+         (const uint8_t*)nullptr, dst, d_h);
+  CKR((run_pairing_pipeline<PkA, SigA>(ctx, n, d_pk, d_sig, d_h, d_status, false, &ok)));
+  *status_out = ok ? BLSGPU_ST_OK : BLSGPU_ST_INVALID_SIGNATURE;
+  return BLSGPU_OK;
+}
+
+int blsgpu_aggregate_verify(blsgpu_ctx* ctx, int impl_id, int scheme, int format, size_t n, const uint8_t* pks, const uint8_t* msgs,
+                            const uint64_t* msg_off, const uint8_t* sig, uint8_t* status_out, int64_t index_out[2]) {
+  if (!ctx) return BLSGPU_E_ARG;
+  int64_t dummy[2];
+  if (!index_out) index_out = dummy;
+  if (!args_ok(impl_id, scheme, format) || !sig || !status_out || !msg_off || (n && !pks)) {
+    ctx->err = "blsgpu_aggregate_verify: bad arguments";
+    return BLSGPU_E_ARG;
+  }
+  CKR(set_device(ctx));
+  return impl_id == 2 ? aggregate_verify_impl<2>(ctx, scheme, format, n, pks, msgs, msg_off, sig, status_out, index_out)
+                      : aggregate_verify_impl<1>(ctx, scheme, format, n, pks, msgs, msg_off, sig, status_out, index_out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+template <class A>
+static int sum_points_impl(blsgpu_ctx* ctx, int format, size_t n, const uint8_t* points, uint8_t* out, uint8_t* status_out,
+                           int64_t* bad_index_out) {
+  typedef typename PtInfo<A>::Jac J;
+  const size_t L = PtInfo<A>::LEN;
+  std::vector<Level> lv = make_levels(std::max<size_t>(n, 1));
+  size_t need = n * (L + sizeof(A) + 1) + levels_total(lv) * sizeof(J) + sizeof(A) + L + 16 * 256;
+  CKR(ensure_arena(ctx, need));
+  uint8_t* d_in;
+  CKR(upload(ctx, d_in, points, n * L));
+  A* d_pts = ctx->arena.take<A>(std::max<size_t>(n, 1));
+  uint8_t* d_st = ctx->arena.take<uint8_t>(std::max<size_t>(n, 1));
+  J* d_tree = ctx->arena.take<J>(levels_total(lv) + 1);
+  A* d_res = ctx->arena.take<A>(1);
+  uint8_t* d_out = ctx->arena.take<uint8_t>(L);
+  *bad_index_out = -1;
+  std::vector<uint8_t> st(n);
+  if (n) {
+    LAUNCH((k_decode<A>), blocks_for(n), TPB, n, (const uint8_t*)d_in, format, d_pts, d_st);
+    CK(cudaMemcpyAsync(st.data(), d_st, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < n; i++)
+      if (st[i] != BLSGPU_ST_OK) {
+        *status_out = st[i];
+        *bad_index_out = (int64_t)i;
+        return BLSGPU_OK;
+      }
+  }
+  // level 1 from the affine leaves, then Jacobian levels
+  size_t n1 = n ? (n + 15) / 16 : 1;
+  LAUNCH((k_reduce_aff<A>), blocks_for(n1), TPB, n, (const A*)d_pts, n1, d_tree);
+  size_t cur = n1;
+  J* src = d_tree;
+  while (cur > 1) {
+    size_t nxt = (cur + 15) / 16;
+    LAUNCH((k_reduce_jac<J>), blocks_for(nxt), TPB, cur, (const J*)src, nxt, src + cur);
+    src += cur;
+    cur = nxt;
+  }
+  LAUNCH((k_to_affine<A>), 1, 32, (size_t)1, (const J*)src, d_res);
+  LAUNCH((k_encode<A>), 1, 32, (size_t)1, (const A*)d_res, format, d_out);
+  CK(cudaMemcpyAsync(out, d_out, L, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *status_out = BLSGPU_ST_OK;
+  return BLSGPU_OK;
+}
+
+int blsgpu_sum_points(blsgpu_ctx* ctx, int group, int format, size_t n, const uint8_t* points, uint8_t* out, uint8_t* status_out,
+                      int64_t* bad_index_out) {
+  if (!ctx) return BLSGPU_E_ARG;
+  int64_t dummy;
+  if (!bad_index_out) bad_index_out = &dummy;
+  if ((group != 1 && group != 2) || (format != 0 && format != 1) || !out || !status_out || (n && !points)) {
+    ctx->err = "blsgpu_sum_points: bad arguments";
+    return BLSGPU_E_ARG;
+  }
+  CKR(set_device(ctx));
+  return group == 1 ? sum_points_impl<G1Aff>(ctx, format, n, points, out, status_out, bad_index_out)
+                    : sum_points_impl<G2Aff>(ctx, format, n, points, out, status_out, bad_index_out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+template <class A>
+static int hash_batch_impl(blsgpu_ctx* ctx, size_t n, const uint8_t* msgs, const uint64_t* msg_off, const DstParam& dst, uint8_t* out) {
+  const size_t L = PtInfo<A>::LEN;
+  size_t msg_bytes = (size_t)msg_off[n];
+  CKR(ensure_arena(ctx, msg_bytes + (n + 1) * 8 + n * (sizeof(A) + L) + 8 * 256));
+  uint8_t* d_msgs;
+  uint64_t* d_off;
+  CKR(upload(ctx, d_msgs, msgs, msg_bytes));
+  CKR(upload(ctx, d_off, msg_off, n + 1));
+  A* d_h = ctx->arena.take<A>(n);
+  uint8_t* d_out = ctx->arena.take<uint8_t>(n * L);
+  LAUNCH((k_hash<A, G1Aff>), blocks_for(n), TPB, n, (const uint8_t*)d_msgs, (const uint64_t*)d_off, 0, (const G1Aff*)nullptr,
+         (const uint8_t*)nullptr, dst, d_h);
+  LAUNCH((k_encode<A>), blocks_for(n), TPB, n, (const A*)d_h, 1, d_out);
+  CK(cudaMemcpyAsync(out, d_out, n * L, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return BLSGPU_OK;
+}
+
+int blsgpu_hash_to_curve_batch(blsgpu_ctx* ctx, int group, size_t n, const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* dst,
+                               size_t dst_len, uint8_t* out) {
+  if (!ctx) return BLSGPU_E_ARG;
+  if ((group != 1 && group != 2) || !msg_off || !dst || dst_len == 0 || dst_len > 63 || (n && !out)) {
+    ctx->err = "blsgpu_hash_to_curve_batch: bad arguments (dst_len must be 1..63)";
+    return BLSGPU_E_ARG;
+  }
+  if (n == 0) return BLSGPU_OK;
+  CKR(set_device(ctx));
+  DstParam d;
+  memset(d.b, 0, sizeof d.b);
+  memcpy(d.b, dst, dst_len);
+  d.len = (uint32_t)dst_len;
+  return group == 1 ? hash_batch_impl<G1Aff>(ctx, n, msgs, msg_off, d, out) : hash_batch_impl<G2Aff>(ctx, n, msgs, msg_off, d, out);
+}
+
+template <class A>
+static int recode_impl(blsgpu_ctx* ctx, int fin, int fout, size_t n, const uint8_t* in, uint8_t* out, uint8_t* status_out) {
+  const size_t L = PtInfo<A>::LEN;
+  CKR(ensure_arena(ctx, n * (2 * L + sizeof(A) + 1) + 8 * 256));
+  uint8_t* d_in;
+  CKR(upload(ctx, d_in, in, n * L));
+  A* d_pts = ctx->arena.take<A>(n);
+  uint8_t* d_st = ctx->arena.take<uint8_t>(n);
+  uint8_t* d_out = ctx->arena.take<uint8_t>(n * L);
+  LAUNCH((k_decode<A>), blocks_for(n), TPB, n, (const uint8_t*)d_in, fin, d_pts, d_st);
+  LAUNCH((k_encode<A>), blocks_for(n), TPB, n, (const A*)d_pts, fout, d_out);
+  CK(cudaMemcpyAsync(out, d_out, n * L, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(status_out, d_st, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return BLSGPU_OK;
+}
+
+int blsgpu_recode_points(blsgpu_ctx* ctx, int group, int format_in, int format_out, size_t n, const uint8_t* in, uint8_t* out,
+                         uint8_t* status_out) {
+  if (!ctx) return BLSGPU_E_ARG;
+  if ((group != 1 && group != 2) || (format_in | format_out) & ~1 || (n && (!in || !out || !status_out))) {
+    ctx->err = "blsgpu_recode_points: bad arguments";
+    return BLSGPU_E_ARG;
+  }
+  if (n == 0) return BLSGPU_OK;
+  CKR(set_device(ctx));
+  return group == 1 ? recode_impl<G1Aff>(ctx, format_in, format_out, n, in, out, status_out)
+                    : recode_impl<G2Aff>(ctx, format_in, format_out, n, in, out, status_out);
+}
+
+int blsgpu_fp_mul_batch(blsgpu_ctx* ctx, int variant, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  if (!ctx) return BLSGPU_E_ARG;
+  if ((variant != 0 && variant != 1) || (n && (!a || !b || !out))) {
+    ctx->err = "blsgpu_fp_mul_batch: bad arguments";
+    return BLSGPU_E_ARG;
+  }
+  if (n == 0) return BLSGPU_OK;
+  CKR(set_device(ctx));
+  CKR(ensure_arena(ctx, 3 * n * 48 + 4 * 256));
+  uint8_t *d_a, *d_b;
+  CKR(upload(ctx, d_a, a, n * 48));
+  CKR(upload(ctx, d_b, b, n * 48));
+  uint8_t* d_o = ctx->arena.take<uint8_t>(n * 48);
+  LAUNCH(k_fp_mul, blocks_for(n), TPB, n, variant, (const uint8_t*)d_a, (const uint8_t*)d_b, d_o);
+  CK(cudaMemcpyAsync(out, d_o, n * 48, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return BLSGPU_OK;
+}
+
+int blsgpu_pairing_product_is_one(blsgpu_ctx* ctx, size_t n, const uint8_t* g1_points, const uint8_t* g2_points, int* is_one_out) {
+  if (!ctx) return BLSGPU_E_ARG;
+  if (!is_one_out || (n && (!g1_points || !g2_points))) {
+    ctx->err = "blsgpu_pairing_product_is_one: bad arguments";
+    return BLSGPU_E_ARG;
+  }
+  if (n == 0) {
+    *is_one_out = 1;
+    return BLSGPU_OK;
+  }
+  CKR(set_device(ctx));
+  std::vector<Level> lv = make_levels(n);
+  CKR(ensure_arena(ctx, n * (48 + 96 + sizeof(G1Aff) + sizeof(G2Aff) + 2) + levels_total(lv) * sizeof(Fp12) + 12 * 256));
+  uint8_t *d_a, *d_b;
+  CKR(upload(ctx, d_a, g1_points, n * 48));
+  CKR(upload(ctx, d_b, g2_points, n * 96));
+  G1Aff* d_p = ctx->arena.take<G1Aff>(n);
+  G2Aff* d_q = ctx->arena.take<G2Aff>(n);
+  uint8_t* d_st = ctx->arena.take<uint8_t>(2 * n);
+  Fp12* d_F = ctx->arena.take<Fp12>(levels_total(lv));
+  uint8_t* d_ok = ctx->arena.take<uint8_t>(1);
+  LAUNCH((k_decode<G1Aff>), blocks_for(n), TPB, n, (const uint8_t*)d_a, 1, d_p, d_st);
+  LAUNCH((k_decode<G2Aff>), blocks_for(n), TPB, n, (const uint8_t*)d_b, 1, d_q, d_st + n);
+  std::vector<uint8_t> st(2 * n);
+  CK(cudaMemcpyAsync(st.data(), d_st, 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (uint8_t s : st)
+    if (s != BLSGPU_ST_OK) {
+      ctx->err = "blsgpu_pairing_product_is_one: undecodable point";
+      return BLSGPU_E_ARG;
+    }
+  LAUNCH(k_miller_pairs, blocks_for(n), TPB, n, (const G1Aff*)d_p, (const G2Aff*)d_q, d_F);
+  for (size_t k = 0; k + 1 < lv.size(); k++)
+    LAUNCH(k_reduce_fp12, blocks_for(lv[k + 1].cnt), TPB, lv[k].cnt, (const Fp12*)(d_F + lv[k].off), lv[k + 1].cnt, d_F + lv[k + 1].off);
+  LAUNCH(k_final_is_one, 1, 32, (const Fp12*)(d_F + lv.back().off), d_ok);
+  uint8_t ok = 0;
+  CK(cudaMemcpyAsync(&ok, d_ok, 1, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *is_one_out = ok;
+  return BLSGPU_OK;
+}
+
+int blsgpu_testdata_sign(blsgpu_ctx* ctx, int impl_id, int scheme, size_t n, const uint8_t* scalars32, const uint8_t* msgs,
+                         const uint64_t* msg_off, uint8_t* out_pks, uint8_t* out_sigs) {
+  if (!ctx) return BLSGPU_E_ARG;
+  if (!args_ok(impl_id, scheme, 1) || (n && (!scalars32 || !msg_off || !out_pks || !out_sigs))) {
+    ctx->err = "blsgpu_testdata_sign: bad arguments";
+    return BLSGPU_E_ARG;
+  }
+  if (n == 0) return BLSGPU_OK;
+  CKR(set_device(ctx));
+  size_t pk_len = impl_id == 2 ? 48 : 96, sig_len = impl_id == 2 ? 96 : 48;
+  size_t msg_bytes = (size_t)msg_off[n];
+  CKR(ensure_arena(ctx, n * (32 + 8 + pk_len + sig_len) + msg_bytes + 16 * 256));
+  uint8_t *d_k, *d_m;
+  uint64_t* d_off;
+  CKR(upload(ctx, d_k, scalars32, n * 32));
+  CKR(upload(ctx, d_m, msgs, msg_bytes));
+  CKR(upload(ctx, d_off, msg_off, n + 1));
+  uint8_t* d_pk = ctx->arena.take<uint8_t>(n * pk_len);
+  uint8_t* d_sig = ctx->arena.take<uint8_t>(n * sig_len);
+  DstParam dst;
+  make_dst(dst, impl_id, scheme, false);
+  int mode = scheme == 1 ? 1 : 0;
+  if (impl_id == 2)
+    LAUNCH((k_testdata_sign<G1Aff, G2Aff>), blocks_for(n), TPB, n, (const uint8_t*)d_k, (const uint8_t*)d_m, (const uint64_t*)d_off, mode, dst,
+           d_pk, d_sig);
+  else
+    LAUNCH((k_testdata_sign<G2Aff, G1Aff>), blocks_for(n), TPB, n, (const uint8_t*)d_k, (const uint8_t*)d_m, (const uint64_t*)d_off, mode, dst,
+           d_pk, d_sig);
+  CK(cudaMemcpyAsync(out_pks, d_pk, n * pk_len, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(out_sigs, d_sig, n * sig_len, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return BLSGPU_OK;
+}
+
+int blsgpu_imad_peak(blsgpu_ctx* ctx, double* mac_per_s_out) {
+  if (!ctx || !mac_per_s_out) return BLSGPU_E_ARG;
+  CKR(set_device(ctx));
+  CKR(ensure_arena(ctx, 4096));
+  uint64_t* d_sink = ctx->arena.take<uint64_t>(1);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, ctx->devices[0]));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256;
+  const uint32_t iters = 4096;
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  LAUNCH(k_imad_peak, blocks, threads, 256u, 12345u, d_sink);  // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    CK(cudaEventRecord(a, ctx->stream));
+    LAUNCH(k_imad_peak, blocks, threads, iters, 12345u + rep, d_sink);
+    CK(cudaEventRecord(b, ctx->stream));
+    CK(cudaEventSynchronize(b));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    best = std::min(best, ms);
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  double macs = (double)blocks * threads * (double)iters * 64.0;
+  *mac_per_s_out = macs / (best * 1e-3);
+  return BLSGPU_OK;
+}
+
+int blsgpu_verify_secure_batch(blsgpu_ctx* ctx, int, int, int, size_t, const uint64_t*, const uint8_t*, const uint8_t*, const uint8_t*,
+                               const uint64_t*, uint8_t*) {
+  if (!ctx) return BLSGPU_E_ARG;
+  ctx->err = "blsgpu_verify_secure_batch: not built yet";
+  return BLSGPU_E_ARG;
+}
+int blsgpu_aggregate_secure_batch(blsgpu_ctx* ctx, int, int, size_t, const uint64_t*, const uint8_t*, const uint8_t*, uint8_t*, uint8_t*) {
+  if (!ctx) return BLSGPU_E_ARG;
+  ctx->err = "blsgpu_aggregate_secure_batch: not built yet";
+  return BLSGPU_E_ARG;
+}
+

@@ -1,0 +1,469 @@
+// Device kernels of the batch verification engine.  One thread per item (signature, public key, tree node ...): the
+// work is ~10^4 field multiplications per item, integer-multiply bound, HBM traffic negligible.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "h2c.cuh"
+#include "pairing.cuh"
+
+namespace bls {
+
+// ---- group-generic glue ------------------------------------------------------------------------------------------
+template <class A>
+struct PtInfo;
+template <>
+struct PtInfo<G1Aff> {
+  static const int LEN = 48;
+  typedef G1Jac Jac;
+};
+template <>
+struct PtInfo<G2Aff> {
+  static const int LEN = 96;
+  typedef G2Jac Jac;
+};
+__device__ __forceinline__ uint8_t pt_decompress(G1Aff& r, const uint8_t* b, bool chk) { return g1_decompress(r, b, chk); }
+__device__ __forceinline__ uint8_t pt_decompress(G2Aff& r, const uint8_t* b, bool chk) { return g2_decompress(r, b, chk); }
+__device__ __forceinline__ void pt_compress(uint8_t* o, const G1Aff& p) { g1_compress(o, p); }
+__device__ __forceinline__ void pt_compress(uint8_t* o, const G2Aff& p) { g2_compress(o, p); }
+__device__ __forceinline__ void pt_generator(G1Aff& g) {
+  fp_set(g.x, K_G1X);
+  fp_set(g.y, K_G1Y);
+  g.inf = 0;
+}
+__device__ __forceinline__ void pt_generator(G2Aff& g) {
+  fp2_set(g.x, K_G2X);
+  fp2_set(g.y, K_G2Y);
+  g.inf = 0;
+}
+template <class A>
+__device__ __forceinline__ void pt_set_inf(A& p) {
+  fzero(p.x);
+  fzero(p.y);
+  p.inf = 1;
+}
+
+// impl_id 2 (Bls12381G2Impl): pk in G1, sig/hash in G2.  impl_id 1 (Bls12381G1Impl): pk in G2, sig/hash in G1.
+template <int IMPL>
+struct ImplT;
+template <>
+struct ImplT<2> {
+  typedef G1Aff PkAff;
+  typedef G2Aff SigAff;
+  typedef G1Jac PkJac;
+  typedef G2Jac SigJac;
+};
+template <>
+struct ImplT<1> {
+  typedef G2Aff PkAff;
+  typedef G1Aff SigAff;
+  typedef G2Jac PkJac;
+  typedef G1Jac SigJac;
+};
+__device__ __forceinline__ void hash_to_group(G2Jac& r, const uint8_t* pre, uint32_t pl, const uint8_t* m, uint32_t ml,
+                                              const uint8_t* dst, uint32_t dl) {
+  hash_to_g2(r, pre, pl, m, ml, dst, dl);
+}
+__device__ __forceinline__ void hash_to_group(G1Jac& r, const uint8_t* pre, uint32_t pl, const uint8_t* m, uint32_t ml,
+                                              const uint8_t* dst, uint32_t dl) {
+  hash_to_g1(r, pre, pl, m, ml, dst, dl);
+}
+
+struct DstParam {
+  uint8_t b[64];
+  uint32_t len;
+};
+struct Digest {
+  uint8_t b[32];
+};
+
+#define BLS_TID() ((size_t)blockIdx.x * blockDim.x + threadIdx.x)
+
+// ---- decode: compressed bytes -> affine Montgomery points, curve + subgroup check --------------------------------
+template <class A>
+__global__ void __launch_bounds__(128) k_decode(size_t n, const uint8_t* __restrict__ in, int format, A* __restrict__ out,
+                                                uint8_t* __restrict__ st) {
+  size_t i = BLS_TID();
+  if (i >= n) return;
+  constexpr int L = PtInfo<A>::LEN;
+  uint8_t b[L];
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(in + i * L);  // 48 | 96 byte records: 4-byte aligned
+#pragma unroll
+  for (int k = 0; k < L / 4; k++) {
+    uint32_t w = src[k];
+    b[4 * k] = (uint8_t)w;
+    b[4 * k + 1] = (uint8_t)(w >> 8);
+    b[4 * k + 2] = (uint8_t)(w >> 16);
+    b[4 * k + 3] = (uint8_t)(w >> 24);
+  }
+  uint8_t s = header_to_modern(b[0], format);
+  A p;
+  if (s == ST_OK) s = pt_decompress(p, b, true);
+  if (s != ST_OK) pt_set_inf(p);
+  out[i] = p;
+  st[i] = s;
+}
+
+// affine points -> compressed bytes in `format`
+template <class A>
+__global__ void __launch_bounds__(128) k_encode(size_t n, const A* __restrict__ in, int format, uint8_t* __restrict__ out) {
+  size_t i = BLS_TID();
+  if (i >= n) return;
+  constexpr int L = PtInfo<A>::LEN;
+  uint8_t b[L];
+  A p = in[i];
+  pt_compress(b, p);
+  header_from_modern(b[0], format);
+  for (int k = 0; k < L; k++) out[i * L + k] = b[k];
+}
+
+// Jacobian -> affine (one inversion per thread)
+template <class A>
+__global__ void __launch_bounds__(128) k_to_affine(size_t n, const typename PtInfo<A>::Jac* __restrict__ in, A* __restrict__ out) {
+  size_t i = BLS_TID();
+  if (i >= n) return;
+  typename PtInfo<A>::Jac p = in[i];
+  A a;
+  jac_to_aff(a, p);
+  out[i] = a;
+}
+
+// per-item status before any pairing work, in the reference's order (sig_core.rs:126-135 after the parse errors)
+template <class PkA, class SigA>
+__global__ void k_prestatus(size_t n, const uint8_t* st_pk, const uint8_t* st_sig, const PkA* pk, const SigA* sig,
+                            uint8_t* out) {
+  size_t i = BLS_TID();
+  if (i >= n) return;
+  uint8_t s = st_pk[i];
+  if (s == ST_OK) s = st_sig[i];
+  if (s == ST_OK && sig[i].inf) s = ST_SIG_IDENTITY;
+  if (s == ST_OK && pk[i].inf) s = ST_PK_IDENTITY;
+  out[i] = s;
+}
+
+// ---- hash_to_curve of the framed message ---------------------------------------------------------------------------
+// msg_mode 0: msg ; 1: pk.to_bytes() || msg (MessageAugmentation, sig_aug.rs:20-24) ; 2: pk.to_bytes() (PoP, sig_pop.rs:66-69)
+template <class HA, class PkA>
+__global__ void __launch_bounds__(128) k_hash(size_t n, const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ msg_off,
+                                              int msg_mode, const PkA* __restrict__ pk, const uint8_t* __restrict__ pre,
+                                              DstParam dst, HA* __restrict__ out) {
+  size_t i = BLS_TID();
+  if (i >= n) return;
+  HA h;
+  if (pre != nullptr && pre[i] != ST_OK) {
+    pt_set_inf(h);
+    out[i] = h;
+    return;
+  }
+  uint8_t prefix[PtInfo<PkA>::LEN];
+  uint32_t plen = 0;
+  if (msg_mode != 0) {
+    PkA p = pk[i];
+    pt_compress(prefix, p);
+    plen = PtInfo<PkA>::LEN;
+  }
+  const uint8_t* m = msgs;
+  uint32_t mlen = 0;
+  if (msg_mode != 2) {
+    uint64_t o0 = msg_off[i], o1 = msg_off[i + 1];
+    m = msgs + o0;
+    mlen = (uint32_t)(o1 - o0);
+  }
+  typename PtInfo<HA>::Jac hj;
+  hash_to_group(hj, prefix, plen, m, mlen, dst.b, dst.len);
+  jac_to_aff(h, hj);
+  out[i] = h;
+}
+
+// ---- deterministic random-linear-combination scalars ----------------------------------------------------------------
+// leaf_i = SHA256(limbs of pk_i, sig_i, H_i); root = 16-ary SHA-256 tree over the leaves; r_i = LE64(SHA256(root||salt||i)).
+template <class PkA, class SigA>
+__global__ void __launch_bounds__(128) k_leaf_digest(size_t n, const PkA* pk, const SigA* sig, const SigA* h, Digest* out) {
+  size_t i = BLS_TID();
+  if (i >= n) return;
+  Sha256 s;
+  sha256_init(s);
+  sha256_update(s, reinterpret_cast<const uint8_t*>(&pk[i]), sizeof(PkA));
+  sha256_update(s, reinterpret_cast<const uint8_t*>(&sig[i]), sizeof(SigA));
+  sha256_update(s, reinterpret_cast<const uint8_t*>(&h[i]), sizeof(SigA));
+  Digest d;
+  sha256_final(s, d.b);
+  out[i] = d;
+}
+__global__ void __launch_bounds__(128) k_digest_reduce(size_t n_in, const Digest* in, size_t n_out, Digest* out) {
+  size_t j = BLS_TID();
+  if (j >= n_out) return;
+  Sha256 s;
+  sha256_init(s);
+  for (int m = 0; m < 16; m++) {
+    size_t idx = j + (size_t)m * n_out;
+    if (idx < n_in) sha256_update(s, in[idx].b, 32);
+  }
+  Digest d;
+  sha256_final(s, d.b);
+  out[j] = d;
+}
+__device__ __forceinline__ void rlc_scalar(uint32_t k[2], const Digest* root, size_t i) {
+  Sha256 s;
+  sha256_init(s);
+  sha256_update(s, root[0].b, 32);  // root[0] = tree root
+  sha256_update(s, root[1].b, 32);  // root[1] = context salt
+  uint8_t ib[8];
+  for (int b = 0; b < 8; b++) ib[b] = (uint8_t)((uint64_t)i >> (8 * b));
+  sha256_update(s, ib, 8);
+  uint8_t d[32];
+  sha256_final(s, d);
+  k[0] = (uint32_t)d[0] | ((uint32_t)d[1] << 8) | ((uint32_t)d[2] << 16) | ((uint32_t)d[3] << 24);
+  k[1] = (uint32_t)d[4] | ((uint32_t)d[5] << 8) | ((uint32_t)d[6] << 16) | ((uint32_t)d[7] << 24);
+  if ((k[0] | k[1]) == 0) k[0] = 1;
+}
+
+// ---- per-item Miller loop  f_i = ML(r_i * pk_i, H_i)  (G2Impl)  |  ML(r_i * H_i, pk_i)  (G1Impl) ---------------------
+__device__ __forceinline__ void miller_item(Fp12& f, const G1Aff& pk, const G2Aff& h, const uint32_t* k, bool scale) {
+  MillerG1 mp;
+  if (scale) {
+    G1Jac pj;
+    jac_mul_aff(pj, pk, k, 2);
+    miller_prepare(mp, pj);
+  } else {
+    miller_prepare(mp, pk);
+  }
+  miller_loop(f, mp, h);
+}
+__device__ __forceinline__ void miller_item(Fp12& f, const G2Aff& pk, const G1Aff& h, const uint32_t* k, bool scale) {
+  miller_item(f, h, pk, k, scale);
+}
+template <class PkA, class HA>
+__global__ void __launch_bounds__(128) k_miller(size_t n, const PkA* __restrict__ pk, const HA* __restrict__ h,
+                                                const uint8_t* __restrict__ pre, const Digest* __restrict__ root, int use_rlc,
+                                                Fp12* __restrict__ out) {
+  size_t i = BLS_TID();
+  if (i >= n) return;
+  Fp12 f;
+  if (pre[i] != ST_OK) {
+    fp12_one(f);
+  } else {
+    uint32_t k[2] = {1, 0};
+    if (use_rlc) rlc_scalar(k, root, i);
+    PkA p = pk[i];
+    HA q = h[i];
+    miller_item(f, p, q, k, use_rlc != 0);
+  }
+  out[i] = f;
+}
+
+// S_i = r_i * sig_i
+template <class SigA>
+__global__ void __launch_bounds__(128) k_scale_sig(size_t n, const SigA* __restrict__ sig, const uint8_t* __restrict__ pre,
+                                                   const Digest* __restrict__ root, typename PtInfo<SigA>::Jac* __restrict__ out) {
+  size_t i = BLS_TID();
+  if (i >= n) return;
+  typename PtInfo<SigA>::Jac s;
+  if (pre[i] != ST_OK) {
+    jac_set_inf(s);
+  } else {
+    uint32_t k[2];
+    rlc_scalar(k, root, i);
+    SigA a = sig[i];
+    jac_mul_aff(s, a, k, 2);
+  }
+  out[i] = s;
+}
+
+// ---- 16-ary strided reduction trees: out[j] = op over in[j + m*n_out], m = 0..15 -------------------------------------
+__global__ void __launch_bounds__(128) k_reduce_fp12(size_t n_in, const Fp12* __restrict__ in, size_t n_out, Fp12* __restrict__ out) {
+  size_t j = BLS_TID();
+  if (j >= n_out) return;
+  Fp12 acc = in[j];
+  for (int m = 1; m < 16; m++) {
+    size_t idx = j + (size_t)m * n_out;
+    if (idx < n_in) {
+      Fp12 t = in[idx];
+      fp12_mul(acc, acc, t);
+    }
+  }
+  out[j] = acc;
+}
+template <class J>
+__global__ void __launch_bounds__(128) k_reduce_jac(size_t n_in, const J* __restrict__ in, size_t n_out, J* __restrict__ out) {
+  size_t j = BLS_TID();
+  if (j >= n_out) return;
+  J acc = in[j];
+  for (int m = 1; m < 16; m++) {
+    size_t idx = j + (size_t)m * n_out;
+    if (idx < n_in) {
+      J t = in[idx];
+      jac_add(acc, acc, t);
+    }
+  }
+  out[j] = acc;
+}
+// same for affine inputs (first level of a plain point sum)
+template <class A>
+__global__ void __launch_bounds__(128) k_reduce_aff(size_t n_in, const A* __restrict__ in, size_t n_out,
+                                                    typename PtInfo<A>::Jac* __restrict__ out) {
+  size_t j = BLS_TID();
+  if (j >= n_out) return;
+  typename PtInfo<A>::Jac acc;
+  jac_set_inf(acc);
+  for (int m = 0; m < 16; m++) {
+    size_t idx = j + (size_t)m * n_out;
+    if (idx < n_in) {
+      A t = in[idx];
+      jac_add_mixed(acc, acc, t);
+    }
+  }
+  out[j] = acc;
+}
+
+// ---- probe: is  F * e'(generator side, S)  == 1 after the final exponentiation? ----------------------------------------
+// G2Impl: F * ML(-g1, S), S in G2.   G1Impl: F * ML(S, -g2), S in G1.
+__device__ __forceinline__ bool probe_node(const Fp12& F, const G2Jac& S) {
+  Fp12 g = F;
+  if (!jac_is_inf(S)) {
+    G2Aff sa;
+    jac_to_aff(sa, S);
+    G1Aff ng;
+    pt_generator(ng);
+    fp_neg(ng.y, ng.y);
+    MillerG1 mp;
+    miller_prepare(mp, ng);
+    Fp12 t;
+    miller_loop(t, mp, sa);
+    fp12_mul(g, g, t);
+  }
+  Fp12 e;
+  final_exponentiation(e, g);
+  return fp12_is_one(e);
+}
+__device__ __forceinline__ bool probe_node(const Fp12& F, const G1Jac& S) {
+  Fp12 g = F;
+  if (!jac_is_inf(S)) {
+    G2Aff ng;
+    pt_generator(ng);
+    fneg(ng.y, ng.y);
+    MillerG1 mp;
+    miller_prepare(mp, S);
+    Fp12 t;
+    miller_loop(t, mp, ng);
+    fp12_mul(g, g, t);
+  }
+  Fp12 e;
+  final_exponentiation(e, g);
+  return fp12_is_one(e);
+}
+// node list: idx[c] indexes into F/S of one tree level (idx == nullptr: identity)
+template <class J>
+__global__ void __launch_bounds__(64) k_probe(size_t cnt, const uint32_t* __restrict__ idx, const Fp12* __restrict__ F,
+                                              const J* __restrict__ S, uint8_t* __restrict__ ok) {
+  size_t c = BLS_TID();
+  if (c >= cnt) return;
+  size_t j = idx ? idx[c] : c;
+  Fp12 f = F[j];
+  J s = S[j];
+  ok[c] = probe_node(f, s) ? 1 : 0;
+}
+
+// leaves that failed their exact check
+__global__ void k_mark_invalid(size_t cnt, const uint32_t* idx, const uint8_t* ok, uint8_t* status) {
+  size_t c = BLS_TID();
+  if (c >= cnt) return;
+  if (!ok[c]) status[idx[c]] = ST_INVALID_SIGNATURE;
+}
+
+// ---- building blocks ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_fp_mul(size_t n, int variant, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  size_t i = BLS_TID();
+  if (i >= n) return;
+  uint8_t ba[48], bb[48];
+  for (int k = 0; k < 48; k++) {
+    ba[k] = a[i * 48 + k];
+    bb[k] = b[i * 48 + k];
+  }
+  Fp ra, rb, x, y, z;
+  fp_from_be48_raw(ra.l, ba);
+  fp_from_be48_raw(rb.l, bb);
+  fp_to_mont(x, ra);
+  fp_to_mont(y, rb);
+  if (variant == 0)
+    fp_mul_inl(z, x, y);
+  else
+    fp_mul_cios(z, x, y);
+  fp_from_mont(ra, z);
+  fp_to_be48_raw(ba, ra.l);
+  for (int k = 0; k < 48; k++) out[i * 48 + k] = ba[k];
+}
+
+// Miller loop of decoded (G1, G2) pairs (no scaling)
+__global__ void __launch_bounds__(128) k_miller_pairs(size_t n, const G1Aff* p, const G2Aff* q, Fp12* out) {
+  size_t i = BLS_TID();
+  if (i >= n) return;
+  Fp12 f;
+  G1Aff a = p[i];
+  G2Aff b = q[i];
+  if (a.inf || b.inf) {
+    fp12_one(f);
+  } else {
+    MillerG1 mp;
+    miller_prepare(mp, a);
+    miller_loop(f, mp, b);
+  }
+  out[i] = f;
+}
+__global__ void k_final_is_one(const Fp12* f, uint8_t* ok) {
+  if (BLS_TID() != 0) return;
+  Fp12 g = f[0], e;
+  final_exponentiation(e, g);
+  ok[0] = fp12_is_one(e) ? 1 : 0;
+}
+
+// synthetic data: pk = [k]G, sig = [k]H(frame(msg))
+template <class PkA, class SigA>
+__global__ void __launch_bounds__(128) k_testdata_sign(size_t n, const uint8_t* scalars, const uint8_t* msgs, const uint64_t* msg_off,
+                                                       int msg_mode, DstParam dst, uint8_t* out_pk, uint8_t* out_sig) {
+  size_t i = BLS_TID();
+  if (i >= n) return;
+  uint32_t k[8];
+  for (int w = 0; w < 8; w++) {
+    const uint8_t* q = scalars + i * 32 + 28 - 4 * w;
+    k[w] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
+  }
+  PkA g, pk;
+  pt_generator(g);
+  typename PtInfo<PkA>::Jac pj;
+  jac_mul_aff(pj, g, k, 8);
+  jac_to_aff(pk, pj);
+  uint8_t pkb[PtInfo<PkA>::LEN];
+  pt_compress(pkb, pk);
+  for (int b = 0; b < PtInfo<PkA>::LEN; b++) out_pk[i * PtInfo<PkA>::LEN + b] = pkb[b];
+  uint64_t o0 = msg_off[i], o1 = msg_off[i + 1];
+  typename PtInfo<SigA>::Jac hj, sj;
+  SigA h, s;
+  hash_to_group(hj, pkb, msg_mode ? PtInfo<PkA>::LEN : 0, msgs + o0, msg_mode == 2 ? 0 : (uint32_t)(o1 - o0), dst.b, dst.len);
+  jac_to_aff(h, hj);
+  jac_mul_aff(sj, h, k, 8);
+  jac_to_aff(s, sj);
+  uint8_t sb[PtInfo<SigA>::LEN];
+  pt_compress(sb, s);
+  for (int b = 0; b < PtInfo<SigA>::LEN; b++) out_sig[i * PtInfo<SigA>::LEN + b] = sb[b];
+}
+
+// INT32 multiply roofline probe: 8 independent 64-bit accumulators per thread, ITER*8 mad.wide.u32 each
+__global__ void __launch_bounds__(256) k_imad_peak(uint32_t iters, uint32_t seed, uint64_t* sink) {
+  uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
+  uint64_t c0 = a, c1 = b, c2 = a + 1, c3 = b + 1, c4 = a + 2, c5 = b + 2, c6 = a + 3, c7 = b + 3;
+  for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      asm volatile(
+          "mad.wide.u32 %0, %8, %9, %0;\n\tmad.wide.u32 %1, %8, %9, %1;\n\tmad.wide.u32 %2, %8, %9, %2;\n\t"
+          "mad.wide.u32 %3, %8, %9, %3;\n\tmad.wide.u32 %4, %8, %9, %4;\n\tmad.wide.u32 %5, %8, %9, %5;\n\t"
+          "mad.wide.u32 %6, %8, %9, %6;\n\tmad.wide.u32 %7, %8, %9, %7;"
+          : "+l"(c0), "+l"(c1), "+l"(c2), "+l"(c3), "+l"(c4), "+l"(c5), "+l"(c6), "+l"(c7)
+          : "r"(a), "r"(b));
+    }
+  }
+  uint64_t r = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+  if (r == 0x123456789abcdefull) sink[0] = r;  // keeps the chains alive
+}
+
+}  // namespace bls

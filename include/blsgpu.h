@@ -1,0 +1,162 @@
+/* blsgpu.h - C ABI of the B200-native batch BLS12-381 verification engine.
+ *
+ * Drop-in boundary for the verification hot path of dashpay/agora-blsful (blsful 3.0.0-pre8): these are the entry
+ * points a `blsful-gpu-sys` FFI crate binds.  Each function cites the reference interface it
+ * replaces (file:line under the reference tree).  Only PUBLIC data (public keys, signatures, messages) crosses this
+ * boundary; there is no secret-key API.  There is NO CPU fallback: every function fails with BLSGPU_E_CUDA when no
+ * usable CUDA device/kernel is available.
+ *
+ * Conventions
+ *   impl_id : 1 = Bls12381G1Impl (sig in G1 48 B, pk in G2 96 B), 2 = Bls12381G2Impl (sig in G2 96 B, pk in G1 48 B)
+ *             (same numbering as reference src/impls.rs:102-109)
+ *   scheme  : 0 Basic, 1 MessageAugmentation, 2 ProofOfPossession   (reference src/sig_types.rs:8-12)
+ *   format  : 0 Legacy (Dash/relic header), 1 Modern (IETF/ZCash)   (reference src/serialization.rs:10-17)
+ *             Legacy exists only for impl_id 2 in the reference (src/signature.rs:201-204, src/impls/legacy.rs:85,129);
+ *             the engine accepts it for both.
+ *   points  : compressed encodings, G1 48 bytes, G2 96 bytes (x.c1 || x.c0), reference src/impls/legacy.rs:19-170
+ *   msgs    : all messages concatenated; msg_off[i]..msg_off[i+1] delimits message i (msg_off has n+1 entries)
+ *   buffers : caller-allocated, caller-owned, HOST memory unless the name ends in _dev; inputs are read-only
+ *   return  : 0 on success or a negative BLSGPU_E_* engine error; per-item outcomes go to status_out (BLSGPU_ST_*),
+ *             which reproduce the reference's BlsResult for that item
+ *   threads : one call at a time per context; contexts are independent
+ */
+#ifndef BLSGPU_H
+#define BLSGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* engine errors (function return values) */
+#define BLSGPU_OK 0
+#define BLSGPU_E_ARG (-1)    /* bad argument (null pointer, unknown impl/scheme/format) */
+#define BLSGPU_E_CUDA (-2)   /* CUDA runtime / launch failure, or no device: see blsgpu_last_error */
+#define BLSGPU_E_ALLOC (-3)  /* device or host allocation failed */
+
+/* per-item status = the reference's outcome for that item */
+#define BLSGPU_ST_OK 0                  /* Ok(()) */
+#define BLSGPU_ST_INVALID_SIGNATURE 1   /* BlsError::InvalidSignature            src/traits/sig_core.rs:144,176 */
+#define BLSGPU_ST_SIG_IDENTITY 2        /* InvalidInputs("signature is the identity point")   sig_core.rs:126-130,155-159 */
+#define BLSGPU_ST_PK_IDENTITY 3         /* InvalidInputs("public key [at i] is the identity point") sig_core.rs:131-135,162-167 */
+#define BLSGPU_ST_DESERIALIZE 4         /* DeserializationError / "Invalid byte sequence"  src/impls/legacy.rs:110,121,154,165; src/public_key.rs:73 */
+#define BLSGPU_ST_LEGACY_FORMAT 5       /* LegacyFormatError                     src/impls/legacy.rs:53-58 */
+#define BLSGPU_ST_INVALID_LENGTH 6      /* InvalidLength (decided by the caller-side binding)  src/public_key.rs:159-164 */
+#define BLSGPU_ST_INVALID_COEFFICIENT 7 /* InvalidCoefficient                    src/secure_aggregation.rs:98-100 */
+#define BLSGPU_ST_DUPLICATE_MESSAGES 8  /* InvalidInputs("duplicate messages detected at {a} and {b}")  src/traits/sig_basic.rs:51-56 */
+#define BLSGPU_ST_SCHEME 9              /* InvalidSignatureScheme / fewer than 2 signatures (binding side) src/aggregate_signature.rs:127-133 */
+#define BLSGPU_ST_MISMATCHED_LENGTHS 10 /* InvalidInputs("Mismatched array lengths")  src/secure_aggregation.rs:125-129 */
+
+typedef struct blsgpu_ctx blsgpu_ctx;
+
+/* Create a context on the given CUDA devices (ndev >= 1).  Large batches are sharded contiguously across the devices
+ * with no collective: each device folds its slice into one partial Fp12 product + one partial point sum. */
+int blsgpu_ctx_create(const int* devices, int ndev, blsgpu_ctx** out);
+void blsgpu_ctx_destroy(blsgpu_ctx* ctx);
+/* Text of the last engine error on this context (or of the last failed blsgpu_ctx_create when ctx is NULL). */
+const char* blsgpu_last_error(const blsgpu_ctx* ctx);
+/* 32-byte salt mixed into the (deterministic) random-linear-combination scalars of the batch checks. */
+int blsgpu_ctx_set_rlc_salt(blsgpu_ctx* ctx, const uint8_t salt[32]);
+
+/* ---- Signature::verify over a slice --------------------------------------------------------------------------
+ * Replaces n calls of Signature::<C>::verify(&pk, msg)   (reference src/signature.rs:130-138 ->
+ * src/traits/sig_basic.rs:36-38 | sig_aug.rs:20-24 | sig_pop.rs:37-39 -> core_verify src/traits/sig_core.rs:120-146)
+ * including the point decoding the reference does at parse time (src/public_key.rs:55-75,158-171,
+ * src/signature.rs:231-253, src/impls/legacy.rs:100-169).
+ * status_out[i]: decode error of pk i, else decode error of sig i, else SIG_IDENTITY, PK_IDENTITY, then OK or
+ * INVALID_SIGNATURE.  Accepts are decided by one random-linear-combination check over the whole batch, rejections by
+ * exact per-item checks reached through bisection, so the vector equals the per-signature reference results. */
+int blsgpu_verify_batch(blsgpu_ctx* ctx, int impl_id, int scheme, int format, size_t n, const uint8_t* pks,
+                        const uint8_t* sigs, const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out);
+/* Same with every input already resident in device memory of the context's first device (benchmark "value" leg);
+ * status_out_dev receives n bytes on the device. */
+int blsgpu_verify_batch_dev(blsgpu_ctx* ctx, int impl_id, int scheme, int format, size_t n, const uint8_t* pks_dev,
+                            const uint8_t* sigs_dev, const uint8_t* msgs_dev, const uint64_t* msg_off_dev,
+                            uint8_t* status_out_dev);
+
+/* ---- ProofOfPossession::verify over a slice:  core_verify(pk, sig, msg = pk.to_bytes(), POP_DST)
+ * (reference src/proof_of_possession.rs:77-81, src/traits/sig_pop.rs:61-70) */
+int blsgpu_pop_verify_batch(blsgpu_ctx* ctx, int impl_id, int format, size_t n, const uint8_t* pks, const uint8_t* sigs,
+                            uint8_t* status_out);
+
+/* ---- AggregateSignature::verify ------------------------------------------------------------------------------
+ * Replaces AggregateSignature::<C>::verify(&[(pk, msg)])  (reference src/aggregate_signature.rs:230-239 ->
+ * aggregate_verify sig_basic.rs:41-64 | sig_aug.rs:27-38 | sig_pop.rs:52-58 -> core_aggregate_verify
+ * sig_core.rs:149-178).  One result in *status_out.  index_out[0..1]: (old, new) positions for DUPLICATE_MESSAGES,
+ * (i+1, -1) for PK_IDENTITY exactly as the reference message reports it, (i, -1) for a pk decode error, else -1. */
+int blsgpu_aggregate_verify(blsgpu_ctx* ctx, int impl_id, int scheme, int format, size_t n, const uint8_t* pks,
+                            const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* sig, uint8_t* status_out,
+                            int64_t index_out[2]);
+
+/* ---- point sums ----------------------------------------------------------------------------------------------
+ * Replaces aggregate_signatures / aggregate_public_keys (reference src/traits/sig_core.rs:38-59),
+ * BlsMultiSignature::from_signatures (src/traits/sig_multi.rs:7-13), BlsMultiKey::from_public_keys
+ * (src/traits/pk_multi.rs:7-13) and the TryFrom<&[Signature]> sums (src/aggregate_signature.rs:123-148,
+ * src/multi_signature.rs:80-107).  group: 1 = G1 points (48 B), 2 = G2 points (96 B).  out receives the compressed
+ * sum in `format`.  *status_out = OK or the decode error of the first bad element (*bad_index_out). */
+int blsgpu_sum_points(blsgpu_ctx* ctx, int group, int format, size_t n, const uint8_t* points, uint8_t* out,
+                      uint8_t* status_out, int64_t* bad_index_out);
+
+/* ---- secure aggregation --------------------------------------------------------------------------------------
+ * q independent key sets ("quorums"); set j owns public keys key_off[j]..key_off[j+1] of `pks`.
+ * verify: replaces Signature::verify_secure[_with_mode] (reference src/signature.rs:177-197,256-276 ->
+ * src/secure_aggregation.rs:173-208 with coefficients from :37-106 / :269-335): sort keys by serialized bytes,
+ * t_i = BE(SHA256(be32(i) || SHA256(sorted keys))) mod r, check core_verify(sum t_i pk_i, sig_j, msg_j, DST(scheme)).
+ * Empty key set: OK iff sig_j is the identity.  status_out[j] per set. */
+int blsgpu_verify_secure_batch(blsgpu_ctx* ctx, int impl_id, int scheme, int format, size_t q, const uint64_t* key_off,
+                               const uint8_t* pks, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* msg_off,
+                               uint8_t* status_out);
+/* aggregate: replaces aggregate_secure[_with_mode] (reference src/secure_aggregation.rs:110-169,338-352) and
+ * AggregateSignature::from_signatures_secure (src/aggregate_signature.rs:191-227): member_sigs holds one signature per
+ * public key (same order as pks); out_sigs receives q aggregated signatures in `format`.  Duplicate keys reuse the
+ * signature of the FIRST equal key, as the reference's `position` lookup does (:140-147). */
+int blsgpu_aggregate_secure_batch(blsgpu_ctx* ctx, int impl_id, int format, size_t q, const uint64_t* key_off,
+                                  const uint8_t* pks, const uint8_t* member_sigs, uint8_t* out_sigs, uint8_t* status_out);
+
+/* ---- building blocks (parity tests, metrics) ------------------------------------------------------------------ */
+/* hash_to_point (reference src/traits/hash_to_point.rs:6-12, src/impls/g2.rs:15-17, src/impls/g1.rs:17-19):
+ * out = compressed Modern points, group 2 -> 96 B each (G2Impl signatures), group 1 -> 48 B each. */
+int blsgpu_hash_to_curve_batch(blsgpu_ctx* ctx, int group, size_t n, const uint8_t* msgs, const uint64_t* msg_off,
+                               const uint8_t* dst, size_t dst_len, uint8_t* out);
+/* LegacyG1Point/LegacyG2Point::deserialize + serialize round trip (reference src/traits/legacy_serdes.rs:25-40,
+ * src/impls/legacy.rs:85-170): decodes n points given in `format_in` (curve + subgroup check) and re-encodes the
+ * accepted ones in `format_out`; status_out[i] = OK / DESERIALIZE / LEGACY_FORMAT. */
+int blsgpu_recode_points(blsgpu_ctx* ctx, int group, int format_in, int format_out, size_t n, const uint8_t* in,
+                         uint8_t* out, uint8_t* status_out);
+/* n Montgomery products of canonical big-endian 48-byte field elements: out = a*b mod p.  variant 0 = the engine's
+ * IMAD.WIDE carry-chain multiplier, 1 = plain CIOS cross-check. */
+int blsgpu_fp_mul_batch(blsgpu_ctx* ctx, int variant, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out);
+/* Miller loops of n (G1, G2) pairs given as compressed Modern points; *is_one_out = 1 iff the product of the n
+ * pairings is the Gt identity (reference src/helpers.rs:41-63 followed by Gt::is_identity). */
+int blsgpu_pairing_product_is_one(blsgpu_ctx* ctx, size_t n, const uint8_t* g1_points, const uint8_t* g2_points,
+                                  int* is_one_out);
+/* Synthetic-data helper for benchmarks and tests (NOT part of the verification path, not a signing API: it takes no
+ * secret-key type and is variable-time): out_pk[i] = [k_i] G, out_sig[i] = [k_i] H(msg_i) for 32-byte big-endian
+ * scalars k_i, framed for (impl_id, scheme). */
+int blsgpu_testdata_sign(blsgpu_ctx* ctx, int impl_id, int scheme, size_t n, const uint8_t* scalars32,
+                         const uint8_t* msgs, const uint64_t* msg_off, uint8_t* out_pks, uint8_t* out_sigs);
+/* INT32 multiply-issue roofline probe: runs independent mad.wide.u32 chains on every SM and returns the measured
+ * 32x32->64 multiply-accumulate rate (MAC/s) of the context's first device. */
+int blsgpu_imad_peak(blsgpu_ctx* ctx, double* mac_per_s_out);
+
+/* ---- metrics ---------------------------------------------------------------------------------------------------
+ * Per-stage device times (CUDA events on the engine's stream) of the LAST verify call on the first device. */
+#define BLSGPU_STAGE_DECODE_PK 0
+#define BLSGPU_STAGE_DECODE_SIG 1
+#define BLSGPU_STAGE_HASH 2
+#define BLSGPU_STAGE_MILLER 3
+#define BLSGPU_STAGE_SCALE_SIG 4
+#define BLSGPU_STAGE_REDUCE 5
+#define BLSGPU_STAGE_FINAL 6
+#define BLSGPU_STAGE_BISECT 7
+#define BLSGPU_STAGE_COUNT 8
+int blsgpu_last_stage_ms(const blsgpu_ctx* ctx, float ms_out[BLSGPU_STAGE_COUNT]);
+/* number of kernel launches issued by this context since creation */
+uint64_t blsgpu_launch_count(const blsgpu_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLSGPU_H */

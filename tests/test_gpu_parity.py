@@ -1,0 +1,218 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI, against the CPU oracle and the reference's golden
+vectors.  Bit-exact for every byte and status code."""
+import hashlib
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import bls_oracle as O
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import blsful_b200 as B
+    e = B.Engine([0])
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def B():
+    import blsful_b200
+    return blsful_b200
+
+
+@pytest.fixture(scope="module")
+def cpp(golden_dir):
+    return json.load(open(os.path.join(golden_dir, "cpp_integration.json")))
+
+
+IDENT1 = bytes([0xC0]) + bytes(47)
+IDENT2 = bytes([0xC0]) + bytes(95)
+
+
+def _be(v):
+    return v.to_bytes(48, "big")
+
+
+def test_fp_mul_matches_bigint(eng):
+    rnd = random.Random(7)
+    n = 20000
+    vals_a = [0, 1, O.P - 1, O.P - 2, (1 << 384) % O.P, 2] + [rnd.randrange(O.P) for _ in range(n - 6)]
+    vals_b = [O.P - 1, O.P - 1, O.P - 1, 1, (1 << 384) % O.P, 0] + [rnd.randrange(O.P) for _ in range(n - 6)]
+    a = np.frombuffer(b"".join(_be(v) for v in vals_a), dtype=np.uint8)
+    b = np.frombuffer(b"".join(_be(v) for v in vals_b), dtype=np.uint8)
+    want = b"".join(_be(x * y % O.P) for x, y in zip(vals_a, vals_b))
+    for variant in (0, 1):
+        got = eng.fp_mul_batch(a, b, variant).tobytes()
+        assert got == want, f"variant {variant}"
+
+
+def test_hash_to_curve_vectors(eng, cpp):
+    dst2 = b"QUUX-V01-CS02-with-BLS12381G2_XMD:SHA-256_SSWU_RO_"
+    dst1 = b"QUUX-V01-CS02-with-BLS12381G1_XMD:SHA-256_SSWU_RO_"
+    msgs = [b"", b"abc", b"hello", bytes(range(200))]
+    got2 = eng.hash_to_curve_batch(2, msgs, dst2)
+    got1 = eng.hash_to_curve_batch(1, msgs, dst1)
+    for m, g2, g1 in zip(msgs, got2, got1):
+        assert g2 == O.g2_serialize(O.hash_to_curve_g2(m, dst2))
+        assert g1 == O.g1_serialize(O.hash_to_curve_g1(m, dst1))
+    kat = eng.hash_to_curve_batch(2, [bytes.fromhex(cpp["message"])], O.sig_dst(O.G2IMPL, O.BASIC))[0]
+    assert kat.hex().startswith("8dbf4d3c426badac1e66421c7d65dc01")
+
+
+def test_recode_points_headers_and_subgroup(eng, B, cpp):
+    pk = bytes.fromhex(cpp["signers"][0]["pk"])
+    sig = bytes.fromhex(cpp["signers"][0]["sig"])
+    for group, enc, deser, ser in ((1, pk, O.g1_deserialize, O.g1_serialize), (2, sig, O.g2_deserialize, O.g2_serialize)):
+        L = len(enc)
+        pt = deser(enc, O.MODERN)
+        cases = [enc, ser(pt, O.LEGACY), (IDENT1 if group == 1 else IDENT2)]
+        for b0 in (0x00, 0x20, 0x40, 0x60, 0x80, 0xA0, 0xC0, 0xE0):  # every header-bit combination on a valid x
+            cases.append(bytes([(enc[0] & 0x1F) | b0]) + enc[1:])
+        bad = bytearray((O.P + 5).to_bytes(48, "big") + bytes(L - 48)); bad[0] |= 0x80
+        cases.append(bytes(bad))                       # x >= p
+        cases.append(bytes([0xC0]) + bytes(L - 2) + b"\x01")  # infinity with non-zero body
+        x = 1
+        while group == 1:  # on-curve, outside the subgroup
+            y = O.fp_sqrt((x ** 3 + 4) % O.P)
+            if y is not None and not O.g1_in_subgroup((x, y)):
+                e = bytearray(x.to_bytes(48, "big")); e[0] |= 0x80
+                cases.append(bytes(e)); break
+            x += 1
+        for fin in (O.MODERN, O.LEGACY):
+            st, outs = eng.recode_points(group, cases, fin, O.MODERN)
+            for c, s, o in zip(cases, st, outs):
+                try:
+                    want_pt = deser(c, fin); want_st = 0
+                except O.BlsError as ex:
+                    want_st = ex.code
+                assert s == want_st, (group, fin, c.hex()[:8], s, want_st)
+                if want_st == 0:
+                    assert o == ser(want_pt, O.MODERN)
+            st2, outs2 = eng.recode_points(group, [enc], O.MODERN, O.LEGACY)
+            assert st2[0] == 0 and outs2[0] == ser(pt, O.LEGACY)
+
+
+def test_verify_batch_cpp_golden(eng, B, cpp):
+    msg = bytes.fromhex(cpp["message"])
+    pks = [bytes.fromhex(s["pk"]) for s in cpp["signers"]]
+    sigs = [bytes.fromhex(s["sig"]) for s in cpp["signers"]]
+    st = eng.verify_batch(B.Bls12381G2Impl, 0, pks, sigs, [msg] * 3)
+    assert st.tolist() == [0, 0, 0]
+    # rejections and error codes, each compared with the oracle
+    pks2 = pks + [pks[0], pks[1], IDENT1, pks[2], IDENT1, pks[0]]
+    sigs2 = sigs + [sigs[1], IDENT2, sigs[0], sigs[2], IDENT2, bytes([sigs[0][0] ^ 0x20]) + sigs[0][1:]]
+    msgs2 = [msg] * 6 + [b"other", msg, msg]
+    st = eng.verify_batch(B.Bls12381G2Impl, 0, pks2, sigs2, msgs2)
+    want = [O.verify(O.G2IMPL, O.BASIC, O.MODERN, p, s, m) for p, s, m in zip(pks2, sigs2, msgs2)]
+    assert st.tolist() == want
+    assert want[:3] == [0, 0, 0] and want[3] == 1 and want[4] == 2 and want[5] == 3 and want[6] == 1
+
+
+@pytest.mark.parametrize("impl", [2, 1])
+@pytest.mark.parametrize("scheme", [0, 1, 2])
+def test_testdata_sign_matches_oracle_and_verifies(eng, impl, scheme):
+    rnd = random.Random(100 + impl * 10 + scheme)
+    n = 3
+    sks = [rnd.randrange(1, O.R) for _ in range(n)]
+    msgs = [bytes(rnd.randrange(256) for _ in range(rnd.choice([0, 5, 32, 77]))) for _ in range(n)]
+    import blsful_b200 as B
+    data, off = B.pack_messages(msgs)
+    k = np.frombuffer(b"".join(sk.to_bytes(32, "big") for sk in sks), dtype=np.uint8)
+    pks, sigs = eng.testdata_sign(impl, scheme, k, data, off)
+    pl, sl = B.pk_len(impl), B.sig_len(impl)
+    C = O.IMPLS[impl]
+    for i in range(n):
+        assert pks[i * pl:(i + 1) * pl].tobytes() == C.pk_ser(O.sk_to_pk(impl, sks[i]))
+        assert sigs[i * sl:(i + 1) * sl].tobytes() == C.sig_ser(O.sign(impl, scheme, sks[i], msgs[i]))
+    st = eng.verify_batch_packed(impl, scheme, pks, sigs, data, off)
+    assert st.tolist() == [0] * n
+    # wrong scheme => different DST/framing => invalid
+    st = eng.verify_batch_packed(impl, (scheme + 1) % 3, pks, sigs, data, off)
+    assert st.tolist() == [1] * n
+
+
+@pytest.mark.parametrize("impl", [2, 1])
+def test_verify_batch_bisection_finds_exact_bad_set(eng, B, impl):
+    rnd = random.Random(5 + impl)
+    n = 700
+    k = np.frombuffer(b"".join(rnd.randrange(1, O.R).to_bytes(32, "big") for _ in range(n)), dtype=np.uint8)
+    msgs = [hashlib.sha256(b"m%d" % i).digest() for i in range(n)]
+    data, off = B.pack_messages(msgs)
+    pks, sigs = eng.testdata_sign(impl, 0, k, data, off)
+    assert eng.verify_batch_packed(impl, 0, pks, sigs, data, off).tolist() == [0] * n
+    sl = B.sig_len(impl)
+    orig = sigs.copy()
+    sigs = sigs.copy()
+    bad = sorted(rnd.sample(range(n), 9))
+    for i in bad:  # another item's signature: a valid subgroup point, but the wrong one
+        src = (i + 1) % n
+        sigs[i * sl:(i + 1) * sl] = orig[src * sl:(src + 1) * sl]
+    st = eng.verify_batch_packed(impl, 0, pks, sigs, data, off)
+    assert [i for i in range(n) if st[i] != 0] == bad
+    assert all(st[i] == 1 for i in bad)
+    for i in bad[:2]:
+        m = msgs[i]
+        assert st[i] == O.verify(impl, O.BASIC, O.MODERN, pks[i * B.pk_len(impl):(i + 1) * B.pk_len(impl)].tobytes(),
+                                 sigs[i * sl:(i + 1) * sl].tobytes(), m)
+
+
+def test_sum_points_golden_and_pairing_product(eng, B, cpp):
+    sigs = [bytes.fromhex(s["sig"]) for s in cpp["signers"]]
+    pks = [bytes.fromhex(s["pk"]) for s in cpp["signers"]]
+    assert eng.sum_points(2, sigs[:2]).hex() == cpp["normal_agg_sig12"]
+    agg_pk = eng.sum_public_keys(B.Bls12381G2Impl, pks[:2])
+    assert agg_pk == O.g1_serialize(O.g1_add(O.g1_deserialize(pks[0]), O.g1_deserialize(pks[1])))
+    # same-message multi-signature verifies with the summed key (cpp_integration_test.rs:171-179, signatures.rs:88-128)
+    msg = bytes.fromhex(cpp["message"])
+    st = eng.verify_batch(B.Bls12381G2Impl, 0, [agg_pk], [bytes.fromhex(cpp["normal_agg_sig12"])], [msg])
+    assert st.tolist() == [0]
+    assert eng.sum_points(1, []) == IDENT1 and eng.sum_points(2, [], O.LEGACY) == IDENT2
+    with pytest.raises(B.BlsError) as e:
+        eng.sum_points(1, [pks[0], bytes(48), pks[1]])
+    assert e.value.status == 4
+    # bilinearity: e(aP, bQ) * e(-abP, Q) == 1
+    a, b = 123456789, 987654321
+    g1 = [O.g1_serialize(O.g1_mul(O.G1_GEN, a)), O.g1_serialize(O.g1_neg(O.g1_mul(O.G1_GEN, a * b)))]
+    g2 = [O.g2_serialize(O.g2_mul(O.G2_GEN, b)), O.g2_serialize(O.G2_GEN)]
+    assert eng.pairing_product_is_one(g1, g2) is True
+    assert eng.pairing_product_is_one(g1, [g2[0], g2[0]]) is False
+
+
+@pytest.mark.parametrize("impl", [2, 1])
+def test_aggregate_verify_semantics(eng, B, impl):
+    rnd = random.Random(77 + impl)
+    n = 40
+    k = np.frombuffer(b"".join(rnd.randrange(1, O.R).to_bytes(32, "big") for _ in range(n)), dtype=np.uint8)
+    msgs = [b"msg-%d" % i for i in range(n)]
+    data, off = B.pack_messages(msgs)
+    pl, sl = B.pk_len(impl), B.sig_len(impl)
+    for scheme in (0, 1, 2):
+        pks, sigs = eng.testdata_sign(impl, scheme, k, data, off)
+        pk_list = [pks[i * pl:(i + 1) * pl].tobytes() for i in range(n)]
+        agg = eng.sum_points(1 if impl == 1 else 2, sigs)
+        assert eng.aggregate_verify_status(impl, scheme, pk_list, msgs, agg)[0] == 0
+        bad_msgs = list(msgs); bad_msgs[7] = b"tampered"
+        assert eng.aggregate_verify_status(impl, scheme, pk_list, bad_msgs, agg)[0] == 1
+        dup = list(msgs); dup[9] = dup[3]
+        st, idx = eng.aggregate_verify_status(impl, scheme, pk_list, dup, agg)
+        if scheme == 0:
+            assert st == 8 and idx == (3, 9)
+        else:
+            assert st == 1
+        ident_pk = IDENT1 if impl == 2 else IDENT2
+        st, idx = eng.aggregate_verify_status(impl, scheme, pk_list[:4] + [ident_pk], msgs[:5], agg)
+        assert st == 3 and idx[0] == 5
+        assert eng.aggregate_verify_status(impl, scheme, [], [], agg)[0] == 1
+        assert eng.aggregate_verify_status(impl, scheme, pk_list, msgs, IDENT2 if impl == 2 else IDENT1)[0] == 2
+    # small case against the oracle end to end
+    pks, sigs = eng.testdata_sign(impl, 0, k[:3 * 32], *B.pack_messages(msgs[:3]))
+    pk_list = [pks[i * pl:(i + 1) * pl].tobytes() for i in range(3)]
+    agg = eng.sum_points(1 if impl == 1 else 2, sigs)
+    assert O.aggregate_verify(impl, O.BASIC, O.MODERN, pk_list, msgs[:3], agg)[0] == 0
