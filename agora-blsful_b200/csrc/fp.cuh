@@ -140,7 +140,7 @@ BLS_HD void fp_dbl(Fp& r, const Fp& a) { fp_add(r, a, a); }
 BLS_HD void chain_mul6(uint32_t* X, const uint32_t* a, uint32_t b) {
 #pragma unroll
   for (int k = 0; k < 6; k++)
-    asm("mul.lo.u32 %0, %2, %3;\n\tmul.hi.u32 %1, %2, %3;" : "=r"(X[2 * k]), "=r"(X[2 * k + 1]) : "r"(a[2 * k]), "r"(b));
+    asm("mul.lo.u32 %0, %2, %3;\n\tmul.hi.u32 %1, %2, %3;" : "=&r"(X[2 * k]), "=r"(X[2 * k + 1]) : "r"(a[2 * k]), "r"(b));  // & : %0 is written before the inputs are dead
 }
 BLS_HD void chain_mad6(uint32_t* X, const uint32_t* a, uint32_t b, uint32_t& top) {
   asm("mad.lo.cc.u32 %0, %13, %19, %0;\n\t"
