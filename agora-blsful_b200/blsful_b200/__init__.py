@@ -94,6 +94,7 @@ def load_library() -> ctypes.CDLL:
         "blsgpu_ctx_destroy": (None, [vp]),
         "blsgpu_last_error": (c.c_char_p, [vp]),
         "blsgpu_ctx_set_rlc_salt": (c.c_int, [vp, u8p]),
+        "blsgpu_ctx_set_stream": (c.c_int, [vp, vp]),
         "blsgpu_verify_batch": (c.c_int, [vp, c.c_int, c.c_int, c.c_int, c.c_size_t, u8p, u8p, u8p, u64p, u8p]),
         "blsgpu_verify_batch_dev": (c.c_int, [vp, c.c_int, c.c_int, c.c_int, c.c_size_t, u8p, u8p, u8p, u64p, u8p]),
         "blsgpu_pop_verify_batch": (c.c_int, [vp, c.c_int, c.c_int, c.c_size_t, u8p, u8p, u8p]),
@@ -118,7 +119,8 @@ def load_library() -> ctypes.CDLL:
 
 
 EXPORTED_SYMBOLS = [
-    "blsgpu_ctx_create", "blsgpu_ctx_destroy", "blsgpu_last_error", "blsgpu_ctx_set_rlc_salt", "blsgpu_verify_batch",
+    "blsgpu_ctx_create", "blsgpu_ctx_destroy", "blsgpu_last_error", "blsgpu_ctx_set_rlc_salt", "blsgpu_ctx_set_stream",
+    "blsgpu_verify_batch",
     "blsgpu_verify_batch_dev", "blsgpu_pop_verify_batch", "blsgpu_aggregate_verify", "blsgpu_sum_points",
     "blsgpu_verify_secure_batch", "blsgpu_aggregate_secure_batch", "blsgpu_hash_to_curve_batch", "blsgpu_recode_points",
     "blsgpu_fp_mul_batch", "blsgpu_pairing_product_is_one", "blsgpu_testdata_sign", "blsgpu_imad_peak",
@@ -182,6 +184,10 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    def set_stream(self, cuda_stream: int) -> None:
+        """Run on a caller-owned CUDA stream (e.g. torch.cuda.Stream().cuda_stream); 0 restores the engine's own."""
+        self._check(self._lib.blsgpu_ctx_set_stream(self._ctx, cuda_stream or None), "blsgpu_ctx_set_stream")
 
     def _check(self, rc: int, what: str):
         if rc != 0:

@@ -58,6 +58,7 @@ struct Level {
 struct blsgpu_ctx {
   std::vector<int> devices;
   cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
   Arena arena;
   std::string err;
   uint8_t salt[32];
@@ -305,7 +306,8 @@ int blsgpu_ctx_create(const int* devices, int ndev, blsgpu_ctx** out) {
   memset(ctx->salt, 0, 32);
   memcpy(ctx->salt, "blsgpu-rlc-v1", 13);
   e = cudaSetDevice(devices[0]);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+  ctx->stream = ctx->own_stream;
   for (int i = 0; e == cudaSuccess && i <= BLSGPU_STAGE_COUNT; i++) e = cudaEventCreate(&ctx->ev[i]);
   if (e != cudaSuccess) {
     g_create_error = std::string("context setup: ") + cudaGetErrorString(e);
@@ -322,11 +324,17 @@ void blsgpu_ctx_destroy(blsgpu_ctx* ctx) {
   cudaSetDevice(ctx->devices[0]);
   if (ctx->arena.base) cudaFree(ctx->arena.base);
   for (int i = 0; i <= BLSGPU_STAGE_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
 
 const char* blsgpu_last_error(const blsgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int blsgpu_ctx_set_stream(blsgpu_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return BLSGPU_E_ARG;
+  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return BLSGPU_OK;
+}
 
 int blsgpu_ctx_set_rlc_salt(blsgpu_ctx* ctx, const uint8_t salt[32]) {
   if (!ctx || !salt) return BLSGPU_E_ARG;

@@ -1,0 +1,261 @@
+#!/usr/bin/env python
+"""bench.py - verified signatures/s of the batch verification hot path (BASELINE.json metric).
+
+Workload (configs[1]): Bls12381G2Impl batch verify of N_SIGS distinct-message signatures (hash_to_curve + pairing),
+from compressed bytes.  A "step" is one pass of blsgpu_verify_batch over one batch.  Per rank (one process per GPU,
+no data-path collective, weak scaling): every rank verifies its own batch.
+
+  value : sigs/s with the batch already resident in HBM (blsgpu_verify_batch_dev), CUDA events on the launching stream
+  e2e   : sigs/s through the host-buffer C-ABI call (pinned host inputs, H2D + D2H inside the timed region)
+  roofline : INT32 multiply-accumulate (IMAD.WIDE) rate of the dominant kernel against the rate measured on this
+             GPU by blsgpu_imad_peak (this path is integer-multiply bound; HBM traffic is ~2 KB per signature)
+  cpu_baseline : the CPU oracle restating the reference's per-signature core_verify, timed on a bounded sample
+
+`--impl reference` times the reference's CPU path (oracle restatement: blsful itself needs cargo + un-vendored crates).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "agora-blsful_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+
+METRIC = "verified sigs/sec, 1M-batch G2Impl"
+UNIT = "sigs/s"
+# algorithmic work per unit (SURVEY.md 8d / BASELINE.md 4): Fp-mul = 300 32x32->64 multiply-accumulates
+MAC_PER_FPMUL = 300
+FPMUL_PER_SIG = 14400
+FPMUL_PER_STAGE = {  # per signature, from compressed bytes (SURVEY.md 8d breakdown)
+    "decode_pk": 1510, "decode_sig": 2200, "hash_to_curve": 5300, "miller": 790 + 4450, "scale_sig": 120,
+    "reduce": 10, "final": 0, "bisect": 0,
+}
+
+
+def synth_batch(eng, n, seed, impl=2, scheme=0):
+    """Deterministic synthetic triples: 31-byte random scalars (non-zero, < r), distinct 32-byte messages; signatures are
+    produced once by the engine's synthetic-data helper (signing is not part of the measured path)."""
+    import blsful_b200 as B
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    scal = np.zeros((n, 32), dtype=np.uint8)
+    scal[:, 1:] = rng.integers(0, 256, size=(n, 31), dtype=np.uint8)
+    scal[:, 31] |= 1
+    msgs = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    msgs[:, :8] = np.arange(n, dtype=np.uint64).view(np.uint8).reshape(n, 8)  # distinct by construction
+    off = (np.arange(n + 1, dtype=np.uint64) * 32)
+    pks = np.empty(n * B.pk_len(impl), dtype=np.uint8)
+    sigs = np.empty(n * B.sig_len(impl), dtype=np.uint8)
+    chunk = 1 << 18
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        o = off[lo:hi + 1] - off[lo]
+        p, s = eng.testdata_sign(impl, scheme, scal[lo:hi].reshape(-1), msgs[lo:hi].reshape(-1), np.ascontiguousarray(o))
+        pks[lo * B.pk_len(impl):hi * B.pk_len(impl)] = p
+        sigs[lo * B.sig_len(impl):hi * B.sig_len(impl)] = s
+    return pks, sigs, msgs.reshape(-1), off
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_baseline(sample, impl=2):
+    """The reference's per-signature path (core_verify: hash, 2 Miller loops, final exp) restated by the oracle."""
+    from oracle import cpu_verify
+    return cpu_verify.time_verify_sample(sample, impl)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import cpu_verify
+    res = cpu_verify.reference_arm(n_per_step=args.ref_sample, steps=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32 limbs (381-bit modular integers)", "data": "synthetic",
+        "config": {"workload": "Bls12381G2Impl Signature::verify, per-signature reference CPU path (configs[0] shape)",
+                   "sample_sigs_per_step": res["n_per_step"]},
+        "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--n", type=int, default=int(os.environ.get("BLSGPU_BENCH_N", 1_000_000)), help="signatures per batch per GPU")
+    ap.add_argument("--ref-sample", type=int, default=0, help="signatures per step for --impl reference (0 = auto)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="signatures for the cpu_baseline leg (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import blsful_b200 as B
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the engine has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    eng = B.Engine([local_rank])
+    stream = torch.cuda.Stream(device=dev)
+    eng.set_stream(stream.cuda_stream)
+    impl, scheme, n = B.Bls12381G2Impl, B.SignatureSchemes.Basic, args.n
+
+    peak_mac = eng.imad_peak()
+    pks, sigs, msgs, off = synth_batch(eng, n, seed=1000 + rank)
+
+    # pinned host copies (e2e leg) and device-resident copies (value leg)
+    def pinned(a):
+        t = torch.from_numpy(a).pin_memory()
+        return t
+    h_pk, h_sig, h_msg, h_off = pinned(pks), pinned(sigs), pinned(msgs), pinned(off.view(np.int64))
+    d_pk, d_sig, d_msg, d_off = (t.to(dev) for t in (h_pk, h_sig, h_msg, h_off))
+    d_status = torch.empty(n, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    def step_dev():
+        eng.verify_batch_dev(impl, scheme, n, d_pk.data_ptr(), d_sig.data_ptr(), d_msg.data_ptr(), d_off.data_ptr(), d_status.data_ptr())
+
+    np_pk, np_sig, np_msg, np_off = h_pk.numpy(), h_sig.numpy(), h_msg.numpy(), h_off.numpy().view(np.uint64)
+
+    def step_host():
+        return eng.verify_batch_packed(impl, scheme, np_pk, np_sig, np_msg, np_off)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        e1.synchronize()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step_dev()
+    assert int(d_status.max().item()) == 0, "synthetic batch must verify"
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = eng.launch_count()
+    ms_total = timed(step_dev, args.steps)
+    launches = eng.launch_count() - launches0
+    stages = eng.last_stage_ms()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    assert int(d_status.max().item()) == 0
+
+    # e2e through the host-buffer call
+    st = step_host()
+    assert int(st.max()) == 0
+    e2e_steps = max(1, min(args.steps, 3))
+    ms_e2e = timed(step_host, e2e_steps)
+
+    value = world * n * args.steps / (ms_total * 1e-3)
+    e2e_value = world * n * e2e_steps / (ms_e2e * 1e-3)
+
+    # roofline of the dominant kernel (largest stage): algorithmic MACs / its CUDA-event duration
+    dom = max(stages, key=lambda k: stages[k])
+    dom_macs = n * FPMUL_PER_STAGE[dom] * MAC_PER_FPMUL
+    achieved = dom_macs / (stages[dom] * 1e-3) / 1e9 if stages[dom] > 0 else 0.0
+    whole = n * FPMUL_PER_SIG * MAC_PER_FPMUL / ((ms_total / args.steps) * 1e-3) / 1e9
+    roofline = {
+        "bound": "int32_imad", "kernel": dom, "achieved": achieved, "peak": peak_mac / 1e9, "unit": "GMAC/s",
+        "frac": achieved / (peak_mac / 1e9), "traffic": None,
+        "whole_step": {"achieved": whole, "frac": whole / (peak_mac / 1e9), "fp_mul_per_sig": FPMUL_PER_SIG},
+        "peak_source": "measured live by blsgpu_imad_peak (independent mad.wide.u32 chains on all SMs); "
+                       "MEASURED_PEAKS.json holds no INT32 figure",
+        "stage_ms": stages,
+    }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32 limbs (381-bit modular integers)", "data": "synthetic",
+        "config": {"workload": f"Bls12381G2Impl Basic batch verify, {n} distinct 32-byte messages per GPU, compressed inputs "
+                               "(48 B pk + 96 B sig), hash_to_curve + pairing, all valid",
+                   "sigs_per_gpu": n, "l2": "inputs (176 B/sig) exceed L2 at 1M; intermediates stream through HBM",
+                   "miller_loops_per_s_per_gpu": n * args.steps / (ms_total * 1e-3)},
+        "roofline": roofline, "clocks": sampler.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 176 + (n + 1) * 8), "d2h_bytes_per_step": int(n)},
+        "gpu_launches": int(launches),
+    }
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(args.cpu_sample)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -57,6 +57,9 @@ int blsgpu_ctx_create(const int* devices, int ndev, blsgpu_ctx** out);
 void blsgpu_ctx_destroy(blsgpu_ctx* ctx);
 /* Text of the last engine error on this context (or of the last failed blsgpu_ctx_create when ctx is NULL). */
 const char* blsgpu_last_error(const blsgpu_ctx* ctx);
+/* Run the engine on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL restores the context's own stream).
+ * Lets the caller bracket calls with its own CUDA events (bench.py does). */
+int blsgpu_ctx_set_stream(blsgpu_ctx* ctx, void* cuda_stream);
 /* 32-byte salt mixed into the (deterministic) random-linear-combination scalars of the batch checks. */
 int blsgpu_ctx_set_rlc_salt(blsgpu_ctx* ctx, const uint8_t salt[32]);
 
