@@ -72,6 +72,8 @@ _LIB_NAME = "libblsgpu.so"
 
 
 def lib_path() -> str:
+    if os.environ.get("BLSGPU_LIB"):  # build experiments only
+        return os.environ["BLSGPU_LIB"]
     return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), _LIB_NAME)
 
 

@@ -62,14 +62,24 @@ BLS_HD void fselect(Fp2& r, bool c, const Fp2& a, const Fp2& b) {
   fp_select(r.c1, c, a.c1, b.c1);
 }
 
+// Inner products: inline copies of the multiplier (BLS_FP2_INLINE_MUL=1) or calls to the single out-of-line fp_mul/fp_sqr
+// (smaller instruction footprint; operands already live in local memory at this level).
+#ifndef BLS_FP2_INLINE_MUL
+#define BLS_FP2_INLINE_MUL 1
+#endif
+#if BLS_FP2_INLINE_MUL
+#define FP2_MUL_(r, a, b) fp_mul_inl(r, a, b)
+#else
+#define FP2_MUL_(r, a, b) fp_mul(r, a, b)
+#endif
 // Karatsuba: 3 Fp products
 BLS_FN void fp2_mul(Fp2& r, const Fp2& a, const Fp2& b) {
   Fp t0, t1, sa, sb, t2;
-  fp_mul_inl(t0, a.c0, b.c0);
-  fp_mul_inl(t1, a.c1, b.c1);
+  FP2_MUL_(t0, a.c0, b.c0);
+  FP2_MUL_(t1, a.c1, b.c1);
   fp_add(sa, a.c0, a.c1);
   fp_add(sb, b.c0, b.c1);
-  fp_mul_inl(t2, sa, sb);
+  FP2_MUL_(t2, sa, sb);
   fp_sub(t2, t2, t0);
   fp_sub(r.c1, t2, t1);
   fp_sub(r.c0, t0, t1);
@@ -79,8 +89,8 @@ BLS_FN void fp2_sqr(Fp2& r, const Fp2& a) {
   Fp s, d, m;
   fp_add(s, a.c0, a.c1);
   fp_sub(d, a.c0, a.c1);
-  fp_mul_inl(m, a.c0, a.c1);
-  fp_mul_inl(r.c0, s, d);
+  FP2_MUL_(m, a.c0, a.c1);
+  FP2_MUL_(r.c0, s, d);
   fp_add(r.c1, m, m);
 }
 BLS_HD void fmul(Fp2& r, const Fp2& a, const Fp2& b) { fp2_mul(r, a, b); }

@@ -77,10 +77,14 @@ struct Digest {
 };
 
 #define BLS_TID() ((size_t)blockIdx.x * blockDim.x + threadIdx.x)
+// resident 128-thread blocks per SM the heavy kernels are compiled for (register cap = 65536 / (128 * BLS_MIN_BLOCKS))
+#ifndef BLS_MIN_BLOCKS
+#define BLS_MIN_BLOCKS 1
+#endif
 
 // ---- decode: compressed bytes -> affine Montgomery points, curve + subgroup check --------------------------------
 template <class A>
-__global__ void __launch_bounds__(128) k_decode(size_t n, const uint8_t* __restrict__ in, int format, A* __restrict__ out,
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_decode(size_t n, const uint8_t* __restrict__ in, int format, A* __restrict__ out,
                                                 uint8_t* __restrict__ st) {
   size_t i = BLS_TID();
   if (i >= n) return;
@@ -105,7 +109,7 @@ __global__ void __launch_bounds__(128) k_decode(size_t n, const uint8_t* __restr
 
 // affine points -> compressed bytes in `format`
 template <class A>
-__global__ void __launch_bounds__(128) k_encode(size_t n, const A* __restrict__ in, int format, uint8_t* __restrict__ out) {
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_encode(size_t n, const A* __restrict__ in, int format, uint8_t* __restrict__ out) {
   size_t i = BLS_TID();
   if (i >= n) return;
   constexpr int L = PtInfo<A>::LEN;
@@ -118,7 +122,7 @@ __global__ void __launch_bounds__(128) k_encode(size_t n, const A* __restrict__ 
 
 // Jacobian -> affine (one inversion per thread)
 template <class A>
-__global__ void __launch_bounds__(128) k_to_affine(size_t n, const typename PtInfo<A>::Jac* __restrict__ in, A* __restrict__ out) {
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_to_affine(size_t n, const typename PtInfo<A>::Jac* __restrict__ in, A* __restrict__ out) {
   size_t i = BLS_TID();
   if (i >= n) return;
   typename PtInfo<A>::Jac p = in[i];
@@ -143,7 +147,7 @@ __global__ void k_prestatus(size_t n, const uint8_t* st_pk, const uint8_t* st_si
 // ---- hash_to_curve of the framed message ---------------------------------------------------------------------------
 // msg_mode 0: msg ; 1: pk.to_bytes() || msg (MessageAugmentation, sig_aug.rs:20-24) ; 2: pk.to_bytes() (PoP, sig_pop.rs:66-69)
 template <class HA, class PkA>
-__global__ void __launch_bounds__(128) k_hash(size_t n, const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ msg_off,
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_hash(size_t n, const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ msg_off,
                                               int msg_mode, const PkA* __restrict__ pk, const uint8_t* __restrict__ pre,
                                               DstParam dst, HA* __restrict__ out) {
   size_t i = BLS_TID();
@@ -177,7 +181,7 @@ __global__ void __launch_bounds__(128) k_hash(size_t n, const uint8_t* __restric
 // ---- deterministic random-linear-combination scalars ----------------------------------------------------------------
 // leaf_i = SHA256(limbs of pk_i, sig_i, H_i); root = 16-ary SHA-256 tree over the leaves; r_i = LE64(SHA256(root||salt||i)).
 template <class PkA, class SigA>
-__global__ void __launch_bounds__(128) k_leaf_digest(size_t n, const PkA* pk, const SigA* sig, const SigA* h, Digest* out) {
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_leaf_digest(size_t n, const PkA* pk, const SigA* sig, const SigA* h, Digest* out) {
   size_t i = BLS_TID();
   if (i >= n) return;
   Sha256 s;
@@ -189,7 +193,7 @@ __global__ void __launch_bounds__(128) k_leaf_digest(size_t n, const PkA* pk, co
   sha256_final(s, d.b);
   out[i] = d;
 }
-__global__ void __launch_bounds__(128) k_digest_reduce(size_t n_in, const Digest* in, size_t n_out, Digest* out) {
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_digest_reduce(size_t n_in, const Digest* in, size_t n_out, Digest* out) {
   size_t j = BLS_TID();
   if (j >= n_out) return;
   Sha256 s;
@@ -233,7 +237,7 @@ __device__ __forceinline__ void miller_item(Fp12& f, const G2Aff& pk, const G1Af
   miller_item(f, h, pk, k, scale);
 }
 template <class PkA, class HA>
-__global__ void __launch_bounds__(128) k_miller(size_t n, const PkA* __restrict__ pk, const HA* __restrict__ h,
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_miller(size_t n, const PkA* __restrict__ pk, const HA* __restrict__ h,
                                                 const uint8_t* __restrict__ pre, const Digest* __restrict__ root, int use_rlc,
                                                 Fp12* __restrict__ out) {
   size_t i = BLS_TID();
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(128) k_miller(size_t n, const PkA* __restrict_
 
 // S_i = r_i * sig_i
 template <class SigA>
-__global__ void __launch_bounds__(128) k_scale_sig(size_t n, const SigA* __restrict__ sig, const uint8_t* __restrict__ pre,
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_scale_sig(size_t n, const SigA* __restrict__ sig, const uint8_t* __restrict__ pre,
                                                    const Digest* __restrict__ root, typename PtInfo<SigA>::Jac* __restrict__ out) {
   size_t i = BLS_TID();
   if (i >= n) return;
@@ -270,7 +274,7 @@ __global__ void __launch_bounds__(128) k_scale_sig(size_t n, const SigA* __restr
 }
 
 // ---- 16-ary strided reduction trees: out[j] = op over in[j + m*n_out], m = 0..15 -------------------------------------
-__global__ void __launch_bounds__(128) k_reduce_fp12(size_t n_in, const Fp12* __restrict__ in, size_t n_out, Fp12* __restrict__ out) {
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_reduce_fp12(size_t n_in, const Fp12* __restrict__ in, size_t n_out, Fp12* __restrict__ out) {
   size_t j = BLS_TID();
   if (j >= n_out) return;
   Fp12 acc = in[j];
@@ -284,7 +288,7 @@ __global__ void __launch_bounds__(128) k_reduce_fp12(size_t n_in, const Fp12* __
   out[j] = acc;
 }
 template <class J>
-__global__ void __launch_bounds__(128) k_reduce_jac(size_t n_in, const J* __restrict__ in, size_t n_out, J* __restrict__ out) {
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_reduce_jac(size_t n_in, const J* __restrict__ in, size_t n_out, J* __restrict__ out) {
   size_t j = BLS_TID();
   if (j >= n_out) return;
   J acc = in[j];
@@ -299,7 +303,7 @@ __global__ void __launch_bounds__(128) k_reduce_jac(size_t n_in, const J* __rest
 }
 // same for affine inputs (first level of a plain point sum)
 template <class A>
-__global__ void __launch_bounds__(128) k_reduce_aff(size_t n_in, const A* __restrict__ in, size_t n_out,
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_reduce_aff(size_t n_in, const A* __restrict__ in, size_t n_out,
                                                     typename PtInfo<A>::Jac* __restrict__ out) {
   size_t j = BLS_TID();
   if (j >= n_out) return;
@@ -371,7 +375,7 @@ __global__ void k_mark_invalid(size_t cnt, const uint32_t* idx, const uint8_t* o
 }
 
 // ---- building blocks ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_fp_mul(size_t n, int variant, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_fp_mul(size_t n, int variant, const uint8_t* a, const uint8_t* b, uint8_t* out) {
   size_t i = BLS_TID();
   if (i >= n) return;
   uint8_t ba[48], bb[48];
@@ -394,7 +398,7 @@ __global__ void __launch_bounds__(128) k_fp_mul(size_t n, int variant, const uin
 }
 
 // Miller loop of decoded (G1, G2) pairs (no scaling)
-__global__ void __launch_bounds__(128) k_miller_pairs(size_t n, const G1Aff* p, const G2Aff* q, Fp12* out) {
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_miller_pairs(size_t n, const G1Aff* p, const G2Aff* q, Fp12* out) {
   size_t i = BLS_TID();
   if (i >= n) return;
   Fp12 f;
@@ -418,7 +422,7 @@ __global__ void k_final_is_one(const Fp12* f, uint8_t* ok) {
 
 // synthetic data: pk = [k]G, sig = [k]H(frame(msg))
 template <class PkA, class SigA>
-__global__ void __launch_bounds__(128) k_testdata_sign(size_t n, const uint8_t* scalars, const uint8_t* msgs, const uint64_t* msg_off,
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_testdata_sign(size_t n, const uint8_t* scalars, const uint8_t* msgs, const uint64_t* msg_off,
                                                        int msg_mode, DstParam dst, uint8_t* out_pk, uint8_t* out_sig) {
   size_t i = BLS_TID();
   if (i >= n) return;
