@@ -46,43 +46,64 @@ BLS_HD void jac_from_aff(Jac<F>& r, const Aff<F>& p) {
 template <class F>
 BLS_HD void jac_neg(Jac<F>& r, const Jac<F>& p) {
   r.X = p.X;
-  fneg(r.Y, p.Y);
+  fneg_k<16>(r.Y, p.Y);
+  fred(r.Y, r.Y);
   r.Z = p.Z;
 }
 template <class F>
 BLS_HD void aff_neg(Aff<F>& r, const Aff<F>& p) {
   r.x = p.x;
-  fneg(r.y, p.y);
+  fneg_k<16>(r.y, p.y);
+  fred(r.y, r.y);
   r.inf = p.inf;
 }
 
-// dbl-2009-l (a = 0): 2M + 5S
+// Bound contract of this file (see fp.cuh): coordinates of every stored point are normalised with value bound <= 8
+// (each point operation ends with fred on X and Y), so the lazy sums below stay far from the limits.
+
+// small multiples (lazy)
+template <class F>
+BLS_HD void fmul2(F& r, const F& a) { fdbl(r, a); }
+template <class F>
+BLS_HD void fmul4(F& r, const F& a) {
+  fdbl(r, a);
+  fdbl(r, r);
+}
+template <class F>
+BLS_HD void fmul8(F& r, const F& a) {
+  fdbl(r, a);
+  fdbl(r, r);
+  fdbl(r, r);
+}
+
+// doubling (a = 0): X3 = E^2 - 8XB, Y3 = E(4XB - X3) - 8C, Z3 = 2YZ with B = Y^2, C = B^2, E = 3X^2  (4S + 3M)
 template <class F>
 BLS_HD void jac_dbl_impl(Jac<F>& r, const Jac<F>& p) {
-  F A, B, C, D, E, Fq, t;
+  F A, B, C, XB, E, Fq, D, D2, T, X3, Y3, YZ;
   fsqr(A, p.X);
   fsqr(B, p.Y);
   fsqr(C, B);
-  fadd(t, p.X, B);
-  fsqr(t, t);
-  fsub(t, t, A);
-  fsub(t, t, C);
-  fdbl(D, t);
+  fmul(XB, p.X, B);
+  fmul(YZ, p.Y, p.Z);  // before X/Y are overwritten (r may alias p)
   fdbl(E, A);
   fadd(E, E, A);
+  fnorm(E, E);  // 3A, value <= 6
   fsqr(Fq, E);
-  fmul(t, p.Y, p.Z);  // before X/Y are overwritten (r may alias p)
-  F X3, Y3;
-  fsub(X3, Fq, D);
-  fsub(X3, X3, D);
-  fsub(Y3, D, X3);
-  fmul(Y3, E, Y3);
-  fdbl(C, C);
-  fdbl(C, C);
-  fdbl(C, C);
-  fsub(r.Y, Y3, C);
+  fmul8(D2, XB);
+  fnorm(D2, D2);  // value <= 16 (Fp) / 80 (Fp2)
+  fsub_k<128>(X3, Fq, D2);
+  fred(X3, X3);
+  fmul4(D, XB);  // value <= 8
+  fsub_k<4>(T, D, X3);
+  fnorm(T, T);
+  fmul(Y3, E, T);
+  fmul8(C, C);
+  fnorm(C, C);  // value <= 16 (Fp) / 32 (Fp2)
+  fsub_k<64>(Y3, Y3, C);
+  fred(r.Y, Y3);
   r.X = X3;
-  fdbl(r.Z, t);
+  fdbl(YZ, YZ);
+  fred(r.Z, YZ);
 }
 
 // madd-2007-bl: 7M + 4S, with the exceptional cases handled (public data, variable time)
@@ -96,13 +117,15 @@ BLS_HD void jac_add_mixed_impl(Jac<F>& r, const Jac<F>& p, const Aff<F>& q) {
     jac_from_aff(r, q);
     return;
   }
-  F Z1Z1, U2, S2, H, HH, I, J, rr, V, t;
+  F Z1Z1, U2, S2, H, HH, I, J, rr, V, t, X3, Y3, Z3;
   fsqr(Z1Z1, p.Z);
   fmul(U2, q.x, Z1Z1);
   fmul(S2, q.y, p.Z);
   fmul(S2, S2, Z1Z1);
-  fsub(H, U2, p.X);
-  fsub(rr, S2, p.Y);
+  fsub_k<16>(H, U2, p.X);
+  fsub_k<16>(rr, S2, p.Y);
+  fred(H, H);
+  fred(rr, rr);
   if (fis_zero(H)) {
     if (fis_zero(rr)) {
       jac_dbl_impl(r, p);
@@ -113,27 +136,28 @@ BLS_HD void jac_add_mixed_impl(Jac<F>& r, const Jac<F>& p, const Aff<F>& q) {
   }
   fdbl(rr, rr);
   fsqr(HH, H);
-  fdbl(I, HH);
-  fdbl(I, I);
+  fmul4(I, HH);  // value <= 8, limbs < 2^30
   fmul(J, H, I);
   fmul(V, p.X, I);
-  F X3, Y3, Z3;
   fsqr(X3, rr);
-  fsub(X3, X3, J);
-  fsub(X3, X3, V);
-  fsub(X3, X3, V);
-  fsub(Y3, V, X3);
+  fdbl(t, V);
+  fadd(t, t, J);  // J + 2V, value <= 6 (Fp) / 30 (Fp2)
+  fsub_k<32>(X3, X3, t);
+  fred(X3, X3);
+  fsub_k<4>(Y3, V, X3);
+  fnorm(Y3, Y3);
   fmul(Y3, rr, Y3);
   fmul(t, p.Y, J);
-  fdbl(t, t);
-  fsub(Y3, Y3, t);
+  fdbl(t, t);  // value <= 4 (Fp) / 20 (Fp2)
+  fsub_k<32>(Y3, Y3, t);
   fadd(Z3, p.Z, H);
+  fnorm(Z3, Z3);
   fsqr(Z3, Z3);
-  fsub(Z3, Z3, Z1Z1);
-  fsub(Z3, Z3, HH);
+  fadd(t, Z1Z1, HH);
+  fsub_k<16>(Z3, Z3, t);
+  fred(r.Y, Y3);
   r.X = X3;
-  r.Y = Y3;
-  r.Z = Z3;
+  fred(r.Z, Z3);
 }
 
 // add-2007-bl: 11M + 5S
@@ -147,7 +171,7 @@ BLS_HD void jac_add_impl(Jac<F>& r, const Jac<F>& p, const Jac<F>& q) {
     r = q;
     return;
   }
-  F Z1Z1, Z2Z2, U1, U2, S1, S2, H, I, J, rr, V, t;
+  F Z1Z1, Z2Z2, U1, U2, S1, S2, H, I, J, rr, V, t, X3, Y3, Z3;
   fsqr(Z1Z1, p.Z);
   fsqr(Z2Z2, q.Z);
   fmul(U1, p.X, Z2Z2);
@@ -156,8 +180,10 @@ BLS_HD void jac_add_impl(Jac<F>& r, const Jac<F>& p, const Jac<F>& q) {
   fmul(S1, S1, Z2Z2);
   fmul(S2, q.Y, p.Z);
   fmul(S2, S2, Z1Z1);
-  fsub(H, U2, U1);
-  fsub(rr, S2, S1);
+  fsub_k<16>(H, U2, U1);
+  fsub_k<16>(rr, S2, S1);
+  fred(H, H);
+  fred(rr, rr);
   if (fis_zero(H)) {
     if (fis_zero(rr)) {
       jac_dbl_impl(r, p);
@@ -171,24 +197,27 @@ BLS_HD void jac_add_impl(Jac<F>& r, const Jac<F>& p, const Jac<F>& q) {
   fsqr(I, I);
   fmul(J, H, I);
   fmul(V, U1, I);
-  F X3, Y3, Z3;
   fsqr(X3, rr);
-  fsub(X3, X3, J);
-  fsub(X3, X3, V);
-  fsub(X3, X3, V);
-  fsub(Y3, V, X3);
+  fdbl(t, V);
+  fadd(t, t, J);
+  fsub_k<32>(X3, X3, t);
+  fred(X3, X3);
+  fsub_k<4>(Y3, V, X3);
+  fnorm(Y3, Y3);
   fmul(Y3, rr, Y3);
   fmul(t, S1, J);
   fdbl(t, t);
-  fsub(Y3, Y3, t);
+  fsub_k<32>(Y3, Y3, t);
   fadd(Z3, p.Z, q.Z);
+  fnorm(Z3, Z3);
   fsqr(Z3, Z3);
-  fsub(Z3, Z3, Z1Z1);
-  fsub(Z3, Z3, Z2Z2);
+  fadd(t, Z1Z1, Z2Z2);
+  fsub_k<16>(Z3, Z3, t);
+  fnorm(Z3, Z3);
   fmul(Z3, Z3, H);
+  fred(r.Y, Y3);
   r.X = X3;
-  r.Y = Y3;
-  r.Z = Z3;
+  fred(r.Z, Z3);
 }
 
 // out-of-line instances (code size: one copy of each per group)
@@ -297,10 +326,13 @@ BLS_HD void g2_psi(G2Jac& r, const G2Jac& p) {
   fp2_set(cx, K_PSI_CX);
   fp2_set(cy, K_PSI_CY);
   fp2_conj(t, p.X);
-  fp2_mul(r.X, t, cx);
+  fp2_mul(t, t, cx);
+  fred(r.X, t);
   fp2_conj(t, p.Y);
-  fp2_mul(r.Y, t, cy);
-  fp2_conj(r.Z, p.Z);
+  fp2_mul(t, t, cy);
+  fred(r.Y, t);
+  fp2_conj(t, p.Z);
+  fred(r.Z, t);
 }
 // psi^2: (x,y) -> (x * K_PSI2_CX, -y)
 BLS_HD void g2_psi2(G2Jac& r, const G2Jac& p) {
@@ -308,6 +340,7 @@ BLS_HD void g2_psi2(G2Jac& r, const G2Jac& p) {
   fp_set(c, K_PSI2_CX);
   fp2_mul_fp(r.X, p.X, c);
   fneg(r.Y, p.Y);
+  fred(r.Y, r.Y);
   r.Z = p.Z;
 }
 // G2: P in G2  <=>  psi(P) = [x]P  (Scott), x = -|x|
@@ -358,14 +391,17 @@ BLS_FN uint8_t g1_decompress(G1Aff& r, const uint8_t* in, bool check_subgroup) {
     return ST_OK;
   }
   Fp raw, x, y2, y, b4;
-  if (!fp_from_be48_raw(raw.l, b)) return ST_DESERIALIZE;
+  if (!fp_from_be48_raw(raw, b)) return ST_DESERIALIZE;
   fp_to_mont(x, raw);
   fp_sqr(y2, x);
   fp_mul(y2, y2, x);
   fp_set(b4, K_B1);
   fp_add(y2, y2, b4);
   if (!fp_sqrt(y, y2)) return ST_DESERIALIZE;
-  if (fp_lex_largest(y) != ((h & 0x20) != 0)) fp_neg(y, y);
+  if (fp_lex_largest(y) != ((h & 0x20) != 0)) {
+    fp_neg(y, y);
+    fp_red(y, y);
+  }
   r.x = x;
   r.y = y;
   r.inf = 0;
@@ -388,8 +424,8 @@ BLS_FN uint8_t g2_decompress(G2Aff& r, const uint8_t* in, bool check_subgroup) {
     return ST_OK;
   }
   Fp raw0, raw1;
-  if (!fp_from_be48_raw(raw1.l, b)) return ST_DESERIALIZE;
-  if (!fp_from_be48_raw(raw0.l, b + 48)) return ST_DESERIALIZE;
+  if (!fp_from_be48_raw(raw1, b)) return ST_DESERIALIZE;
+  if (!fp_from_be48_raw(raw0, b + 48)) return ST_DESERIALIZE;
   Fp2 x, y2, y, b2, one;
   fp_to_mont(x.c0, raw0);
   fp_to_mont(x.c1, raw1);
@@ -399,7 +435,10 @@ BLS_FN uint8_t g2_decompress(G2Aff& r, const uint8_t* in, bool check_subgroup) {
   fadd(y2, y2, b2);
   fone(one);
   if (!fp2_sqrt_ratio(y, y2, one)) return ST_DESERIALIZE;
-  if (fp2_lex_largest(y) != ((h & 0x20) != 0)) fneg(y, y);
+  if (fp2_lex_largest(y) != ((h & 0x20) != 0)) {
+    fneg(y, y);
+    fred(y, y);
+  }
   r.x = x;
   r.y = y;
   r.inf = 0;
@@ -415,7 +454,7 @@ BLS_HD void g1_compress(uint8_t* out, const G1Aff& p) {
   }
   Fp raw;
   fp_from_mont(raw, p.x);
-  fp_to_be48_raw(out, raw.l);
+  fp_to_be48_raw(out, raw);
   out[0] |= 0x80 | (fp_lex_largest(p.y) ? 0x20 : 0);
 }
 BLS_HD void g2_compress(uint8_t* out, const G2Aff& p) {
@@ -426,9 +465,9 @@ BLS_HD void g2_compress(uint8_t* out, const G2Aff& p) {
   }
   Fp raw;
   fp_from_mont(raw, p.x.c1);
-  fp_to_be48_raw(out, raw.l);
+  fp_to_be48_raw(out, raw);
   fp_from_mont(raw, p.x.c0);
-  fp_to_be48_raw(out + 48, raw.l);
+  fp_to_be48_raw(out + 48, raw);
   out[0] |= 0x80 | (fp2_lex_largest(p.y) ? 0x20 : 0);
 }
 

@@ -1,13 +1,23 @@
-// Fp: the BLS12-381 base field, 12 x 32-bit little-endian limbs, Montgomery form (R = 2^384), values kept in [0, p).
+// Fp: the BLS12-381 base field in a carry-free redundant radix: 14 limbs of 28 bits in 32-bit words,
+// Montgomery form with R = 2^392.
 //
 // Replaces (for public-input work) the Fp arithmetic the reference obtains from blstrs_plus/blst
 // (reference src/impls.rs:185-215 re-exports the types; there is no arithmetic in the reference tree).
 //
-// Multiplication is the hot instruction stream of the whole engine: 288 IMAD.WIDE.U32 per product, arranged as
-// two carry chains per row (even / odd columns) so that every 32x32->64 product is accumulated 64-bit aligned and
-// the carries ride the CC flag (mad.lo.cc / madc.hi.cc pairs, which ptxas fuses into IMAD.WIDE.U32[.X]).
-// The same row schedule is also expressed with portable C "chains" (BLS_PORTABLE_CHAINS) so the logic can be
-// exercised by the CPU test harness (tests/hostemu) - that harness is test infrastructure, never a fallback.
+// Why this shape on sm_100a: every 28x28-bit product is < 2^56, so a whole column of a 14-limb product (and of the
+// Montgomery m*p correction) accumulates in one 64-bit register pair with plain IMAD.WIDE.U32 - no carry flag, no
+// predicate chains.  (A 12x32-bit CIOS built on mad.lo.cc/madc.hi.cc was tried first: ptxas interleaves the independent
+// carry chains until it runs out of predicate registers and then spills carries through P2R/LOP3 - ~1000 LOP3 per 828
+// IMAD.WIDE in fp2_mul)  The 4 spare bits per word make additions and subtractions 14
+// independent IADD3 with no reduction at all ("lazy"); values are only brought back below 2p by the next multiplication.
+//
+// Bound discipline (checked mechanically by the host test harness when BLS_TRACK is defined - test infrastructure only):
+//   vb = value bound in units of p, lb = bound on limbs 0..12.
+//   fp_mul/fp_sqr : need 14*lb_a*lb_b + 14*2^56 < 2^63 and vb_a*vb_b <= 2000; give lb < 2^28, vb <= 2
+//   fp_add        : limbwise, lb and vb add up
+//   fp_sub<K>     : a + spread(K*p) - b, needs vb_b < K and lb_b <= 2^30-4; vb_out = vb_a + K
+//   fp_norm       : one parallel carry pass, lb -> 2^28 + (lb >> 28)
+//   fp_canon      : the unique representative in [0,p) with 28-bit limbs (for ==, is_zero, sgn0, serialisation)
 #pragma once
 #include <stdint.h>
 
@@ -23,340 +33,355 @@
 
 #include "consts_gen.h"
 
-#if defined(__CUDA_ARCH__) && !defined(BLS_PORTABLE_CHAINS)
-#define BLS_ASM_CHAINS 1
+#if defined(BLS_TRACK)
+#include <cstdio>
+#include <cstdlib>
+#include <execinfo.h>
+#define BLS_REQ(cond, what)                                                                  \
+  do {                                                                                       \
+    if (!(cond)) {                                                                           \
+      fprintf(stderr, "BLS_TRACK bound violation: %s (%s:%d)\n", what, __FILE__, __LINE__);  \
+      void* bt_[24];                                                                         \
+      int n_ = backtrace(bt_, 24);                                                           \
+      backtrace_symbols_fd(bt_, n_, 2);                                                      \
+      abort();                                                                               \
+    }                                                                                        \
+  } while (0)
 #endif
 
 namespace bls {
 
-struct Fp {
-  uint32_t l[12];
+constexpr int NL = 14;
+constexpr uint32_t M28 = 0x0fffffffu;
+
+// 14 limbs + 2 zero pad words: 64 bytes, 16-byte aligned, so that every load/store of a field element in local or global
+// memory is four 128-bit transactions.
+struct alignas(16) Fp {
+  uint32_t l[NL + 2];
+#if defined(BLS_TRACK)
+  double vb;
+  uint64_t lb;
+#endif
 };
 
-// p as immediates (folded by the compiler after unrolling)
-BLS_HD constexpr uint32_t p_limb(int i) {
-  return i == 0 ? 0xffffaaabu : i == 1 ? 0xb9feffffu : i == 2 ? 0xb153ffffu : i == 3 ? 0x1eabfffeu
-       : i == 4 ? 0xf6b0f624u : i == 5 ? 0x6730d2a0u : i == 6 ? 0xf38512bfu : i == 7 ? 0x64774b84u
-       : i == 8 ? 0x434bacd7u : i == 9 ? 0x4b1ba7b6u : i == 10 ? 0x397fe69au : 0x1a0111eau;
+#if defined(BLS_TRACK)
+#define TRK(r, v, b) \
+  do {               \
+    (r).vb = (v);    \
+    (r).lb = (b);    \
+  } while (0)
+#else
+#define TRK(r, v, b) \
+  do {               \
+  } while (0)
+#endif
+
+// p in radix 2^28
+BLS_HD constexpr uint32_t p28(int i) {
+  constexpr uint32_t t[NL] = {K_P28_LIMBS};
+  return t[i];
+}
+// spread(K*p): K*p written with every limb 0..12 raised by 2^30 (borrowed from the limb above) so that a limbwise
+// "a + spread - b" never goes negative for b with limbs <= 2^30-4 and value < K*p
+template <int K>
+BLS_HD constexpr uint32_t kps(int i) {
+  static_assert(K == 4 || K == 8 || K == 16 || K == 32 || K == 64 || K == 128 || K == 256 || K == 512, "no spread constant");
+  constexpr uint32_t t4[NL] = {K_KPS_4}, t8[NL] = {K_KPS_8}, t16[NL] = {K_KPS_16}, t32[NL] = {K_KPS_32}, t64[NL] = {K_KPS_64},
+                     t128[NL] = {K_KPS_128}, t256[NL] = {K_KPS_256}, t512[NL] = {K_KPS_512};
+  return K == 4 ? t4[i] : K == 8 ? t8[i] : K == 16 ? t16[i] : K == 32 ? t32[i] : K == 64 ? t64[i] : K == 128 ? t128[i]
+       : K == 256 ? t256[i] : t512[i];
 }
 
 BLS_HD void fp_set(Fp& r, const uint32_t* c) {
 #pragma unroll
-  for (int i = 0; i < 12; i++) r.l[i] = c[i];
+  for (int i = 0; i < NL; i++) r.l[i] = c[i];
+  r.l[NL] = r.l[NL + 1] = 0;
+  TRK(r, 1.0, M28);
 }
 BLS_HD void fp_zero(Fp& r) {
 #pragma unroll
-  for (int i = 0; i < 12; i++) r.l[i] = 0;
+  for (int i = 0; i < NL + 2; i++) r.l[i] = 0;
+  TRK(r, 0.0, 0);
 }
 BLS_HD void fp_one(Fp& r) { fp_set(r, K_ONE); }
+
+// ---- lazy additive operations --------------------------------------------------------------------------------------
+BLS_HD void fp_add(Fp& r, const Fp& a, const Fp& b) {
+#if defined(BLS_TRACK)
+  BLS_REQ(a.lb + b.lb < (1ull << 32), "fp_add limb overflow");
+  BLS_REQ(a.vb + b.vb < 2000.0, "fp_add value overflow");
+  double v_ = a.vb + b.vb;
+  uint64_t l_ = a.lb + b.lb;
+#endif
+#pragma unroll
+  for (int i = 0; i < NL; i++) r.l[i] = a.l[i] + b.l[i];
+  r.l[NL] = r.l[NL + 1] = 0;
+  TRK(r, v_, l_);
+}
+BLS_HD void fp_dbl(Fp& r, const Fp& a) { fp_add(r, a, a); }
+
+template <int K>
+BLS_HD void fp_sub_k(Fp& r, const Fp& a, const Fp& b) {
+#if defined(BLS_TRACK)
+  BLS_REQ(b.vb < (double)K, "fp_sub: subtrahend value bound >= K");
+  BLS_REQ(b.lb <= (1ull << 30) - 4, "fp_sub: subtrahend limbs too large");
+  BLS_REQ(a.lb + (1ull << 30) + (1ull << 28) < (1ull << 32), "fp_sub limb overflow");
+  BLS_REQ(a.vb + K < 2000.0, "fp_sub value overflow");
+  double v_ = a.vb + K;
+  uint64_t l_ = a.lb + (1ull << 30) + (1ull << 28);
+#endif
+#pragma unroll
+  for (int i = 0; i < NL; i++) r.l[i] = a.l[i] + kps<K>(i) - b.l[i];
+  r.l[NL] = r.l[NL + 1] = 0;
+  TRK(r, v_, l_);
+}
+template <int K>
+BLS_HD void fp_neg_k(Fp& r, const Fp& a) {
+#if defined(BLS_TRACK)
+  BLS_REQ(a.vb < (double)K, "fp_neg: value bound >= K");
+  BLS_REQ(a.lb <= (1ull << 30) - 4, "fp_neg: limbs too large");
+  double v_ = K;
+#endif
+#pragma unroll
+  for (int i = 0; i < NL; i++) r.l[i] = kps<K>(i) - a.l[i];
+  r.l[NL] = r.l[NL + 1] = 0;
+  TRK(r, v_, (1ull << 30) + (1ull << 28));
+}
+
+// one parallel carry pass: limbs 0..12 end up <= 2^28 + (lb >> 28); the top limb absorbs the rest
+BLS_HD void fp_norm(Fp& r, const Fp& a) {
+  uint32_t c[NL];
+#pragma unroll
+  for (int i = 0; i < NL - 1; i++) c[i] = a.l[i] >> 28;
+  uint32_t top = a.l[NL - 1] + c[NL - 2];
+#pragma unroll
+  for (int i = NL - 2; i >= 1; i--) r.l[i] = (a.l[i] & M28) + c[i - 1];
+  r.l[0] = a.l[0] & M28;
+  r.l[NL - 1] = top;
+  r.l[NL] = r.l[NL + 1] = 0;
+#if defined(BLS_TRACK)
+  double v_ = a.vb;
+  uint64_t l_ = M28 + (a.lb >> 28);
+#endif
+  TRK(r, v_, l_);
+}
+
+// default flavours: subtrahend value < 16, result normalised (the raw lazy forms are the _k templates)
+BLS_HD void fp_sub(Fp& r, const Fp& a, const Fp& b) {
+  fp_sub_k<16>(r, a, b);
+  fp_norm(r, r);
+}
+BLS_HD void fp_neg(Fp& r, const Fp& a) {
+  fp_neg_k<16>(r, a);
+  fp_norm(r, r);
+}
+
+// ---- Montgomery multiplication ---------------------------------------------------------------------------------------
+// Keeps a value in a 32-bit register across the optimiser: without it LLVM widens `m` to 64 bits and ptxas lowers each
+// m*p_j into IMAD.WIDE plus a dead high-word IADD3 (one extra ALU instruction per multiply-accumulate).
+BLS_HD uint32_t opaque32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  asm("" : "+r"(x));
+#endif
+  return x;
+}
+
+// r = a*b/R mod p.  Operand scanning with the reduction interleaved; the 14 column accumulators shift down one place per
+// row (register renaming after unrolling), so every multiply-accumulate is ONE IMAD.WIDE.U32 with its 64-bit addend:
+// 14 (a_j b_i) + 1 + 13 (m p_j) per row, 406 in all, and ~6 ALU instructions per row for m and the carry.
+BLS_HD void fp_mul_inl(Fp& r, const Fp& a, const Fp& b) {
+#if defined(BLS_TRACK)
+  BLS_REQ((double)a.lb * (double)b.lb * 14.0 + 14.0 * 72057594037927936.0 < 9.2e18, "fp_mul column overflow");
+  BLS_REQ(a.vb * b.vb <= 2000.0, "fp_mul value bound");
+#endif
+  uint64_t t[NL];
+#pragma unroll
+  for (int j = 0; j < NL; j++) t[j] = 0;
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+    const uint32_t bi = b.l[i];
+#pragma unroll
+    for (int j = 0; j < NL; j++) t[j] += (uint64_t)a.l[j] * bi;
+    const uint32_t m = opaque32(((uint32_t)t[0] * K_PINV28) & M28);
+    const uint64_t c = (t[0] + (uint64_t)m * p28(0)) >> 28;
+#pragma unroll
+    for (int j = 1; j < NL; j++) t[j - 1] = t[j] + (uint64_t)m * p28(j);
+    t[0] += c;
+    t[NL - 1] = 0;
+  }
+  uint64_t c = 0;
+#pragma unroll
+  for (int j = 0; j < NL - 1; j++) {
+    c += t[j];
+    r.l[j] = (uint32_t)c & M28;
+    c >>= 28;
+  }
+  r.l[NL - 1] = (uint32_t)(c + t[NL - 1]);
+  r.l[NL] = r.l[NL + 1] = 0;
+  TRK(r, 2.0, M28);
+}
+
+// squaring: cross products once with a doubled operand (105 + 196 + 14 multiply-accumulates instead of 406)
+BLS_HD void fp_sqr_inl(Fp& r, const Fp& a) {
+#if defined(BLS_TRACK)
+  BLS_REQ((double)a.lb * (double)a.lb * 2.0 * 14.0 + 14.0 * 72057594037927936.0 < 9.2e18, "fp_sqr column overflow");
+  BLS_REQ(a.vb * a.vb <= 2000.0, "fp_sqr value bound");
+#endif
+  uint64_t t[2 * NL];
+  uint32_t a2[NL];
+#pragma unroll
+  for (int i = 0; i < NL; i++) a2[i] = a.l[i] << 1;
+#pragma unroll
+  for (int i = 0; i < 2 * NL; i++) t[i] = 0;
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+    t[2 * i] += (uint64_t)a.l[i] * a.l[i];
+#pragma unroll
+    for (int j = i + 1; j < NL; j++) t[i + j] += (uint64_t)a2[i] * a.l[j];
+  }
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+    const uint32_t m = opaque32(((uint32_t)t[i] * K_PINV28) & M28);
+#pragma unroll
+    for (int j = 0; j < NL; j++) t[i + j] += (uint64_t)m * p28(j);
+    t[i + 1] += t[i] >> 28;
+  }
+#pragma unroll
+  for (int k = NL; k < 2 * NL - 1; k++) {
+    t[k + 1] += t[k] >> 28;
+    r.l[k - NL] = (uint32_t)t[k] & M28;
+  }
+  r.l[NL - 1] = (uint32_t)t[2 * NL - 1];
+  r.l[NL] = r.l[NL + 1] = 0;
+  TRK(r, 2.0, M28);
+}
+
+// out-of-line instances for everything that is not an innermost loop (keeps the instruction footprint bounded)
+BLS_FN void fp_mul(Fp& r, const Fp& a, const Fp& b) { fp_mul_inl(r, a, b); }
+BLS_FN void fp_sqr(Fp& r, const Fp& a) { fp_sqr_inl(r, a); }
+
+// ---- reductions ---------------------------------------------------------------------------------------------------------
+// exact sequential normalisation followed by one quotient-estimate subtraction: limbs < 2^28, value < 3p.
+// Accepts any lazily reduced input (limbs < 2^32, value < 2000 p).  ~110 instructions: used where bounds must be reset
+// without a multiplication.
+BLS_HD void fp_red_inl(uint32_t* x, const Fp& a) {
+  uint64_t c = 0;
+#pragma unroll
+  for (int i = 0; i < NL - 1; i++) {
+    c += a.l[i];
+    x[i] = (uint32_t)c & M28;
+    c >>= 28;
+  }
+  c += a.l[NL - 1];
+  x[NL - 1] = (uint32_t)c;  // value < 2^392 keeps this below 2^28
+  // quotient estimate from the top limb: p >> 364 = 0x1a011; q <= floor(value / p) <= q + 2
+  uint32_t q = (uint32_t)(((uint64_t)x[NL - 1] * 40322ull) >> 32);
+  int64_t s = 0;
+#pragma unroll
+  for (int i = 0; i < NL - 1; i++) {
+    s += (int64_t)x[i] - (int64_t)((uint64_t)q * p28(i));
+    x[i] = (uint32_t)s & M28;
+    s >>= 28;  // arithmetic shift: borrows propagate as negative carries
+  }
+  s += (int64_t)x[NL - 1] - (int64_t)((uint64_t)q * p28(NL - 1));
+  x[NL - 1] = (uint32_t)s;
+}
+BLS_FN void fp_red(Fp& r, const Fp& a) {
+  uint32_t x[NL];
+  fp_red_inl(x, a);
+#pragma unroll
+  for (int i = 0; i < NL; i++) r.l[i] = x[i];
+  r.l[NL] = r.l[NL + 1] = 0;
+  TRK(r, 3.0, M28);
+}
+// r = the representative of a in [0,p), limbs < 2^28 (for ==, is_zero, sgn0, serialisation)
+BLS_FN void fp_canon(Fp& r, const Fp& a) {
+  uint32_t x[NL];
+  fp_red_inl(x, a);
+  // at most three conditional subtractions of p
+  for (int rep = 0; rep < 3; rep++) {
+    uint32_t d[NL];
+    int32_t br = 0;
+#pragma unroll
+    for (int i = 0; i < NL; i++) {
+      int32_t t = (int32_t)x[i] - (int32_t)p28(i) + br;
+      br = t >> 31;  // 0 or -1
+      d[i] = (uint32_t)t & M28;
+    }
+    if (br == 0) {
+#pragma unroll
+      for (int i = 0; i < NL; i++) x[i] = d[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NL; i++) r.l[i] = x[i];
+  r.l[NL] = r.l[NL + 1] = 0;
+  TRK(r, 1.0, M28);
+}
+
 BLS_HD bool fp_is_zero(const Fp& a) {
+  Fp c;
+  fp_canon(c, a);
   uint32_t t = 0;
 #pragma unroll
-  for (int i = 0; i < 12; i++) t |= a.l[i];
+  for (int i = 0; i < NL; i++) t |= c.l[i];
   return t == 0;
 }
 BLS_HD bool fp_eq(const Fp& a, const Fp& b) {
+  Fp ca, cb;
+  fp_canon(ca, a);
+  fp_canon(cb, b);
   uint32_t t = 0;
 #pragma unroll
-  for (int i = 0; i < 12; i++) t |= a.l[i] ^ b.l[i];
+  for (int i = 0; i < NL; i++) t |= ca.l[i] ^ cb.l[i];
   return t == 0;
 }
 // r = c ? a : b
 BLS_HD void fp_select(Fp& r, bool c, const Fp& a, const Fp& b) {
 #pragma unroll
-  for (int i = 0; i < 12; i++) r.l[i] = c ? a.l[i] : b.l[i];
-}
-
-// returns borrow of (a - p); r = a - p (mod 2^384)
-BLS_HD uint32_t fp_sub_p_raw(uint32_t* r, const uint32_t* a) {
-  uint64_t br = 0;
-#pragma unroll
-  for (int i = 0; i < 12; i++) {
-    uint64_t t = (uint64_t)a[i] - p_limb(i) - br;
-    r[i] = (uint32_t)t;
-    br = (t >> 32) & 1;
-  }
-  return (uint32_t)br;
-}
-
-BLS_HD void fp_add(Fp& r, const Fp& a, const Fp& b) {
-  uint32_t s[12], d[12];
-  uint64_t c = 0;
-#pragma unroll
-  for (int i = 0; i < 12; i++) {
-    c += (uint64_t)a.l[i] + b.l[i];
-    s[i] = (uint32_t)c;
-    c >>= 32;
-  }
-  uint32_t br = fp_sub_p_raw(d, s);
-#pragma unroll
-  for (int i = 0; i < 12; i++) r.l[i] = br ? s[i] : d[i];
-}
-
-BLS_HD void fp_sub(Fp& r, const Fp& a, const Fp& b) {
-  uint32_t d[12];
-  uint64_t br = 0;
-#pragma unroll
-  for (int i = 0; i < 12; i++) {
-    uint64_t t = (uint64_t)a.l[i] - b.l[i] - br;
-    d[i] = (uint32_t)t;
-    br = (t >> 32) & 1;
-  }
-  uint32_t mask = 0u - (uint32_t)br;
-  uint64_t c = 0;
-#pragma unroll
-  for (int i = 0; i < 12; i++) {
-    c += (uint64_t)d[i] + (p_limb(i) & mask);
-    r.l[i] = (uint32_t)c;
-    c >>= 32;
-  }
-}
-
-BLS_HD void fp_neg(Fp& r, const Fp& a) {
-  uint32_t nz = 0;
-#pragma unroll
-  for (int i = 0; i < 12; i++) nz |= a.l[i];
-  uint32_t mask = nz ? 0xffffffffu : 0u;
-  uint64_t br = 0;
-#pragma unroll
-  for (int i = 0; i < 12; i++) {
-    uint64_t t = (uint64_t)p_limb(i) - a.l[i] - br;
-    r.l[i] = (uint32_t)t & mask;
-    br = (t >> 32) & 1;
-  }
-}
-
-BLS_HD void fp_dbl(Fp& r, const Fp& a) { fp_add(r, a, a); }
-
-// ---------------------------------------------------------------------------------------------------------
-// carry chains.  X[0..11] is a 12-limb accumulator; "pairs" are (X[2k], X[2k+1]).
-//   chain_mul6 : X = {a[0],a[2],..,a[10]} * b                       (no carries between pairs needed)
-//   chain_mad6 : X += {a[0],a[2],..} * b, carry out added into top
-//   chain_mad6_shift : X0 += Z[1]; Z[k] = Z[k+2] + {a[0],a[2],..}*b for k=0..9 (carry-in from the X0 add),
-//                      (Z[10],Z[11]) = a[10]*b + carry
-// a points at the first of 6 limbs taken with stride 2.
-// ---------------------------------------------------------------------------------------------------------
-#if defined(BLS_ASM_CHAINS)
-BLS_HD void chain_mul6(uint32_t* X, const uint32_t* a, uint32_t b) {
-#pragma unroll
-  for (int k = 0; k < 6; k++)
-    asm("mul.lo.u32 %0, %2, %3;\n\tmul.hi.u32 %1, %2, %3;" : "=&r"(X[2 * k]), "=r"(X[2 * k + 1]) : "r"(a[2 * k]), "r"(b));  // & : %0 is written before the inputs are dead
-}
-BLS_HD void chain_mad6(uint32_t* X, const uint32_t* a, uint32_t b, uint32_t& top) {
-  asm("mad.lo.cc.u32 %0, %13, %19, %0;\n\t"
-      "madc.hi.cc.u32 %1, %13, %19, %1;\n\t"
-      "madc.lo.cc.u32 %2, %14, %19, %2;\n\t"
-      "madc.hi.cc.u32 %3, %14, %19, %3;\n\t"
-      "madc.lo.cc.u32 %4, %15, %19, %4;\n\t"
-      "madc.hi.cc.u32 %5, %15, %19, %5;\n\t"
-      "madc.lo.cc.u32 %6, %16, %19, %6;\n\t"
-      "madc.hi.cc.u32 %7, %16, %19, %7;\n\t"
-      "madc.lo.cc.u32 %8, %17, %19, %8;\n\t"
-      "madc.hi.cc.u32 %9, %17, %19, %9;\n\t"
-      "madc.lo.cc.u32 %10, %18, %19, %10;\n\t"
-      "madc.hi.cc.u32 %11, %18, %19, %11;\n\t"
-      "addc.u32 %12, %12, 0;"
-      : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]), "+r"(X[8]),
-        "+r"(X[9]), "+r"(X[10]), "+r"(X[11]), "+r"(top)
-      : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(a[8]), "r"(a[10]), "r"(b));
-}
-// same without carry out (the caller knows it is zero)
-BLS_HD void chain_mad6_nc(uint32_t* X, const uint32_t* a, uint32_t b) {
-  asm("mad.lo.cc.u32 %0, %12, %18, %0;\n\t"
-      "madc.hi.cc.u32 %1, %12, %18, %1;\n\t"
-      "madc.lo.cc.u32 %2, %13, %18, %2;\n\t"
-      "madc.hi.cc.u32 %3, %13, %18, %3;\n\t"
-      "madc.lo.cc.u32 %4, %14, %18, %4;\n\t"
-      "madc.hi.cc.u32 %5, %14, %18, %5;\n\t"
-      "madc.lo.cc.u32 %6, %15, %18, %6;\n\t"
-      "madc.hi.cc.u32 %7, %15, %18, %7;\n\t"
-      "madc.lo.cc.u32 %8, %16, %18, %8;\n\t"
-      "madc.hi.cc.u32 %9, %16, %18, %9;\n\t"
-      "madc.lo.cc.u32 %10, %17, %18, %10;\n\t"
-      "madc.hi.u32 %11, %17, %18, %11;"
-      : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]), "+r"(X[8]),
-        "+r"(X[9]), "+r"(X[10]), "+r"(X[11])
-      : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(a[8]), "r"(a[10]), "r"(b));
-}
-BLS_HD void chain_mad6_shift(uint32_t& X0, uint32_t* Z, const uint32_t* a, uint32_t b) {
-  asm("add.cc.u32 %12, %12, %1;\n\t"
-      "madc.lo.cc.u32 %0, %13, %19, %2;\n\t"
-      "madc.hi.cc.u32 %1, %13, %19, %3;\n\t"
-      "madc.lo.cc.u32 %2, %14, %19, %4;\n\t"
-      "madc.hi.cc.u32 %3, %14, %19, %5;\n\t"
-      "madc.lo.cc.u32 %4, %15, %19, %6;\n\t"
-      "madc.hi.cc.u32 %5, %15, %19, %7;\n\t"
-      "madc.lo.cc.u32 %6, %16, %19, %8;\n\t"
-      "madc.hi.cc.u32 %7, %16, %19, %9;\n\t"
-      "madc.lo.cc.u32 %8, %17, %19, %10;\n\t"
-      "madc.hi.cc.u32 %9, %17, %19, %11;\n\t"
-      "madc.lo.cc.u32 %10, %18, %19, 0;\n\t"
-      "madc.hi.u32 %11, %18, %19, 0;"
-      : "+r"(Z[0]), "+r"(Z[1]), "+r"(Z[2]), "+r"(Z[3]), "+r"(Z[4]), "+r"(Z[5]), "+r"(Z[6]), "+r"(Z[7]), "+r"(Z[8]),
-        "+r"(Z[9]), "+r"(Z[10]), "+r"(Z[11]), "+r"(X0)
-      : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(a[8]), "r"(a[10]), "r"(b));
-}
-#else
-BLS_HD void chain_mul6(uint32_t* X, const uint32_t* a, uint32_t b) {
-#pragma unroll
-  for (int k = 0; k < 6; k++) {
-    uint64_t t = (uint64_t)a[2 * k] * b;
-    X[2 * k] = (uint32_t)t;
-    X[2 * k + 1] = (uint32_t)(t >> 32);
-  }
-}
-BLS_HD uint32_t chain_mad6_core(uint32_t* X, const uint32_t* a, uint32_t b) {
-  uint64_t c = 0;
-#pragma unroll
-  for (int k = 0; k < 6; k++) {
-    uint64_t pr = (uint64_t)a[2 * k] * b;
-    uint64_t lo = (uint64_t)X[2 * k] + (uint32_t)pr + c;
-    X[2 * k] = (uint32_t)lo;
-    uint64_t hi = (uint64_t)X[2 * k + 1] + (uint32_t)(pr >> 32) + (lo >> 32);
-    X[2 * k + 1] = (uint32_t)hi;
-    c = hi >> 32;
-  }
-  return (uint32_t)c;
-}
-BLS_HD void chain_mad6(uint32_t* X, const uint32_t* a, uint32_t b, uint32_t& top) { top += chain_mad6_core(X, a, b); }
-BLS_HD void chain_mad6_nc(uint32_t* X, const uint32_t* a, uint32_t b) { (void)chain_mad6_core(X, a, b); }
-BLS_HD void chain_mad6_shift(uint32_t& X0, uint32_t* Z, const uint32_t* a, uint32_t b) {
-  uint64_t c = (uint64_t)X0 + Z[1];
-  X0 = (uint32_t)c;
-  c >>= 32;
-#pragma unroll
-  for (int k = 0; k < 6; k++) {
-    uint64_t pr = (uint64_t)a[2 * k] * b;
-    uint32_t in_lo = (k < 5) ? Z[2 * k + 2] : 0u;
-    uint32_t in_hi = (k < 5) ? Z[2 * k + 3] : 0u;
-    uint64_t lo = (uint64_t)in_lo + (uint32_t)pr + c;
-    uint64_t hi = (uint64_t)in_hi + (uint32_t)(pr >> 32) + (lo >> 32);
-    Z[2 * k] = (uint32_t)lo;
-    Z[2 * k + 1] = (uint32_t)hi;
-    c = hi >> 32;
-  }
-}
+  for (int i = 0; i < NL; i++) r.l[i] = c ? a.l[i] : b.l[i];
+  r.l[NL] = r.l[NL + 1] = 0;
+#if defined(BLS_TRACK)
+  r.vb = a.vb > b.vb ? a.vb : b.vb;
+  r.lb = a.lb > b.lb ? a.lb : b.lb;
 #endif
-
-// One Montgomery row: (X,Y) hold the running value V = X + Y*2^32 (X[k] at limb k, Y[k] at limb k+1).
-// FIRST row: V = a*b0.  Other rows: Z is the previous row's X array (its limb 0 is zero), X is the previous Y;
-// the value is shifted down one limb while a*bi is added.  Then m*p is added so that X[0] becomes 0.
-template <bool FIRST>
-BLS_HD void mont_row(uint32_t* X, uint32_t* Z, const uint32_t* a, uint32_t bi) {
-  const uint32_t pl[12] = {p_limb(0), p_limb(1), p_limb(2), p_limb(3), p_limb(4), p_limb(5),
-                           p_limb(6), p_limb(7), p_limb(8), p_limb(9), p_limb(10), p_limb(11)};
-  if (FIRST) {
-    chain_mul6(X, a, bi);
-    chain_mul6(Z, a + 1, bi);
-  } else {
-    chain_mad6_shift(X[0], Z, a + 1, bi);
-    chain_mad6(X, a, bi, Z[11]);
-  }
-  uint32_t m = X[0] * K_PINV32;
-  chain_mad6_nc(Z, pl + 1, m);
-  chain_mad6(X, pl, m, Z[11]);
 }
 
-// r = a*b*R^-1 mod p, inputs < p (or any a,b with a*b < p*R), output in [0,p)
-BLS_HD void fp_mul_inl(Fp& r, const Fp& a, const Fp& b) {
-  uint32_t U[12], V[12];
-  mont_row<true>(U, V, a.l, b.l[0]);
-#pragma unroll
-  for (int i = 1; i < 12; i += 2) {
-    mont_row<false>(V, U, a.l, b.l[i]);
-    if (i + 1 < 12) mont_row<false>(U, V, a.l, b.l[i + 1]);
-  }
-  // after row 11: X = V (limb 0 zero), Y = U.  result limb k = X[k+1] + Y[k]
-  uint32_t s[12], d[12];
-  uint64_t c = 0;
-#pragma unroll
-  for (int k = 0; k < 12; k++) {
-    c += (uint64_t)U[k] + (k < 11 ? V[k + 1] : 0u);
-    s[k] = (uint32_t)c;
-    c >>= 32;
-  }
-  uint32_t br = fp_sub_p_raw(d, s);
-#pragma unroll
-  for (int k = 0; k < 12; k++) r.l[k] = br ? s[k] : d[k];
-}
-
-BLS_HD void fp_sqr_inl(Fp& r, const Fp& a) { fp_mul_inl(r, a, a); }
-// out-of-line instances for everything that is not an innermost loop (keeps the instruction footprint bounded)
-BLS_FN void fp_mul(Fp& r, const Fp& a, const Fp& b) { fp_mul_inl(r, a, b); }
-BLS_FN void fp_sqr(Fp& r, const Fp& a) { fp_mul_inl(r, a, a); }
-
-// plain reference multiplication (CIOS with 64-bit temporaries); used by parity kernels to cross-check fp_mul
-BLS_HD void fp_mul_cios(Fp& r, const Fp& a, const Fp& b) {
-  uint32_t t[14];
-#pragma unroll
-  for (int i = 0; i < 14; i++) t[i] = 0;
-#pragma unroll
-  for (int i = 0; i < 12; i++) {
-    uint64_t c = 0;
-#pragma unroll
-    for (int j = 0; j < 12; j++) {
-      c += (uint64_t)a.l[j] * b.l[i] + t[j];
-      t[j] = (uint32_t)c;
-      c >>= 32;
-    }
-    c += t[12];
-    t[12] = (uint32_t)c;
-    t[13] = (uint32_t)(c >> 32);
-    uint32_t m = t[0] * K_PINV32;
-    c = ((uint64_t)m * p_limb(0) + t[0]) >> 32;
-#pragma unroll
-    for (int j = 1; j < 12; j++) {
-      c += (uint64_t)m * p_limb(j) + t[j];
-      t[j - 1] = (uint32_t)c;
-      c >>= 32;
-    }
-    c += t[12];
-    t[11] = (uint32_t)c;
-    t[12] = t[13] + (uint32_t)(c >> 32);
-  }
-  uint32_t d[12];
-  uint32_t br = fp_sub_p_raw(d, t);
-  bool keep = br && t[12] == 0;
-#pragma unroll
-  for (int k = 0; k < 12; k++) r.l[k] = keep ? t[k] : d[k];
-}
-
-// Montgomery <-> canonical
-BLS_HD void fp_to_mont(Fp& r, const Fp& a) {
+// Montgomery <-> plain integers.  "raw" Fp values hold a plain integer < p in canonical limbs.
+BLS_HD void fp_to_mont(Fp& r, const Fp& raw) {
   Fp r2;
   fp_set(r2, K_R2);
-  fp_mul(r, a, r2);
+  fp_mul(r, raw, r2);
 }
-BLS_HD void fp_from_mont(Fp& r, const Fp& a) {
-  Fp one;
+// canonical plain integer of a Montgomery value
+BLS_HD void fp_from_mont(Fp& raw, const Fp& a) {
+  Fp one, t;
   fp_zero(one);
   one.l[0] = 1;
-  fp_mul(r, a, one);
+  TRK(one, 1.0, 1);
+  fp_mul(t, a, one);
+  fp_canon(raw, t);
 }
 
-// raw integer compare helpers on canonical (non-Montgomery) limbs
-BLS_HD bool raw_ge_p(const uint32_t* a) {
-  uint32_t d[12];
-  return fp_sub_p_raw(d, a) == 0;
-}
-// canonical a > (p-1)/2 ?
-BLS_HD bool raw_gt_half(const uint32_t* a) {
-  uint64_t br = 0;
+// raw (canonical plain) value > (p-1)/2 ?
+BLS_HD bool raw_gt_half(const Fp& raw) {
+  int32_t br = 0;
 #pragma unroll
-  for (int i = 0; i < 12; i++) {
-    uint64_t t = (uint64_t)K_HALF_P[i] - a[i] - br;
-    br = (t >> 32) & 1;
+  for (int i = 0; i < NL; i++) {
+    int32_t t = (int32_t)K_HALF_P28[i] - (int32_t)raw.l[i] + br;
+    br = t >> 31;
   }
   return br != 0;
 }
 
-// r = a^e for a fixed 384-bit exponent given as RAW limbs (4-bit fixed window).  Variable time on e only.
+// r = a^e for a fixed exponent given as 12 little-endian 32-bit words (4-bit fixed window).  Variable time on e only.
 BLS_FN void fp_pow_fixed(Fp& r, const Fp& a, const uint32_t* e) {
   Fp tbl[16];
   fp_one(tbl[0]);
-  tbl[1] = a;
-  for (int i = 2; i < 16; i++) fp_mul(tbl[i], tbl[i - 1], a);
+  fp_norm(tbl[1], a);
+  for (int i = 2; i < 16; i++) fp_mul(tbl[i], tbl[i - 1], tbl[1]);
   Fp acc;
+  fp_one(acc);
   bool started = false;
   for (int limb = 11; limb >= 0; limb--) {
     uint32_t w = e[limb];
@@ -390,24 +415,53 @@ BLS_HD bool fp_sqrt(Fp& r, const Fp& a) {
   return fp_eq(chk, a);
 }
 
-// 48 big-endian bytes (top three bits already masked by the caller) -> canonical limbs; returns false if >= p
-BLS_HD bool fp_from_be48_raw(uint32_t* raw, const uint8_t* b) {
+// 48 big-endian bytes (top three bits already masked by the caller) -> raw value; returns false if >= p
+BLS_HD bool fp_from_be48_raw(Fp& raw, const uint8_t* b) {
+  // bit k of the integer lives in byte 47 - k/8
 #pragma unroll
-  for (int i = 0; i < 12; i++) {
-    const uint8_t* q = b + 44 - 4 * i;
-    raw[i] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | (uint32_t)q[3];
+  for (int i = 0; i < NL; i++) {
+    uint64_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {  // 5 bytes cover 28 bits at any alignment
+      int byte_index = (28 * i) / 8 + k;
+      if (byte_index < 48) v |= (uint64_t)b[47 - byte_index] << (8 * k);
+    }
+    raw.l[i] = (uint32_t)(v >> ((28 * i) % 8)) & M28;
   }
-  return !raw_ge_p(raw);
+  raw.l[NL] = raw.l[NL + 1] = 0;
+  TRK(raw, 1.0, M28);
+  // < p ?
+  int32_t br = 0;
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+    int32_t t = (int32_t)raw.l[i] - (int32_t)p28(i) + br;
+    br = t >> 31;
+  }
+  return br != 0;
 }
-BLS_HD void fp_to_be48_raw(uint8_t* b, const uint32_t* raw) {
+BLS_HD void fp_to_be48_raw(uint8_t* b, const Fp& raw) {
 #pragma unroll
-  for (int i = 0; i < 12; i++) {
-    uint8_t* q = b + 44 - 4 * i;
-    q[0] = (uint8_t)(raw[i] >> 24);
-    q[1] = (uint8_t)(raw[i] >> 16);
-    q[2] = (uint8_t)(raw[i] >> 8);
-    q[3] = (uint8_t)raw[i];
+  for (int byte_index = 0; byte_index < 48; byte_index++) {
+    int bit = 8 * byte_index;
+    int i = bit / 28, sh = bit % 28;
+    uint32_t v = raw.l[i] >> sh;
+    if (sh > 20 && i + 1 < NL) v |= raw.l[i + 1] << (28 - sh);
+    b[47 - byte_index] = (uint8_t)v;
   }
+}
+// little-endian 32-bit words (n <= 12) of a plain integer < 2^(32 n) -> raw limbs (used by hash_to_field)
+BLS_HD void fp_raw_from_words(Fp& raw, const uint32_t* w, int n) {
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+    int bit = 28 * i;
+    int wi = bit / 32, sh = bit % 32;
+    uint64_t v = 0;
+    if (wi < n) v = w[wi];
+    if (wi + 1 < n) v |= (uint64_t)w[wi + 1] << 32;
+    raw.l[i] = (uint32_t)(v >> sh) & M28;
+  }
+  raw.l[NL] = raw.l[NL + 1] = 0;
+  TRK(raw, 1.0, M28);
 }
 
 }  // namespace bls

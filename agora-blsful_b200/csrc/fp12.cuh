@@ -13,32 +13,51 @@ struct Fp12 {
   Fp6 c0, c1;
 };
 
+// Bound contract of the tower (fp.cuh explains vb/lb): "reduced" = output of fred: value < 3p, limbs < 2^28.
+//   fp6_mul / fp6_mul_by_01 / fp6_mul_by_1 (the _lazy forms): inputs value <= 11 per Fp2 coefficient part, limbs <= 2^29+64;
+//     outputs normalised (limbs <= 2^28+16), value <= 108 - NOT reduced: the Fp12 caller combines them and reduces once.
+//   fp12_* : inputs reduced (or value <= 5), outputs reduced.
 BLS_HD void fp6_add(Fp6& r, const Fp6& a, const Fp6& b) {
   fadd(r.c0, a.c0, b.c0);
   fadd(r.c1, a.c1, b.c1);
   fadd(r.c2, a.c2, b.c2);
 }
-BLS_HD void fp6_sub(Fp6& r, const Fp6& a, const Fp6& b) {
-  fsub(r.c0, a.c0, b.c0);
-  fsub(r.c1, a.c1, b.c1);
-  fsub(r.c2, a.c2, b.c2);
+template <int K>
+BLS_HD void fp6_sub_k(Fp6& r, const Fp6& a, const Fp6& b) {
+  fsub_k<K>(r.c0, a.c0, b.c0);
+  fsub_k<K>(r.c1, a.c1, b.c1);
+  fsub_k<K>(r.c2, a.c2, b.c2);
 }
+BLS_HD void fp6_norm(Fp6& r, const Fp6& a) {
+  fnorm(r.c0, a.c0);
+  fnorm(r.c1, a.c1);
+  fnorm(r.c2, a.c2);
+}
+BLS_HD void fp6_red(Fp6& r, const Fp6& a) {
+  fred(r.c0, a.c0);
+  fred(r.c1, a.c1);
+  fred(r.c2, a.c2);
+}
+// reduced in, reduced out
 BLS_HD void fp6_neg(Fp6& r, const Fp6& a) {
-  fneg(r.c0, a.c0);
-  fneg(r.c1, a.c1);
-  fneg(r.c2, a.c2);
+  fneg_k<4>(r.c0, a.c0);
+  fneg_k<4>(r.c1, a.c1);
+  fneg_k<4>(r.c2, a.c2);
+  fp6_red(r, r);
 }
-BLS_HD void fp6_mul_by_v(Fp6& r, const Fp6& a) {
+// a * v, lazily: K bounds the value of a.c2's imaginary part; result c0 not normalised
+template <int K>
+BLS_HD void fp6_mul_by_v_k(Fp6& r, const Fp6& a) {
   Fp2 t;
-  fp2_mul_xi(t, a.c2);
+  fp2_mul_xi_k<K>(t, a.c2);
   r.c2 = a.c1;
   r.c1 = a.c0;
   r.c0 = t;
 }
 BLS_HD bool fp6_is_zero(const Fp6& a) { return fis_zero(a.c0) && fis_zero(a.c1) && fis_zero(a.c2); }
 
-BLS_FN void fp6_mul(Fp6& r, const Fp6& a, const Fp6& b) {
-  Fp2 t0, t1, t2, s, u, x;
+BLS_FN void fp6_mul_lazy(Fp6& r, const Fp6& a, const Fp6& b) {
+  Fp2 t0, t1, t2, s, u, x, y;
   fp2_mul(t0, a.c0, b.c0);
   fp2_mul(t1, a.c1, b.c1);
   fp2_mul(t2, a.c2, b.c2);
@@ -46,103 +65,129 @@ BLS_FN void fp6_mul(Fp6& r, const Fp6& a, const Fp6& b) {
   fadd(s, a.c1, a.c2);
   fadd(u, b.c1, b.c2);
   fp2_mul(x, s, u);
-  fsub(x, x, t1);
-  fsub(x, x, t2);
-  fp2_mul_xi(x, x);
+  fsub_k<16>(x, x, t1);
+  fsub_k<16>(x, x, t2);
+  fnorm(x, x);
+  fp2_mul_xi_k<64>(y, x);
   Fp2 c0;
-  fadd(c0, x, t0);
+  fadd(c0, y, t0);
   // c1 = (a0+a1)(b0+b1) - t0 - t1 + xi t2
   fadd(s, a.c0, a.c1);
   fadd(u, b.c0, b.c1);
   fp2_mul(x, s, u);
-  fsub(x, x, t0);
-  fsub(x, x, t1);
+  fsub_k<16>(x, x, t0);
+  fsub_k<16>(x, x, t1);
+  fnorm(x, x);
+  fp2_mul_xi_k<16>(y, t2);
   Fp2 c1;
-  fp2_mul_xi(s, t2);
-  fadd(c1, x, s);
+  fadd(c1, x, y);
   // c2 = (a0+a2)(b0+b2) - t0 - t2 + t1
   fadd(s, a.c0, a.c2);
   fadd(u, b.c0, b.c2);
   fp2_mul(x, s, u);
-  fsub(x, x, t0);
-  fsub(x, x, t2);
-  fadd(r.c2, x, t1);
-  r.c0 = c0;
-  r.c1 = c1;
+  fsub_k<16>(x, x, t0);
+  fsub_k<16>(x, x, t2);
+  fadd(x, x, t1);
+  fnorm(r.c2, x);
+  fnorm(r.c0, c0);
+  fnorm(r.c1, c1);
+}
+BLS_FN void fp6_mul(Fp6& r, const Fp6& a, const Fp6& b) {
+  fp6_mul_lazy(r, a, b);
+  fp6_red(r, r);
 }
 
+// inputs reduced
 BLS_FN void fp6_sqr(Fp6& r, const Fp6& a) {
-  Fp2 s0, s1, s2, s3, s4, t;
+  Fp2 s0, s1, s2, s3, s4, t, y;
   fp2_sqr(s0, a.c0);
   fp2_mul(s1, a.c0, a.c1);
   fdbl(s1, s1);
-  fsub(t, a.c0, a.c1);
+  fsub_k<4>(t, a.c0, a.c1);
   fadd(t, t, a.c2);
+  fnorm(t, t);
   fp2_sqr(s2, t);
   fp2_mul(s3, a.c1, a.c2);
   fdbl(s3, s3);
   fp2_sqr(s4, a.c2);
-  fp2_mul_xi(t, s3);
-  fadd(r.c0, s0, t);
-  fp2_mul_xi(t, s4);
-  fadd(r.c1, s1, t);
+  fp2_mul_xi_k<32>(y, s3);
+  fadd(y, y, s0);
+  fred(r.c0, y);
+  fp2_mul_xi_k<16>(y, s4);
+  fadd(y, y, s1);
+  fred(r.c1, y);
   fadd(t, s1, s2);
   fadd(t, t, s3);
-  fsub(t, t, s0);
-  fsub(r.c2, t, s4);
+  fsub_k<16>(t, t, s0);
+  fnorm(t, t);
+  fsub_k<16>(t, t, s4);
+  fred(r.c2, t);
 }
 
 // a * (b0 + b1 v)
-BLS_FN void fp6_mul_by_01(Fp6& r, const Fp6& a, const Fp2& b0, const Fp2& b1) {
+BLS_FN void fp6_mul_by_01_lazy(Fp6& r, const Fp6& a, const Fp2& b0, const Fp2& b1) {
   Fp2 t0, t1, s, u, x, y;
   fp2_mul(t0, a.c0, b0);
   fp2_mul(t1, a.c1, b1);
   fadd(s, a.c0, a.c1);
   fadd(u, b0, b1);
   fp2_mul(x, s, u);
-  fsub(x, x, t0);
-  fsub(x, x, t1);  // c1
+  fsub_k<16>(x, x, t0);
+  fsub_k<16>(x, x, t1);  // c1
   fp2_mul(y, a.c2, b1);
-  fp2_mul_xi(y, y);
+  fp2_mul_xi_k<16>(y, y);
   fp2_mul(s, a.c2, b0);
-  fadd(r.c0, t0, y);
-  r.c1 = x;
-  fadd(r.c2, t1, s);
+  fadd(y, y, t0);
+  fnorm(r.c0, y);
+  fnorm(r.c1, x);
+  fadd(y, t1, s);
+  fnorm(r.c2, y);
 }
 // a * (b1 v)
-BLS_FN void fp6_mul_by_1(Fp6& r, const Fp6& a, const Fp2& b1) {
+BLS_FN void fp6_mul_by_1_lazy(Fp6& r, const Fp6& a, const Fp2& b1) {
   Fp2 t0, t1, t2;
   fp2_mul(t2, a.c2, b1);
   fp2_mul(t0, a.c0, b1);
   fp2_mul(t1, a.c1, b1);
-  fp2_mul_xi(r.c0, t2);
+  fp2_mul_xi_k<16>(t2, t2);
+  fnorm(r.c0, t2);
   r.c1 = t0;
   r.c2 = t1;
 }
 
+// input reduced
 BLS_FN void fp6_inv(Fp6& r, const Fp6& a) {
   Fp2 t0, t1, t2, x, d;
   fp2_sqr(t0, a.c0);
   fp2_mul(x, a.c1, a.c2);
-  fp2_mul_xi(x, x);
-  fsub(t0, t0, x);  // a0^2 - xi a1 a2
+  fp2_mul_xi_k<16>(x, x);
+  fnorm(x, x);
+  fsub_k<32>(t0, t0, x);  // a0^2 - xi a1 a2
+  fred(t0, t0);
   fp2_sqr(t1, a.c2);
-  fp2_mul_xi(t1, t1);
+  fp2_mul_xi_k<16>(t1, t1);
   fp2_mul(x, a.c0, a.c1);
-  fsub(t1, t1, x);  // xi a2^2 - a0 a1
+  fsub_k<16>(t1, t1, x);  // xi a2^2 - a0 a1
+  fred(t1, t1);
   fp2_sqr(t2, a.c1);
   fp2_mul(x, a.c0, a.c2);
-  fsub(t2, t2, x);  // a1^2 - a0 a2
+  fsub_k<16>(t2, t2, x);  // a1^2 - a0 a2
+  fred(t2, t2);
   fp2_mul(d, a.c2, t1);
   fp2_mul(x, a.c1, t2);
   fadd(d, d, x);
-  fp2_mul_xi(d, d);
+  fnorm(d, d);
+  fp2_mul_xi_k<32>(d, d);
   fp2_mul(x, a.c0, t0);
   fadd(d, d, x);
+  fred(d, d);
   fp2_inv(d, d);
-  fp2_mul(r.c0, t0, d);
-  fp2_mul(r.c1, t1, d);
-  fp2_mul(r.c2, t2, d);
+  fp2_mul(x, t0, d);
+  fred(r.c0, x);
+  fp2_mul(x, t1, d);
+  fred(r.c1, x);
+  fp2_mul(x, t2, d);
+  fred(r.c2, x);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -170,78 +215,90 @@ BLS_HD void fp12_conj(Fp12& r, const Fp12& a) {
 
 BLS_FN void fp12_mul(Fp12& r, const Fp12& a, const Fp12& b) {
   Fp6 t0, t1, s, u, x;
-  fp6_mul(t0, a.c0, b.c0);
-  fp6_mul(t1, a.c1, b.c1);
+  fp6_mul_lazy(t0, a.c0, b.c0);
+  fp6_mul_lazy(t1, a.c1, b.c1);
   fp6_add(s, a.c0, a.c1);
   fp6_add(u, b.c0, b.c1);
-  fp6_mul(x, s, u);
-  fp6_sub(x, x, t0);
-  fp6_sub(r.c1, x, t1);
-  fp6_mul_by_v(t1, t1);
-  fp6_add(r.c0, t0, t1);
+  fp6_norm(u, u);  // second operands must stay normalised: their Karatsuba sums meet the 2^30 limbs of the first
+  fp6_mul_lazy(x, s, u);
+  fp6_sub_k<128>(x, x, t0);
+  fp6_sub_k<128>(x, x, t1);
+  fp6_red(r.c1, x);
+  fp6_mul_by_v_k<128>(t1, t1);
+  fp6_add(t0, t0, t1);
+  fp6_red(r.c0, t0);
 }
 
 BLS_FN void fp12_sqr(Fp12& r, const Fp12& a) {
   Fp6 t, s, u, x;
-  fp6_mul(t, a.c0, a.c1);
+  fp6_mul_lazy(t, a.c0, a.c1);
   fp6_add(s, a.c0, a.c1);
-  fp6_mul_by_v(u, a.c1);
+  fp6_mul_by_v_k<4>(u, a.c1);
   fp6_add(u, u, a.c0);
-  fp6_mul(x, s, u);
-  fp6_sub(x, x, t);
-  fp6_mul_by_v(u, t);
-  fp6_sub(r.c0, x, u);
-  fp6_add(r.c1, t, t);
+  fp6_norm(u, u);
+  fp6_mul_lazy(x, s, u);
+  fp6_sub_k<128>(x, x, t);
+  fp6_mul_by_v_k<128>(u, t);
+  fp6_norm(u, u);
+  fp6_sub_k<256>(x, x, u);
+  fp6_red(r.c0, x);
+  fp6_add(t, t, t);
+  fp6_red(r.c1, t);
 }
 
-// f * ((c0 + c1 v) + (c4 v) w): the sparse shape of a Miller-loop line (w^0, w^2, w^3 coefficients)
+// f * ((c0 + c1 v) + (c4 v) w): the sparse shape of a Miller-loop line (w^0, w^2, w^3 coefficients).
+// f reduced; line coefficients normalised with value <= 13.
 BLS_FN void fp12_mul_by_014(Fp12& f, const Fp2& c0, const Fp2& c1, const Fp2& c4) {
   Fp6 aa, bb, s, x;
   Fp2 c14;
-  fp6_mul_by_01(aa, f.c0, c0, c1);
-  fp6_mul_by_1(bb, f.c1, c4);
+  fp6_mul_by_01_lazy(aa, f.c0, c0, c1);
+  fp6_mul_by_1_lazy(bb, f.c1, c4);
   fadd(c14, c1, c4);
+  fnorm(c14, c14);
   fp6_add(s, f.c0, f.c1);
-  fp6_mul_by_01(x, s, c0, c14);
-  fp6_sub(x, x, aa);
-  fp6_sub(f.c1, x, bb);
-  fp6_mul_by_v(bb, bb);
-  fp6_add(f.c0, aa, bb);
+  fp6_mul_by_01_lazy(x, s, c0, c14);
+  fp6_sub_k<64>(x, x, aa);
+  fp6_sub_k<32>(x, x, bb);
+  fp6_red(f.c1, x);
+  fp6_mul_by_v_k<16>(bb, bb);
+  fp6_add(aa, aa, bb);
+  fp6_red(f.c0, aa);
 }
 
 BLS_FN void fp12_inv(Fp12& r, const Fp12& a) {
   Fp6 t0, t1;
   fp6_sqr(t0, a.c0);
   fp6_sqr(t1, a.c1);
-  fp6_mul_by_v(t1, t1);
-  fp6_sub(t0, t0, t1);
+  fp6_mul_by_v_k<4>(t1, t1);
+  fp6_norm(t1, t1);
+  fp6_sub_k<16>(t0, t0, t1);
+  fp6_red(t0, t0);
   fp6_inv(t0, t0);
   fp6_mul(r.c0, a.c0, t0);
   fp6_mul(t1, a.c1, t0);
   fp6_neg(r.c1, t1);
 }
 
-// f^p : coefficient of w^i -> conj(c_i) * K_FROB1[i]
-BLS_FN void fp12_frob1(Fp12& r, const Fp12& a) {
+// f^p : coefficient of w^i -> conj(c_i) * K_FROB1[i]   (reduced in, reduced out)
+BLS_HD void frob1_coeff(Fp2& r, const Fp2& a, int i) {
   Fp2 g, t;
-  fp2_conj(r.c0.c0, a.c0.c0);
-  fp2_conj(t, a.c1.c0);
-  fp2_set(g, K_FROB1[1]);
-  fp2_mul(r.c1.c0, t, g);
-  fp2_conj(t, a.c0.c1);
-  fp2_set(g, K_FROB1[2]);
-  fp2_mul(r.c0.c1, t, g);
-  fp2_conj(t, a.c1.c1);
-  fp2_set(g, K_FROB1[3]);
-  fp2_mul(r.c1.c1, t, g);
-  fp2_conj(t, a.c0.c2);
-  fp2_set(g, K_FROB1[4]);
-  fp2_mul(r.c0.c2, t, g);
-  fp2_conj(t, a.c1.c2);
-  fp2_set(g, K_FROB1[5]);
-  fp2_mul(r.c1.c2, t, g);
+  fp2_conj_k<4>(t, a);
+  fnorm(t, t);
+  fp2_set(g, K_FROB1[i]);
+  fp2_mul(t, t, g);
+  fred(r, t);
 }
-// f^(p^2) : coefficient of w^i -> c_i * K_FROB2[i]  (Fp scalars)
+BLS_FN void fp12_frob1(Fp12& r, const Fp12& a) {
+  Fp2 t;
+  fp2_conj_k<4>(t, a.c0.c0);
+  fred(r.c0.c0, t);
+  frob1_coeff(r.c1.c0, a.c1.c0, 1);
+  frob1_coeff(r.c0.c1, a.c0.c1, 2);
+  frob1_coeff(r.c1.c1, a.c1.c1, 3);
+  frob1_coeff(r.c0.c2, a.c0.c2, 4);
+  frob1_coeff(r.c1.c2, a.c1.c2, 5);
+}
+// f^(p^2) : coefficient of w^i -> c_i * K_FROB2[i]  (Fp scalars; products are < 2p with 28-bit limbs: reduced)
 BLS_FN void fp12_frob2(Fp12& r, const Fp12& a) {
   Fp g;
   r.c0.c0 = a.c0.c0;
@@ -257,48 +314,52 @@ BLS_FN void fp12_frob2(Fp12& r, const Fp12& a) {
   fp2_mul_fp(r.c1.c2, a.c1.c2, g);
 }
 
-// (a + b s)^2 in Fp4 = Fp2[s]/(s^2 - xi): c0 = a^2 + xi b^2, c1 = 2ab
+// (a + b s)^2 in Fp4 = Fp2[s]/(s^2 - xi): c0 = a^2 + xi b^2, c1 = 2ab.  a, b reduced; outputs lazy: c0 <= (12,10), c1 <= 20
 BLS_HD void fp4_sqr(Fp2& c0, Fp2& c1, const Fp2& a, const Fp2& b) {
   Fp2 t0, t1, t2;
   fp2_sqr(t0, a);
   fp2_sqr(t1, b);
   fadd(t2, a, b);
   fp2_sqr(t2, t2);
-  fsub(t2, t2, t0);
-  fsub(c1, t2, t1);
-  fp2_mul_xi(t1, t1);
-  fadd(c0, t0, t1);
+  fsub_k<8>(t2, t2, t0);
+  fsub_k<8>(t2, t2, t1);
+  fnorm(c1, t2);
+  fp2_mul_xi_k<8>(t1, t1);
+  fadd(t0, t0, t1);
+  fnorm(c0, t0);
+}
+// 3t - 2z  and  3t + 2z  with t lazy (value <= 48), z reduced; reduced results
+BLS_HD void cyc_3t_m2z(Fp2& r, const Fp2& t, const Fp2& z) {
+  Fp2 x;
+  fsub_k<4>(x, t, z);
+  fdbl(x, x);
+  fadd(x, x, t);
+  fred(r, x);
+}
+BLS_HD void cyc_3t_p2z(Fp2& r, const Fp2& t, const Fp2& z) {
+  Fp2 x;
+  fadd(x, t, z);
+  fdbl(x, x);
+  fadd(x, x, t);
+  fred(r, x);
 }
 
 // Granger-Scott squaring for elements of the cyclotomic subgroup (after the easy part of the final exponentiation)
 BLS_FN void fp12_cyclo_sqr(Fp12& r, const Fp12& a) {
   Fp2 z0 = a.c0.c0, z4 = a.c0.c1, z3 = a.c0.c2, z2 = a.c1.c0, z1 = a.c1.c1, z5 = a.c1.c2;
-  Fp2 t0, t1, t2, t3, x;
+  Fp2 t0, t1, t2, t3;
   fp4_sqr(t0, t1, z0, z1);
-  // z0 = 3 t0 - 2 z0 ; z1 = 3 t1 + 2 z1
-  fsub(x, t0, z0);
-  fdbl(x, x);
-  fadd(z0, x, t0);
-  fadd(x, t1, z1);
-  fdbl(x, x);
-  fadd(z1, x, t1);
+  cyc_3t_m2z(z0, t0, z0);
+  cyc_3t_p2z(z1, t1, z1);
   fp4_sqr(t0, t1, z2, z3);
   fp4_sqr(t2, t3, z4, z5);
-  // z4 = 3 t0 - 2 z4 ; z5 = 3 t1 + 2 z5
-  fsub(x, t0, z4);
-  fdbl(x, x);
-  fadd(z4, x, t0);
-  fadd(x, t1, z5);
-  fdbl(x, x);
-  fadd(z5, x, t1);
+  cyc_3t_m2z(z4, t0, z4);
+  cyc_3t_p2z(z5, t1, z5);
   // z2 = 3 xi t3 + 2 z2 ; z3 = 3 t2 - 2 z3
-  fp2_mul_xi(t0, t3);
-  fadd(x, t0, z2);
-  fdbl(x, x);
-  fadd(z2, x, t0);
-  fsub(x, t2, z3);
-  fdbl(x, x);
-  fadd(z3, x, t2);
+  fp2_mul_xi_k<32>(t0, t3);
+  fnorm(t0, t0);
+  cyc_3t_p2z(z2, t0, z2);
+  cyc_3t_m2z(z3, t2, z3);
   r.c0.c0 = z0;
   r.c0.c1 = z4;
   r.c0.c2 = z3;

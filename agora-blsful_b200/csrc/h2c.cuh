@@ -150,21 +150,23 @@ BLS_FN void expand_message_xmd(uint8_t* out, uint32_t out_len, const uint8_t* pr
 
 // 64 big-endian bytes -> Fp (Montgomery), i.e. OS2IP(bytes) mod p
 BLS_HD void fp_from_be64_mod(Fp& r, const uint8_t* b) {
-  Fp hi, lo, c, t;
+  uint32_t wl[8], wh[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     const uint8_t* q = b + 60 - 4 * i;  // low 256 bits: bytes 32..63
-    lo.l[i] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
+    wl[i] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
     const uint8_t* qh = b + 28 - 4 * i;  // high 256 bits: bytes 0..31
-    hi.l[i] = ((uint32_t)qh[0] << 24) | ((uint32_t)qh[1] << 16) | ((uint32_t)qh[2] << 8) | qh[3];
+    wh[i] = ((uint32_t)qh[0] << 24) | ((uint32_t)qh[1] << 16) | ((uint32_t)qh[2] << 8) | qh[3];
   }
-#pragma unroll
-  for (int i = 8; i < 12; i++) lo.l[i] = hi.l[i] = 0;
+  Fp hi, lo, c, t;
+  fp_raw_from_words(lo, wl, 8);
+  fp_raw_from_words(hi, wh, 8);
   fp_set(c, K_R2);
   fp_mul(lo, lo, c);
   fp_set(c, K_R2_256);
   fp_mul(t, hi, c);
   fp_add(r, lo, t);
+  fp_norm(r, r);
 }
 
 // ------------------------------------------------------------------------------------------------ G2 suite
@@ -212,7 +214,7 @@ BLS_FN void sswu_g2(Fp2& xn, Fp2& xd, Fp2& y, const Fp2& u) {
 }
 
 // evaluates sum k_i xn^i xd^(deg-i) by Horner on the pair (xn, xd); pw[j] = xd^j precomputed
-BLS_HD void iso_poly2(Fp2& r, const uint32_t (*k)[2][12], int deg, const Fp2& xn, const Fp2* pw) {
+BLS_HD void iso_poly2(Fp2& r, const uint32_t (*k)[2][NL], int deg, const Fp2& xn, const Fp2* pw) {
   Fp2 acc, c, t;
   fp2_set(acc, k[deg]);
   for (int i = deg - 1; i >= 0; i--) {
@@ -336,7 +338,7 @@ BLS_FN void sswu_g1(Fp& xn, Fp& xd, Fp& y, const Fp& u) {
   if (fp_sgn0(u) != fp_sgn0(y)) fp_neg(y, y);
 }
 
-BLS_HD void iso_poly1(Fp& r, const uint32_t (*k)[12], int deg, const Fp& xn, const Fp* pw) {
+BLS_HD void iso_poly1(Fp& r, const uint32_t (*k)[NL], int deg, const Fp& xn, const Fp* pw) {
   Fp acc, c, t;
   fp_set(acc, k[deg]);
   for (int i = deg - 1; i >= 0; i--) {

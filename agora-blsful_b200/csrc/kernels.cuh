@@ -384,16 +384,18 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_fp_mul(size_t n, int va
     bb[k] = b[i * 48 + k];
   }
   Fp ra, rb, x, y, z;
-  fp_from_be48_raw(ra.l, ba);
-  fp_from_be48_raw(rb.l, bb);
+  fp_from_be48_raw(ra, ba);
+  fp_from_be48_raw(rb, bb);
   fp_to_mont(x, ra);
   fp_to_mont(y, rb);
   if (variant == 0)
     fp_mul_inl(z, x, y);
+  else if (variant == 1)
+    fp_mul(z, x, y);
   else
-    fp_mul_cios(z, x, y);
+    fp_sqr_inl(z, x);
   fp_from_mont(ra, z);
-  fp_to_be48_raw(ba, ra.l);
+  fp_to_be48_raw(ba, ra);
   for (int k = 0; k < 48; k++) out[i * 48 + k] = ba[k];
 }
 

@@ -9,13 +9,13 @@ using namespace bls;
 
 static void fp_in(Fp& r, const uint8_t* b) {
   Fp raw;
-  fp_from_be48_raw(raw.l, b);
+  fp_from_be48_raw(raw, b);
   fp_to_mont(r, raw);
 }
 static void fp_out(uint8_t* b, const Fp& a) {
   Fp raw;
   fp_from_mont(raw, a);
-  fp_to_be48_raw(b, raw.l);
+  fp_to_be48_raw(b, raw);
 }
 static void fp2_in(Fp2& r, const uint8_t* b) { fp_in(r.c0, b); fp_in(r.c1, b + 48); }
 static void fp2_out(uint8_t* b, const Fp2& a) { fp_out(b, a.c0); fp_out(b + 48, a.c1); }
@@ -33,7 +33,7 @@ extern "C" {
 void emu_fp_mul(const uint8_t* a, const uint8_t* b, uint8_t* out, int which) {
   Fp x, y, z;
   fp_in(x, a); fp_in(y, b);
-  if (which == 0) fp_mul(z, x, y); else fp_mul_cios(z, x, y);
+  if (which == 0) fp_mul_inl(z, x, y); else if (which == 1) fp_mul(z, x, y); else fp_sqr_inl(z, x);
   fp_out(out, z);
 }
 void emu_fp_addsub(const uint8_t* a, const uint8_t* b, uint8_t* out_add, uint8_t* out_sub, uint8_t* out_neg) {

@@ -1,0 +1,235 @@
+"""CPU-only checks of the engine's device headers (csrc/*.cuh) compiled for the host by tests/hostemu/emu.cpp, against
+the big-int oracle.  Two builds are exercised: the plain one, and one with -DBLS_TRACK, in which every Fp carries the
+worst-case value/limb bounds of the lazy-reduction discipline (csrc/fp.cuh) and every operation aborts if a bound could
+be exceeded for ANY input - so one pass over each code path proves the absence of limb/column overflow on the GPU too.
+TEST INFRASTRUCTURE ONLY: nothing here is on the product path (the C-ABI library has no CPU fallback)."""
+import ctypes
+import hashlib
+import json
+import os
+import random
+import subprocess
+
+import pytest
+
+from oracle import bls_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "hostemu", "emu.cpp")
+CSRC = os.path.join(ROOT, "agora-blsful_b200", "csrc")
+P = O.P
+
+
+def _build(out, flags):
+    deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    if os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    subprocess.run(["g++", "-shared", "-fPIC", "-o", out, SRC] + flags, check=True)
+    return out
+
+
+@pytest.fixture(scope="module", params=["plain", "track"])
+def L(request):
+    if request.param == "plain":
+        so = _build(os.path.join(ROOT, "tests", "_hostemu.so"), ["-O2"])
+    else:
+        so = _build(os.path.join(ROOT, "tests", "_hostemu_track.so"), ["-O1", "-g", "-DBLS_TRACK", "-rdynamic"])
+    return ctypes.CDLL(so)
+
+
+def be(v):
+    return v.to_bytes(48, "big")
+
+
+def buf(n):
+    return ctypes.create_string_buffer(n)
+
+
+def limbs(k, n):
+    return (ctypes.c_uint32 * n)(*[(k >> (32 * i)) & 0xFFFFFFFF for i in range(n)])
+
+
+def f2b(x):
+    return be(x[0]) + be(x[1])
+
+
+def bf2(b):
+    return (int.from_bytes(b[:48], "big"), int.from_bytes(b[48:96], "big"))
+
+
+def f12b(f):
+    return b"".join(be(c[0]) + be(c[1]) for c in f)
+
+
+def bf12(b):
+    return tuple(bf2(b[96 * i:96 * i + 96]) for i in range(6))
+
+
+def test_fp_ops(L):
+    rnd = random.Random(1)
+    for i in range(600):
+        a, b = rnd.randrange(P), rnd.randrange(P)
+        if i < 4:
+            a = [0, 1, P - 1, P - 2][i]
+        o, o2, o3 = buf(48), buf(48), buf(48)
+        L.emu_fp_mul(be(a), be(b), o, 0)
+        L.emu_fp_mul(be(a), be(b), o2, 1)
+        L.emu_fp_mul(be(a), be(a), o3, 2)
+        assert int.from_bytes(o.raw, "big") == a * b % P
+        assert int.from_bytes(o2.raw, "big") == a * b % P
+        assert int.from_bytes(o3.raw, "big") == a * a % P
+        s, d, n = buf(48), buf(48), buf(48)
+        L.emu_fp_addsub(be(a), be(b), s, d, n)
+        assert int.from_bytes(s.raw, "big") == (a + b) % P
+        assert int.from_bytes(d.raw, "big") == (a - b) % P
+        assert int.from_bytes(n.raw, "big") == (-a) % P
+    for i in range(12):
+        a = rnd.randrange(1, P)
+        o = buf(48)
+        L.emu_fp_inv(be(a), o)
+        assert int.from_bytes(o.raw, "big") * a % P == 1
+        ok = L.emu_fp_sqrt(be(a), o)
+        r = int.from_bytes(o.raw, "big")
+        assert bool(ok) == (pow(a, (P - 1) // 2, P) == 1)
+        if ok:
+            assert r * r % P == a
+
+
+def test_fp2_sqrt_ratio(L):
+    rnd = random.Random(11)
+    nsq = 0
+    for i in range(40):
+        n = (rnd.randrange(P), rnd.randrange(P))
+        d = (rnd.randrange(P), rnd.randrange(1, P))
+        if i % 5 == 0:
+            n = (n[0], 0)
+        if i % 7 == 0:
+            d = (1, 0)
+        if i == 3:
+            n = (0, n[1])
+        o = buf(96)
+        ok = L.emu_fp2_sqrt_ratio(f2b(n), f2b(d), o)
+        r = bf2(o.raw)
+        ratio = O.f2_mul(n, O.f2_inv(d))
+        if ok:
+            assert O.f2_sqr(r) == ratio
+        else:
+            nsq += 1
+            assert O.f2_sqr(r) == O.f2_mul(O.SSWU_G2_Z, ratio)
+        assert bool(ok) == (O.f2_sqrt(ratio) is not None)
+    assert nsq > 5
+    a, b = (rnd.randrange(P), rnd.randrange(P)), (rnd.randrange(P), rnd.randrange(P))
+    m, s, v = buf(96), buf(96), buf(96)
+    L.emu_fp2_mul(f2b(a), f2b(b), m, s, v)
+    assert bf2(m.raw) == O.f2_mul(a, b) and bf2(s.raw) == O.f2_sqr(a) and O.f2_mul(bf2(v.raw), a) == (1, 0)
+
+
+def test_fp12_tower_and_final_exp(L):
+    rnd = random.Random(3)
+    a = tuple((rnd.randrange(P), rnd.randrange(P)) for _ in range(6))
+    b = tuple((rnd.randrange(P), rnd.randrange(P)) for _ in range(6))
+    o = [buf(576) for _ in range(5)]
+    L.emu_fp12_ops(f12b(a), f12b(b), *o)
+    assert bf12(o[0].raw) == O.f12_mul(a, b)
+    assert bf12(o[1].raw) == O.f12_mul(a, a)
+    assert O.f12_mul(bf12(o[2].raw), a) == O.F12_ONE
+    assert bf12(o[3].raw) == O.f12_pow(a, P)
+    assert bf12(o[4].raw) == O.f12_pow(a, P * P)
+    assert L.emu_cyclo_check(f12b(a)) == 1
+    fe = buf(576)
+    L.emu_final_exp(f12b(a), fe)
+    ref = O.final_exponentiation(a)
+    assert bf12(fe.raw) == O.f12_mul(O.f12_mul(ref, ref), ref)  # the engine computes the cube (fp12.cuh)
+
+
+def test_pairing_and_golden_verify(L, golden_dir):
+    rnd = random.Random(5)
+    pa, qb = O.g1_mul(O.G1_GEN, 7), O.g2_mul(O.G2_GEN, 11)
+    ml, fe = buf(576), buf(576)
+    assert L.emu_pairing(O.g1_serialize(pa), O.g2_serialize(qb), limbs(0, 1), 0, ml, fe) == 0
+    e = O.pairing(pa, qb)
+    assert bf12(fe.raw) == O.f12_pow(e, 3)
+    assert O.final_exponentiation(bf12(ml.raw)) == e
+    k = rnd.randrange(2 ** 64)
+    assert L.emu_pairing(O.g1_serialize(pa), O.g2_serialize(qb), limbs(k, 2), 2, ml, fe) == 0
+    assert bf12(fe.raw) == O.f12_pow(e, 3 * k)  # Jacobian (scaled) G1 argument
+    g = json.load(open(os.path.join(golden_dir, "cpp_integration.json")))
+    s = g["signers"][0]
+    H = O.hash_to_curve_g2(bytes.fromhex(g["message"]), O.sig_dst(2, 0))
+    ng = O.g1_serialize(O.g1_neg(O.G1_GEN))
+    assert L.emu_pairing_check2(bytes.fromhex(s["pk"]), O.g2_serialize(H), ng, bytes.fromhex(s["sig"])) == 1
+    assert L.emu_pairing_check2(bytes.fromhex(s["pk"]), O.g2_serialize(H), ng,
+                                bytes.fromhex(g["signers"][1]["sig"])) == 0
+
+
+def test_curve_ops_and_codecs(L):
+    rnd = random.Random(2)
+    g1, g2 = O.g1_serialize(O.G1_GEN), O.g2_serialize(O.G2_GEN)
+    for _ in range(2):
+        k, k2 = rnd.randrange(O.R), rnd.randrange(O.R)
+        o = buf(48)
+        assert L.emu_g1_mul(g1, limbs(k, 8), 8, 1, o) == 0 and o.raw == O.g1_serialize(O.g1_mul(O.G1_GEN, k))
+        o2 = buf(96)
+        assert L.emu_g2_mul(g2, limbs(k, 8), 8, 1, o2) == 0 and o2.raw == O.g2_serialize(O.g2_mul(O.G2_GEN, k))
+        a, b = O.g1_mul(O.G1_GEN, k), O.g1_mul(O.G1_GEN, k2)
+        for x, y in ((a, b), (a, a), (a, O.g1_neg(a))):
+            assert L.emu_g1_add(O.g1_serialize(x), O.g1_serialize(y), o) == 0
+            assert o.raw == O.g1_serialize(O.g1_add(x, y))
+        a, b = O.g2_mul(O.G2_GEN, k), O.g2_mul(O.G2_GEN, k2)
+        for x, y in ((a, b), (a, a)):
+            assert L.emu_g2_add(O.g2_serialize(x), O.g2_serialize(y), o2) == 0
+            assert o2.raw == O.g2_serialize(O.g2_add(x, y))
+    xy, inf = buf(192), ctypes.c_int(0)
+    for fmt in (0, 1):
+        for k in (1, 2, 12345, O.R - 1):
+            pt = O.g1_mul(O.G1_GEN, k)
+            assert L.emu_g1_decompress(O.g1_serialize(pt, fmt), fmt, xy, ctypes.byref(inf)) == 0
+            assert (int.from_bytes(xy.raw[:48], "big"), int.from_bytes(xy.raw[48:96], "big")) == pt
+            pt = O.g2_mul(O.G2_GEN, k)
+            assert L.emu_g2_decompress(O.g2_serialize(pt, fmt), fmt, xy, ctypes.byref(inf)) == 0
+            assert (bf2(xy.raw[:96]), bf2(xy.raw[96:192])) == pt
+    cnt, x = 0, 5
+    while cnt < 3:  # on-curve points outside G1 / x without a y
+        x += 1
+        y = O.fp_sqrt((x ** 3 + 4) % P)
+        enc = bytearray(be(x))
+        enc[0] |= 0x80
+        assert L.emu_g1_decompress(bytes(enc), 1, xy, ctypes.byref(inf)) == 4
+        if y is not None:
+            assert L.emu_subgroup(bytes(enc), 0) == int(O.g1_in_subgroup((x, y)))
+            cnt += 1
+    cnt, x0 = 0, 7
+    while cnt < 2:
+        x0 += 1
+        xx = (x0, 3)
+        y = O.f2_sqrt(O.f2_add(O.f2_mul(O.f2_sqr(xx), xx), O.B2))
+        enc = bytearray(be(xx[1]) + be(xx[0]))
+        enc[0] |= 0x80
+        if y is None:
+            assert L.emu_g2_decompress(bytes(enc), 1, xy, ctypes.byref(inf)) == 4
+            continue
+        assert L.emu_subgroup(bytes(enc), 1) == int(O.g2_in_subgroup((xx, y))) == 0
+        cnt += 1
+
+
+def test_sha256_and_hash_to_curve(L):
+    rnd = random.Random(9)
+    for n in (0, 1, 55, 56, 63, 64, 65, 200):
+        m = bytes(rnd.randrange(256) for _ in range(n))
+        o = buf(32)
+        L.emu_sha256(m, n, o)
+        assert o.raw == hashlib.sha256(m).digest()
+    q2 = b"QUUX-V01-CS02-with-BLS12381G2_XMD:SHA-256_SSWU_RO_"
+    q1 = b"QUUX-V01-CS02-with-BLS12381G1_XMD:SHA-256_SSWU_RO_"
+    for msg, dst in ((b"", q2), (b"hello", O.sig_dst(2, 0)), (b"x" * 100, O.sig_dst(2, 1))):
+        o = buf(96)
+        L.emu_hash_to_g2(b"", 0, msg, len(msg), dst, len(dst), o)
+        assert o.raw == O.g2_serialize(O.hash_to_curve_g2(msg, dst))
+    for msg, dst in ((b"", q1), (b"abc", q1), (b"hello", O.sig_dst(1, 0))):
+        o = buf(48)
+        L.emu_hash_to_g1(b"", 0, msg, len(msg), dst, len(dst), o)
+        assert o.raw == O.g1_serialize(O.hash_to_curve_g1(msg, dst))
+    pk = O.g1_serialize(O.g1_mul(O.G1_GEN, 99))
+    o = buf(96)
+    L.emu_hash_to_g2(pk, 48, b"aug", 3, O.sig_dst(2, 1), 43, o)  # MessageAugmentation framing: pk || msg
+    assert o.raw == O.g2_serialize(O.hash_to_curve_g2(pk + b"aug", O.sig_dst(2, 1)))
