@@ -197,7 +197,12 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
     stage_mark(ctx, BLSGPU_STAGE_COUNT);
     return BLSGPU_OK;
   }
-  if (!ok) {
+  if (!ok && lv.size() == 1) {
+    // a single item: the root probe WAS its exact check
+    uint8_t inv = BLSGPU_ST_INVALID_SIGNATURE;
+    CK(cudaMemcpyAsync(d_status, &inv, 1, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  } else if (!ok) {
     // walk down the 16-ary tree: children of node j at level k+1 are {j + m * cnt(k+1)} at level k
     std::vector<uint32_t> bad{0};
     for (size_t k = lv.size() - 1; k-- > 0;) {
@@ -233,6 +238,21 @@ size_t pipeline_bytes(size_t n) {
   return total * (sizeof(Fp12) + sizeof(SigJ) + sizeof(Digest)) + (n + 64) * 8 + 16 * 256 + 4096;
 }
 
+// verify over decoded points: per-item pre-status, hash_to_curve of the framed message, pairing pipeline
+template <int IMPL>
+int verify_points(blsgpu_ctx* ctx, int msg_mode, const DstParam& dst, size_t n, const typename ImplT<IMPL>::PkAff* d_pk,
+                  const typename ImplT<IMPL>::SigAff* d_sig, const uint8_t* d_stpk, const uint8_t* d_stsig, const uint8_t* d_msgs,
+                  const uint64_t* d_moff, uint8_t* d_status_out) {
+  typedef typename ImplT<IMPL>::PkAff PkA;
+  typedef typename ImplT<IMPL>::SigAff SigA;
+  SigA* d_h = ctx->arena.take<SigA>(n);
+  LAUNCH((k_prestatus<PkA, SigA>), blocks_for(n), TPB, n, d_stpk, d_stsig, d_pk, d_sig, d_status_out);
+  stage_mark(ctx, BLSGPU_STAGE_HASH);
+  LAUNCH((k_hash<SigA, PkA>), blocks_for(n), TPB, n, d_msgs, d_moff, msg_mode, d_pk, (const uint8_t*)d_status_out, dst, d_h);
+  CKR((run_pairing_pipeline<PkA, SigA>(ctx, n, d_pk, d_sig, d_h, d_status_out, true, nullptr)));
+  return BLSGPU_OK;
+}
+
 // verify over device-resident compressed inputs.  msg_mode: 0 msg, 1 pk||msg, 2 pk bytes (PoP)
 template <int IMPL>
 int verify_dev(blsgpu_ctx* ctx, int msg_mode, const DstParam& dst, int format, size_t n, const uint8_t* d_pks, const uint8_t* d_sigs,
@@ -242,7 +262,6 @@ int verify_dev(blsgpu_ctx* ctx, int msg_mode, const DstParam& dst, int format, s
   (void)arena_reserved;
   PkA* d_pk = ctx->arena.take<PkA>(n);
   SigA* d_sig = ctx->arena.take<SigA>(n);
-  SigA* d_h = ctx->arena.take<SigA>(n);
   uint8_t* d_stpk = ctx->arena.take<uint8_t>(n);
   uint8_t* d_stsig = ctx->arena.take<uint8_t>(n);
   stage_reset(ctx);
@@ -250,10 +269,7 @@ int verify_dev(blsgpu_ctx* ctx, int msg_mode, const DstParam& dst, int format, s
   LAUNCH((k_decode<PkA>), blocks_for(n), TPB, n, d_pks, format, d_pk, d_stpk);
   stage_mark(ctx, BLSGPU_STAGE_DECODE_SIG);
   LAUNCH((k_decode<SigA>), blocks_for(n), TPB, n, d_sigs, format, d_sig, d_stsig);
-  LAUNCH((k_prestatus<PkA, SigA>), blocks_for(n), TPB, n, d_stpk, d_stsig, d_pk, d_sig, d_status_out);
-  stage_mark(ctx, BLSGPU_STAGE_HASH);
-  LAUNCH((k_hash<SigA, PkA>), blocks_for(n), TPB, n, d_msgs, d_moff, msg_mode, (const PkA*)d_pk, (const uint8_t*)d_status_out, dst, d_h);
-  CKR((run_pairing_pipeline<PkA, SigA>(ctx, n, d_pk, d_sig, d_h, d_status_out, true, nullptr)));
+  CKR((verify_points<IMPL>(ctx, msg_mode, dst, n, d_pk, d_sig, d_stpk, d_stsig, d_msgs, d_moff, d_status_out)));
   stage_collect(ctx);
   return BLSGPU_OK;
 }
@@ -776,15 +792,242 @@ int blsgpu_imad_peak(blsgpu_ctx* ctx, double* mac_per_s_out) {
   return BLSGPU_OK;
 }
 
-int blsgpu_verify_secure_batch(blsgpu_ctx* ctx, int, int, int, size_t, const uint64_t*, const uint8_t*, const uint8_t*, const uint8_t*,
-                               const uint64_t*, uint8_t*) {
-  if (!ctx) return BLSGPU_E_ARG;
-  ctx->err = "blsgpu_verify_secure_batch: not built yet";
-  return BLSGPU_E_ARG;
-}
-int blsgpu_aggregate_secure_batch(blsgpu_ctx* ctx, int, int, size_t, const uint64_t*, const uint8_t*, const uint8_t*, uint8_t*, uint8_t*) {
-  if (!ctx) return BLSGPU_E_ARG;
-  ctx->err = "blsgpu_aggregate_secure_batch: not built yet";
-  return BLSGPU_E_ARG;
+// ---------------------------------------------------------------------------------------------------------------------
+// Secure aggregation.  Host side: the reference's ordering rules (stable sort of the serialized keys, first-match lookup
+// for duplicate keys); device side: SHA-256 coefficient derivation, the t_i * P_i scalar multiplications, segmented sums.
+namespace {
+
+struct SecurePlan {
+  size_t q = 0, M = 0;
+  std::vector<uint32_t> ord, set_of, pos, first;  // per sorted member: original key index, key set, position; first equal key
+  std::vector<uint32_t> c_start, c_cnt, s_start, s_cnt;  // level-1 chunks of 16 members, level-2 chunk ranges per key set
+};
+
+// sorts every key set by serialized bytes (reference src/secure_aggregation.rs:42,281: sort_by on the byte strings; the
+// sort is stable, and a valid compressed encoding is canonical, so the caller's bytes are the reference's sort keys)
+SecurePlan make_secure_plan(size_t q, const uint64_t* key_off, const uint8_t* pks, size_t L) {
+  SecurePlan pl;
+  pl.q = q;
+  pl.M = (size_t)key_off[q];
+  pl.ord.resize(pl.M);
+  pl.set_of.resize(pl.M);
+  pl.pos.resize(pl.M);
+  pl.first.resize(pl.M);
+  for (size_t j = 0; j < q; j++) {
+    size_t lo = (size_t)key_off[j], hi = (size_t)key_off[j + 1];
+    for (size_t i = lo; i < hi; i++) pl.ord[i] = (uint32_t)i;
+    std::stable_sort(pl.ord.begin() + lo, pl.ord.begin() + hi,
+                     [&](uint32_t a, uint32_t b) { return memcmp(pks + (size_t)a * L, pks + (size_t)b * L, L) < 0; });
+    for (size_t i = lo; i < hi; i++) {
+      pl.set_of[i] = (uint32_t)j;
+      pl.pos[i] = (uint32_t)(i - lo);
+      // equal keys are adjacent after sorting and keep their original order: the run's first element is the first match
+      if (i > lo && memcmp(pks + (size_t)pl.ord[i] * L, pks + (size_t)pl.ord[i - 1] * L, L) == 0)
+        pl.first[i] = pl.first[i - 1];
+      else
+        pl.first[i] = pl.ord[i];
+    }
+    pl.s_start.push_back((uint32_t)pl.c_start.size());
+    for (size_t i = lo; i < hi; i += 16) {
+      pl.c_start.push_back((uint32_t)i);
+      pl.c_cnt.push_back((uint32_t)std::min<size_t>(16, hi - i));
+    }
+    pl.s_cnt.push_back((uint32_t)pl.c_start.size() - pl.s_start.back());
+  }
+  return pl;
 }
 
+// device part shared by verify and aggregate: out_sum[j] = sum_i t_i * points[src(i)] ; zero_out[m] flags t_m == 0
+template <class A>
+int secure_weighted_sums(blsgpu_ctx* ctx, const SecurePlan& pl, const uint64_t* key_off, const uint8_t* d_key_bytes, int key_len, const std::vector<uint32_t>& src,
+                         const A* d_points, typename PtInfo<A>::Jac* d_sum, uint8_t* d_zero) {
+  typedef typename PtInfo<A>::Jac J;
+  uint32_t *d_ord, *d_set, *d_pos, *d_src, *d_cs, *d_cc, *d_ss, *d_sc;
+  uint64_t* d_koff;
+  CKR(upload(ctx, d_koff, key_off, pl.q + 1));
+  CKR(upload(ctx, d_ord, pl.ord.data(), pl.M));
+  CKR(upload(ctx, d_set, pl.set_of.data(), pl.M));
+  CKR(upload(ctx, d_pos, pl.pos.data(), pl.M));
+  CKR(upload(ctx, d_src, src.data(), pl.M));
+  CKR(upload(ctx, d_cs, pl.c_start.data(), pl.c_start.size()));
+  CKR(upload(ctx, d_cc, pl.c_cnt.data(), pl.c_cnt.size()));
+  CKR(upload(ctx, d_ss, pl.s_start.data(), pl.q));
+  CKR(upload(ctx, d_sc, pl.s_cnt.data(), pl.q));
+  Digest* d_base = ctx->arena.take<Digest>(pl.q);
+  J* d_scaled = ctx->arena.take<J>(std::max<size_t>(pl.M, 1));
+  J* d_part = ctx->arena.take<J>(std::max<size_t>(pl.c_start.size(), 1));
+  LAUNCH(k_secure_base, blocks_for(pl.q), TPB, pl.q, (const uint64_t*)d_koff, (const uint32_t*)d_ord, d_key_bytes, key_len, d_base);
+  if (pl.M) {
+    LAUNCH((k_secure_scale<A>), blocks_for(pl.M), TPB, pl.M, (const uint32_t*)d_set, (const uint32_t*)d_pos, (const uint32_t*)d_src,
+           (const Digest*)d_base, d_points, d_scaled, d_zero);
+    LAUNCH((k_seg_sum<J>), blocks_for(pl.c_start.size()), TPB, pl.c_start.size(), (const uint32_t*)d_cs, (const uint32_t*)d_cc,
+           (const J*)d_scaled, d_part);
+  }
+  LAUNCH((k_seg_sum<J>), blocks_for(pl.q), TPB, pl.q, (const uint32_t*)d_ss, (const uint32_t*)d_sc, (const J*)d_part, d_sum);
+  return BLSGPU_OK;
+}
+
+size_t secure_plan_bytes(const SecurePlan& pl, size_t jac_size) {
+  return (pl.q + 1) * 8 + pl.M * 16 + pl.c_start.size() * 8 + pl.q * 8 + pl.q * 32 + (pl.M + pl.c_start.size() + 2) * jac_size + 24 * 256;
+}
+
+template <int IMPL>
+int verify_secure_impl(blsgpu_ctx* ctx, int scheme, int format, size_t q, const uint64_t* key_off, const uint8_t* pks, const uint8_t* sigs,
+                       const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out) {
+  typedef typename ImplT<IMPL>::PkAff PkA;
+  typedef typename ImplT<IMPL>::SigAff SigA;
+  typedef typename ImplT<IMPL>::PkJac PkJ;
+  const size_t Lp = PtInfo<PkA>::LEN, Ls = PtInfo<SigA>::LEN;
+  SecurePlan pl = make_secure_plan(q, key_off, pks, Lp);
+  const size_t M = pl.M, msg_bytes = (size_t)msg_off[q];
+  size_t need = M * (Lp + sizeof(PkA) + 2) + q * (Ls + 2 * sizeof(SigA) + sizeof(PkA) + sizeof(PkJ) + 8) + msg_bytes + (q + 1) * 8 +
+                secure_plan_bytes(pl, sizeof(PkJ)) + verify_bytes<IMPL>(q) + 32 * 256;
+  CKR(ensure_arena(ctx, need));
+  stage_reset(ctx);
+  uint8_t *d_pkb, *d_sigb, *d_msgs;
+  uint64_t* d_moff;
+  CKR(upload(ctx, d_pkb, pks, M * Lp));
+  CKR(upload(ctx, d_sigb, sigs, q * Ls));
+  CKR(upload(ctx, d_msgs, msgs, msg_bytes));
+  CKR(upload(ctx, d_moff, msg_off, q + 1));
+  PkA* d_pk = ctx->arena.take<PkA>(std::max<size_t>(M, 1));
+  SigA* d_sig = ctx->arena.take<SigA>(q);
+  uint8_t* d_stpk = ctx->arena.take<uint8_t>(std::max<size_t>(M, 1));
+  uint8_t* d_stsig = ctx->arena.take<uint8_t>(q);
+  uint8_t* d_zero = ctx->arena.take<uint8_t>(std::max<size_t>(M, 1));
+  PkJ* d_sum = ctx->arena.take<PkJ>(q);
+  PkA* d_agg = ctx->arena.take<PkA>(q);
+  uint8_t* d_setst = ctx->arena.take<uint8_t>(q);
+  uint8_t* d_status = ctx->arena.take<uint8_t>(q);
+  if (M) LAUNCH((k_decode<PkA>), blocks_for(M), TPB, M, (const uint8_t*)d_pkb, format, d_pk, d_stpk);
+  LAUNCH((k_decode<SigA>), blocks_for(q), TPB, q, (const uint8_t*)d_sigb, format, d_sig, d_stsig);
+  CKR((secure_weighted_sums<PkA>(ctx, pl, key_off, d_pkb, (int)Lp, pl.ord, d_pk, d_sum, d_zero)));
+  LAUNCH((k_to_affine<PkA>), blocks_for(q), TPB, q, (const PkJ*)d_sum, d_agg);
+  std::vector<uint8_t> stpk(M), stsig(q), zero(M);
+  std::vector<uint32_t> siginf(q);
+  if (M) CK(cudaMemcpyAsync(stpk.data(), d_stpk, M, cudaMemcpyDeviceToHost, ctx->stream));
+  if (M) CK(cudaMemcpyAsync(zero.data(), d_zero, M, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(stsig.data(), d_stsig, q, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpy2DAsync(siginf.data(), 4, reinterpret_cast<const uint8_t*>(d_sig) + offsetof(SigA, inf), sizeof(SigA), 4, q,
+                       cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  // set-level status in the reference's order: key decode errors (first bad key), signature decode error, empty key set
+  // (secure_aggregation.rs:189-195), zero coefficient (:98-100); everything else is core_verify on the device
+  std::vector<uint8_t> pre(q, BLSGPU_ST_OK);
+  for (size_t j = 0; j < q; j++) {
+    size_t lo = (size_t)key_off[j], hi = (size_t)key_off[j + 1];
+    uint8_t s = BLSGPU_ST_OK;
+    for (size_t i = lo; i < hi && s == BLSGPU_ST_OK; i++) s = stpk[i];
+    if (s == BLSGPU_ST_OK) s = stsig[j];
+    if (s == BLSGPU_ST_OK && lo == hi) s = siginf[j] ? 0xff : BLSGPU_ST_INVALID_SIGNATURE;  // 0xff: "OK, nothing to check"
+    if (s == BLSGPU_ST_OK)
+      for (size_t i = lo; i < hi; i++)
+        if (zero[i]) s = BLSGPU_ST_INVALID_COEFFICIENT;
+    pre[j] = s;
+  }
+  CK(cudaMemcpyAsync(d_setst, pre.data(), q, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(d_stsig, 0, q, ctx->stream));
+  DstParam dst;
+  make_dst(dst, IMPL, scheme, false);
+  // MessageAugmentation uses its DST but does NOT prepend the aggregated key here (secure_aggregation.rs:236-247)
+  CKR((verify_points<IMPL>(ctx, 0, dst, q, d_agg, d_sig, d_setst, d_stsig, d_msgs, d_moff, d_status)));
+  CK(cudaMemcpyAsync(status_out, d_status, q, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (size_t j = 0; j < q; j++)
+    if (status_out[j] == 0xff) status_out[j] = BLSGPU_ST_OK;
+  stage_collect(ctx);
+  return BLSGPU_OK;
+}
+
+template <int IMPL>
+int aggregate_secure_impl(blsgpu_ctx* ctx, int format, size_t q, const uint64_t* key_off, const uint8_t* pks, const uint8_t* member_sigs,
+                          uint8_t* out_sigs, uint8_t* status_out) {
+  typedef typename ImplT<IMPL>::PkAff PkA;
+  typedef typename ImplT<IMPL>::SigAff SigA;
+  typedef typename ImplT<IMPL>::SigJac SigJ;
+  const size_t Lp = PtInfo<PkA>::LEN, Ls = PtInfo<SigA>::LEN;
+  SecurePlan pl = make_secure_plan(q, key_off, pks, Lp);
+  const size_t M = pl.M;
+  size_t need = M * (Lp + Ls + sizeof(PkA) + sizeof(SigA) + 3) + q * (Ls + sizeof(SigA) + sizeof(SigJ) + 8) +
+                secure_plan_bytes(pl, sizeof(SigJ)) + 32 * 256;
+  CKR(ensure_arena(ctx, need));
+  uint8_t *d_pkb, *d_sigb;
+  CKR(upload(ctx, d_pkb, pks, M * Lp));
+  CKR(upload(ctx, d_sigb, member_sigs, M * Ls));
+  PkA* d_pk = ctx->arena.take<PkA>(std::max<size_t>(M, 1));
+  SigA* d_sig = ctx->arena.take<SigA>(std::max<size_t>(M, 1));
+  uint8_t* d_stpk = ctx->arena.take<uint8_t>(std::max<size_t>(M, 1));
+  uint8_t* d_stsig = ctx->arena.take<uint8_t>(std::max<size_t>(M, 1));
+  uint8_t* d_zero = ctx->arena.take<uint8_t>(std::max<size_t>(M, 1));
+  SigJ* d_sum = ctx->arena.take<SigJ>(q);
+  SigA* d_agg = ctx->arena.take<SigA>(q);
+  uint8_t* d_out = ctx->arena.take<uint8_t>(q * Ls);
+  if (M) {
+    LAUNCH((k_decode<PkA>), blocks_for(M), TPB, M, (const uint8_t*)d_pkb, format, d_pk, d_stpk);
+    LAUNCH((k_decode<SigA>), blocks_for(M), TPB, M, (const uint8_t*)d_sigb, format, d_sig, d_stsig);
+  }
+  // sum_i t_i * sig[first original index whose key bytes equal sorted key i]   (secure_aggregation.rs:138-153)
+  CKR((secure_weighted_sums<SigA>(ctx, pl, key_off, d_pkb, (int)Lp, pl.first, d_sig, d_sum, d_zero)));
+  LAUNCH((k_to_affine<SigA>), blocks_for(q), TPB, q, (const SigJ*)d_sum, d_agg);
+  LAUNCH((k_encode<SigA>), blocks_for(q), TPB, q, (const SigA*)d_agg, format, d_out);
+  std::vector<uint8_t> stpk(M), stsig(M), zero(M);
+  if (M) {
+    CK(cudaMemcpyAsync(stpk.data(), d_stpk, M, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(stsig.data(), d_stsig, M, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(zero.data(), d_zero, M, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaMemcpyAsync(out_sigs, d_out, q * Ls, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (size_t j = 0; j < q; j++) {
+    size_t lo = (size_t)key_off[j], hi = (size_t)key_off[j + 1];
+    uint8_t s = BLSGPU_ST_OK;
+    for (size_t i = lo; i < hi && s == BLSGPU_ST_OK; i++) s = stpk[i];
+    for (size_t i = lo; i < hi && s == BLSGPU_ST_OK; i++) s = stsig[i];
+    if (s == BLSGPU_ST_OK)
+      for (size_t i = lo; i < hi; i++)
+        if (zero[i]) s = BLSGPU_ST_INVALID_COEFFICIENT;
+    status_out[j] = s;
+    if (s != BLSGPU_ST_OK) memset(out_sigs + j * Ls, 0, Ls);
+  }
+  return BLSGPU_OK;
+}
+
+}  // namespace
+
+int blsgpu_verify_secure_batch(blsgpu_ctx* ctx, int impl_id, int scheme, int format, size_t q, const uint64_t* key_off, const uint8_t* pks,
+                               const uint8_t* sigs, const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out) {
+  if (!ctx) return BLSGPU_E_ARG;
+  if (!args_ok(impl_id, scheme, format) || (q && (!key_off || !sigs || !msg_off || !status_out)) || (q && key_off[q] && !pks) ||
+      (impl_id == 1 && format == 0)) {
+    ctx->err = "blsgpu_verify_secure_batch: bad arguments (Legacy mode exists only for Bls12381G2Impl)";
+    return BLSGPU_E_ARG;
+  }
+  if (q == 0) return BLSGPU_OK;
+  for (size_t j = 0; j < q; j++)
+    if (key_off[j + 1] < key_off[j] || key_off[q] > 0xfffffff0ull) {
+      ctx->err = "blsgpu_verify_secure_batch: key_off must be non-decreasing and below 2^32";
+      return BLSGPU_E_ARG;
+    }
+  CKR(set_device(ctx));
+  return impl_id == 2 ? verify_secure_impl<2>(ctx, scheme, format, q, key_off, pks, sigs, msgs, msg_off, status_out)
+                      : verify_secure_impl<1>(ctx, scheme, format, q, key_off, pks, sigs, msgs, msg_off, status_out);
+}
+
+int blsgpu_aggregate_secure_batch(blsgpu_ctx* ctx, int impl_id, int format, size_t q, const uint64_t* key_off, const uint8_t* pks,
+                                  const uint8_t* member_sigs, uint8_t* out_sigs, uint8_t* status_out) {
+  if (!ctx) return BLSGPU_E_ARG;
+  if (!args_ok(impl_id, 0, format) || (q && (!key_off || !out_sigs || !status_out)) || (q && key_off[q] && (!pks || !member_sigs)) ||
+      (impl_id == 1 && format == 0)) {
+    ctx->err = "blsgpu_aggregate_secure_batch: bad arguments (Legacy mode exists only for Bls12381G2Impl)";
+    return BLSGPU_E_ARG;
+  }
+  if (q == 0) return BLSGPU_OK;
+  for (size_t j = 0; j < q; j++)
+    if (key_off[j + 1] < key_off[j] || key_off[q] > 0xfffffff0ull) {
+      ctx->err = "blsgpu_aggregate_secure_batch: key_off must be non-decreasing and below 2^32";
+      return BLSGPU_E_ARG;
+    }
+  CKR(set_device(ctx));
+  return impl_id == 2 ? aggregate_secure_impl<2>(ctx, format, q, key_off, pks, member_sigs, out_sigs, status_out)
+                      : aggregate_secure_impl<1>(ctx, format, q, key_off, pks, member_sigs, out_sigs, status_out);
+}

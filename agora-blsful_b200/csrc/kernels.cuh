@@ -374,6 +374,81 @@ __global__ void k_mark_invalid(size_t cnt, const uint32_t* idx, const uint8_t* o
   if (!ok[c]) status[idx[c]] = ST_INVALID_SIGNATURE;
 }
 
+// ---- secure aggregation (reference src/secure_aggregation.rs) ------------------------------------------------------------
+// base_j = SHA256(sorted key bytes of key set j)            (:45-59, :284-298)
+__global__ void __launch_bounds__(128) k_secure_base(size_t q, const uint64_t* __restrict__ key_off, const uint32_t* __restrict__ ord,
+                                                     const uint8_t* __restrict__ key_bytes, int key_len, Digest* __restrict__ base) {
+  size_t j = BLS_TID();
+  if (j >= q) return;
+  Sha256 s;
+  sha256_init(s);
+  for (uint64_t i = key_off[j]; i < key_off[j + 1]; i++) sha256_update(s, key_bytes + (size_t)ord[i] * key_len, (uint32_t)key_len);
+  Digest d;
+  sha256_final(s, d.b);
+  base[j] = d;
+}
+// t = BE(SHA256(be32(pos) || base)) mod r as 8 little-endian words; returns false if t == 0   (:61-103, :300-331)
+__device__ __forceinline__ bool secure_coefficient(uint32_t t[8], uint32_t pos, const Digest& base) {
+  Sha256 s;
+  sha256_init(s);
+  uint8_t ib[4] = {(uint8_t)(pos >> 24), (uint8_t)(pos >> 16), (uint8_t)(pos >> 8), (uint8_t)pos};
+  sha256_update(s, ib, 4);
+  sha256_update(s, base.b, 32);
+  uint8_t d[32];
+  sha256_final(s, d);
+  for (int w = 0; w < 8; w++) {
+    const uint8_t* p = d + 28 - 4 * w;
+    t[w] = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+  }
+  // 2^256 < 3r: at most two subtractions of r
+  for (int rep = 0; rep < 2; rep++) {
+    uint32_t u[8];
+    int64_t br = 0;
+    for (int w = 0; w < 8; w++) {
+      int64_t v = (int64_t)t[w] - (int64_t)K_R_ORDER[w] + br;
+      u[w] = (uint32_t)v;
+      br = v >> 32;
+    }
+    if (br == 0)
+      for (int w = 0; w < 8; w++) t[w] = u[w];
+  }
+  uint32_t any = 0;
+  for (int w = 0; w < 8; w++) any |= t[w];
+  return any != 0;
+}
+// out[m] = t_m * points[src[m]] for every member m (sorted position pos[m] of key set set_of[m]); zero[m] = 1 if t_m == 0
+template <class A>
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_secure_scale(size_t M, const uint32_t* __restrict__ set_of, const uint32_t* __restrict__ pos,
+                                                     const uint32_t* __restrict__ src, const Digest* __restrict__ base,
+                                                     const A* __restrict__ points, typename PtInfo<A>::Jac* __restrict__ out,
+                                                     uint8_t* __restrict__ zero) {
+  size_t m = BLS_TID();
+  if (m >= M) return;
+  uint32_t t[8];
+  Digest b = base[set_of[m]];
+  bool nz = secure_coefficient(t, pos[m], b);
+  zero[m] = nz ? 0 : 1;
+  A p = points[src[m]];
+  typename PtInfo<A>::Jac r;
+  jac_mul_aff(r, p, t, 8);
+  out[m] = r;
+}
+// segmented sums: out[c] = sum of in[start[c] .. start[c] + cnt[c])
+template <class J>
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_seg_sum(size_t nseg, const uint32_t* __restrict__ start, const uint32_t* __restrict__ cnt,
+                                                const J* __restrict__ in, J* __restrict__ out) {
+  size_t c = BLS_TID();
+  if (c >= nseg) return;
+  J acc;
+  jac_set_inf(acc);
+  uint32_t s0 = start[c], n = cnt[c];
+  for (uint32_t i = 0; i < n; i++) {
+    J t = in[s0 + i];
+    jac_add(acc, acc, t);
+  }
+  out[c] = acc;
+}
+
 // ---- building blocks ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_fp_mul(size_t n, int variant, const uint8_t* a, const uint8_t* b, uint8_t* out) {
   size_t i = BLS_TID();
@@ -453,22 +528,31 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_testdata_sign(size_t n,
   for (int b = 0; b < PtInfo<SigA>::LEN; b++) out_sig[i * PtInfo<SigA>::LEN + b] = sb[b];
 }
 
-// INT32 multiply roofline probe: 8 independent 64-bit accumulators per thread, ITER*8 mad.wide.u32 each
+// INT32 multiply roofline probe: 8 independent 64-bit accumulators per thread, iters*64 IMAD.WIDE.U32 each.  The operands
+// change every group of 8 (a += low word of an accumulator, b += odd constant) so that neither nvcc nor ptxas can hoist
+// the product out of the loop - an earlier probe with loop-invariant operands compiled to 64-bit ADDs and overstated the
+// peak by 2x.  SASS check: the loop body must show 64 IMAD.WIDE.U32 per iteration.
 __global__ void __launch_bounds__(256) k_imad_peak(uint32_t iters, uint32_t seed, uint64_t* sink) {
-  uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
-  uint64_t c0 = a, c1 = b, c2 = a + 1, c3 = b + 1, c4 = a + 2, c5 = b + 2, c6 = a + 3, c7 = b + 3;
+  uint32_t a[8], b = seed * 3 + blockIdx.x;
+  uint64_t c[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    a[k] = seed + threadIdx.x * 8 + k;
+    c[k] = a[k];
+  }
   for (uint32_t it = 0; it < iters; it++) {
 #pragma unroll
     for (int u = 0; u < 8; u++) {
-      asm volatile(
-          "mad.wide.u32 %0, %8, %9, %0;\n\tmad.wide.u32 %1, %8, %9, %1;\n\tmad.wide.u32 %2, %8, %9, %2;\n\t"
-          "mad.wide.u32 %3, %8, %9, %3;\n\tmad.wide.u32 %4, %8, %9, %4;\n\tmad.wide.u32 %5, %8, %9, %5;\n\t"
-          "mad.wide.u32 %6, %8, %9, %6;\n\tmad.wide.u32 %7, %8, %9, %7;"
-          : "+l"(c0), "+l"(c1), "+l"(c2), "+l"(c3), "+l"(c4), "+l"(c5), "+l"(c6), "+l"(c7)
-          : "r"(a), "r"(b));
+#pragma unroll
+      for (int k = 0; k < 8; k++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c[k]) : "r"(a[k]), "r"(b));
+      b += 0x9e3779b9u;
     }
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] ^= (uint32_t)c[(k + 1) & 7];
   }
-  uint64_t r = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+  uint64_t r = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) r ^= c[k];
   if (r == 0x123456789abcdefull) sink[0] = r;  // keeps the chains alive
 }
 

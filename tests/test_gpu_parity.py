@@ -113,6 +113,11 @@ def test_verify_batch_cpp_golden(eng, B, cpp):
     want = [O.verify(O.G2IMPL, O.BASIC, O.MODERN, p, s, m) for p, s, m in zip(pks2, sigs2, msgs2)]
     assert st.tolist() == want
     assert want[:3] == [0, 0, 0] and want[3] == 1 and want[4] == 2 and want[5] == 3 and want[6] == 1
+    # batches of one (the tree is a single leaf) and of two
+    assert eng.verify_batch(B.Bls12381G2Impl, 0, [pks[0]], [sigs[1]], [msg]).tolist() == [1]
+    assert eng.verify_batch(B.Bls12381G2Impl, 0, [pks[0]], [sigs[0]], [msg]).tolist() == [0]
+    assert eng.verify_batch(B.Bls12381G2Impl, 0, [pks[0], pks[1]], [sigs[0], sigs[0]], [msg, msg]).tolist() == [0, 1]
+    assert eng.verify_batch(B.Bls12381G2Impl, 0, [], [], []).tolist() == []
 
 
 @pytest.mark.parametrize("impl", [2, 1])
@@ -216,3 +221,78 @@ def test_aggregate_verify_semantics(eng, B, impl):
     pk_list = [pks[i * pl:(i + 1) * pl].tobytes() for i in range(3)]
     agg = eng.sum_points(1 if impl == 1 else 2, sigs)
     assert O.aggregate_verify(impl, O.BASIC, O.MODERN, pk_list, msgs[:3], agg)[0] == 0
+
+
+# ---- secure aggregation (reference src/secure_aggregation.rs; tests/secure_aggregation_test.rs, cpp_integration_test.rs) ----
+@pytest.fixture(scope="module")
+def sec57(golden_dir):
+    return json.load(open(os.path.join(golden_dir, "secure_57.json")))
+
+
+def test_verify_secure_production_57_key_vector(eng, B, sec57):
+    # secure_aggregation_test.rs:143-235: 57 production keys, one aggregate signature
+    pks = [bytes.fromhex(k) for k in sec57["keys"]]
+    sig = bytes.fromhex(sec57["sig"])
+    msg = bytes.fromhex(sec57["message"])
+    st = eng.verify_secure_batch(B.Bls12381G2Impl, 0, [pks, pks[::-1], pks[:-1], pks], [sig, sig, sig, sig],
+                                 [msg, msg, msg, msg + b"x"])
+    assert st.tolist() == [0, 0, 1, 1]  # order independent; missing key / wrong message fail (secure_aggregation.rs:562-602)
+
+
+def test_secure_aggregate_then_verify_cpp_golden(eng, B, cpp):
+    # cpp_integration_test.rs:86-192
+    msg = bytes.fromhex(cpp["message"])
+    pks = [bytes.fromhex(s["pk"]) for s in cpp["signers"]]
+    sigs = [bytes.fromhex(s["sig"]) for s in cpp["signers"]]
+    sets = [pks[:2], pks[:3], pks[:1]]
+    st, aggs = eng.aggregate_secure_batch(B.Bls12381G2Impl, sets, [sigs[:2], sigs[:3], sigs[:1]])
+    assert st.tolist() == [0, 0, 0]
+    for ks, ss, a in zip(sets, [sigs[:2], sigs[:3], sigs[:1]], aggs):
+        assert (0, a) == O.aggregate_secure(O.G2IMPL, O.MODERN, ks, ss)
+    normal = bytes.fromhex(cpp["normal_agg_sig12"])
+    st = eng.verify_secure_batch(B.Bls12381G2Impl, 0, sets + [pks[:2]], aggs + [normal], [msg] * 4)
+    assert st.tolist() == [0, 0, 0, 1]  # the plain (rogue-key-prone) aggregate must fail (:169-192)
+
+
+@pytest.mark.parametrize("impl,fmt", [(2, 1), (2, 0), (1, 1)])
+def test_secure_semantics_against_oracle(eng, B, impl, fmt):
+    rnd = random.Random(31 + impl * 7 + fmt)
+    C = O.IMPLS[impl]
+    msg = b"quorum message"
+    sks = [rnd.randrange(1, O.R) for _ in range(5)]
+    pk_pts = [O.sk_to_pk(impl, sk) for sk in sks]
+    pks = [C.pk_ser(p, fmt) for p in pk_pts]
+    ident_sig = bytes([0xC0]) + bytes(B.sig_len(impl) - 1)
+    ident_pk = bytes([0xC0]) + bytes(B.pk_len(impl) - 1)
+    for scheme in ((0, 1, 2) if (impl, fmt) == (2, 1) else ((impl + fmt) % 3,)):
+        # verify_secure hashes the bare message under the scheme's DST (no pk prefix even for MessageAugmentation)
+        sigs = [C.sig_ser(C.sig_mul(C.hash(msg, O.sig_dst(impl, scheme)), sk), fmt) for sk in sks]
+        dup_keys = pks[:3] + [pks[1]]
+        dup_sigs = sigs[:3] + [sigs[0]]  # the duplicate key must reuse the FIRST match's signature (sigs[1]), not this one
+        key_sets = [pks, pks[:4], dup_keys, []]
+        sig_sets = [sigs, sigs[:4], dup_sigs, []]
+        st, aggs = eng.aggregate_secure_batch(impl, key_sets, sig_sets, fmt)
+        for ks, ss, s, a in zip(key_sets, sig_sets, st, aggs):
+            want_st, want = O.aggregate_secure(impl, fmt, ks, ss)
+            assert s == want_st and a == want
+        # verify: good, shuffled, wrong message, subset of keys, empty set with identity / non-identity signature,
+        # identity signature with keys, one undecodable key, one undecodable signature
+        bad_key = bytes(B.pk_len(impl))
+        bad_sig = bytes(B.sig_len(impl))
+        cases = [
+            (pks, aggs[0], msg), (pks[::-1], aggs[0], msg), (pks, aggs[0], msg + b"!"), (pks[:4], aggs[0], msg),
+            ([], ident_sig, msg), ([], aggs[0], msg), (pks, ident_sig, msg), (pks[:2] + [bad_key], aggs[0], msg),
+            (pks, bad_sig, msg), ([ident_pk], aggs[0], msg), (pks[:4], aggs[1], msg),
+        ]
+        got = eng.verify_secure_batch(impl, scheme, [c[0] for c in cases], [c[1] for c in cases], [c[2] for c in cases], fmt)
+        want = [O.verify_secure(impl, scheme, fmt, c[0], c[1], c[2]) for c in cases]
+        assert got.tolist() == want, (impl, fmt, scheme)
+        assert want[0] == 0 and want[1] == 0 and want[4] == 0 and want[10] == 0
+    if impl == 2:
+        # cross-mode must fail: keys/signature of one format checked under the other coefficient derivation (legacy_test.rs:109-171)
+        other = 1 - fmt
+        st2, agg2 = eng.aggregate_secure_batch(impl, [[C.pk_ser(p, other) for p in pk_pts]],
+                                               [[C.sig_ser(C.sig_deser(s, fmt), other) for s in sigs]], other)
+        re = C.sig_ser(C.sig_deser(agg2[0], other), fmt)
+        assert eng.verify_secure_batch(impl, 2, [pks], [re], [msg], fmt).tolist() == \
+            [O.verify_secure(impl, 2, fmt, pks, re, msg)]
