@@ -143,6 +143,32 @@ def _ptr(a: Optional[np.ndarray]):
     return None if a is None or a.size == 0 else a.ctypes.data
 
 
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous slice [lo, hi) of an n-item batch owned by `rank` of `world` (one process per GPU; the slices are
+    independent units - there is no data-path collective)."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad rank/world")
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def verify_batch_sharded(verify_slice, n: int, rank: int, world: int, gather=None) -> np.ndarray:
+    """Runs `verify_slice(lo, hi) -> uint8[hi-lo]` on this rank's slice and, if `gather` (a torch.distributed-style
+    all_gather_object callable) is given, assembles the full status vector on every rank in batch order."""
+    lo, hi = shard_range(n, rank, world)
+    mine = np.asarray(verify_slice(lo, hi), dtype=np.uint8)
+    if mine.shape != (hi - lo,):
+        raise ValueError("verify_slice returned the wrong number of statuses")
+    if gather is None or world == 1:
+        return mine
+    parts = gather((lo, mine))
+    out = np.empty(n, dtype=np.uint8)
+    for plo, part in parts:
+        out[plo:plo + part.size] = part
+    return out
+
+
 def pack_messages(msgs: Sequence[bytes]) -> Tuple[np.ndarray, np.ndarray]:
     off = np.zeros(len(msgs) + 1, dtype=np.uint64)
     if len(msgs):

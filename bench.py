@@ -162,6 +162,8 @@ def main():
     impl, scheme, n = B.Bls12381G2Impl, B.SignatureSchemes.Basic, args.n
 
     peak_mac = eng.imad_peak()
+    lo, hi = B.shard_range(world * n, rank, world)  # weak scaling: the job is world*n signatures, rank r owns [lo, hi)
+    assert hi - lo == n
     pks, sigs, msgs, off = synth_batch(eng, n, seed=1000 + rank)
 
     # pinned host copies (e2e leg) and device-resident copies (value leg)
@@ -231,8 +233,9 @@ def main():
         "bound": "int32_imad", "kernel": dom, "achieved": achieved, "peak": peak_mac / 1e9, "unit": "GMAC/s",
         "frac": achieved / (peak_mac / 1e9), "traffic": None,
         "whole_step": {"achieved": whole, "frac": whole / (peak_mac / 1e9), "fp_mul_per_sig": FPMUL_PER_SIG},
-        "peak_source": "measured live by blsgpu_imad_peak (independent mad.wide.u32 chains on all SMs); "
-                       "MEASURED_PEAKS.json holds no INT32 figure",
+        "peak_source": "measured live by blsgpu_imad_peak (8 independent IMAD.WIDE.U32 chains per thread with changing "
+                       "operands on all SMs); MEASURED_PEAKS.json holds no INT32 figure; ncu counterpart: "
+                       "sm__pipe_fmaheavy_cycles_active",
         "stage_ms": stages,
     }
 
