@@ -152,26 +152,42 @@ template <class PkA, class SigA>
 int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA* d_sig, const SigA* d_h, uint8_t* d_status,
                          bool use_rlc, int* agg_ok) {
   typedef typename PtInfo<SigA>::Jac SigJ;
-  std::vector<Level> lv = make_levels(n);
+  // leaves of the product/sum trees are GROUPS of 6 consecutive items (the cooperative Miller kernel's unit)
+  const size_t ng = (n + M6_GROUP - 1) / M6_GROUP;
+  std::vector<Level> lv = make_levels(ng);
   size_t total = levels_total(lv);
   Fp12* d_F = ctx->arena.take<Fp12>(total);
   SigJ* d_S = ctx->arena.take<SigJ>(use_rlc ? total : 1);
-  Digest* d_dig = ctx->arena.take<Digest>(total + 2);
-  Digest* d_root = d_dig + total;  // [root, salt]
+  SigJ* d_Sitem = ctx->arena.take<SigJ>(use_rlc ? n : 1);
+  Digest* d_dig = ctx->arena.take<Digest>(levels_total(make_levels(n)) + 2);
+  Digest* d_root = d_dig + levels_total(make_levels(n));  // [root, salt]
   uint8_t* d_ok = ctx->arena.take<uint8_t>(std::max<size_t>(n, 16));
   uint32_t* d_idx = ctx->arena.take<uint32_t>(std::max<size_t>(n, 16));
 
   if (use_rlc) {
+    std::vector<Level> ld = make_levels(n);
     LAUNCH((k_leaf_digest<PkA, SigA>), blocks_for(n), TPB, n, d_pk, d_sig, d_h, d_dig);
-    for (size_t k = 0; k + 1 < lv.size(); k++)
-      LAUNCH(k_digest_reduce, blocks_for(lv[k + 1].cnt), TPB, lv[k].cnt, d_dig + lv[k].off, lv[k + 1].cnt, d_dig + lv[k + 1].off);
-    CK(cudaMemcpyAsync(d_root, d_dig + lv.back().off, sizeof(Digest), cudaMemcpyDeviceToDevice, ctx->stream));
+    for (size_t k = 0; k + 1 < ld.size(); k++)
+      LAUNCH(k_digest_reduce, blocks_for(ld[k + 1].cnt), TPB, ld[k].cnt, d_dig + ld[k].off, ld[k + 1].cnt, d_dig + ld[k + 1].off);
+    CK(cudaMemcpyAsync(d_root, d_dig + ld.back().off, sizeof(Digest), cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_root + 1, ctx->salt, 32, cudaMemcpyHostToDevice, ctx->stream));
   }
   stage_mark(ctx, BLSGPU_STAGE_MILLER);
-  LAUNCH((k_miller<PkA, SigA>), blocks_for(n), TPB, n, d_pk, d_h, d_status, d_root, use_rlc ? 1 : 0, d_F);
+  {
+    static bool attr_done = false;  // per template instance
+    if (!attr_done) {
+      CK(cudaFuncSetAttribute(k_miller6<PkA, SigA>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_SMEM_BYTES));
+      attr_done = true;
+    }
+    k_miller6<PkA, SigA><<<blocks_for(n, M6_ITEMS_PER_BLOCK), 128, M6_SMEM_BYTES, ctx->stream>>>(n, d_pk, d_h, d_status, d_root,
+                                                                                                 use_rlc ? 1 : 0, d_F);
+    CKR(check_launch(ctx, "k_miller6"));
+  }
   stage_mark(ctx, BLSGPU_STAGE_SCALE_SIG);
-  if (use_rlc) LAUNCH((k_scale_sig<SigA>), blocks_for(n), TPB, n, d_sig, d_status, d_root, d_S);
+  if (use_rlc) {
+    LAUNCH((k_scale_sig<SigA>), blocks_for(n), TPB, n, d_sig, d_status, d_root, d_Sitem);
+    LAUNCH((k_group_sum<SigJ>), blocks_for(ng), TPB, n, (const SigJ*)d_Sitem, ng, d_S);
+  }
   stage_mark(ctx, BLSGPU_STAGE_REDUCE);
   for (size_t k = 0; k + 1 < lv.size(); k++) {
     LAUNCH(k_reduce_fp12, blocks_for(lv[k + 1].cnt), TPB, lv[k].cnt, d_F + lv[k].off, lv[k + 1].cnt, d_F + lv[k + 1].off);
@@ -179,12 +195,7 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
       LAUNCH((k_reduce_jac<SigJ>), blocks_for(lv[k + 1].cnt), TPB, lv[k].cnt, d_S + lv[k].off, lv[k + 1].cnt, d_S + lv[k + 1].off);
   }
   stage_mark(ctx, BLSGPU_STAGE_FINAL);
-  if (!use_rlc) {
-    // S = the single aggregate signature
-    typedef typename PtInfo<SigA>::Jac J;
-    LAUNCH((k_reduce_aff<SigA>), 1, 32, (size_t)1, d_sig, (size_t)1, d_S);
-    (void)sizeof(J);
-  }
+  if (!use_rlc) LAUNCH((k_reduce_aff<SigA>), 1, 32, (size_t)1, d_sig, (size_t)1, d_S);  // S = the single aggregate signature
   const Fp12* rootF = d_F + lv.back().off;
   const SigJ* rootS = use_rlc ? d_S + lv.back().off : d_S;
   LAUNCH((k_probe<SigJ>), 1, 64, (size_t)1, (const uint32_t*)nullptr, rootF, rootS, d_ok);
@@ -197,13 +208,8 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
     stage_mark(ctx, BLSGPU_STAGE_COUNT);
     return BLSGPU_OK;
   }
-  if (!ok && lv.size() == 1) {
-    // a single item: the root probe WAS its exact check
-    uint8_t inv = BLSGPU_ST_INVALID_SIGNATURE;
-    CK(cudaMemcpyAsync(d_status, &inv, 1, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-  } else if (!ok) {
-    // walk down the 16-ary tree: children of node j at level k+1 are {j + m * cnt(k+1)} at level k
+  if (!ok) {
+    // walk down the 16-ary tree to the failing groups: children of node j at level k+1 are {j + m * cnt(k+1)} at level k
     std::vector<uint32_t> bad{0};
     for (size_t k = lv.size() - 1; k-- > 0;) {
       std::vector<uint32_t> cand;
@@ -217,7 +223,6 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
       CK(cudaMemcpyAsync(d_idx, cand.data(), cand.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
       LAUNCH((k_probe<SigJ>), blocks_for(cand.size(), 64), 64, cand.size(), (const uint32_t*)d_idx, d_F + lv[k].off, d_S + lv[k].off,
              d_ok);
-      if (k == 0) LAUNCH(k_mark_invalid, blocks_for(cand.size()), TPB, cand.size(), (const uint32_t*)d_idx, (const uint8_t*)d_ok, d_status);
       std::vector<uint8_t> res(cand.size());
       CK(cudaMemcpyAsync(res.data(), d_ok, cand.size(), cudaMemcpyDeviceToHost, ctx->stream));
       CK(cudaStreamSynchronize(ctx->stream));
@@ -225,6 +230,23 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
       for (size_t c = 0; c < cand.size(); c++)
         if (!res[c]) bad.push_back(cand[c]);
       if (bad.empty()) break;  // cannot happen for a failing parent; defensive
+    }
+    // every item of a failing group is decided by its own exact equation e(pk_i, H_i) e(-g, sig_i) == 1
+    std::vector<uint32_t> items;
+    for (uint32_t gidx : bad)
+      for (int m = 0; m < M6_GROUP; m++) {
+        size_t i = (size_t)gidx * M6_GROUP + m;
+        if (i < n) items.push_back((uint32_t)i);
+      }
+    if (!items.empty()) {
+      CK(cudaMemcpyAsync(d_idx, items.data(), items.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+      Fp12* d_Fx = ctx->arena.take<Fp12>(items.size());
+      SigJ* d_Sx = ctx->arena.take<SigJ>(items.size());
+      LAUNCH((k_exact_leaves<PkA, SigA>), blocks_for(items.size()), TPB, items.size(), (const uint32_t*)d_idx, d_pk, d_h, d_sig,
+             (const uint8_t*)d_status, d_Fx, d_Sx);
+      LAUNCH((k_probe<SigJ>), blocks_for(items.size(), 64), 64, items.size(), (const uint32_t*)nullptr, (const Fp12*)d_Fx, (const SigJ*)d_Sx, d_ok);
+      LAUNCH(k_mark_invalid, blocks_for(items.size()), TPB, items.size(), (const uint32_t*)d_idx, (const uint8_t*)d_ok, d_status);
+      CK(cudaStreamSynchronize(ctx->stream));
     }
   }
   stage_mark(ctx, BLSGPU_STAGE_COUNT);
@@ -235,7 +257,8 @@ template <class PkA, class SigA>
 size_t pipeline_bytes(size_t n) {
   typedef typename PtInfo<SigA>::Jac SigJ;
   size_t total = levels_total(make_levels(std::max<size_t>(n, 1)));
-  return total * (sizeof(Fp12) + sizeof(SigJ) + sizeof(Digest)) + (n + 64) * 8 + 16 * 256 + 4096;
+  size_t gtotal = levels_total(make_levels((std::max<size_t>(n, 1) + M6_GROUP - 1) / M6_GROUP));
+  return gtotal * (sizeof(Fp12) + sizeof(SigJ)) + n * (sizeof(SigJ) + sizeof(Fp12) + sizeof(SigJ)) + total * sizeof(Digest) + (n + 64) * 8 + 16 * 256 + 4096;
 }
 
 // verify over decoded points: per-item pre-status, hash_to_curve of the framed message, pairing pipeline

@@ -5,6 +5,7 @@
 
 #include "h2c.cuh"
 #include "pairing.cuh"
+#include "miller6.cuh"
 
 namespace bls {
 
@@ -255,6 +256,75 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_miller(size_t n, const 
   out[i] = f;
 }
 
+// ---- cooperative Miller loop (miller6.cuh): groups of 6 consecutive items, F_g = prod_{i in g} ML(r_i * pk_i, H_i) -------
+// A warp runs 5 groups (lanes 0..29; lanes 30,31 idle along), a 128-thread block 20 groups = 120 items.
+// Shared memory per warp: 36 accumulator coefficients + 32 x 3 line coefficients of 112 bytes.
+constexpr int M6_ITEMS_PER_BLOCK = 120;
+constexpr int M6_SMEM_BYTES = 4 * (36 + 96) * (int)sizeof(SFp2);
+__device__ __forceinline__ void m6_prepare(M6Pair& s, const G1Aff* pk, const G2Aff* h, size_t i, const uint32_t* k, bool scale) {
+  G1Aff p = pk[i];
+  if (scale) {
+    G1Jac pj;
+    jac_mul_aff(pj, p, k, 2);
+    miller_prepare(s.P, pj);
+  } else {
+    miller_prepare(s.P, p);
+  }
+  s.Q = &h[i];
+  G2Aff q = h[i];
+  jac_from_aff(s.R, q);
+}
+__device__ __forceinline__ void m6_prepare(M6Pair& s, const G2Aff* pk, const G1Aff* h, size_t i, const uint32_t* k, bool scale) {
+  m6_prepare(s, h, pk, i, k, scale);
+}
+template <class PkA, class HA>
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_miller6(size_t n, const PkA* __restrict__ pk, const HA* __restrict__ h,
+                                                 const uint8_t* __restrict__ pre, const Digest* __restrict__ root, int use_rlc,
+                                                 Fp12* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t m6_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane / 6, k = lane - 6 * g;  // lanes 30, 31 form an idle sixth "group"
+  SFp2* F = reinterpret_cast<SFp2*>(m6_smem) + warp * 36 + 6 * g;
+  SFp2* L = reinterpret_cast<SFp2*>(m6_smem) + 4 * 36 + warp * 96;  // line of lane j: L[3 j .. 3 j + 2]
+  const size_t group = ((size_t)blockIdx.x * 4 + warp) * 5 + g;
+  const size_t item = group * 6 + k;
+  const bool active = g < 5 && item < n && pre[item] == ST_OK;
+  M6Pair pr;
+  if (active) {
+    uint32_t sc[2] = {1, 0};
+    if (use_rlc) rlc_scalar(sc, root, item);
+    m6_prepare(pr, pk, h, item, sc, use_rlc != 0);
+  }
+  const unsigned gmask = (__ballot_sync(0xffffffffu, active) >> (6 * g)) & 63u;
+  if (k == 0) sfp2_one(F[0]); else sfp2_zero(F[k]);
+  __syncwarp();
+  SFp2 t;
+  const uint64_t e = K_X_ABS;
+  for (int i = 62; i >= 0; i--) {
+    if (i != 62) {
+      m6_sqr_lane(t, F, k);
+      __syncwarp();
+      F[k] = t;
+      __syncwarp();
+    }
+    for (int pass = 0; pass < 2; pass++) {
+      if (pass == 1 && !((e >> i) & 1)) break;
+      if (active) {
+        if (pass == 0) m6_dbl_line(L + 3 * lane, pr); else m6_add_line(L + 3 * lane, pr);
+      }
+      __syncwarp();
+      for (int j = 0; j < 6; j++) {
+        const bool on = (gmask >> j) & 1u;
+        if (on) m6_mul_line_lane(t, F, L + 3 * (6 * g + j), k);
+        __syncwarp();
+        if (on) F[k] = t;
+        __syncwarp();
+      }
+    }
+  }
+  if (g < 5 && group * 6 < n) m6_finish_lane(*fp12_coeff(out[group], k), F[k], k);
+}
+
 // S_i = r_i * sig_i
 template <class SigA>
 __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_scale_sig(size_t n, const SigA* __restrict__ sig, const uint8_t* __restrict__ pre,
@@ -365,6 +435,49 @@ __global__ void __launch_bounds__(64) k_probe(size_t cnt, const uint32_t* __rest
   Fp12 f = F[j];
   J s = S[j];
   ok[c] = probe_node(f, s) ? 1 : 0;
+}
+
+// S_g = sum of the (up to) 6 consecutive per-item points of group g
+template <class J>
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_group_sum(size_t n, const J* __restrict__ in, size_t ng, J* __restrict__ out) {
+  size_t g = BLS_TID();
+  if (g >= ng) return;
+  J acc = in[g * M6_GROUP];
+  for (int m = 1; m < M6_GROUP; m++) {
+    size_t idx = g * M6_GROUP + m;
+    if (idx < n) {
+      J t = in[idx];
+      jac_add(acc, acc, t);
+    }
+  }
+  out[g] = acc;
+}
+
+// exact per-item decision for the items of a failing group, e(pk_i, H_i) e(-g, sig_i) == 1 ?  (sig_core.rs:138-145):
+// the unscaled per-item Miller value and the signature itself, probed by k_probe like any tree node
+template <class PkA, class SigA>
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_exact_leaves(size_t cnt, const uint32_t* __restrict__ idx, const PkA* __restrict__ pk,
+                                                      const SigA* __restrict__ h, const SigA* __restrict__ sig,
+                                                      const uint8_t* __restrict__ status, Fp12* __restrict__ F,
+                                                      typename PtInfo<SigA>::Jac* __restrict__ S) {
+  size_t c = BLS_TID();
+  if (c >= cnt) return;
+  const size_t i = idx[c];
+  Fp12 f;
+  typename PtInfo<SigA>::Jac sj;
+  if (status[i] != ST_OK) {
+    fp12_one(f);
+    jac_set_inf(sj);
+  } else {
+    PkA p = pk[i];
+    SigA q = h[i];
+    const uint32_t one[2] = {1, 0};
+    miller_item(f, p, q, one, false);
+    SigA sa = sig[i];
+    jac_from_aff(sj, sa);
+  }
+  F[c] = f;
+  S[c] = sj;
 }
 
 // leaves that failed their exact check

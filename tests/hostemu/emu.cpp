@@ -4,6 +4,7 @@
 #include <cstring>
 #include "../../agora-blsful_b200/csrc/pairing.cuh"
 #include "../../agora-blsful_b200/csrc/h2c.cuh"
+#include "../../agora-blsful_b200/csrc/miller6.cuh"
 
 using namespace bls;
 
@@ -142,5 +143,60 @@ int emu_pairing_check2(const uint8_t* p1, const uint8_t* q1, const uint8_t* p2, 
   MillerG1 m1, m2; miller_prepare(m1, a); miller_prepare(m2, c);
   Fp12 f, g; miller_loop(f, m1, b); miller_loop(g, m2, d); fp12_mul(f, f, g); final_exponentiation(g, f);
   return fp12_is_one(g);
+}
+
+// one fused sum of products: r = a*b + xi*(2c - d)*(e + f) + conj(b)*k  (k an Fp scalar), plain Fp2 in and out
+void emu_sop2s(const uint8_t* in, const uint8_t* k48, uint8_t* out) {
+  Fp2 v[6], one2; SFp2 s[6], ks, r, so;
+  fone(one2); sfp2_from_fp2(so, one2);
+  SopT t[3];
+  for (int i = 0; i < 6; i++) {  // unsigned form -> balanced S-form through one multiplication by 1
+    fp2_in(v[i], in + 96 * i); fred(v[i], v[i]); sfp2_from_fp2(s[i], v[i]);
+    t[0] = sop_t(&s[i], &so); sop2s(s[i], t, 1);
+  }
+  Fp kk; fp_in(kk, k48); sfp2_from_fp(ks, kk);
+  t[0] = sop_t(&s[0], &s[1]);
+  t[1] = sop_t2(&s[2], 2, &s[3], -1, &s[4], 1, &s[5], 1, SOP_XI);
+  t[2] = sop_t(&s[1], &ks, 1, SOP_CONJ | SOP_BFP);
+  sop2s(r, t, 3);
+  Fp2 o; fp2_from_sfp2(o, r); fp2_out(out, o);
+  // chained: r2 = r * r (aliasing the output with both operands), returned after the first result
+  t[0] = sop_t(&r, &r);
+  sop2s(r, t, 1);
+  fp2_from_sfp2(o, r); fp2_out(out + 96, o);
+}
+// cooperative Miller loop of miller6.cuh, lanes emulated one after the other: f = prod_j ML(k_j * P_j, Q_j), j < n <= 6
+int emu_miller6(int n, const uint8_t* p48, const uint8_t* q96, const uint32_t* k, int nl, uint8_t* ml_out, uint8_t* fe_out) {
+  M6Pair pr[6];
+  G2Aff qa[6];
+  for (int j = 0; j < n; j++) {
+    G1Aff p; G2Aff& q = qa[j];
+    if (g1_decompress(p, p48 + 48 * j, false) || g2_decompress(q, q96 + 96 * j, false)) return -1;
+    if (nl) { G1Jac pj; jac_mul_aff(pj, p, k + nl * j, nl); miller_prepare(pr[j].P, pj); } else miller_prepare(pr[j].P, p);
+    pr[j].Q = &qa[j]; jac_from_aff(pr[j].R, q);
+  }
+  SFp2 F[6], T[6], line[6][3];
+  sfp2_one(F[0]);
+  for (int c = 1; c < 6; c++) sfp2_zero(F[c]);
+  const uint64_t e = K_X_ABS;
+  for (int i = 62; i >= 0; i--) {
+    if (i != 62) {
+      for (int c = 0; c < 6; c++) m6_sqr_lane(T[c], F, c);
+      for (int c = 0; c < 6; c++) F[c] = T[c];
+    }
+    for (int pass = 0; pass < 2; pass++) {
+      if (pass == 1 && !((e >> i) & 1)) break;
+      for (int j = 0; j < n; j++) { if (pass == 0) m6_dbl_line(line[j], pr[j]); else m6_add_line(line[j], pr[j]); }
+      for (int j = 0; j < n; j++) {
+        for (int c = 0; c < 6; c++) m6_mul_line_lane(T[c], F, line[j], c);
+        for (int c = 0; c < 6; c++) F[c] = T[c];
+      }
+    }
+  }
+  Fp12 f, g;
+  for (int c = 0; c < 6; c++) m6_finish_lane(*fp12_coeff(f, c), F[c], c);
+  fp12_out(ml_out, f);
+  final_exponentiation(g, f); fp12_out(fe_out, g);
+  return 0;
 }
 }

@@ -233,3 +233,42 @@ def test_sha256_and_hash_to_curve(L):
     o = buf(96)
     L.emu_hash_to_g2(pk, 48, b"aug", 3, O.sig_dst(2, 1), 43, o)  # MessageAugmentation framing: pk || msg
     assert o.raw == O.g2_serialize(O.hash_to_curve_g2(pk + b"aug", O.sig_dst(2, 1)))
+
+
+def test_sop2s_fused_unit(L):
+    """csrc/sfp.cuh: signed-limb sum of Fp2 products with ONE reduction per coefficient (operand sums, xi, conj, Fp scalar)."""
+    rnd = random.Random(21)
+    XI = (1, 1)
+    mul, add, sub = O.f2_mul, O.f2_add, O.f2_sub
+    conj = lambda x: (x[0], (-x[1]) % P)
+    sc = lambda s, x: ((s * x[0]) % P, (s * x[1]) % P)
+    for it in range(40):
+        v = [(rnd.randrange(P), rnd.randrange(P)) for _ in range(6)]
+        if it == 0:
+            v = [(P - 1, P - 1)] * 6
+        if it == 1:
+            v = [(0, 0), (P - 1, 0), (0, P - 1), (1, 0), (0, 1), (P - 1, 1)]
+        a, b, c, d, e, f = v
+        k = rnd.randrange(P)
+        out = buf(192)
+        L.emu_sop2s(b"".join(f2b(x) for x in v), be(k), out)
+        want = add(add(mul(a, b), mul(mul(XI, sub(sc(2, c), d)), add(e, f))), mul(conj(b), (k, 0)))
+        assert bf2(out.raw[:96]) == want
+        assert bf2(out.raw[96:]) == mul(want, want)
+
+
+def test_miller6_cooperative(L):
+    """csrc/miller6.cuh: six pairings, one shared accumulator spread over six lanes == the product of the pairings."""
+    rnd = random.Random(77)
+    for n, nl in ((6, 2), (1, 0), (3, 2)):
+        ps = [O.g1_mul(O.G1_GEN, rnd.randrange(1, O.R)) for _ in range(n)]
+        qs = [O.g2_mul(O.G2_GEN, rnd.randrange(1, O.R)) for _ in range(n)]
+        ks = [rnd.randrange(1, 2 ** 64) for _ in range(n)]
+        karr = (ctypes.c_uint32 * (2 * n))(*[w for k in ks for w in (k & 0xFFFFFFFF, k >> 32)])
+        ml, fe = buf(576), buf(576)
+        assert L.emu_miller6(n, b"".join(O.g1_serialize(p) for p in ps), b"".join(O.g2_serialize(q) for q in qs),
+                             karr, nl, ml, fe) == 0
+        want = O.F12_ONE
+        for p, q, k in zip(ps, qs, ks):
+            want = O.f12_mul(want, O.f12_pow(O.pairing(p, q), 3 * (k if nl else 1)))
+        assert bf12(fe.raw) == want
