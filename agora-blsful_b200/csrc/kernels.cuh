@@ -263,16 +263,15 @@ constexpr int M6_ITEMS_PER_BLOCK = 120;
 constexpr int M6_SMEM_BYTES = 4 * (36 + 96) * (int)sizeof(SFp2);
 __device__ __forceinline__ void m6_prepare(M6Pair& s, const G1Aff* pk, const G2Aff* h, size_t i, const uint32_t* k, bool scale) {
   G1Aff p = pk[i];
+  MillerG1 mp;
   if (scale) {
     G1Jac pj;
     jac_mul_aff(pj, p, k, 2);
-    miller_prepare(s.P, pj);
+    miller_prepare(mp, pj);
   } else {
-    miller_prepare(s.P, p);
+    miller_prepare(mp, p);
   }
-  s.Q = &h[i];
-  G2Aff q = h[i];
-  jac_from_aff(s.R, q);
+  m6_init_pair(s, mp, &h[i]);
 }
 __device__ __forceinline__ void m6_prepare(M6Pair& s, const G2Aff* pk, const G1Aff* h, size_t i, const uint32_t* k, bool scale) {
   m6_prepare(s, h, pk, i, k, scale);

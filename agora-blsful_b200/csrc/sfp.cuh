@@ -90,71 +90,67 @@ struct SopBnd {  // BLS_TRACK only: limb magnitude bounds of the prepared operan
 struct alignas(16) SopI4 {
   int32_t x, y, z, w;
 };
-BLS_HD void sop_ld28(int32_t* x0, int32_t* x1, const SFp2* p, bool fp_only) {
+BLS_HD void sop_ld28(int32_t* t, const SFp2* p) {
   const SopI4* q = reinterpret_cast<const SopI4*>(p->w);  // 128-bit loads: the records are 16-byte aligned
-  int32_t t[2 * NL];
 #pragma unroll
-  for (int i = 0; i < (fp_only ? 4 : 7); i++) {
+  for (int i = 0; i < 7; i++) {
     SopI4 v = q[i];
     t[4 * i] = v.x;
     t[4 * i + 1] = v.y;
     t[4 * i + 2] = v.z;
     t[4 * i + 3] = v.w;
   }
-#pragma unroll
-  for (int i = 0; i < NL; i++) {
-    x0[i] = t[i];
-    x1[i] = fp_only ? 0 : t[NL + i];
-  }
 }
 
-// x = s*p + s2*p2, then CONJ, then XI
-BLS_HD SopBnd sop_load(int32_t* x0, int32_t* x1, const SFp2* p, int32_t s, const SFp2* p2, int32_t s2, uint32_t fl, bool fp_only) {
+// The operand of integer product number `pass` (0: c0 half, 1: c1 half, 2: c0 + c1) of  s*p + s2*p2  [conj] [* xi].
+// fp_only: the c1 half is taken as zero.
+BLS_HD SopBnd sop_operand(int32_t* x, int pass, const SFp2* p, int32_t s, const SFp2* p2, int32_t s2, uint32_t fl, bool fp_only) {
   SopBnd bd;
   bd.l0 = bd.l1 = bd.vb = 0;
-  sop_ld28(x0, x1, p, fp_only);
+  int32_t t[2 * NL];
+  sop_ld28(t, p);
   if (s != 1) {
 #pragma unroll
-    for (int i = 0; i < NL; i++) {
-      x0[i] *= s;
-      x1[i] *= s;
-    }
+    for (int i = 0; i < 2 * NL; i++) t[i] *= s;
   }
 #if defined(BLS_TRACK)
   {
     double as = s < 0 ? -(double)s : (double)s;
-    bd.l0 = as * p->lb;
-    bd.l1 = fp_only ? 0.0 : as * p->lb;
+    bd.l0 = bd.l1 = as * p->lb;
     bd.vb = as * p->vb;
   }
 #endif
   if (p2 != nullptr) {
-    int32_t y0[NL], y1[NL];
-    sop_ld28(y0, y1, p2, fp_only);
+    int32_t u[2 * NL];
+    sop_ld28(u, p2);
 #pragma unroll
-    for (int i = 0; i < NL; i++) {
-      x0[i] += y0[i] * s2;
-      x1[i] += y1[i] * s2;
-    }
+    for (int i = 0; i < 2 * NL; i++) t[i] += u[i] * s2;
 #if defined(BLS_TRACK)
     {
       double as = s2 < 0 ? -(double)s2 : (double)s2;
       bd.l0 += as * p2->lb;
-      bd.l1 += fp_only ? 0.0 : as * p2->lb;
+      bd.l1 += as * p2->lb;
       bd.vb += as * p2->vb;
     }
 #endif
   }
+  if (fp_only) {
+#pragma unroll
+    for (int i = 0; i < NL; i++) t[NL + i] = 0;
+#if defined(BLS_TRACK)
+    bd.l1 = 0;
+#endif
+  }
   if (fl & SOP_CONJ) {
 #pragma unroll
-    for (int i = 0; i < NL; i++) x1[i] = -x1[i];
+    for (int i = 0; i < NL; i++) t[NL + i] = -t[NL + i];
   }
   if (fl & SOP_XI) {
 #pragma unroll
     for (int i = 0; i < NL; i++) {
-      int32_t t0 = x0[i] - x1[i], t1 = x0[i] + x1[i];
-      x0[i] = t0;
-      x1[i] = t1;
+      int32_t t0 = t[i] - t[NL + i], t1 = t[i] + t[NL + i];
+      t[i] = t0;
+      t[NL + i] = t1;
     }
 #if defined(BLS_TRACK)
     bd.l0 = bd.l1 = bd.l0 + bd.l1;
@@ -164,6 +160,8 @@ BLS_HD SopBnd sop_load(int32_t* x0, int32_t* x1, const SFp2* p, int32_t s, const
 #if defined(BLS_TRACK)
   BLS_REQ(bd.l0 < 1073741824.0 && bd.l1 < 1073741824.0, "sop operand limb overflow (>= 2^30)");
 #endif
+#pragma unroll
+  for (int i = 0; i < NL; i++) x[i] = pass == 0 ? t[i] : pass == 1 ? t[NL + i] : t[i] + t[NL + i];
   return bd;
 }
 
@@ -197,79 +195,154 @@ BLS_HD void sop_redc(int32_t* out, uint64_t* T) {
   out[NL - 1] = (int32_t)(c + (int64_t)T[2 * NL - 1]);
 }
 
+// A 28 x u64 scratch record that stays in LOCAL memory and is moved with 128-bit local accesses (a plain array would be
+// promoted to 56 registers; a laundered generic pointer costs 64-bit generic accesses plus address bookkeeping).
+struct alignas(16) SopKeep {
+  uint64_t v[2 * NL];
+};
+BLS_HD void sop_keep_st(SopKeep& k, int i, uint64_t a, uint64_t b) {  // v[2i], v[2i+1]
+#if defined(__CUDA_ARCH__)
+  asm volatile("st.local.v2.u64 [%0], {%1, %2};" ::"l"(__cvta_generic_to_local(&k.v[2 * i])), "l"(a), "l"(b) : "memory");
+#else
+  k.v[2 * i] = a;
+  k.v[2 * i + 1] = b;
+#endif
+}
+BLS_HD void sop_keep_ld(const SopKeep& k, int i, uint64_t& a, uint64_t& b) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("ld.local.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(__cvta_generic_to_local(&k.v[2 * i])) : "memory");
+#else
+  a = k.v[2 * i];
+  b = k.v[2 * i + 1];
+#endif
+}
+
 // The unit.  r may alias any operand: results are written after the last operand read.
+// Code-size discipline (the SM's instruction caches are 6 KB / 32 KB): ONE product body, ONE
+// reduction body; the three Karatsuba products P0 = sum a0 b0, P1 = sum a1 b1, P2 = sum (a0+a1)(b0+b1) are three trips
+// through the same loop, P0 (then P0 + P1) waits in local memory meanwhile.
+//   real = P0 - P1 ,  imag = P2 - (P0 + P1)
 BLS_FN void sop2s(SFp2& r, const SopT* t, int nt) {
-  uint64_t A0[2 * NL], A1[2 * NL];
-#pragma unroll
-  for (int i = 0; i < 2 * NL; i++) A0[i] = A1[i] = 0;
+  SopKeep keep;
+  int32_t res[2 * NL];
 #if defined(BLS_TRACK)
   double col_re = 0, col_im = 0, vsum = 0;
   BLS_REQ(nt >= 1 && nt <= SOP_MAX_TERMS, "sop2s term count");
 #endif
-  // ---- pass 1: A0 += a0 b0 ; A1 += a1 b1
 #pragma unroll 1
-  for (int k = 0; k < nt; k++) {
-    const bool bfp = (t[k].fl & SOP_BFP) != 0;
-    int32_t a0[NL], a1[NL], b0[NL], b1[NL];
-    SopBnd ba = sop_load(a0, a1, t[k].a, t[k].sa, t[k].a2, t[k].sa2, t[k].fl, false);
-    SopBnd bb = sop_load(b0, b1, t[k].b, t[k].sb, t[k].b2, t[k].sb2, 0, bfp);
-    sop_acc(A0, a0, b0);
-    if (!bfp) sop_acc(A1, a1, b1);
+  for (int pass = 0; pass < 3; pass++) {
+    uint64_t T[2 * NL];
+#pragma unroll
+    for (int i = 0; i < 2 * NL; i++) T[i] = 0;
+#pragma unroll 1
+    for (int k = 0; k < nt; k++) {
+      const bool bfp = (t[k].fl & SOP_BFP) != 0;
+      if (bfp && pass == 1) continue;
+      int32_t x[NL], y[NL];
+      SopBnd ba = sop_operand(x, pass, t[k].a, t[k].sa, t[k].a2, t[k].sa2, t[k].fl, false);
+      SopBnd bb = sop_operand(y, pass, t[k].b, t[k].sb, t[k].b2, t[k].sb2, 0, bfp);
+      sop_acc(T, x, y);
 #if defined(BLS_TRACK)
-    col_re += 14.0 * (ba.l0 * bb.l0 + ba.l1 * bb.l1);
-    col_im += 14.0 * (ba.l0 * bb.l1 + ba.l1 * bb.l0);
-    vsum += 2.0 * ba.vb * bb.vb;
+      if (pass == 0) {
+        col_re += 14.0 * (ba.l0 * bb.l0 + ba.l1 * bb.l1);
+        col_im += 14.0 * (ba.l0 * bb.l1 + ba.l1 * bb.l0);
+        vsum += 2.0 * ba.vb * bb.vb;
+      }
 #else
-    (void)ba;
-    (void)bb;
+      (void)ba;
+      (void)bb;
 #endif
-  }
+    }
+    if (pass == 0) {
+#pragma unroll
+      for (int i = 0; i < NL; i++) sop_keep_st(keep, i, T[2 * i], T[2 * i + 1]);
+      continue;
+    }
 #if defined(BLS_TRACK)
-  {
-    // true column values + the reduction's own growth (14 * 2^56 for m*p, < 2^36 of carries) must fit int64
-    const double lim = 9223372036854775808.0 - 15.0 * 72057594037927936.0;
-    BLS_REQ(col_re < lim && col_im < lim, "sop2s column overflow");
-    BLS_REQ(vsum / 2500.0 + 1.0 < 8.0, "sop2s result value bound");
-  }
+    {
+      // true column values + the reduction's own growth (14 * 2^56 for m*p, < 2^36 of carries) must fit int64
+      const double lim = 9223372036854775808.0 - 15.0 * 72057594037927936.0;
+      BLS_REQ(col_re < lim && col_im < lim, "sop2s column overflow");
+      BLS_REQ(vsum / 2500.0 + 1.0 < 16.0, "sop2s result value bound");
+    }
 #endif
-  // real part D = A0 - A1 ; S = A0 + A1 is kept for the imaginary part
-#pragma unroll
-  for (int i = 0; i < 2 * NL - 1; i++) {
-    const uint64_t x = A0[i], y = A1[i];
-    A0[i] = x - y;
-    A1[i] = x + y;
-  }
-  A0[2 * NL - 1] = 0;
-  int32_t c0[NL];
-  sop_redc(c0, A0);
-  // ---- pass 2: A2 += (a0 + a1)(b0 + b1) ; E = A2 - S
-#pragma unroll
-  for (int i = 0; i < 2 * NL; i++) A0[i] = 0;
-#pragma unroll 1
-  for (int k = 0; k < nt; k++) {
-    const bool bfp = (t[k].fl & SOP_BFP) != 0;
-    int32_t a0[NL], a1[NL], b0[NL], b1[NL];
-    sop_load(a0, a1, t[k].a, t[k].sa, t[k].a2, t[k].sa2, t[k].fl, false);
-    sop_load(b0, b1, t[k].b, t[k].sb, t[k].b2, t[k].sb2, 0, bfp);
+    // pass 1: U = P0 - P1, keep <- P0 + P1 ;  pass 2: U = P2 - keep
 #pragma unroll
     for (int i = 0; i < NL; i++) {
-      a0[i] += a1[i];
-      b0[i] += b1[i];
+      uint64_t s0, s1;
+      sop_keep_ld(keep, i, s0, s1);
+      const uint64_t v0 = T[2 * i], v1 = T[2 * i + 1];
+      if (pass == 1) sop_keep_st(keep, i, s0 + v0, s1 + v1);
+      T[2 * i] = pass == 1 ? s0 - v0 : v0 - s0;
+      T[2 * i + 1] = pass == 1 ? s1 - v1 : v1 - s1;
     }
-    sop_acc(A0, a0, b0);
+    T[2 * NL - 1] = 0;
+    int32_t c[NL];
+    sop_redc(c, T);
+#pragma unroll
+    for (int i = 0; i < NL; i++) {
+      if (pass == 1) res[i] = c[i]; else res[NL + i] = c[i];
+    }
   }
 #pragma unroll
-  for (int i = 0; i < 2 * NL - 1; i++) A0[i] -= A1[i];
-  A0[2 * NL - 1] = 0;
-  int32_t c1[NL];
-  sop_redc(c1, A0);
-#pragma unroll
-  for (int i = 0; i < NL; i++) {
-    r.w[i] = c0[i];
-    r.w[NL + i] = c1[i];
-  }
+  for (int i = 0; i < 2 * NL; i++) r.w[i] = res[i];
 #if defined(BLS_TRACK)
   STRK(r, vsum / 2500.0 + 1.0, 134217728.0);
+#endif
+}
+
+// r = sx * [xi] x + sy * y + sz * z  (y, z optional), limbs renormalised (balanced) - no multiplication, no reduction.
+// r may alias the inputs.
+BLS_FN void sfp2_lin(SFp2& r, const SFp2* x, int32_t sx, uint32_t flx, const SFp2* y, int32_t sy, const SFp2* z, int32_t sz) {
+  int32_t t[2 * NL];
+  int64_t v[2 * NL];
+  sop_ld28(t, x);
+  if (flx & SOP_XI) {
+#pragma unroll
+    for (int i = 0; i < NL; i++) {
+      const int32_t d = t[i] - t[NL + i], e = t[i] + t[NL + i];  // limbs < 2^30 (checked): no overflow
+      v[i] = (int64_t)sx * (int64_t)d;
+      v[NL + i] = (int64_t)sx * (int64_t)e;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 2 * NL; i++) v[i] = (int64_t)sx * (int64_t)t[i];
+  }
+#if defined(BLS_TRACK)
+  double vb = (sx < 0 ? -(double)sx : (double)sx) * x->vb * ((flx & SOP_XI) ? 2.0 : 1.0);
+  BLS_REQ(x->lb < 1073741824.0, "sfp2_lin limb");
+#endif
+  if (y != nullptr) {
+    sop_ld28(t, y);
+#pragma unroll
+    for (int i = 0; i < 2 * NL; i++) v[i] += (int64_t)sy * (int64_t)t[i];
+#if defined(BLS_TRACK)
+    vb += (sy < 0 ? -(double)sy : (double)sy) * y->vb;
+#endif
+  }
+  if (z != nullptr) {
+    sop_ld28(t, z);
+#pragma unroll
+    for (int i = 0; i < 2 * NL; i++) v[i] += (int64_t)sz * (int64_t)t[i];
+#if defined(BLS_TRACK)
+    vb += (sz < 0 ? -(double)sz : (double)sz) * z->vb;
+#endif
+  }
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    int64_t c = 0;
+#pragma unroll
+    for (int j = 0; j < NL - 1; j++) {
+      c += v[h * NL + j];
+      const int64_t u = c + (1 << 27);
+      r.w[h * NL + j] = (int32_t)((uint32_t)u & M28) - (1 << 27);
+      c = u >> 28;
+    }
+    r.w[h * NL + NL - 1] = (int32_t)(c + v[h * NL + NL - 1]);
+  }
+#if defined(BLS_TRACK)
+  BLS_REQ(vb < 1000.0, "sfp2_lin value bound");  // keeps the top limb below 2^27
+  STRK(r, vb, 134217728.0);
 #endif
 }
 

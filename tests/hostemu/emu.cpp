@@ -172,8 +172,9 @@ int emu_miller6(int n, const uint8_t* p48, const uint8_t* q96, const uint32_t* k
   for (int j = 0; j < n; j++) {
     G1Aff p; G2Aff& q = qa[j];
     if (g1_decompress(p, p48 + 48 * j, false) || g2_decompress(q, q96 + 96 * j, false)) return -1;
-    if (nl) { G1Jac pj; jac_mul_aff(pj, p, k + nl * j, nl); miller_prepare(pr[j].P, pj); } else miller_prepare(pr[j].P, p);
-    pr[j].Q = &qa[j]; jac_from_aff(pr[j].R, q);
+    MillerG1 mp;
+    if (nl) { G1Jac pj; jac_mul_aff(pj, p, k + nl * j, nl); miller_prepare(mp, pj); } else miller_prepare(mp, p);
+    m6_init_pair(pr[j], mp, &qa[j]);
   }
   SFp2 F[6], T[6], line[6][3];
   sfp2_one(F[0]);
