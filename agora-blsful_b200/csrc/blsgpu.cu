@@ -34,6 +34,7 @@ thread_local std::string g_create_error;
   } while (0)
 
 constexpr int TPB = 128;
+constexpr size_t M6_CHUNK = 1024 * 120;  // items per pass of the Miller kernels (a multiple of 6 and of 120): 2.8 GB of lines, twice
 inline unsigned blocks_for(size_t n, int tpb = TPB) { return (unsigned)((n + tpb - 1) / tpb); }
 
 // bump allocator over one device buffer, regrown between calls
@@ -59,6 +60,9 @@ struct blsgpu_ctx {
   std::vector<int> devices;
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
+  // the Miller stage runs its two big kernels on two side streams so that one block of each shares every SM (kernels.cuh)
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_lines[2] = {nullptr, nullptr}, ev_accum[2] = {nullptr, nullptr};
   Arena arena;
   std::string err;
   uint8_t salt[32];
@@ -176,12 +180,44 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
   {
     static bool attr_done = false;  // per template instance
     if (!attr_done) {
-      CK(cudaFuncSetAttribute(k_miller6<PkA, SigA>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_SMEM_BYTES));
+      CK(cudaFuncSetAttribute(k_m6_lines<PkA, SigA>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_LINES_SMEM));
       attr_done = true;
     }
-    k_miller6<PkA, SigA><<<blocks_for(n, M6_ITEMS_PER_BLOCK), 128, M6_SMEM_BYTES, ctx->stream>>>(n, d_pk, d_h, d_status, d_root,
-                                                                                                 use_rlc ? 1 : 0, d_F);
-    CKR(check_launch(ctx, "k_miller6"));
+    // The line stream is 22.8 KB per item: the batch goes through in chunks with two line buffers.  Chunk c's lines are
+    // produced on side stream 0 while chunk c-1's accumulator consumes the other buffer on side stream 1: k_m6_lines is
+    // limited to ONE block per SM by its shared-memory record file and leaves half of the registers and the multiplier
+    // pipe's idle slots to one block of k_m6_accum - two kernels that cannot fill an SM alone fill it together.
+    const size_t chunk = std::min(n, M6_CHUNK);
+    const int nbuf = n > M6_CHUNK ? 2 : 1;
+    M6Arg* d_args[2];
+    SFp2* d_lines[2];
+    for (int b = 0; b < nbuf; b++) {
+      d_args[b] = ctx->arena.take<M6Arg>(chunk);
+      d_lines[b] = ctx->arena.take<SFp2>(chunk * M6_LINE_RECS);
+    }
+    CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->side[0], ctx->ev_fork, 0));
+    CK(cudaStreamWaitEvent(ctx->side[1], ctx->ev_fork, 0));
+    size_t ci = 0;
+    for (size_t base = 0; base < n; base += M6_CHUNK, ci++) {
+      const size_t cn = std::min(M6_CHUNK, n - base);
+      const int b = (int)(ci % nbuf);
+      if (ci >= (size_t)nbuf) CK(cudaStreamWaitEvent(ctx->side[0], ctx->ev_accum[b], 0));  // the buffer's previous reader is done
+      k_m6_prep<PkA, SigA><<<blocks_for(cn), TPB, 0, ctx->side[0]>>>(cn, base, d_pk, d_h, (const uint8_t*)d_status, (const Digest*)d_root,
+                                                                      use_rlc ? 1 : 0, d_args[b]);
+      CKR(check_launch(ctx, "k_m6_prep"));
+      k_m6_lines<PkA, SigA><<<blocks_for(cn, M6_LINES_TPB), M6_LINES_TPB, M6_LINES_SMEM, ctx->side[0]>>>(
+          cn, base, d_args[b], d_pk, d_h, d_status, d_lines[b]);
+      CKR(check_launch(ctx, "k_m6_lines"));
+      CK(cudaEventRecord(ctx->ev_lines[b], ctx->side[0]));
+      CK(cudaStreamWaitEvent(ctx->side[1], ctx->ev_lines[b], 0));
+      k_m6_accum<<<blocks_for(cn, M6_ITEMS_PER_BLOCK), 128, M6_ACCUM_SMEM, ctx->side[1]>>>(cn, base, d_status, d_lines[b], d_F);
+      CKR(check_launch(ctx, "k_m6_accum"));
+      CK(cudaEventRecord(ctx->ev_accum[b], ctx->side[1]));
+    }
+    // join: everything later on the caller's stream waits for the last accumulator (which waited for every line kernel)
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_accum[(ci - 1) % nbuf], 0));
+    if (ci >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_accum[(ci - 2) % nbuf], 0));
   }
   stage_mark(ctx, BLSGPU_STAGE_SCALE_SIG);
   if (use_rlc) {
@@ -258,7 +294,8 @@ size_t pipeline_bytes(size_t n) {
   typedef typename PtInfo<SigA>::Jac SigJ;
   size_t total = levels_total(make_levels(std::max<size_t>(n, 1)));
   size_t gtotal = levels_total(make_levels((std::max<size_t>(n, 1) + M6_GROUP - 1) / M6_GROUP));
-  return gtotal * (sizeof(Fp12) + sizeof(SigJ)) + n * (sizeof(SigJ) + sizeof(Fp12) + sizeof(SigJ)) + total * sizeof(Digest) + (n + 64) * 8 + 16 * 256 + 4096;
+  return gtotal * (sizeof(Fp12) + sizeof(SigJ)) + n * (sizeof(SigJ) + sizeof(Fp12) + sizeof(SigJ)) +
+         2 * std::min(std::max<size_t>(n, 1), M6_CHUNK) * (sizeof(M6Arg) + M6_LINE_RECS * sizeof(SFp2) + 512) + total * sizeof(Digest) + (n + 64) * 8 + 16 * 256 + 4096;
 }
 
 // verify over decoded points: per-item pre-status, hash_to_curve of the framed message, pairing pipeline
@@ -347,6 +384,16 @@ int blsgpu_ctx_create(const int* devices, int ndev, blsgpu_ctx** out) {
   e = cudaSetDevice(devices[0]);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
   ctx->stream = ctx->own_stream;
+  int prio_lo = 0, prio_hi = 0;
+  if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  for (int i = 0; e == cudaSuccess && i < 2; i++) {
+    // side[0] (k_m6_lines, one block per SM) outranks side[1] (k_m6_accum): free SM resources go to a line block first,
+    // the accumulator kernel takes what is left - that is what makes the two kernels share every SM
+    e = cudaStreamCreateWithPriority(&ctx->side[i], cudaStreamNonBlocking, i == 0 ? prio_hi : prio_lo);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_lines[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_accum[i], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   for (int i = 0; e == cudaSuccess && i <= BLSGPU_STAGE_COUNT; i++) e = cudaEventCreate(&ctx->ev[i]);
   if (e != cudaSuccess) {
     g_create_error = std::string("context setup: ") + cudaGetErrorString(e);
@@ -364,6 +411,12 @@ void blsgpu_ctx_destroy(blsgpu_ctx* ctx) {
   if (ctx->arena.base) cudaFree(ctx->arena.base);
   for (int i = 0; i <= BLSGPU_STAGE_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  for (int i = 0; i < 2; i++) {
+    if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
+    if (ctx->ev_lines[i]) cudaEventDestroy(ctx->ev_lines[i]);
+    if (ctx->ev_accum[i]) cudaEventDestroy(ctx->ev_accum[i]);
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   delete ctx;
 }
 

@@ -257,71 +257,129 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_miller(size_t n, const 
 }
 
 // ---- cooperative Miller loop (miller6.cuh): groups of 6 consecutive items, F_g = prod_{i in g} ML(r_i * pk_i, H_i) -------
-// A warp runs 5 groups (lanes 0..29; lanes 30,31 idle along), a 128-thread block 20 groups = 120 items.
-// Shared memory per warp: 36 accumulator coefficients + 32 x 3 line coefficients of 112 bytes.
-constexpr int M6_ITEMS_PER_BLOCK = 120;
-constexpr int M6_SMEM_BYTES = 4 * (36 + 96) * (int)sizeof(SFp2);
-__device__ __forceinline__ void m6_prepare(M6Pair& s, const G1Aff* pk, const G2Aff* h, size_t i, const uint32_t* k, bool scale) {
-  G1Aff p = pk[i];
+// Three kernels, so that each keeps its working set on chip:
+//   k_m6_prep   one thread per item: the RLC scalar and r_i * pk_i, stored as the three Fp scalars the lines need (336 B)
+//   k_m6_lines  one thread per item: the 68 line evaluations of the pair, record file in SHARED memory (14 records per
+//               thread, record-major: conflict-free 128-bit accesses), lines streamed to HBM (22.8 KB per item)
+//   k_m6_accum  six lanes per group: the shared Fp12 accumulator, one coefficient per lane, double-buffered in shared
+//               memory; the lines come back from HBM one step ahead of their use (sop2f's prefetch)
+constexpr int M6_LINES_TPB = 128;
+constexpr int M6_LINES_SMEM = M6_NREG * M6_LINES_TPB * (int)sizeof(SFp2);  // 200,704 B: one block per SM
+constexpr int M6_ITEMS_PER_BLOCK = 120;                                   // k_m6_accum: 4 warps x 5 groups x 6 lanes
+constexpr int M6_ACCUM_SMEM = 4 * 60 * (int)sizeof(SFp2);
+constexpr size_t M6_LINE_RECS = (size_t)M6_STEPS * 3;                     // records per item in the line stream
+
+__device__ __forceinline__ const G1Aff& m6_g1(const G1Aff* pk, const G2Aff* h, size_t i) { return pk[i]; }
+__device__ __forceinline__ const G1Aff& m6_g1(const G2Aff* pk, const G1Aff* h, size_t i) { return h[i]; }
+__device__ __forceinline__ const G2Aff& m6_g2(const G1Aff* pk, const G2Aff* h, size_t i) { return h[i]; }
+__device__ __forceinline__ const G2Aff& m6_g2(const G2Aff* pk, const G1Aff* h, size_t i) { return pk[i]; }
+
+// items [base, base + n) of the batch -> args[0..n)
+template <class PkA, class HA>
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_m6_prep(size_t n, size_t base, const PkA* __restrict__ pk, const HA* __restrict__ h,
+                                                 const uint8_t* __restrict__ pre, const Digest* __restrict__ root, int use_rlc,
+                                                 M6Arg* __restrict__ args) {
+  size_t c = BLS_TID();
+  if (c >= n) return;
+  const size_t i = base + c;
+  if (pre[i] != ST_OK) return;
+  G1Aff p = m6_g1(pk, h, i);
   MillerG1 mp;
-  if (scale) {
+  if (use_rlc) {
+    uint32_t sc[2];
+    rlc_scalar(sc, root, i);
     G1Jac pj;
-    jac_mul_aff(pj, p, k, 2);
+    jac_mul_aff(pj, p, sc, 2);
     miller_prepare(mp, pj);
   } else {
     miller_prepare(mp, p);
   }
-  m6_init_pair(s, mp, &h[i]);
+  M6Arg a;
+  m6_make_arg(a, mp);
+  args[c] = a;
 }
-__device__ __forceinline__ void m6_prepare(M6Pair& s, const G2Aff* pk, const G1Aff* h, size_t i, const uint32_t* k, bool scale) {
-  m6_prepare(s, h, pk, i, k, scale);
-}
+
 template <class PkA, class HA>
-__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_miller6(size_t n, const PkA* __restrict__ pk, const HA* __restrict__ h,
-                                                 const uint8_t* __restrict__ pre, const Digest* __restrict__ root, int use_rlc,
-                                                 Fp12* __restrict__ out) {
+__global__ void __launch_bounds__(M6_LINES_TPB, 1) k_m6_lines(size_t n, size_t base, const M6Arg* __restrict__ args, const PkA* __restrict__ pk,
+                                                             const HA* __restrict__ h, const uint8_t* __restrict__ pre, SFp2* __restrict__ lines) {
+  extern __shared__ __align__(16) uint8_t m6_smem[];
+  size_t c = BLS_TID();
+  if (c >= n || pre[base + c] != ST_OK) return;
+  const G2Aff& q = m6_g2(pk, h, base + c);
+  SFp2* out = lines + c * M6_LINE_RECS;
+  SopSpaces cx = m6_spaces_line(reinterpret_cast<SFp2*>(m6_smem) + threadIdx.x, M6_LINES_TPB, args + c, out);
+  {
+    const G2Aff qv = q;
+    m6_init_point(cx, qv);
+  }
+  const uint64_t e = K_X_ABS;
+#pragma unroll 1
+  for (int i = 62; i >= 0; i--) {
+    m6_dbl_line(cx);
+    cx.line += 3;
+    if ((e >> i) & 1) {
+      const G2Aff qv = q;
+      m6_add_line(cx, qv);
+      cx.line += 3;
+    }
+  }
+}
+
+#ifndef M6_ACC_BLOCKS
+#define M6_ACC_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(128, M6_ACC_BLOCKS) k_m6_accum(size_t n, size_t base, const uint8_t* __restrict__ pre, const SFp2* __restrict__ lines,
+                                                     Fp12* __restrict__ out) {
   extern __shared__ __align__(16) uint8_t m6_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane / 6, k = lane - 6 * g;  // lanes 30, 31 form an idle sixth "group"
-  SFp2* F = reinterpret_cast<SFp2*>(m6_smem) + warp * 36 + 6 * g;
-  SFp2* L = reinterpret_cast<SFp2*>(m6_smem) + 4 * 36 + warp * 96;  // line of lane j: L[3 j .. 3 j + 2]
-  const size_t group = ((size_t)blockIdx.x * 4 + warp) * 5 + g;
+  const int g = lane / 6, k = lane - 6 * g;
+  const bool lane_on = g < 5;  // lanes 30, 31 only keep the warp's barriers company
+  SFp2* F = reinterpret_cast<SFp2*>(m6_smem) + warp * 60 + 6 * (lane_on ? g : 0);  // current value; F + 30: next
+  SFp2* G = F + 30;
+  const size_t group = ((size_t)blockIdx.x * 4 + warp) * 5 + g;  // within the chunk (base is a multiple of 6)
   const size_t item = group * 6 + k;
-  const bool active = g < 5 && item < n && pre[item] == ST_OK;
-  M6Pair pr;
-  if (active) {
-    uint32_t sc[2] = {1, 0};
-    if (use_rlc) rlc_scalar(sc, root, item);
-    m6_prepare(pr, pk, h, item, sc, use_rlc != 0);
+  const bool active = lane_on && item < n && pre[base + item] == ST_OK;
+  const unsigned ball = __ballot_sync(0xffffffffu, active);
+  const unsigned gmask = lane_on ? (ball >> (6 * g)) & 63u : 0u;
+  if (lane_on) {
+    if (k == 0) sfp2_one(F[0]); else sfp2_zero(F[k]);
   }
-  const unsigned gmask = (__ballot_sync(0xffffffffu, active) >> (6 * g)) & 63u;
-  if (k == 0) sfp2_one(F[0]); else sfp2_zero(F[k]);
   __syncwarp();
-  SFp2 t;
+  const SFp2* gl = lines + group * 6 * M6_LINE_RECS;  // the group's six line streams
   const uint64_t e = K_X_ABS;
+  int step = 0;
+#pragma unroll 1
   for (int i = 62; i >= 0; i--) {
     if (i != 62) {
-      m6_sqr_lane(t, F, k);
+      if (lane_on) m6_sqr_lane(G + k, F, k);
       __syncwarp();
-      F[k] = t;
-      __syncwarp();
+      SFp2* t = F; F = G; G = t;
     }
-    for (int pass = 0; pass < 2; pass++) {
-      if (pass == 1 && !((e >> i) & 1)) break;
-      if (active) {
-        if (pass == 0) m6_dbl_line(L + 3 * lane, pr); else m6_add_line(L + 3 * lane, pr);
-      }
-      __syncwarp();
+    const int nst = 1 + (int)((e >> i) & 1);
+#pragma unroll 1
+    for (int st = 0; st < nst; st++, step++) {
+#pragma unroll 1
       for (int j = 0; j < 6; j++) {
-        const bool on = (gmask >> j) & 1u;
-        if (on) m6_mul_line_lane(t, F, L + 3 * (6 * g + j), k);
-        __syncwarp();
-        if (on) F[k] = t;
+        {
+          // the NEXT line of this group (336 B in HBM, used once by all six lanes) starts its way into L1 now: sop2f
+          // prefetches within a call, but the first operands of a call would otherwise wait for HBM
+          const int jn = j == 5 ? 0 : j + 1;
+          const int sn = j == 5 ? step + 1 : step;
+          if (k < 3 && sn < M6_STEPS) {
+            const SFp2* nx = gl + (size_t)jn * M6_LINE_RECS + 3 * sn + k;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(nx) + 96));
+          }
+        }
+        if ((gmask >> j) & 1u) {  // uniform within the group; the barrier below is outside
+          m6_mul_line_lane(G + k, F, gl + (size_t)j * M6_LINE_RECS + 3 * step, k);
+          SFp2* t = F; F = G; G = t;
+        }
         __syncwarp();
       }
     }
   }
-  if (g < 5 && group * 6 < n) m6_finish_lane(*fp12_coeff(out[group], k), F[k], k);
+  if (lane_on && group * 6 < n) m6_finish_lane(*fp12_coeff(out[base / 6 + group], k), F[k], k);
 }
 
 // S_i = r_i * sig_i

@@ -20,37 +20,40 @@ namespace bls {
 constexpr int M6_GROUP = 6;
 
 // f^2, coefficient k:  sum over unordered {i,j}, i+j = k (mod 6), of  s * a_i * a_j  [* xi when i+j >= 6]
-// entry = ia | ib << 3 | xi << 6 | scale << 7   (scale 0: unused slot)
-#define M6_E(ia, ib, xi, sc) (uint16_t)((ia) | ((ib) << 3) | ((xi) << 6) | ((sc) << 7))
-BLS_CONST uint16_t K_M6_SQR[6][4] = {
-    {M6_E(0, 0, 0, 1), M6_E(1, 5, 1, 2), M6_E(2, 4, 1, 2), M6_E(3, 3, 1, 1)},
-    {M6_E(0, 1, 0, 2), M6_E(2, 5, 1, 2), M6_E(3, 4, 1, 2), M6_E(0, 0, 0, 0)},
-    {M6_E(0, 2, 0, 2), M6_E(1, 1, 0, 1), M6_E(3, 5, 1, 2), M6_E(4, 4, 1, 1)},
-    {M6_E(0, 3, 0, 2), M6_E(1, 2, 0, 2), M6_E(4, 5, 1, 2), M6_E(0, 0, 0, 0)},
-    {M6_E(0, 4, 0, 2), M6_E(1, 3, 0, 2), M6_E(2, 2, 0, 1), M6_E(5, 5, 1, 1)},
-    {M6_E(0, 5, 0, 2), M6_E(1, 4, 0, 2), M6_E(2, 3, 0, 2), M6_E(0, 0, 0, 0)},
+// (sh: s = 1 << sh; odd coefficients have three cross terms: their fourth slot repeats the last one with half weight)
+#define M6_S(ia, ib, xi, sh) {SOPX_F + ia, SOPX_F + ib, sh, 0, (xi) ? SOP_XI : 0, 0, 0, 0}
+BLS_CONST SopTerm K_M6_SQR[6][4] = {
+    {M6_S(0, 0, 0, 0), M6_S(1, 5, 1, 1), M6_S(2, 4, 1, 1), M6_S(3, 3, 1, 0)},
+    {M6_S(0, 1, 0, 1), M6_S(2, 5, 1, 1), M6_S(3, 4, 1, 0), M6_S(3, 4, 1, 0)},
+    {M6_S(0, 2, 0, 1), M6_S(1, 1, 0, 0), M6_S(3, 5, 1, 1), M6_S(4, 4, 1, 0)},
+    {M6_S(0, 3, 0, 1), M6_S(1, 2, 0, 1), M6_S(4, 5, 1, 0), M6_S(4, 5, 1, 0)},
+    {M6_S(0, 4, 0, 1), M6_S(1, 3, 0, 1), M6_S(2, 2, 0, 0), M6_S(5, 5, 1, 0)},
+    {M6_S(0, 5, 0, 1), M6_S(1, 4, 0, 1), M6_S(2, 3, 0, 0), M6_S(2, 3, 0, 0)},
 };
-#undef M6_E
+#undef M6_S
+// f * (l0 + l2 w^2 + l3 w^3), coefficient k:  f_k l0 + f_{k-2} l2 [xi if k < 2] + f_{k-3} l3 [xi if k < 3]
+BLS_CONST SopTerm K_M6_MUL_LINE[3] = {
+    {SOPX_FREL + 0, SOPX_JL + 0, 0, 0, 0, 0, 0, 0},
+    {SOPX_FREL + 2, SOPX_JL + 1, 0, 0, SOP_XI_LT2, 0, 0, 0},
+    {SOPX_FREL + 3, SOPX_JL + 2, 0, 0, SOP_XI_LT3, 0, 0, 0},
+};
 
-// F: the group's six coefficients (w^0..w^5).  out = coefficient k of f^2.
-BLS_HD void m6_sqr_lane(SFp2& out, const SFp2* F, int k) {
-  SopT t[4];
-#pragma unroll
-  for (int s = 0; s < 4; s++) {
-    const uint32_t e = K_M6_SQR[k][s];
-    t[s] = sop_t(&F[e & 7u], &F[(e >> 3) & 7u], (int32_t)((e >> 7) & 3u), ((e >> 6) & 1u) ? SOP_XI : 0u);
-  }
-  sop2s(out, t, 4);
+// F: the group's six coefficients (w^0..w^5).  *out = coefficient k of f^2   (out must not be one of F's records)
+BLS_HD SopSpaces m6_spaces_f(const SFp2* F, const SFp2* jl, int k) {
+  SopSpaces c;
+  c.reg = nullptr;
+  c.reg_stride = 1;
+  c.P = nullptr;
+  c.line = nullptr;
+  c.F = F;
+  c.jl = jl;
+  c.k = k;
+  return c;
 }
-
-// out = coefficient k of  f * (l0 + l2 w^2 + l3 w^3)   (line[0..2] = l0, l2, l3: the sparse shape of a Miller line)
-BLS_HD void m6_mul_line_lane(SFp2& out, const SFp2* F, const SFp2* line, int k) {
-  SopT t[3];
-  const int k2 = k >= 2 ? k - 2 : k + 4, k3 = k >= 3 ? k - 3 : k + 3;
-  t[0] = sop_t(&F[k], &line[0]);
-  t[1] = sop_t(&F[k2], &line[1], 1, k < 2 ? SOP_XI : 0u);
-  t[2] = sop_t(&F[k3], &line[2], 1, k < 3 ? SOP_XI : 0u);
-  sop2s(out, t, 3);
+BLS_HD void m6_sqr_lane(SFp2* out, const SFp2* F, int k) { sop2f(out, K_M6_SQR[k], 4, 0, m6_spaces_f(F, nullptr, k)); }
+// *out = coefficient k of  f * (l0 + l2 w^2 + l3 w^3)   (line[0..2] = l0, l2, l3: the sparse shape of a Miller line)
+BLS_HD void m6_mul_line_lane(SFp2* out, const SFp2* F, const SFp2* line, int k) {
+  sop2f(out, K_M6_MUL_LINE, 3, 0, m6_spaces_f(F, line, k));
 }
 
 // slot of coefficient k (of w^k) in the tower layout of fp12.cuh: w^0..w^5 = c0.c0, c1.c0, c0.c1, c1.c1, c0.c2, c1.c2
@@ -69,123 +72,140 @@ BLS_HD void m6_finish_lane(Fp2& out, const SFp2& fk, int k) {
 }
 
 // ---- the line computation of one pair, as a PROGRAM over S-form records ---------------------------------------------
-// Every step is one call of sop2s (a sum of at most two Fp2 products, lazily reduced) or of sfp2_lin; the steps are rows
-// of a constant table run by a ten-line interpreter, so the hot code of the whole Miller loop is sop2s + sfp2_lin + this
-// interpreter (instruction caches: 6 KB / 32 KB per SM sub-partition / SM) instead of 24 KB of
+// Every step is one call of sop2f (a sum of at most two Fp2 products, lazily reduced) or of sfp2_lin; the steps are rows
+// of a constant table run by a ten-line interpreter, so the hot code of the whole Miller loop is sop2f + sfp2_lin + this
+// interpreter (instruction caches: 6 KB per SM sub-partition, 32 KB per SM) instead of 24 KB of
 // inlined field glue per step function.
 //
 // Running point T = (X : Y : Z) in HOMOGENEOUS projective coordinates on the twist y^2 = x^3 + 4 xi; the G1 argument
-// enters as three Fp scalars px = Xp Zp, py = Yp, pz = Zp^3 (affine: x, y, 1), so a Jacobian r_i * pk_i needs no inversion.
-// Lines are scaled by factors in proper subfields (erased by the final exponentiation):
-//   doubling:  B = Y^2, C = Z^2, J = X^2, E = 12 xi C, F = 3E
-//              X3 = 2XY (B - F),  Y3 = (B + F)^2 - 12 E^2,  Z3 = 8 B YZ          (4 x the textbook (X3:Y3:Z3))
-//              l0 = (B - E) pz,  l2 = -3J px,  l3 = 2YZ py
+// enters as three Fp scalars px = Xp Zp, -py = -Yp, pz = Zp^3 (affine: x, -y, 1), so a Jacobian r_i * pk_i needs no
+// inversion.  Lines are scaled by factors in proper subfields (erased by the final exponentiation):
+//   doubling:  B = Y^2, C = Z^2, J = X^2, G = xi C;   U = B - 36G, V = B + 36G
+//              X3 = 2XY U,  Y3 = V^2 - 48G 36G,  Z3 = 8 B YZ                    (4 x the textbook (X3:Y3:Z3))
+//              l0 = (12G - B) pz,  l2 = 3J px,  l3 = 2YZ (-py)
 //   addition:  u = y2 Z - Y, v = x2 Z - X, A = u^2 Z - v^3 - 2 v^2 X
 //              X3 = v A,  Y3 = u (v^2 X - A) - v^3 Y,  Z3 = v^3 Z
-//              l0 = (u x2 - v y2) pz,  l2 = -u px,  l3 = v py
+//              l0 = (v y2 - u x2) pz,  l2 = u px,  l3 = v (-py)
 // (derivation checked against the big-int oracle in tools/proto_lines.py; bounds by the BLS_TRACK build)
 enum : uint8_t {
-  RX = 0, RY, RZ, RPX, RPY, RPZ, RQX, RQY, RT0, RT1, RT2, RT3, RT4, RT5, RT6,
-  M6_NREG,
-  RL0 = 32, RL2 = 33, RL3 = 34,  // the lane's line record (shared memory on the device)
-  RNONE = 255
-};
-struct M6Term {
-  uint8_t a, a2, b, b2;
-  int8_t sa, sa2, sb, sb2;
-  uint8_t fl;
+  RX = 0, RY, RZ, RNQX, RQY, RT0, RT1, RT2, RT3, RT4, RT5, RT6, RT7, RT8,
+  M6_NREG,                                            // 14 records per pair in the thread's record file
+  RPX = SOPX_P, RNPY = SOPX_P + 1, RPZ = SOPX_P + 2,  // the prepared G1 argument: read-only records (M6Arg)
+  RL0 = SOPX_LINE, RL2 = SOPX_LINE + 1, RL3 = SOPX_LINE + 2,  // the lane's line record (shared memory on the device)
+  RNONE = SOPX_NONE
 };
 struct M6Op {
-  uint8_t kind;  // 0: sop2s, 1: sfp2_lin (t[0]: sa*[xi]a + sa2*a2 + sb*b)
-  uint8_t dst, nt;
-  M6Term t[2];
+  uint8_t kind;  // 0: sop2f, 1: sfp2_lin  (dst = lx * [xi] xr + ly * yr + lz * zr)
+  uint8_t dst, nt, fp;
+  SopTerm t[2];
+  int8_t lx, ly, lz;
+  uint8_t xr, yr, zr, lfl, pad;
 };
-#define M6_T1(a, b) {a, RNONE, b, RNONE, 1, 0, 1, 0, 0}
-#define M6_NOT {RNONE, RNONE, RNONE, RNONE, 0, 0, 0, 0, 0}
+#define M6_T(a, b) {a, b, 0, 0, 0, 0, 0, 0}
+#define M6_TS(a, sha, b, shb, fl) {a, b, sha, shb, fl, 0, 0, 0}
+#define M6_SOP1(dst, t0) {0, dst, 1, 0, {t0, t0}, 0, 0, 0, RNONE, RNONE, RNONE, 0, 0}
+#define M6_SOP2(dst, t0, t1) {0, dst, 2, 0, {t0, t1}, 0, 0, 0, RNONE, RNONE, RNONE, 0, 0}
+#define M6_SOPFP(dst, t0) {0, dst, 1, 1, {t0, t0}, 0, 0, 0, RNONE, RNONE, RNONE, 0, 0}
+#define M6_LIN(dst, x, lx, fl, y, ly, z, lz) {1, dst, 0, 0, {M6_T(RNONE, RNONE), M6_T(RNONE, RNONE)}, lx, ly, lz, x, y, z, fl, 0}
 BLS_CONST M6Op K_M6_DBL[] = {
-    {0, RT0, 1, {M6_T1(RY, RY), M6_NOT}},                                                         // B
-    {0, RT1, 1, {M6_T1(RZ, RZ), M6_NOT}},                                                         // C
-    {0, RT2, 1, {M6_T1(RX, RX), M6_NOT}},                                                         // J
-    {0, RT3, 1, {M6_T1(RX, RY), M6_NOT}},                                                         // XY
-    {0, RT4, 1, {M6_T1(RY, RZ), M6_NOT}},                                                         // YZ
-    {1, RT5, 1, {{RT1, RNONE, RNONE, RNONE, 12, 0, 0, 0, SOP_XI}, M6_NOT}},                       // E = 12 xi C
-    {1, RT6, 1, {{RT5, RNONE, RNONE, RNONE, 3, 0, 0, 0, 0}, M6_NOT}},                             // F = 3E
-    {0, RX, 1, {{RT3, RNONE, RT0, RT6, 2, 0, 1, -1, 0}, M6_NOT}},                                 // X3 = 2XY (B - F)
-    {0, RY, 2, {{RT0, RT6, RT0, RT6, 1, 1, 1, 1, 0}, {RT5, RNONE, RT6, RNONE, -4, 0, 1, 0, 0}}},  // Y3 = (B+F)^2 - 4E F
-    {0, RZ, 1, {{RT0, RNONE, RT4, RNONE, 4, 0, 2, 0, 0}, M6_NOT}},                                // Z3 = 4B 2YZ
-    {0, RL0, 1, {{RT0, RT5, RPZ, RNONE, 1, -1, 1, 0, SOP_BFP}, M6_NOT}},                          // l0 = (B - E) pz
-    {0, RL2, 1, {{RT2, RNONE, RPX, RNONE, -3, 0, 1, 0, SOP_BFP}, M6_NOT}},                        // l2 = -3J px
-    {0, RL3, 1, {{RT4, RNONE, RPY, RNONE, 2, 0, 1, 0, SOP_BFP}, M6_NOT}},                         // l3 = 2YZ py
+    M6_SOP1(RT0, M6_T(RY, RY)),                                   // B
+    M6_SOP1(RT1, M6_T(RZ, RZ)),                                   // C
+    M6_SOP1(RT2, M6_T(RX, RX)),                                   // J
+    M6_SOP1(RT3, M6_T(RX, RY)),                                   // XY
+    M6_SOP1(RT4, M6_T(RY, RZ)),                                   // YZ
+    M6_LIN(RT5, RT1, -36, SOP_XI, RT0, 1, RNONE, 0),              // U = B - 36 xi C
+    M6_LIN(RT6, RT1, 36, SOP_XI, RT0, 1, RNONE, 0),               // V = B + 36 xi C
+    M6_LIN(RT7, RT1, 36, SOP_XI, RNONE, 0, RNONE, 0),             // F = 36 xi C
+    M6_LIN(RT8, RT1, -48, SOP_XI, RNONE, 0, RNONE, 0),            // E4 = -48 xi C
+    M6_LIN(RT1, RT1, 12, SOP_XI, RT0, -1, RNONE, 0),              // W = 12 xi C - B   (in place)
+    M6_LIN(RT2, RT2, 3, 0, RNONE, 0, RNONE, 0),                   // J3 = 3J           (in place)
+    M6_SOP1(RX, M6_TS(RT3, 1, RT5, 0, 0)),                        // X3 = 2XY U
+    M6_SOP2(RY, M6_T(RT6, RT6), M6_T(RT8, RT7)),                  // Y3 = V^2 + E4 F
+    M6_SOP1(RZ, M6_TS(RT0, 2, RT4, 1, 0)),                        // Z3 = 4B 2YZ
+    M6_SOPFP(RL0, M6_T(RT1, RPZ)),                                // l0 = W pz
+    M6_SOPFP(RL2, M6_T(RT2, RPX)),                                // l2 = 3J px
+    M6_SOPFP(RL3, M6_TS(RT4, 1, RNPY, 0, 0)),                     // l3 = 2YZ (-py)
 };
 BLS_CONST M6Op K_M6_ADD[] = {
-    {0, RT0, 1, {M6_T1(RQY, RZ), M6_NOT}},                                                        // y2 Z
-    {0, RT1, 1, {M6_T1(RQX, RZ), M6_NOT}},                                                        // x2 Z
-    {1, RT0, 1, {{RT0, RY, RNONE, RNONE, 1, -1, 0, 0, 0}, M6_NOT}},                               // u
-    {1, RT1, 1, {{RT1, RX, RNONE, RNONE, 1, -1, 0, 0, 0}, M6_NOT}},                               // v
-    {0, RT2, 1, {M6_T1(RT1, RT1), M6_NOT}},                                                       // vv
-    {0, RT3, 1, {M6_T1(RT1, RT2), M6_NOT}},                                                       // vvv
-    {0, RT4, 1, {M6_T1(RT2, RX), M6_NOT}},                                                        // Rr = vv X
-    {0, RT5, 1, {M6_T1(RT0, RT0), M6_NOT}},                                                       // uu
-    {0, RT5, 1, {M6_T1(RT5, RZ), M6_NOT}},                                                        // uu Z
-    {1, RT5, 1, {{RT5, RT3, RT4, RNONE, 1, -1, -2, 0, 0}, M6_NOT}},                               // A = uu Z - vvv - 2 Rr
-    {0, RT6, 2, {M6_T1(RT0, RQX), {RT1, RNONE, RQY, RNONE, -1, 0, 1, 0, 0}}},                     // u x2 - v y2
-    {0, RL0, 1, {{RT6, RNONE, RPZ, RNONE, 1, 0, 1, 0, SOP_BFP}, M6_NOT}},                         // l0
-    {0, RL2, 1, {{RT0, RNONE, RPX, RNONE, -1, 0, 1, 0, SOP_BFP}, M6_NOT}},                        // l2 = -u px
-    {0, RL3, 1, {{RT1, RNONE, RPY, RNONE, 1, 0, 1, 0, SOP_BFP}, M6_NOT}},                         // l3 = v py
-    {0, RX, 1, {M6_T1(RT1, RT5), M6_NOT}},                                                        // X3 = v A
-    {0, RY, 2, {{RT0, RNONE, RT4, RT5, 1, 0, 1, -1, 0}, {RT3, RNONE, RY, RNONE, -1, 0, 1, 0, 0}}},  // Y3 = u (Rr - A) - vvv Y
-    {0, RZ, 1, {M6_T1(RT3, RZ), M6_NOT}},                                                         // Z3 = vvv Z
+    M6_SOP1(RT0, M6_T(RQY, RZ)),                                  // y2 Z
+    M6_SOP1(RT1, M6_TS(RNQX, 0, RZ, 0, SOP_NEG)),                 // x2 Z
+    M6_LIN(RT0, RT0, 1, 0, RY, -1, RNONE, 0),                     // u
+    M6_LIN(RT1, RT1, 1, 0, RX, -1, RNONE, 0),                     // v
+    M6_SOP1(RT2, M6_T(RT1, RT1)),                                 // vv
+    M6_SOP1(RT3, M6_T(RT1, RT2)),                                 // vvv
+    M6_SOP1(RT4, M6_T(RT2, RX)),                                  // Rr = vv X
+    M6_SOP1(RT5, M6_T(RT0, RT0)),                                 // uu
+    M6_SOP1(RT5, M6_T(RT5, RZ)),                                  // uu Z
+    M6_LIN(RT5, RT5, 1, 0, RT3, -1, RT4, -2),                     // A = uu Z - vvv - 2 Rr
+    M6_LIN(RT6, RT4, 1, 0, RT5, -1, RNONE, 0),                    // D = Rr - A
+    M6_SOP2(RT7, M6_T(RT1, RQY), M6_T(RT0, RNQX)),                // v y2 - u x2
+    M6_SOPFP(RL0, M6_T(RT7, RPZ)),                                // l0
+    M6_SOPFP(RL2, M6_T(RT0, RPX)),                                // l2 = u px
+    M6_SOPFP(RL3, M6_T(RT1, RNPY)),                               // l3 = v (-py)
+    M6_SOP1(RX, M6_T(RT1, RT5)),                                  // X3 = v A
+    M6_SOP2(RY, M6_T(RT0, RT6), M6_TS(RT3, 0, RY, 0, SOP_NEG)),   // Y3 = u D - vvv Y
+    M6_SOP1(RZ, M6_T(RT3, RZ)),                                   // Z3 = vvv Z
 };
-#undef M6_T1
-#undef M6_NOT
+#undef M6_T
+#undef M6_TS
+#undef M6_SOP1
+#undef M6_SOP2
+#undef M6_SOPFP
+#undef M6_LIN
 constexpr int K_M6_DBL_N = (int)(sizeof(K_M6_DBL) / sizeof(M6Op));
 constexpr int K_M6_ADD_N = (int)(sizeof(K_M6_ADD) / sizeof(M6Op));
 
-BLS_HD SFp2* m6_rec(SFp2* reg, SFp2* line, uint32_t i) { return i == RNONE ? nullptr : i >= RL0 ? line + (i - RL0) : reg + i; }
-
-BLS_FN void m6_run(const M6Op* prog, int n, SFp2* reg, SFp2* line) {
+BLS_FN void m6_run(const M6Op* prog, int n, const SopSpaces& cx) {
 #pragma unroll 1
   for (int i = 0; i < n; i++) {
-    const M6Op& op = prog[i];
-    SFp2* dst = m6_rec(reg, line, op.dst);
-    if (op.kind == 0) {
-      SopT t[2];
-#pragma unroll
-      for (int k = 0; k < 2; k++) {
-        const M6Term& m = op.t[k];
-        t[k] = sop_t2(m6_rec(reg, line, m.a), m.sa, m6_rec(reg, line, m.a2), m.sa2, m6_rec(reg, line, m.b), m.sb,
-                      m6_rec(reg, line, m.b2), m.sb2, m.fl);
-      }
-      sop2s(*dst, t, op.nt);
+    const M6Op* op = prog + i;
+    SFp2* dst = sop_rec(cx, op->dst);
+    if (op->kind == 0) {
+      sop2f(dst, op->t, op->nt, op->fp, cx);
     } else {
-      const M6Term& m = op.t[0];
-      sfp2_lin(*dst, m6_rec(reg, line, m.a), m.sa, m.fl, m6_rec(reg, line, m.a2), m.sa2, m6_rec(reg, line, m.b), m.sb);
+      sfp2_lin(*dst, sop_rec(cx, op->xr), op->lx, op->lfl, op->yr == RNONE ? nullptr : sop_rec(cx, op->yr), op->ly,
+               op->zr == RNONE ? nullptr : sop_rec(cx, op->zr), op->lz);
     }
   }
 }
 
-// per-lane private state: the record file of the line programs
-struct M6Pair {
-  SFp2 reg[M6_NREG];
-  const G2Aff* Q;  // stays where it is (HBM): only the 5 addition steps read it
+// the prepared G1 argument of one pair: px, -py, pz as Fp scalars in the c0 halves of three records (HBM, read-only)
+struct M6Arg {
+  SFp2 px, npy, pz;
 };
-// P prepared by miller_prepare (pairing.cuh), Q affine and not the identity
-BLS_HD void m6_init_pair(M6Pair& s, const MillerG1& P, const G2Aff* Q) {
-  const G2Aff q = *Q;
-  s.Q = Q;
-  sfp2_from_fp2(s.reg[RX], q.x);
-  sfp2_from_fp2(s.reg[RY], q.y);
-  sfp2_one(s.reg[RZ]);
-  sfp2_from_fp(s.reg[RPX], P.px);
-  sfp2_from_fp(s.reg[RPY], P.py);
-  sfp2_from_fp(s.reg[RPZ], P.pz);
+// P prepared by miller_prepare (pairing.cuh)
+BLS_HD void m6_make_arg(M6Arg& a, const MillerG1& P) {
+  sfp2_from_fp(a.px, P.px);
+  sfp2_from_fp(a.npy, P.py);
+  sfp2_neg(a.npy, a.npy);
+  sfp2_from_fp(a.pz, P.pz);
 }
-BLS_HD void m6_dbl_line(SFp2* line, M6Pair& s) { m6_run(K_M6_DBL, K_M6_DBL_N, s.reg, line); }
-BLS_HD void m6_add_line(SFp2* line, M6Pair& s) {
-  const G2Aff q = *s.Q;
-  sfp2_from_fp2(s.reg[RQX], q.x);
-  sfp2_from_fp2(s.reg[RQY], q.y);
-  m6_run(K_M6_ADD, K_M6_ADD_N, s.reg, line);
+// the spaces of one pair's line programs: record file `reg` (stride in records), argument, and the line record to produce
+BLS_HD SopSpaces m6_spaces_line(SFp2* reg, int stride, const M6Arg* arg, SFp2* line) {
+  SopSpaces c;
+  c.reg = reg;
+  c.reg_stride = stride;
+  c.P = &arg->px;
+  c.line = line;
+  c.F = nullptr;
+  c.jl = nullptr;
+  c.k = 0;
+  return c;
 }
+// T <- Q (affine, not the identity)
+BLS_HD void m6_init_point(const SopSpaces& cx, const G2Aff& q) {
+  sfp2_from_fp2(*sop_rec(cx, RX), q.x);
+  sfp2_from_fp2(*sop_rec(cx, RY), q.y);
+  sfp2_one(*sop_rec(cx, RZ));
+}
+BLS_HD void m6_dbl_line(const SopSpaces& cx) { m6_run(K_M6_DBL, K_M6_DBL_N, cx); }
+BLS_HD void m6_add_line(const SopSpaces& cx, const G2Aff& q) {
+  SFp2* nqx = sop_rec(cx, RNQX);
+  sfp2_from_fp2(*nqx, q.x);
+  sfp2_neg(*nqx, *nqx);
+  sfp2_from_fp2(*sop_rec(cx, RQY), q.y);
+  m6_run(K_M6_ADD, K_M6_ADD_N, cx);
+}
+constexpr int M6_STEPS = 68;  // 63 doublings + 5 additions: line records per pair
 
 }  // namespace bls

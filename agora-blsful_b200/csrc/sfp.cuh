@@ -1,11 +1,11 @@
-// S-form Fp2 and the fused sum-of-products unit `sop2s`:
+// S-form Fp2 and the fused sum-of-products unit `sop2f`:
 //
 //     r = ( sum_t  A_t * B_t ) / R            (Fp2, Montgomery form, R = 2^392, up to SOP_MAX_TERMS terms)
 //
-// with A_t = sa*a + sa2*a2 (optionally conjugated, optionally times xi = 1+u) and B_t = sb*b + sb2*b2 read from memory, and
-// ONE Montgomery reduction per output coefficient: the 64-bit column accumulators of all terms are summed before
-// reducing (lazy reduction), so a coefficient of an Fp12 product that is a sum of three or four Fp2 products costs
-// 3 integer products per term (Karatsuba) plus 2 reductions, and no additive "glue" pass through local memory.
+// with A_t = +-(a << sha) [* xi], B_t = b << shb records read from memory, and ONE Montgomery reduction per output
+// coefficient: the 64-bit column accumulators of all terms are summed before reducing (lazy reduction), so a coefficient
+// of an Fp12 product that is a sum of three or four Fp2 products costs 3 integer products per term (Karatsuba) plus
+// 2 reductions, and no additive "glue" pass through local memory.
 // This is the arithmetic under the cooperative Miller loop (miller6.cuh): it replaces what blsful takes from
 // blstrs_plus/blst below `multi_miller_loop` (reference src/helpers.rs:50,62; there is no arithmetic in the reference tree).
 //
@@ -43,49 +43,44 @@ struct alignas(16) SFp2 {
 #endif
 
 enum : uint32_t {
-  SOP_XI = 1u,    // A operand times xi = 1 + u
-  SOP_CONJ = 2u,  // A operand conjugated (applied before xi)
-  SOP_BFP = 4u,   // B is an Fp scalar: its c1 is ignored (taken as zero): 2 integer products instead of 3
+  SOP_XI = 1u,        // A operand times xi = 1 + u
+  SOP_NEG = 2u,       // A operand negated
+  SOP_XI_LT2 = 8u,    // A operand times xi when the lane's coefficient index k < 2   (Fp12 wrap-around, miller6.cuh)
+  SOP_XI_LT3 = 16u,   //                                                      k < 3
 };
 constexpr int SOP_MAX_TERMS = 8;
 
-struct SopT {
-  const SFp2 *a, *a2, *b, *b2;  // a2 / b2 may be nullptr
-  int32_t sa, sa2, sb, sb2;     // small integer scales
-  uint32_t fl;
+// Operand references are one-byte indices into a few record spaces, so that a whole computation is a constant table
+// (no descriptor is ever built in local memory; the table is read through the constant cache):
+//   0..23   the thread's record file: reg[i * reg_stride]     24..31  read-only per-item records P[i - 24] (HBM)
+//   32..34  the line record being produced (destination of the line programs)
+//   48..53  accumulator coefficient F[i - 48]                  56..58  coefficient i - 56 of the line being multiplied in
+//   64..69  accumulator coefficient F[(k - (i - 64)) mod 6], k = the lane's coefficient index        255 none
+enum : uint8_t { SOPX_P = 24, SOPX_LINE = 32, SOPX_F = 48, SOPX_JL = 56, SOPX_FREL = 64, SOPX_NONE = 255 };
+// one product term  +-(a << sha) [xi]  *  (b << shb)
+struct SopTerm {
+  uint8_t a, b, sha, shb, fl, pad0, pad1, pad2;
 };
-BLS_HD SopT sop_t(const SFp2* a, const SFp2* b, int32_t sa = 1, uint32_t fl = 0) {
-  SopT t;
-  t.a = a;
-  t.a2 = nullptr;
-  t.b = b;
-  t.b2 = nullptr;
-  t.sa = sa;
-  t.sa2 = 0;
-  t.sb = 1;
-  t.sb2 = 0;
-  t.fl = fl;
-  return t;
-}
-BLS_HD SopT sop_t2(const SFp2* a, int32_t sa, const SFp2* a2, int32_t sa2, const SFp2* b, int32_t sb, const SFp2* b2, int32_t sb2,
-                   uint32_t fl = 0) {
-  SopT t;
-  t.a = a;
-  t.a2 = a2;
-  t.b = b;
-  t.b2 = b2;
-  t.sa = sa;
-  t.sa2 = sa2;
-  t.sb = sb;
-  t.sb2 = sb2;
-  t.fl = fl;
-  return t;
-}
-
-// ---- operand load -------------------------------------------------------------------------------------------------
-struct SopBnd {  // BLS_TRACK only: limb magnitude bounds of the prepared operand halves and its value bound
-  double l0, l1, vb;
+struct SopSpaces {
+  SFp2* reg;
+  int reg_stride;  // in records: 1 = the thread's records are contiguous; blockDim.x = record-major shared memory
+  const SFp2* P;
+  SFp2* line;
+  const SFp2* F;
+  const SFp2* jl;
+  int k;
 };
+// record reference -> address (branch-free: the callers sit inside the software-pipelined loop)
+BLS_HD SFp2* sop_rec(const SopSpaces& c, uint32_t i) {
+  const int is_reg = i < SOPX_P, is_p = (i >= SOPX_P) & (i < SOPX_LINE), is_line = (i >= SOPX_LINE) & (i < SOPX_F),
+            is_jl = (i >= SOPX_JL) & (i < SOPX_FREL), is_rel = i >= SOPX_FREL;
+  int jr = c.k - ((int)i - SOPX_FREL);
+  jr += jr < 0 ? 6 : 0;
+  const int j = is_reg ? (int)i * c.reg_stride : is_p ? (int)i - SOPX_P : is_line ? (int)i - SOPX_LINE : is_jl ? (int)i - SOPX_JL
+              : is_rel ? jr : (int)i - SOPX_F;
+  SFp2* base = is_reg ? c.reg : is_p ? const_cast<SFp2*>(c.P) : is_line ? c.line : is_jl ? const_cast<SFp2*>(c.jl) : const_cast<SFp2*>(c.F);
+  return base + j;
+}
 
 struct alignas(16) SopI4 {
   int32_t x, y, z, w;
@@ -100,69 +95,6 @@ BLS_HD void sop_ld28(int32_t* t, const SFp2* p) {
     t[4 * i + 2] = v.z;
     t[4 * i + 3] = v.w;
   }
-}
-
-// The operand of integer product number `pass` (0: c0 half, 1: c1 half, 2: c0 + c1) of  s*p + s2*p2  [conj] [* xi].
-// fp_only: the c1 half is taken as zero.
-BLS_HD SopBnd sop_operand(int32_t* x, int pass, const SFp2* p, int32_t s, const SFp2* p2, int32_t s2, uint32_t fl, bool fp_only) {
-  SopBnd bd;
-  bd.l0 = bd.l1 = bd.vb = 0;
-  int32_t t[2 * NL];
-  sop_ld28(t, p);
-  if (s != 1) {
-#pragma unroll
-    for (int i = 0; i < 2 * NL; i++) t[i] *= s;
-  }
-#if defined(BLS_TRACK)
-  {
-    double as = s < 0 ? -(double)s : (double)s;
-    bd.l0 = bd.l1 = as * p->lb;
-    bd.vb = as * p->vb;
-  }
-#endif
-  if (p2 != nullptr) {
-    int32_t u[2 * NL];
-    sop_ld28(u, p2);
-#pragma unroll
-    for (int i = 0; i < 2 * NL; i++) t[i] += u[i] * s2;
-#if defined(BLS_TRACK)
-    {
-      double as = s2 < 0 ? -(double)s2 : (double)s2;
-      bd.l0 += as * p2->lb;
-      bd.l1 += as * p2->lb;
-      bd.vb += as * p2->vb;
-    }
-#endif
-  }
-  if (fp_only) {
-#pragma unroll
-    for (int i = 0; i < NL; i++) t[NL + i] = 0;
-#if defined(BLS_TRACK)
-    bd.l1 = 0;
-#endif
-  }
-  if (fl & SOP_CONJ) {
-#pragma unroll
-    for (int i = 0; i < NL; i++) t[NL + i] = -t[NL + i];
-  }
-  if (fl & SOP_XI) {
-#pragma unroll
-    for (int i = 0; i < NL; i++) {
-      int32_t t0 = t[i] - t[NL + i], t1 = t[i] + t[NL + i];
-      t[i] = t0;
-      t[NL + i] = t1;
-    }
-#if defined(BLS_TRACK)
-    bd.l0 = bd.l1 = bd.l0 + bd.l1;
-    bd.vb *= 2.0;
-#endif
-  }
-#if defined(BLS_TRACK)
-  BLS_REQ(bd.l0 < 1073741824.0 && bd.l1 < 1073741824.0, "sop operand limb overflow (>= 2^30)");
-#endif
-#pragma unroll
-  for (int i = 0; i < NL; i++) x[i] = pass == 0 ? t[i] : pass == 1 ? t[NL + i] : t[i] + t[NL + i];
-  return bd;
 }
 
 // T[i+j] += a[i] * b[j]   (196 signed IMAD.WIDE; columns wrap modulo 2^64 by design)
@@ -196,7 +128,7 @@ BLS_HD void sop_redc(int32_t* out, uint64_t* T) {
 }
 
 // A 28 x u64 scratch record that stays in LOCAL memory and is moved with 128-bit local accesses (a plain array would be
-// promoted to 56 registers; a laundered generic pointer costs 64-bit generic accesses plus address bookkeeping).
+// promoted to 56 registers, which the pipelined loop below cannot spare).
 struct alignas(16) SopKeep {
   uint64_t v[2 * NL];
 };
@@ -217,77 +149,150 @@ BLS_HD void sop_keep_ld(const SopKeep& k, int i, uint64_t& a, uint64_t& b) {
 #endif
 }
 
-// The unit.  r may alias any operand: results are written after the last operand read.
-// Code-size discipline (the SM's instruction caches are 6 KB / 32 KB): ONE product body, ONE
-// reduction body; the three Karatsuba products P0 = sum a0 b0, P1 = sum a1 b1, P2 = sum (a0+a1)(b0+b1) are three trips
-// through the same loop, P0 (then P0 + P1) waits in local memory meanwhile.
-//   real = P0 - P1 ,  imag = P2 - (P0 + P1)
-BLS_FN void sop2s(SFp2& r, const SopT* t, int nt) {
-  SopKeep keep;
-  int32_t res[2 * NL];
-#if defined(BLS_TRACK)
-  double col_re = 0, col_im = 0, vsum = 0;
-  BLS_REQ(nt >= 1 && nt <= SOP_MAX_TERMS, "sop2s term count");
-#endif
-#pragma unroll 1
-  for (int pass = 0; pass < 3; pass++) {
-    uint64_t T[2 * NL];
+// ---- the unit ---------------------------------------------------------------------------------------------------------
+// One branch-free loop body per integer product: the 128-bit loads of the NEXT product's two records are issued first,
+// then the 196 IMAD.WIDE of the current product, and the next operands are prepared with ALU instructions only (masks,
+// shifts, negations: the multiplier pipe sees nothing but the products) - loads and preparation hide under the
+// multiplier stream of the same warp instead of alternating with it.  Code-size discipline (instruction caches: 6 KB per
+// SM sub-partition, 32 KB per SM): ONE product body, ONE reduction body, no second variant.
+//   fp_mode 0:  three Karatsuba trips  P0 = sum a0 b0, P1 = sum a1 b1, P2 = sum (a0+a1)(b0+b1):
+//               real = P0 - P1 ,  imag = P2 - (P0 + P1)
+//   fp_mode 1:  every B is an Fp scalar (its c0): two trips, real = sum a0 b0, imag = sum a1 b0
+struct SopPrep {  // operand of one integer product from the raw halves: x = +-(((h0 & m0) + (((h1 ^ n1) - n1) & m1)) << sh)
+  int32_t m0, m1, n1, ng, sh;
+};
+BLS_HD SopPrep sop_prep(int half, int xi, int neg, int sh) {  // half: 0 c0, 1 c1, 2 c0 + c1.  Branch-free.
+  SopPrep p;
+  // plain: (a0), (a1), (a0 + a1) ;  xi: (a0 - a1), (a0 + a1), (2 a0)
+  const int p0 = half == 0, p1 = half == 1, p2 = half == 2;
+  p.m0 = -((p1 ^ 1) | xi);
+  p.m1 = -(((p2 & xi) ^ 1) & ((p0 & (xi ^ 1)) ^ 1));
+  p.n1 = -(p0 & xi);
+  p.ng = -neg;
+  p.sh = sh + (p2 & xi);
+  return p;
+}
+BLS_HD void sop_prep_apply(int32_t* x, const SopI4* r, const SopPrep& p) {
+  int32_t t[2 * NL];
 #pragma unroll
-    for (int i = 0; i < 2 * NL; i++) T[i] = 0;
-#pragma unroll 1
-    for (int k = 0; k < nt; k++) {
-      const bool bfp = (t[k].fl & SOP_BFP) != 0;
-      if (bfp && pass == 1) continue;
-      int32_t x[NL], y[NL];
-      SopBnd ba = sop_operand(x, pass, t[k].a, t[k].sa, t[k].a2, t[k].sa2, t[k].fl, false);
-      SopBnd bb = sop_operand(y, pass, t[k].b, t[k].sb, t[k].b2, t[k].sb2, 0, bfp);
-      sop_acc(T, x, y);
-#if defined(BLS_TRACK)
-      if (pass == 0) {
-        col_re += 14.0 * (ba.l0 * bb.l0 + ba.l1 * bb.l1);
-        col_im += 14.0 * (ba.l0 * bb.l1 + ba.l1 * bb.l0);
-        vsum += 2.0 * ba.vb * bb.vb;
-      }
-#else
-      (void)ba;
-      (void)bb;
-#endif
-    }
-    if (pass == 0) {
-#pragma unroll
-      for (int i = 0; i < NL; i++) sop_keep_st(keep, i, T[2 * i], T[2 * i + 1]);
-      continue;
-    }
-#if defined(BLS_TRACK)
-    {
-      // true column values + the reduction's own growth (14 * 2^56 for m*p, < 2^36 of carries) must fit int64
-      const double lim = 9223372036854775808.0 - 15.0 * 72057594037927936.0;
-      BLS_REQ(col_re < lim && col_im < lim, "sop2s column overflow");
-      BLS_REQ(vsum / 2500.0 + 1.0 < 16.0, "sop2s result value bound");
-    }
-#endif
-    // pass 1: U = P0 - P1, keep <- P0 + P1 ;  pass 2: U = P2 - keep
-#pragma unroll
-    for (int i = 0; i < NL; i++) {
-      uint64_t s0, s1;
-      sop_keep_ld(keep, i, s0, s1);
-      const uint64_t v0 = T[2 * i], v1 = T[2 * i + 1];
-      if (pass == 1) sop_keep_st(keep, i, s0 + v0, s1 + v1);
-      T[2 * i] = pass == 1 ? s0 - v0 : v0 - s0;
-      T[2 * i + 1] = pass == 1 ? s1 - v1 : v1 - s1;
-    }
-    T[2 * NL - 1] = 0;
-    int32_t c[NL];
-    sop_redc(c, T);
-#pragma unroll
-    for (int i = 0; i < NL; i++) {
-      if (pass == 1) res[i] = c[i]; else res[NL + i] = c[i];
-    }
+  for (int i = 0; i < 7; i++) {
+    t[4 * i] = r[i].x;
+    t[4 * i + 1] = r[i].y;
+    t[4 * i + 2] = r[i].z;
+    t[4 * i + 3] = r[i].w;
   }
 #pragma unroll
-  for (int i = 0; i < 2 * NL; i++) r.w[i] = res[i];
+  for (int i = 0; i < NL; i++) {
+    const int32_t v = (int32_t)((uint32_t)((t[i] & p.m0) + (((t[NL + i] ^ p.n1) - p.n1) & p.m1)) << p.sh);
+    x[i] = (v ^ p.ng) - p.ng;
+  }
+}
+BLS_HD void sop_fetch(SopI4* r, const SFp2* p) {
+  const SopI4* q = reinterpret_cast<const SopI4*>(p->w);
+#pragma unroll
+  for (int i = 0; i < 7; i++) r[i] = q[i];
+}
+BLS_HD int sop_term_xi(uint32_t fl, int lane_k) {
+  return (int)((fl & SOP_XI) != 0) | ((int)((fl & SOP_XI_LT2) != 0) & (int)(lane_k < 2)) | ((int)((fl & SOP_XI_LT3) != 0) & (int)(lane_k < 3));
+}
+
+// dst may alias any operand: results are written after the last operand read.
+BLS_FN void sop2f(SFp2* dst, const SopTerm* t, int nt, int fp_mode, const SopSpaces& cx) {
+  const int lane_k = cx.k;
+  uint64_t T[2 * NL];
+  SopKeep keep;
+  int32_t res[2 * NL], x[NL], y[NL];
+  SopI4 ra[7], rb[7];
 #if defined(BLS_TRACK)
-  STRK(r, vsum / 2500.0 + 1.0, 134217728.0);
+  double col = 0, vsum = 0;
+  BLS_REQ(nt >= 1 && nt <= SOP_MAX_TERMS, "sop2f term count");
+  for (int k = 0; k < nt; k++) {
+    const SopTerm m = t[k];
+    const SFp2 *pa = sop_rec(cx, m.a), *pb = sop_rec(cx, m.b);
+    const double xi = sop_term_xi(m.fl, lane_k) ? 2.0 : 1.0;
+    const double la = pa->lb * (double)(1 << m.sha) * xi, lb = pb->lb * (double)(1 << m.shb);
+    BLS_REQ(la < 1073741824.0 && lb < 1073741824.0 && m.sha < 4 && m.shb < 4, "sop2f operand limb overflow");
+    col += 14.0 * 2.0 * la * lb;
+    vsum += 2.0 * pa->vb * (double)(1 << m.sha) * xi * pb->vb * (double)(1 << m.shb);
+  }
+  {
+    // true column values + the reduction's own growth (14 * 2^56 for m*p, < 2^36 of carries) must fit int64
+    const double lim = 9223372036854775808.0 - 15.0 * 72057594037927936.0;
+    BLS_REQ(col < lim, "sop2f column overflow");
+    BLS_REQ(vsum / 2500.0 + 1.0 < 16.0, "sop2f result value bound");
+  }
+#endif
+#pragma unroll
+  for (int i = 0; i < 2 * NL; i++) T[i] = 0;
+  // prologue: operands of step 0
+  {
+    const SopTerm m = t[0];
+    sop_fetch(ra, sop_rec(cx, m.a));
+    sop_fetch(rb, sop_rec(cx, m.b));
+    sop_prep_apply(x, ra, sop_prep(0, sop_term_xi(m.fl, lane_k), (m.fl & SOP_NEG) != 0, m.sha));
+    sop_prep_apply(y, rb, sop_prep(0, 0, 0, m.shb));
+  }
+  int pass = 0, k = 0;
+  const int npass = fp_mode ? 2 : 3;
+  const int nsteps = npass * nt;
+#pragma unroll 1
+  for (int s = 0; s < nsteps; s++) {
+    const int wrap = (k + 1 == nt);
+    const int k1 = wrap ? 0 : k + 1, p1 = pass + wrap;
+    const int pn = p1 >= npass ? npass - 1 : p1;  // after the last step: a harmless refetch
+    const SopTerm m = t[k1];
+    sop_fetch(ra, sop_rec(cx, m.a));
+    sop_fetch(rb, sop_rec(cx, m.b));
+    sop_acc(T, x, y);
+    sop_prep_apply(x, ra, sop_prep(pn, sop_term_xi(m.fl, lane_k), (m.fl & SOP_NEG) != 0, m.sha));
+    sop_prep_apply(y, rb, sop_prep(fp_mode ? 0 : pn, 0, 0, m.shb));
+    if (wrap) {  // a product sum is complete
+      if (pass == 0 && !fp_mode) {
+#pragma unroll
+        for (int i = 0; i < NL; i++) {
+          sop_keep_st(keep, i, T[2 * i], T[2 * i + 1]);
+          T[2 * i] = T[2 * i + 1] = 0;
+        }
+      } else {
+        // Karatsuba: pass 1: U = P0 - P1, keep <- P0 + P1 ;  pass 2: U = P2 - keep.   Fp scalars: U = T as it is.
+        if (!fp_mode) {
+#pragma unroll
+          for (int i = 0; i < NL; i++) {
+            uint64_t u0, u1;
+            sop_keep_ld(keep, i, u0, u1);
+            const uint64_t v0 = T[2 * i], v1 = T[2 * i + 1];
+            if (pass == 1) sop_keep_st(keep, i, u0 + v0, u1 + v1);
+            T[2 * i] = pass == 1 ? u0 - v0 : v0 - u0;
+            T[2 * i + 1] = pass == 1 ? u1 - v1 : v1 - u1;
+          }
+        }
+        T[2 * NL - 1] = 0;
+        int32_t c[NL];
+        sop_redc(c, T);
+        const bool real_part = fp_mode ? pass == 0 : pass == 1;
+#pragma unroll
+        for (int i = 0; i < NL; i++) {
+          if (real_part) res[i] = c[i]; else res[NL + i] = c[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 2 * NL; i++) T[i] = 0;
+      }
+    }
+    k = k1;
+    pass = p1;
+  }
+  SopI4* q = reinterpret_cast<SopI4*>(dst->w);
+#pragma unroll
+  for (int i = 0; i < 7; i++) {
+    SopI4 v;
+    v.x = res[4 * i];
+    v.y = res[4 * i + 1];
+    v.z = res[4 * i + 2];
+    v.w = res[4 * i + 3];
+    q[i] = v;
+  }
+#if defined(BLS_TRACK)
+  STRK(*dst, vsum / 2500.0 + 1.0, 134217728.0);
 #endif
 }
 

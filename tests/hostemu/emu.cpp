@@ -145,53 +145,65 @@ int emu_pairing_check2(const uint8_t* p1, const uint8_t* q1, const uint8_t* p2, 
   return fp12_is_one(g);
 }
 
-// one fused sum of products: r = a*b + xi*(2c - d)*(e + f) + conj(b)*k  (k an Fp scalar), plain Fp2 in and out
-void emu_sop2s(const uint8_t* in, const uint8_t* k48, uint8_t* out) {
-  Fp2 v[6], one2; SFp2 s[6], ks, r, so;
-  fone(one2); sfp2_from_fp2(so, one2);
-  SopT t[3];
+// fused sums of products (plain Fp2 in and out): out0 = a*b + xi*(2c)*d - e*(4f) ; out1 = out0^2 (output aliasing both
+// operands) ; out2 = a*k - xi*b*k  (k an Fp scalar: the two-trip mode)
+void emu_sop2f(const uint8_t* in, const uint8_t* k48, uint8_t* out) {
+  Fp2 v[6], one2; SFp2 s[10];  // records 0..5 inputs, 6: k, 7: one, 8: r
+  SopSpaces cx = m6_spaces_line(s, 1, nullptr, nullptr);
+  fone(one2); sfp2_from_fp2(s[7], one2);
   for (int i = 0; i < 6; i++) {  // unsigned form -> balanced S-form through one multiplication by 1
     fp2_in(v[i], in + 96 * i); fred(v[i], v[i]); sfp2_from_fp2(s[i], v[i]);
-    t[0] = sop_t(&s[i], &so); sop2s(s[i], t, 1);
+    const SopTerm t = {(uint8_t)i, 7, 0, 0, 0, 0, 0, 0};
+    sop2f(&s[i], &t, 1, 0, cx);
   }
-  Fp kk; fp_in(kk, k48); sfp2_from_fp(ks, kk);
-  t[0] = sop_t(&s[0], &s[1]);
-  t[1] = sop_t2(&s[2], 2, &s[3], -1, &s[4], 1, &s[5], 1, SOP_XI);
-  t[2] = sop_t(&s[1], &ks, 1, SOP_CONJ | SOP_BFP);
-  sop2s(r, t, 3);
-  Fp2 o; fp2_from_sfp2(o, r); fp2_out(out, o);
-  // chained: r2 = r * r (aliasing the output with both operands), returned after the first result
-  t[0] = sop_t(&r, &r);
-  sop2s(r, t, 1);
-  fp2_from_sfp2(o, r); fp2_out(out + 96, o);
+  Fp kk; fp_in(kk, k48); sfp2_from_fp(s[6], kk);
+  const SopTerm t3[3] = {{0, 1, 0, 0, 0, 0, 0, 0}, {2, 3, 1, 0, SOP_XI, 0, 0, 0}, {4, 5, 0, 2, SOP_NEG, 0, 0, 0}};
+  sop2f(&s[8], t3, 3, 0, cx);
+  Fp2 o; fp2_from_sfp2(o, s[8]); fp2_out(out, o);
+  const SopTerm sq = {8, 8, 0, 0, 0, 0, 0, 0};
+  sop2f(&s[8], &sq, 1, 0, cx);
+  fp2_from_sfp2(o, s[8]); fp2_out(out + 96, o);
+  const SopTerm t2[2] = {{0, 6, 0, 0, 0, 0, 0, 0}, {1, 6, 0, 0, SOP_XI | SOP_NEG, 0, 0, 0}};
+  sop2f(&s[9], t2, 2, 1, cx);
+  fp2_from_sfp2(o, s[9]); fp2_out(out + 192, o);
 }
-// cooperative Miller loop of miller6.cuh, lanes emulated one after the other: f = prod_j ML(k_j * P_j, Q_j), j < n <= 6
+// cooperative Miller loop of miller6.cuh, lanes emulated one after the other: f = prod_j ML(k_j * P_j, Q_j), j < n <= 6.
+// Mirrors the two device kernels: every pair's 68 line records first (k_m6_lines), then the shared accumulator (k_m6_accum).
 int emu_miller6(int n, const uint8_t* p48, const uint8_t* q96, const uint32_t* k, int nl, uint8_t* ml_out, uint8_t* fe_out) {
-  M6Pair pr[6];
-  G2Aff qa[6];
+  static SFp2 lines[6][M6_STEPS][3];
+  const uint64_t e = K_X_ABS;
   for (int j = 0; j < n; j++) {
-    G1Aff p; G2Aff& q = qa[j];
+    G1Aff p; G2Aff q;
     if (g1_decompress(p, p48 + 48 * j, false) || g2_decompress(q, q96 + 96 * j, false)) return -1;
     MillerG1 mp;
     if (nl) { G1Jac pj; jac_mul_aff(pj, p, k + nl * j, nl); miller_prepare(mp, pj); } else miller_prepare(mp, p);
-    m6_init_pair(pr[j], mp, &qa[j]);
+    M6Arg arg; m6_make_arg(arg, mp);
+    SFp2 reg[2 * M6_NREG];  // exercised with a record stride of 2
+    SopSpaces cx = m6_spaces_line(reg, 2, &arg, nullptr);
+    m6_init_point(cx, q);
+    int step = 0;
+    for (int i = 62; i >= 0; i--) {
+      cx.line = lines[j][step++]; m6_dbl_line(cx);
+      if ((e >> i) & 1) { cx.line = lines[j][step++]; m6_add_line(cx, q); }
+    }
+    if (step != M6_STEPS) return -2;
   }
-  SFp2 F[6], T[6], line[6][3];
+  SFp2 F[6], T[6];
   sfp2_one(F[0]);
   for (int c = 1; c < 6; c++) sfp2_zero(F[c]);
-  const uint64_t e = K_X_ABS;
+  int step = 0;
   for (int i = 62; i >= 0; i--) {
     if (i != 62) {
-      for (int c = 0; c < 6; c++) m6_sqr_lane(T[c], F, c);
+      for (int c = 0; c < 6; c++) m6_sqr_lane(&T[c], F, c);
       for (int c = 0; c < 6; c++) F[c] = T[c];
     }
     for (int pass = 0; pass < 2; pass++) {
       if (pass == 1 && !((e >> i) & 1)) break;
-      for (int j = 0; j < n; j++) { if (pass == 0) m6_dbl_line(line[j], pr[j]); else m6_add_line(line[j], pr[j]); }
       for (int j = 0; j < n; j++) {
-        for (int c = 0; c < 6; c++) m6_mul_line_lane(T[c], F, line[j], c);
+        for (int c = 0; c < 6; c++) m6_mul_line_lane(&T[c], F, lines[j][step], c);
         for (int c = 0; c < 6; c++) F[c] = T[c];
       }
+      step++;
     }
   }
   Fp12 f, g;

@@ -235,12 +235,12 @@ def test_sha256_and_hash_to_curve(L):
     assert o.raw == O.g2_serialize(O.hash_to_curve_g2(pk + b"aug", O.sig_dst(2, 1)))
 
 
-def test_sop2s_fused_unit(L):
-    """csrc/sfp.cuh: signed-limb sum of Fp2 products with ONE reduction per coefficient (operand sums, xi, conj, Fp scalar)."""
+def test_sop2f_fused_unit(L):
+    """csrc/sfp.cuh: signed-limb sum of Fp2 products with ONE reduction per coefficient (shifts, xi, negation, the
+    Fp-scalar mode, output aliasing)."""
     rnd = random.Random(21)
     XI = (1, 1)
     mul, add, sub = O.f2_mul, O.f2_add, O.f2_sub
-    conj = lambda x: (x[0], (-x[1]) % P)
     sc = lambda s, x: ((s * x[0]) % P, (s * x[1]) % P)
     for it in range(40):
         v = [(rnd.randrange(P), rnd.randrange(P)) for _ in range(6)]
@@ -250,11 +250,12 @@ def test_sop2s_fused_unit(L):
             v = [(0, 0), (P - 1, 0), (0, P - 1), (1, 0), (0, 1), (P - 1, 1)]
         a, b, c, d, e, f = v
         k = rnd.randrange(P)
-        out = buf(192)
-        L.emu_sop2s(b"".join(f2b(x) for x in v), be(k), out)
-        want = add(add(mul(a, b), mul(mul(XI, sub(sc(2, c), d)), add(e, f))), mul(conj(b), (k, 0)))
+        out = buf(288)
+        L.emu_sop2f(b"".join(f2b(x) for x in v), be(k), out)
+        want = sub(add(mul(a, b), mul(mul(XI, sc(2, c)), d)), mul(e, sc(4, f)))
         assert bf2(out.raw[:96]) == want
-        assert bf2(out.raw[96:]) == mul(want, want)
+        assert bf2(out.raw[96:192]) == mul(want, want)
+        assert bf2(out.raw[192:]) == sub(sc(k, a), sc(k, mul(XI, b)))
 
 
 def test_miller6_cooperative(L):
