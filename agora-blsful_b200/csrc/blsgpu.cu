@@ -34,6 +34,7 @@ thread_local std::string g_create_error;
   } while (0)
 
 constexpr int TPB = 128;
+constexpr size_t MSM_MIN_ITEMS = 4096;  // below this the per-item scaling is as fast as the bucket method's fixed costs
 constexpr size_t M6_CHUNK = 1024 * 120;  // items per pass of the Miller kernels (a multiple of 6 and of 120): 2.8 GB of lines, twice
 inline unsigned blocks_for(size_t n, int tpb = TPB) { return (unsigned)((n + tpb - 1) / tpb); }
 
@@ -220,20 +221,46 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
     if (ci >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_accum[(ci - 2) % nbuf], 0));
   }
   stage_mark(ctx, BLSGPU_STAGE_SCALE_SIG);
-  if (use_rlc) {
+  // S = sum r_i sig_i.  Large batches: bucket multi-scalar multiplication for the total only (the per-group sums the
+  // bisection needs are computed if the batch fails).  Small batches: per-item scaling right away.
+  const bool use_msm = use_rlc && n >= MSM_MIN_ITEMS;
+  SigJ* d_msm_root = nullptr;
+  if (use_msm) {
+    int c = 4;
+    while (c < 16 && ((size_t)1 << (c + 4)) <= n) c++;  // ~16 signatures per bucket
+    const int nwin = (64 + c - 1) / c;
+    const size_t nb = (size_t)1 << c, nbuckets = nb * nwin, nchunks = nbuckets / MSM_CHUNK;
+    uint64_t* d_r = ctx->arena.take<uint64_t>(n);
+    uint32_t* d_cnt = ctx->arena.take<uint32_t>(3 * nbuckets);
+    uint32_t *d_off = d_cnt + nbuckets, *d_cur = d_off + nbuckets;
+    uint32_t* d_sorted = ctx->arena.take<uint32_t>((size_t)nwin * n);
+    SigJ* d_B = ctx->arena.take<SigJ>(nbuckets);
+    std::vector<Level> lm = make_levels(nchunks);
+    SigJ* d_V = ctx->arena.take<SigJ>(levels_total(lm));
+    CK(cudaMemsetAsync(d_cnt, 0, nbuckets * sizeof(uint32_t), ctx->stream));
+    LAUNCH(k_msm_count, blocks_for(n), TPB, n, (const uint8_t*)d_status, (const Digest*)d_root, c, nwin, d_r, d_cnt);
+    LAUNCH(k_msm_scan, (unsigned)nwin, 1024, c, (const uint32_t*)d_cnt, d_off, d_cur);
+    LAUNCH(k_msm_scatter, blocks_for(n), TPB, n, (const uint64_t*)d_r, c, nwin, (const uint32_t*)d_off, d_cur, d_sorted);
+    LAUNCH((k_msm_bucket<SigA>), blocks_for(nbuckets), TPB, n, nbuckets, d_sig, c, (const uint32_t*)d_cnt, (const uint32_t*)d_off,
+           (const uint32_t*)d_sorted, d_B);
+    LAUNCH((k_msm_chunk<SigJ>), blocks_for(nchunks), TPB, nchunks, c, (const SigJ*)d_B, d_V);
+    for (size_t k = 0; k + 1 < lm.size(); k++)
+      LAUNCH((k_reduce_jac<SigJ>), blocks_for(lm[k + 1].cnt), TPB, lm[k].cnt, d_V + lm[k].off, lm[k + 1].cnt, d_V + lm[k + 1].off);
+    d_msm_root = d_V + lm.back().off;
+  } else if (use_rlc) {
     LAUNCH((k_scale_sig<SigA>), blocks_for(n), TPB, n, d_sig, d_status, d_root, d_Sitem);
     LAUNCH((k_group_sum<SigJ>), blocks_for(ng), TPB, n, (const SigJ*)d_Sitem, ng, d_S);
   }
   stage_mark(ctx, BLSGPU_STAGE_REDUCE);
   for (size_t k = 0; k + 1 < lv.size(); k++) {
     LAUNCH(k_reduce_fp12, blocks_for(lv[k + 1].cnt), TPB, lv[k].cnt, d_F + lv[k].off, lv[k + 1].cnt, d_F + lv[k + 1].off);
-    if (use_rlc)
+    if (use_rlc && !use_msm)
       LAUNCH((k_reduce_jac<SigJ>), blocks_for(lv[k + 1].cnt), TPB, lv[k].cnt, d_S + lv[k].off, lv[k + 1].cnt, d_S + lv[k + 1].off);
   }
   stage_mark(ctx, BLSGPU_STAGE_FINAL);
   if (!use_rlc) LAUNCH((k_reduce_aff<SigA>), 1, 32, (size_t)1, d_sig, (size_t)1, d_S);  // S = the single aggregate signature
   const Fp12* rootF = d_F + lv.back().off;
-  const SigJ* rootS = use_rlc ? d_S + lv.back().off : d_S;
+  const SigJ* rootS = use_msm ? d_msm_root : use_rlc ? d_S + lv.back().off : d_S;
   LAUNCH((k_probe<SigJ>), 1, 64, (size_t)1, (const uint32_t*)nullptr, rootF, rootS, d_ok);
   uint8_t ok = 0;
   CK(cudaMemcpyAsync(&ok, d_ok, 1, cudaMemcpyDeviceToHost, ctx->stream));
@@ -243,6 +270,13 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
     *agg_ok = ok;
     stage_mark(ctx, BLSGPU_STAGE_COUNT);
     return BLSGPU_OK;
+  }
+  if (!ok && use_msm) {
+    // the batch failed: now the bisection needs the per-group sums of r_i sig_i
+    LAUNCH((k_scale_sig<SigA>), blocks_for(n), TPB, n, d_sig, d_status, d_root, d_Sitem);
+    LAUNCH((k_group_sum<SigJ>), blocks_for(ng), TPB, n, (const SigJ*)d_Sitem, ng, d_S);
+    for (size_t k = 0; k + 1 < lv.size(); k++)
+      LAUNCH((k_reduce_jac<SigJ>), blocks_for(lv[k + 1].cnt), TPB, lv[k].cnt, d_S + lv[k].off, lv[k + 1].cnt, d_S + lv[k + 1].off);
   }
   if (!ok) {
     // walk down the 16-ary tree to the failing groups: children of node j at level k+1 are {j + m * cnt(k+1)} at level k
@@ -295,7 +329,8 @@ size_t pipeline_bytes(size_t n) {
   size_t total = levels_total(make_levels(std::max<size_t>(n, 1)));
   size_t gtotal = levels_total(make_levels((std::max<size_t>(n, 1) + M6_GROUP - 1) / M6_GROUP));
   return gtotal * (sizeof(Fp12) + sizeof(SigJ)) + n * (sizeof(SigJ) + sizeof(Fp12) + sizeof(SigJ)) +
-         2 * std::min(std::max<size_t>(n, 1), M6_CHUNK) * (sizeof(M6Arg) + M6_LINE_RECS * sizeof(SFp2) + 512) + total * sizeof(Digest) + (n + 64) * 8 + 16 * 256 + 4096;
+         2 * std::min(std::max<size_t>(n, 1), M6_CHUNK) * (sizeof(M6Arg) + M6_LINE_RECS * sizeof(SFp2) + 512) + total * sizeof(Digest) +
+         n * (8 + 4 * 16) + ((size_t)16 << 16) * (12 + 2 * sizeof(SigJ)) + (1 << 20) + (n + 64) * 8 + 16 * 256 + 4096;
 }
 
 // verify over decoded points: per-item pre-status, hash_to_curve of the framed message, pairing pipeline

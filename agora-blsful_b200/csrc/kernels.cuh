@@ -400,6 +400,134 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_scale_sig(size_t n, con
   out[i] = s;
 }
 
+// ---- S = sum_i r_i * sig_i as a bucket (Pippenger) multi-scalar multiplication ------------------------------------------
+// The per-item double-and-add (k_scale_sig: 64 doublings + ~32 additions per signature) is only needed when a batch FAILS
+// and the bisection wants per-group sums; the accept path needs the total only: with c-bit windows every signature costs
+// one mixed addition per window (4 at c = 16 instead of ~96 point operations).
+//   k_msm_count   r_i -> digits, histogram of every window (global atomics)
+//   k_msm_scan    exclusive prefix sums of the histograms (one block per window)
+//   k_msm_scatter item indices sorted by digit (counting sort; order inside a bucket is irrelevant to the sum)
+//   k_msm_bucket  one thread per (window, digit): B = sum of its signatures
+//   k_msm_chunk   one thread per 16 buckets: 2^(c w) * sum_j j B_j over the chunk (running sums), then a flat tree sum
+constexpr int MSM_CHUNK = 16;
+__global__ void __launch_bounds__(128) k_msm_count(size_t n, const uint8_t* __restrict__ pre, const Digest* __restrict__ root, int c, int nwin,
+                                                   uint64_t* __restrict__ r_out, uint32_t* __restrict__ counts) {
+  size_t i = BLS_TID();
+  if (i >= n) return;
+  uint64_t r = 0;
+  if (pre[i] == ST_OK) {
+    uint32_t k[2];
+    rlc_scalar(k, root, i);
+    r = (uint64_t)k[0] | ((uint64_t)k[1] << 32);
+  }
+  r_out[i] = r;
+  const uint32_t mask = (1u << c) - 1u;
+  for (int w = 0; w < nwin; w++) {
+    const uint32_t d = (uint32_t)(r >> (c * w)) & mask;
+    if (d) atomicAdd(&counts[((size_t)w << c) + d], 1u);
+  }
+}
+// counts -> exclusive offsets (per window); cursors zeroed.  One block of 1024 threads per window, nb = 2^c entries.
+__global__ void __launch_bounds__(1024) k_msm_scan(int c, const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
+                                                   uint32_t* __restrict__ cursor) {
+  __shared__ uint32_t part[1024];
+  const size_t nb = (size_t)1 << c;
+  const uint32_t* cnt = counts + (size_t)blockIdx.x * nb;
+  uint32_t* off = offsets + (size_t)blockIdx.x * nb;
+  uint32_t* cur = cursor + (size_t)blockIdx.x * nb;
+  const size_t per = (nb + 1023) / 1024;
+  const size_t lo = (size_t)threadIdx.x * per, hi = lo + per < nb ? lo + per : nb;
+  uint32_t sum = 0;
+  for (size_t j = lo; j < hi; j++) sum += cnt[j];
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
+    uint32_t v = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  uint32_t run = part[threadIdx.x] - sum;
+  for (size_t j = lo; j < hi; j++) {
+    off[j] = run;
+    cur[j] = 0;
+    run += cnt[j];
+  }
+}
+__global__ void __launch_bounds__(128) k_msm_scatter(size_t n, const uint64_t* __restrict__ r_in, int c, int nwin, const uint32_t* __restrict__ offsets,
+                                                     uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+  size_t i = BLS_TID();
+  if (i >= n) return;
+  const uint64_t r = r_in[i];
+  const uint32_t mask = (1u << c) - 1u;
+  for (int w = 0; w < nwin; w++) {
+    const uint32_t d = (uint32_t)(r >> (c * w)) & mask;
+    if (d) {
+      const size_t b = ((size_t)w << c) + d;
+      const uint32_t pos = offsets[b] + atomicAdd(&cursor[b], 1u);
+      sorted[(size_t)w * n + pos] = (uint32_t)i;
+    }
+  }
+}
+template <class SigA>
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_msm_bucket(size_t n, size_t nbuckets, const SigA* __restrict__ sig, int c,
+                                                    const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
+                                                    const uint32_t* __restrict__ sorted, typename PtInfo<SigA>::Jac* __restrict__ B) {
+  size_t b = BLS_TID();
+  if (b >= nbuckets) return;
+  typename PtInfo<SigA>::Jac acc;
+  jac_set_inf(acc);
+  const size_t w = b >> c;
+  const uint32_t cnt = counts[b], off = offsets[b];
+  const uint32_t* idx = sorted + w * n + off;
+  for (uint32_t t = 0; t < cnt; t++) {
+    SigA a = sig[idx[t]];
+    jac_add_mixed(acc, acc, a);
+  }
+  B[b] = acc;
+}
+template <class J>
+__device__ __forceinline__ void jac_mul_small(J& r, const J& p, uint32_t k) {
+  J acc;
+  jac_set_inf(acc);
+  for (int b = 31; b >= 0; b--) {
+    jac_dbl(acc, acc);
+    if ((k >> b) & 1u) jac_add(acc, acc, p);
+  }
+  r = acc;
+}
+template <class J>
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_msm_chunk(size_t nchunks, int c, const J* __restrict__ B, J* __restrict__ V) {
+  size_t t = BLS_TID();
+  if (t >= nchunks) return;
+  const size_t per_win = ((size_t)1 << c) / MSM_CHUNK;  // chunks per window
+  const size_t w = t / per_win, tc = t % per_win;
+  const size_t j0 = (w << c) + tc * MSM_CHUNK;             // first bucket of the chunk; its digit is tc * MSM_CHUNK
+  J run, ws;
+  jac_set_inf(run);
+  jac_set_inf(ws);
+  for (int j = MSM_CHUNK - 1; j >= 0; j--) {
+    J bj = B[j0 + j];
+    jac_add(run, run, bj);
+    jac_add(ws, ws, run);  // ws = sum_j (j + 1) B_{j0 + j}
+  }
+  // sum_j (digit_j) B = ws + (tc * MSM_CHUNK - 1) * run
+  const uint32_t base = (uint32_t)(tc * MSM_CHUNK);
+  J res;
+  if (base == 0) {
+    J nr;
+    jac_neg(nr, run);
+    jac_add(res, ws, nr);
+  } else {
+    J m;
+    jac_mul_small(m, run, base - 1u);
+    jac_add(res, ws, m);
+  }
+  if (!jac_is_inf(res))
+    for (size_t s = 0; s < w * (size_t)c; s++) jac_dbl(res, res);
+  V[t] = res;
+}
+
 // ---- 16-ary strided reduction trees: out[j] = op over in[j + m*n_out], m = 0..15 -------------------------------------
 __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_reduce_fp12(size_t n_in, const Fp12* __restrict__ in, size_t n_out, Fp12* __restrict__ out) {
   size_t j = BLS_TID();

@@ -168,6 +168,44 @@ def test_verify_batch_bisection_finds_exact_bad_set(eng, B, impl):
                                  sigs[i * sl:(i + 1) * sl].tobytes(), m)
 
 
+@pytest.mark.parametrize("impl", [2, 1])
+def test_verify_batch_large_batch_bucket_msm_and_chunks(eng, B, impl):
+    """Batches of >= 4096 items take the bucket multi-scalar multiplication for sum r_i sig_i; a failing batch falls back
+    to per-group sums for the bisection.  Also covers identity / undecodable items inside cooperative groups of six."""
+    rnd = random.Random(50 + impl)
+    n = 4500
+    k = np.frombuffer(b"".join(rnd.randrange(1, O.R).to_bytes(32, "big") for _ in range(n)), dtype=np.uint8)
+    msgs = [hashlib.sha256(b"big%d" % i).digest() for i in range(n)]
+    data, off = B.pack_messages(msgs)
+    pks, sigs = eng.testdata_sign(impl, 0, k, data, off)
+    assert eng.verify_batch_packed(impl, 0, pks, sigs, data, off).tolist() == [0] * n
+    sl, pl = B.sig_len(impl), B.pk_len(impl)
+    orig = sigs.copy()
+    sigs = sigs.copy()
+    pks = pks.copy()
+    bad = sorted(rnd.sample(range(n), 5))
+    for i in bad:
+        src = (i + 7) % n
+        sigs[i * sl:(i + 1) * sl] = orig[src * sl:(src + 1) * sl]
+    ident = [11, 4002]  # identity signature -> status 2, excluded from the batch equation
+    for i in ident:
+        sigs[i * sl:(i + 1) * sl] = np.frombuffer(bytes([0xC0]) + bytes(sl - 1), dtype=np.uint8)
+    junk = [12]  # undecodable public key -> status 4
+    for i in junk:
+        pks[i * pl:(i + 1) * pl] = np.frombuffer(bytes([0x80]) + bytes([0xFF]) * (pl - 1), dtype=np.uint8)
+    st = eng.verify_batch_packed(impl, 0, pks, sigs, data, off)
+    want = [0] * n
+    for i in bad:
+        want[i] = 1
+    for i in ident:
+        want[i] = 2
+    for i in junk:
+        want[i] = 4
+    assert st.tolist() == want
+    i = junk[0]
+    assert O.verify(impl, O.BASIC, O.MODERN, pks[i * pl:(i + 1) * pl].tobytes(), sigs[i * sl:(i + 1) * sl].tobytes(), msgs[i]) == 4
+
+
 def test_sum_points_golden_and_pairing_product(eng, B, cpp):
     sigs = [bytes.fromhex(s["sig"]) for s in cpp["signers"]]
     pks = [bytes.fromhex(s["pk"]) for s in cpp["signers"]]
