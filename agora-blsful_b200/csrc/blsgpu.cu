@@ -182,6 +182,7 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
     static bool attr_done = false;  // per template instance
     if (!attr_done) {
       CK(cudaFuncSetAttribute(k_m6_lines<PkA, SigA>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_LINES_SMEM));
+      CK(cudaFuncSetAttribute(k_m6_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_ACCUM_SMEM));
       attr_done = true;
     }
     // The line stream is 22.8 KB per item: the batch goes through in chunks with two line buffers.  Chunk c's lines are
@@ -191,10 +192,10 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
     const size_t chunk = std::min(n, M6_CHUNK);
     const int nbuf = n > M6_CHUNK ? 2 : 1;
     M6Arg* d_args[2];
-    SFp2* d_lines[2];
+    SLineRec* d_lines[2];
     for (int b = 0; b < nbuf; b++) {
       d_args[b] = ctx->arena.take<M6Arg>(chunk);
-      d_lines[b] = ctx->arena.take<SFp2>(chunk * M6_LINE_RECS);
+      d_lines[b] = ctx->arena.take<SLineRec>(chunk * M6_LINE_RECS);
     }
     CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->side[0], ctx->ev_fork, 0));
@@ -329,7 +330,7 @@ size_t pipeline_bytes(size_t n) {
   size_t total = levels_total(make_levels(std::max<size_t>(n, 1)));
   size_t gtotal = levels_total(make_levels((std::max<size_t>(n, 1) + M6_GROUP - 1) / M6_GROUP));
   return gtotal * (sizeof(Fp12) + sizeof(SigJ)) + n * (sizeof(SigJ) + sizeof(Fp12) + sizeof(SigJ)) +
-         2 * std::min(std::max<size_t>(n, 1), M6_CHUNK) * (sizeof(M6Arg) + M6_LINE_RECS * sizeof(SFp2) + 512) + total * sizeof(Digest) +
+         2 * std::min(std::max<size_t>(n, 1), M6_CHUNK) * (sizeof(M6Arg) + M6_LINE_RECS * sizeof(SLineRec) + 512) + total * sizeof(Digest) +
          n * (8 + 4 * 16) + ((size_t)16 << 16) * (12 + 2 * sizeof(SigJ)) + (1 << 20) + (n + 64) * 8 + 16 * 256 + 4096;
 }
 

@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_miller(size_t n, const 
 constexpr int M6_LINES_TPB = 128;
 constexpr int M6_LINES_SMEM = M6_NREG * M6_LINES_TPB * (int)sizeof(SFp2);  // 200,704 B: one block per SM
 constexpr int M6_ITEMS_PER_BLOCK = 120;                                   // k_m6_accum: 4 warps x 5 groups x 6 lanes
-constexpr int M6_ACCUM_SMEM = 4 * 60 * (int)sizeof(SFp2);
+constexpr int M6_ACCUM_SMEM = 4 * 60 * (int)sizeof(SAccRec);
 constexpr size_t M6_LINE_RECS = (size_t)M6_STEPS * 3;                     // records per item in the line stream
 
 __device__ __forceinline__ const G1Aff& m6_g1(const G1Aff* pk, const G2Aff* h, size_t i) { return pk[i]; }
@@ -301,12 +301,12 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_m6_prep(size_t n, size_
 
 template <class PkA, class HA>
 __global__ void __launch_bounds__(M6_LINES_TPB, 1) k_m6_lines(size_t n, size_t base, const M6Arg* __restrict__ args, const PkA* __restrict__ pk,
-                                                             const HA* __restrict__ h, const uint8_t* __restrict__ pre, SFp2* __restrict__ lines) {
+                                                             const HA* __restrict__ h, const uint8_t* __restrict__ pre, SLineRec* __restrict__ lines) {
   extern __shared__ __align__(16) uint8_t m6_smem[];
   size_t c = BLS_TID();
   if (c >= n || pre[base + c] != ST_OK) return;
   const G2Aff& q = m6_g2(pk, h, base + c);
-  SFp2* out = lines + c * M6_LINE_RECS;
+  SLineRec* out = lines + c * M6_LINE_RECS;
   SopSpaces cx = m6_spaces_line(reinterpret_cast<SFp2*>(m6_smem) + threadIdx.x, M6_LINES_TPB, args + c, out);
   {
     const G2Aff qv = q;
@@ -328,24 +328,26 @@ __global__ void __launch_bounds__(M6_LINES_TPB, 1) k_m6_lines(size_t n, size_t b
 #ifndef M6_ACC_BLOCKS
 #define M6_ACC_BLOCKS 2
 #endif
-__global__ void __launch_bounds__(128, M6_ACC_BLOCKS) k_m6_accum(size_t n, size_t base, const uint8_t* __restrict__ pre, const SFp2* __restrict__ lines,
+__global__ void __launch_bounds__(128, M6_ACC_BLOCKS) k_m6_accum(size_t n, size_t base, const uint8_t* __restrict__ pre, const SLineRec* __restrict__ lines,
                                                      Fp12* __restrict__ out) {
   extern __shared__ __align__(16) uint8_t m6_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane / 6, k = lane - 6 * g;
   const bool lane_on = g < 5;  // lanes 30, 31 only keep the warp's barriers company
-  SFp2* F = reinterpret_cast<SFp2*>(m6_smem) + warp * 60 + 6 * (lane_on ? g : 0);  // current value; F + 30: next
-  SFp2* G = F + 30;
+  SAccRec* F = reinterpret_cast<SAccRec*>(m6_smem) + warp * 60 + 6 * (lane_on ? g : 0);  // current value; F + 30: next
+  SAccRec* G = F + 30;
   const size_t group = ((size_t)blockIdx.x * 4 + warp) * 5 + g;  // within the chunk (base is a multiple of 6)
   const size_t item = group * 6 + k;
   const bool active = lane_on && item < n && pre[base + item] == ST_OK;
   const unsigned ball = __ballot_sync(0xffffffffu, active);
   const unsigned gmask = lane_on ? (ball >> (6 * g)) & 63u : 0u;
   if (lane_on) {
-    if (k == 0) sfp2_one(F[0]); else sfp2_zero(F[k]);
+    SFp2 init;
+    if (k == 0) sfp2_one(init); else sfp2_zero(init);
+    sacc_from_sfp2(F[k], init);
   }
   __syncwarp();
-  const SFp2* gl = lines + group * 6 * M6_LINE_RECS;  // the group's six line streams
+  const SLineRec* gl = lines + group * 6 * M6_LINE_RECS;  // the group's six line streams
   const uint64_t e = K_X_ABS;
   int step = 0;
 #pragma unroll 1
@@ -353,7 +355,7 @@ __global__ void __launch_bounds__(128, M6_ACC_BLOCKS) k_m6_accum(size_t n, size_
     if (i != 62) {
       if (lane_on) m6_sqr_lane(G + k, F, k);
       __syncwarp();
-      SFp2* t = F; F = G; G = t;
+      SAccRec* t = F; F = G; G = t;
     }
     const int nst = 1 + (int)((e >> i) & 1);
 #pragma unroll 1
@@ -366,14 +368,14 @@ __global__ void __launch_bounds__(128, M6_ACC_BLOCKS) k_m6_accum(size_t n, size_
           const int jn = j == 5 ? 0 : j + 1;
           const int sn = j == 5 ? step + 1 : step;
           if (k < 3 && sn < M6_STEPS) {
-            const SFp2* nx = gl + (size_t)jn * M6_LINE_RECS + 3 * sn + k;
+            const SLineRec* nx = gl + (size_t)jn * M6_LINE_RECS + 3 * sn + k;
             asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(nx) + 96));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(nx) + 128));
           }
         }
         if ((gmask >> j) & 1u) {  // uniform within the group; the barrier below is outside
           m6_mul_line_lane(G + k, F, gl + (size_t)j * M6_LINE_RECS + 3 * step, k);
-          SFp2* t = F; F = G; G = t;
+          SAccRec* t = F; F = G; G = t;
         }
         __syncwarp();
       }

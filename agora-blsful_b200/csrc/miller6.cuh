@@ -38,23 +38,10 @@ BLS_CONST SopTerm K_M6_MUL_LINE[3] = {
     {SOPX_FREL + 3, SOPX_JL + 2, 0, 0, SOP_XI_LT3, 0, 0, 0},
 };
 
-// F: the group's six coefficients (w^0..w^5).  *out = coefficient k of f^2   (out must not be one of F's records)
-BLS_HD SopSpaces m6_spaces_f(const SFp2* F, const SFp2* jl, int k) {
-  SopSpaces c;
-  c.reg = nullptr;
-  c.reg_stride = 1;
-  c.P = nullptr;
-  c.line = nullptr;
-  c.F = F;
-  c.jl = jl;
-  c.k = k;
-  return c;
-}
-BLS_HD void m6_sqr_lane(SFp2* out, const SFp2* F, int k) { sop2f(out, K_M6_SQR[k], 4, 0, m6_spaces_f(F, nullptr, k)); }
+// F: the group's six coefficients (w^0..w^5), expanded records.  *out = coefficient k of f^2   (out is not one of F's records)
+BLS_HD void m6_sqr_lane(SAccRec* out, const SAccRec* F, int k) { sopw(out, K_M6_SQR[k], 4, F, nullptr, k); }
 // *out = coefficient k of  f * (l0 + l2 w^2 + l3 w^3)   (line[0..2] = l0, l2, l3: the sparse shape of a Miller line)
-BLS_HD void m6_mul_line_lane(SFp2* out, const SFp2* F, const SFp2* line, int k) {
-  sop2f(out, K_M6_MUL_LINE, 3, 0, m6_spaces_f(F, line, k));
-}
+BLS_HD void m6_mul_line_lane(SAccRec* out, const SAccRec* F, const SLineRec* line, int k) { sopw(out, K_M6_MUL_LINE, 3, F, line, k); }
 
 // slot of coefficient k (of w^k) in the tower layout of fp12.cuh: w^0..w^5 = c0.c0, c1.c0, c0.c1, c1.c1, c0.c2, c1.c2
 BLS_HD Fp2* fp12_coeff(Fp12& f, int k) {
@@ -63,8 +50,10 @@ BLS_HD Fp2* fp12_coeff(Fp12& f, int k) {
 }
 
 // lane k's share of the epilogue: conjugate (x < 0), back to the unsigned form of the tower, reduced
-BLS_HD void m6_finish_lane(Fp2& out, const SFp2& fk, int k) {
-  SFp2 t = fk;
+BLS_HD void m6_finish_lane(Fp2& out, const SAccRec& fa, int k) {
+  SFp2 fk, t;
+  sfp2_from_sacc(fk, fa);
+  t = fk;
   if (k & 1) sfp2_neg(t, fk);
   Fp2 u;
   fp2_from_sfp2(u, t);
@@ -159,9 +148,10 @@ BLS_FN void m6_run(const M6Op* prog, int n, const SopSpaces& cx) {
 #pragma unroll 1
   for (int i = 0; i < n; i++) {
     const M6Op* op = prog + i;
-    SFp2* dst = sop_rec(cx, op->dst);
+    const bool to_line = op->dst >= SOPX_LINE;  // the line record takes the expanded form (sop results only)
+    SFp2* dst = to_line ? nullptr : sop_rec(cx, op->dst);
     if (op->kind == 0) {
-      sop2f(dst, op->t, op->nt, op->fp, cx);
+      sop2f(dst, to_line ? cx.line + (op->dst - SOPX_LINE) : nullptr, op->t, op->nt, op->fp, cx);
     } else {
       sfp2_lin(*dst, sop_rec(cx, op->xr), op->lx, op->lfl, op->yr == RNONE ? nullptr : sop_rec(cx, op->yr), op->ly,
                op->zr == RNONE ? nullptr : sop_rec(cx, op->zr), op->lz);
@@ -181,7 +171,7 @@ BLS_HD void m6_make_arg(M6Arg& a, const MillerG1& P) {
   sfp2_from_fp(a.pz, P.pz);
 }
 // the spaces of one pair's line programs: record file `reg` (stride in records), argument, and the line record to produce
-BLS_HD SopSpaces m6_spaces_line(SFp2* reg, int stride, const M6Arg* arg, SFp2* line) {
+BLS_HD SopSpaces m6_spaces_line(SFp2* reg, int stride, const M6Arg* arg, SLineRec* line) {
   SopSpaces c;
   c.reg = reg;
   c.reg_stride = stride;

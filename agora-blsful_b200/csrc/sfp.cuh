@@ -30,6 +30,25 @@ struct alignas(16) SFp2 {
 #endif
 };
 
+// "Expanded" records: the operand halves of the three Karatsuba products stored side by side, 16 words apiece, so that the
+// consumer's operand of ANY product is one run of four 128-bit loads and nothing else (no masks, sums or differences in
+// the consumer's loop).  The producer pays 28 additions and a few more stores once.
+//   SLineRec  (B operands only):  b0 | b1 | b0 + b1                 192 bytes   - the line records streamed through HBM
+//   SAccRec   (A and B operands): a0 | a1 | a0 + a1 | a0 - a1       256 bytes   - the accumulator coefficients
+// (xi * a has the halves a0 - a1, a0 + a1 and their sum 2 a0: every one is a stored run, the last with a shift.)
+struct alignas(16) SLineRec {
+  int32_t w[48];
+#if defined(BLS_TRACK)
+  double vb, lb;  // bounds of the value and of the limbs of b0 / b1 (the sum run has twice the limb bound)
+#endif
+};
+struct alignas(16) SAccRec {
+  int32_t w[64];
+#if defined(BLS_TRACK)
+  double vb, lb;
+#endif
+};
+
 #if defined(BLS_TRACK)
 #define STRK(r, v, l) \
   do {                \
@@ -65,20 +84,18 @@ struct SopSpaces {
   SFp2* reg;
   int reg_stride;  // in records: 1 = the thread's records are contiguous; blockDim.x = record-major shared memory
   const SFp2* P;
-  SFp2* line;
+  SLineRec* line;  // destination only
   const SFp2* F;
   const SFp2* jl;
   int k;
 };
 // record reference -> address (branch-free: the callers sit inside the software-pipelined loop)
 BLS_HD SFp2* sop_rec(const SopSpaces& c, uint32_t i) {
-  const int is_reg = i < SOPX_P, is_p = (i >= SOPX_P) & (i < SOPX_LINE), is_line = (i >= SOPX_LINE) & (i < SOPX_F),
-            is_jl = (i >= SOPX_JL) & (i < SOPX_FREL), is_rel = i >= SOPX_FREL;
+  const int is_reg = i < SOPX_P, is_p = (i >= SOPX_P) & (i < SOPX_LINE), is_jl = (i >= SOPX_JL) & (i < SOPX_FREL), is_rel = i >= SOPX_FREL;
   int jr = c.k - ((int)i - SOPX_FREL);
   jr += jr < 0 ? 6 : 0;
-  const int j = is_reg ? (int)i * c.reg_stride : is_p ? (int)i - SOPX_P : is_line ? (int)i - SOPX_LINE : is_jl ? (int)i - SOPX_JL
-              : is_rel ? jr : (int)i - SOPX_F;
-  SFp2* base = is_reg ? c.reg : is_p ? const_cast<SFp2*>(c.P) : is_line ? c.line : is_jl ? const_cast<SFp2*>(c.jl) : const_cast<SFp2*>(c.F);
+  const int j = is_reg ? (int)i * c.reg_stride : is_p ? (int)i - SOPX_P : is_jl ? (int)i - SOPX_JL : is_rel ? jr : (int)i - SOPX_F;
+  SFp2* base = is_reg ? c.reg : is_p ? const_cast<SFp2*>(c.P) : is_jl ? const_cast<SFp2*>(c.jl) : const_cast<SFp2*>(c.F);
   return base + j;
 }
 
@@ -197,7 +214,8 @@ BLS_HD int sop_term_xi(uint32_t fl, int lane_k) {
 }
 
 // dst may alias any operand: results are written after the last operand read.
-BLS_FN void sop2f(SFp2* dst, const SopTerm* t, int nt, int fp_mode, const SopSpaces& cx) {
+// dst_line: the result goes to that line record (expanded form) instead of *dst
+BLS_FN void sop2f(SFp2* dst, SLineRec* dst_line, const SopTerm* t, int nt, int fp_mode, const SopSpaces& cx) {
   const int lane_k = cx.k;
   uint64_t T[2 * NL];
   SopKeep keep;
@@ -281,6 +299,31 @@ BLS_FN void sop2f(SFp2* dst, const SopTerm* t, int nt, int fp_mode, const SopSpa
     k = k1;
     pass = p1;
   }
+  if (dst_line != nullptr) {
+    SopI4* q = reinterpret_cast<SopI4*>(dst_line->w);
+#pragma unroll
+    for (int h = 0; h < 3; h++) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        int32_t e[4];
+#pragma unroll
+        for (int z = 0; z < 4; z++) {
+          const int j = 4 * i + z;
+          e[z] = j >= NL ? 0 : h == 0 ? res[j] : h == 1 ? res[NL + j] : res[j] + res[NL + j];
+        }
+        SopI4 v;
+        v.x = e[0];
+        v.y = e[1];
+        v.z = e[2];
+        v.w = e[3];
+        q[4 * h + i] = v;
+      }
+    }
+#if defined(BLS_TRACK)
+    STRK(*dst_line, vsum / 2500.0 + 1.0, 134217728.0);
+#endif
+    return;
+  }
   SopI4* q = reinterpret_cast<SopI4*>(dst->w);
 #pragma unroll
   for (int i = 0; i < 7; i++) {
@@ -290,6 +333,146 @@ BLS_FN void sop2f(SFp2* dst, const SopTerm* t, int nt, int fp_mode, const SopSpa
     v.z = res[4 * i + 2];
     v.w = res[4 * i + 3];
     q[i] = v;
+  }
+#if defined(BLS_TRACK)
+  STRK(*dst, vsum / 2500.0 + 1.0, 134217728.0);
+#endif
+}
+
+// ---- sopw: the same unit over EXPANDED records (the accumulator kernel) -------------------------------------------------
+// A operands: accumulator coefficients (SAccRec), absolute (SOPX_F) or relative to the lane (SOPX_FREL); B operands:
+// accumulator coefficients or the incoming line (SOPX_JL, SLineRec).  Terms use sha and the xi flags only.
+// Per integer product the loop body is: 8 loads for the NEXT product, 196 IMAD.WIDE, 14 shifts.
+BLS_HD const int32_t* sopw_run_a(const SAccRec* F, int lane_k, uint32_t i, int pass, int xi) {
+  int jr = lane_k - ((int)i - SOPX_FREL);
+  jr += jr < 0 ? 6 : 0;
+  const int j = i >= SOPX_FREL ? jr : (int)i - SOPX_F;
+  const int run = xi ? (pass == 0 ? 3 : pass == 1 ? 2 : 0) : pass;
+  return F[j].w + 16 * run;
+}
+BLS_HD const int32_t* sopw_run_b(const SAccRec* F, const SLineRec* jl, uint32_t i, int pass) {
+  const int is_jl = (i >= SOPX_JL) & (i < SOPX_FREL);
+  const int32_t* base = is_jl ? jl[is_jl ? (int)i - SOPX_JL : 0].w : F[is_jl ? 0 : (int)i - SOPX_F].w;
+  return base + 16 * pass;
+}
+BLS_HD void sopw_fetch(SopI4* r, const int32_t* p) {
+  const SopI4* q = reinterpret_cast<const SopI4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; i++) r[i] = q[i];
+}
+BLS_HD void sopw_take(int32_t* x, const SopI4* r, int sh) {
+  int32_t t[16];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    t[4 * i] = r[i].x;
+    t[4 * i + 1] = r[i].y;
+    t[4 * i + 2] = r[i].z;
+    t[4 * i + 3] = r[i].w;
+  }
+#pragma unroll
+  for (int i = 0; i < NL; i++) x[i] = (int32_t)((uint32_t)t[i] << sh);
+}
+BLS_FN void sopw(SAccRec* dst, const SopTerm* t, int nt, const SAccRec* F, const SLineRec* jl, int lane_k) {
+  uint64_t T[2 * NL];
+  SopKeep keep;
+  int32_t res[2 * NL], x[NL], y[NL];
+  SopI4 ra[4], rb[4];
+#if defined(BLS_TRACK)
+  double col = 0, vsum = 0;
+  BLS_REQ(nt >= 1 && nt <= SOP_MAX_TERMS, "sopw term count");
+  for (int k = 0; k < nt; k++) {
+    const SopTerm m = t[k];
+    const double xi = sop_term_xi(m.fl, lane_k) ? 2.0 : 1.0;
+    int jr = lane_k - ((int)m.a - SOPX_FREL);
+    jr += jr < 0 ? 6 : 0;
+    const SAccRec& A = F[m.a >= SOPX_FREL ? jr : (int)m.a - SOPX_F];
+    const bool bj = m.b >= SOPX_JL && m.b < SOPX_FREL;
+    const double lbb = bj ? jl[m.b - SOPX_JL].lb : F[m.b - SOPX_F].lb, vbb = bj ? jl[m.b - SOPX_JL].vb : F[m.b - SOPX_F].vb;
+    const double la = A.lb * (double)(1 << m.sha) * xi;
+    BLS_REQ(la < 1073741824.0 && lbb < 1073741824.0 && m.sha < 4 && m.shb == 0 && !(m.fl & SOP_NEG), "sopw operand");
+    col += 14.0 * 2.0 * la * lbb;
+    vsum += 2.0 * A.vb * (double)(1 << m.sha) * xi * vbb;
+  }
+  {
+    const double lim = 9223372036854775808.0 - 15.0 * 72057594037927936.0;
+    BLS_REQ(col < lim, "sopw column overflow");
+    BLS_REQ(vsum / 2500.0 + 1.0 < 16.0, "sopw result value bound");
+  }
+#endif
+#pragma unroll
+  for (int i = 0; i < 2 * NL; i++) T[i] = 0;
+  {
+    const SopTerm m = t[0];
+    const int xi = sop_term_xi(m.fl, lane_k);
+    sopw_fetch(ra, sopw_run_a(F, lane_k, m.a, 0, xi));
+    sopw_fetch(rb, sopw_run_b(F, jl, m.b, 0));
+    sopw_take(x, ra, m.sha);
+    sopw_take(y, rb, 0);
+  }
+  int pass = 0, k = 0;
+  const int nsteps = 3 * nt;
+#pragma unroll 1
+  for (int s = 0; s < nsteps; s++) {
+    const int wrap = (k + 1 == nt);
+    const int k1 = wrap ? 0 : k + 1, p1 = pass + wrap;
+    const int pn = p1 > 2 ? 2 : p1;  // after the last step: a harmless refetch
+    const SopTerm m = t[k1];
+    const int xi = sop_term_xi(m.fl, lane_k);
+    sopw_fetch(ra, sopw_run_a(F, lane_k, m.a, pn, xi));
+    sopw_fetch(rb, sopw_run_b(F, jl, m.b, pn));
+    sop_acc(T, x, y);
+    sopw_take(x, ra, m.sha + (xi & (pn == 2)));
+    sopw_take(y, rb, 0);
+    if (wrap) {  // a product sum is complete
+      if (pass == 0) {
+#pragma unroll
+        for (int i = 0; i < NL; i++) {
+          sop_keep_st(keep, i, T[2 * i], T[2 * i + 1]);
+          T[2 * i] = T[2 * i + 1] = 0;
+        }
+      } else {
+        // pass 1: U = P0 - P1, keep <- P0 + P1 ;  pass 2: U = P2 - keep
+#pragma unroll
+        for (int i = 0; i < NL; i++) {
+          uint64_t u0, u1;
+          sop_keep_ld(keep, i, u0, u1);
+          const uint64_t v0 = T[2 * i], v1 = T[2 * i + 1];
+          if (pass == 1) sop_keep_st(keep, i, u0 + v0, u1 + v1);
+          T[2 * i] = pass == 1 ? u0 - v0 : v0 - u0;
+          T[2 * i + 1] = pass == 1 ? u1 - v1 : v1 - u1;
+        }
+        T[2 * NL - 1] = 0;
+        int32_t c[NL];
+        sop_redc(c, T);
+#pragma unroll
+        for (int i = 0; i < NL; i++) {
+          if (pass == 1) res[i] = c[i]; else res[NL + i] = c[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 2 * NL; i++) T[i] = 0;
+      }
+    }
+    k = k1;
+    pass = p1;
+  }
+  SopI4* q = reinterpret_cast<SopI4*>(dst->w);
+#pragma unroll
+  for (int h = 0; h < 4; h++) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int32_t e[4];
+#pragma unroll
+      for (int z = 0; z < 4; z++) {
+        const int j = 4 * i + z;
+        e[z] = j >= NL ? 0 : h == 0 ? res[j] : h == 1 ? res[NL + j] : h == 2 ? res[j] + res[NL + j] : res[j] - res[NL + j];
+      }
+      SopI4 v;
+      v.x = e[0];
+      v.y = e[1];
+      v.z = e[2];
+      v.w = e[3];
+      q[4 * h + i] = v;
+    }
   }
 #if defined(BLS_TRACK)
   STRK(*dst, vsum / 2500.0 + 1.0, 134217728.0);
@@ -407,6 +590,26 @@ BLS_HD void sfp2_one(SFp2& r) {
   Fp2 o;
   fone(o);
   sfp2_from_fp2(r, o);
+}
+// expanded accumulator record from a compact one (initial values) and back (the halves are its first two runs)
+BLS_HD void sacc_from_sfp2(SAccRec& r, const SFp2& a) {
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const int32_t a0 = i < NL ? a.w[i] : 0, a1 = i < NL ? a.w[NL + i] : 0;
+    r.w[i] = a0;
+    r.w[16 + i] = a1;
+    r.w[32 + i] = a0 + a1;
+    r.w[48 + i] = a0 - a1;
+  }
+  STRK(r, a.vb, a.lb);
+}
+BLS_HD void sfp2_from_sacc(SFp2& r, const SAccRec& a) {
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+    r.w[i] = a.w[i];
+    r.w[NL + i] = a.w[16 + i];
+  }
+  STRK(r, a.vb, a.lb);
 }
 BLS_HD void sfp2_neg(SFp2& r, const SFp2& a) {
 #pragma unroll

@@ -154,23 +154,23 @@ void emu_sop2f(const uint8_t* in, const uint8_t* k48, uint8_t* out) {
   for (int i = 0; i < 6; i++) {  // unsigned form -> balanced S-form through one multiplication by 1
     fp2_in(v[i], in + 96 * i); fred(v[i], v[i]); sfp2_from_fp2(s[i], v[i]);
     const SopTerm t = {(uint8_t)i, 7, 0, 0, 0, 0, 0, 0};
-    sop2f(&s[i], &t, 1, 0, cx);
+    sop2f(&s[i], nullptr, &t, 1, 0, cx);
   }
   Fp kk; fp_in(kk, k48); sfp2_from_fp(s[6], kk);
   const SopTerm t3[3] = {{0, 1, 0, 0, 0, 0, 0, 0}, {2, 3, 1, 0, SOP_XI, 0, 0, 0}, {4, 5, 0, 2, SOP_NEG, 0, 0, 0}};
-  sop2f(&s[8], t3, 3, 0, cx);
+  sop2f(&s[8], nullptr, t3, 3, 0, cx);
   Fp2 o; fp2_from_sfp2(o, s[8]); fp2_out(out, o);
   const SopTerm sq = {8, 8, 0, 0, 0, 0, 0, 0};
-  sop2f(&s[8], &sq, 1, 0, cx);
+  sop2f(&s[8], nullptr, &sq, 1, 0, cx);
   fp2_from_sfp2(o, s[8]); fp2_out(out + 96, o);
   const SopTerm t2[2] = {{0, 6, 0, 0, 0, 0, 0, 0}, {1, 6, 0, 0, SOP_XI | SOP_NEG, 0, 0, 0}};
-  sop2f(&s[9], t2, 2, 1, cx);
+  sop2f(&s[9], nullptr, t2, 2, 1, cx);
   fp2_from_sfp2(o, s[9]); fp2_out(out + 192, o);
 }
 // cooperative Miller loop of miller6.cuh, lanes emulated one after the other: f = prod_j ML(k_j * P_j, Q_j), j < n <= 6.
 // Mirrors the two device kernels: every pair's 68 line records first (k_m6_lines), then the shared accumulator (k_m6_accum).
 int emu_miller6(int n, const uint8_t* p48, const uint8_t* q96, const uint32_t* k, int nl, uint8_t* ml_out, uint8_t* fe_out) {
-  static SFp2 lines[6][M6_STEPS][3];
+  static SLineRec lines[6][M6_STEPS][3];
   const uint64_t e = K_X_ABS;
   for (int j = 0; j < n; j++) {
     G1Aff p; G2Aff q;
@@ -188,9 +188,8 @@ int emu_miller6(int n, const uint8_t* p48, const uint8_t* q96, const uint32_t* k
     }
     if (step != M6_STEPS) return -2;
   }
-  SFp2 F[6], T[6];
-  sfp2_one(F[0]);
-  for (int c = 1; c < 6; c++) sfp2_zero(F[c]);
+  SAccRec F[6], T[6];
+  { SFp2 o, z; sfp2_one(o); sfp2_zero(z); sacc_from_sfp2(F[0], o); for (int c = 1; c < 6; c++) sacc_from_sfp2(F[c], z); }
   int step = 0;
   for (int i = 62; i >= 0; i--) {
     if (i != 62) {
