@@ -208,7 +208,7 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
       k_m6_prep<PkA, SigA><<<blocks_for(cn), TPB, 0, ctx->side[0]>>>(cn, base, d_pk, d_h, (const uint8_t*)d_status, (const Digest*)d_root,
                                                                       use_rlc ? 1 : 0, d_args[b]);
       CKR(check_launch(ctx, "k_m6_prep"));
-      k_m6_lines<PkA, SigA><<<blocks_for(cn, M6_LINES_TPB), M6_LINES_TPB, M6_LINES_SMEM, ctx->side[0]>>>(
+      k_m6_lines<PkA, SigA><<<blocks_for(cn, M6_LINES_PAIRS), M6_LINES_TPB, M6_LINES_SMEM, ctx->side[0]>>>(
           cn, base, d_args[b], d_pk, d_h, d_status, d_lines[b]);
       CKR(check_launch(ctx, "k_m6_lines"));
       CK(cudaEventRecord(ctx->ev_lines[b], ctx->side[0]));

@@ -259,12 +259,13 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_miller(size_t n, const 
 // ---- cooperative Miller loop (miller6.cuh): groups of 6 consecutive items, F_g = prod_{i in g} ML(r_i * pk_i, H_i) -------
 // Three kernels, so that each keeps its working set on chip:
 //   k_m6_prep   one thread per item: the RLC scalar and r_i * pk_i, stored as the three Fp scalars the lines need (336 B)
-//   k_m6_lines  one thread per item: the 68 line evaluations of the pair, record file in SHARED memory (14 records per
-//               thread, record-major: conflict-free 128-bit accesses), lines streamed to HBM (22.8 KB per item)
+//   k_m6_lines  two lanes per item: the 68 line evaluations of the pair, record file in SHARED memory (14 records per
+//               pair, record-major: conflict-free 128-bit accesses), lines streamed to HBM (39 KB per item)
 //   k_m6_accum  six lanes per group: the shared Fp12 accumulator, one coefficient per lane, double-buffered in shared
 //               memory; the lines come back from HBM one step ahead of their use (sop2f's prefetch)
 constexpr int M6_LINES_TPB = 128;
-constexpr int M6_LINES_SMEM = M6_NREG * M6_LINES_TPB * (int)sizeof(SFp2);  // 200,704 B: one block per SM
+constexpr int M6_LINES_PAIRS = M6_LINES_TPB / 2;
+constexpr int M6_LINES_SMEM = M6_NREG * M6_LINES_PAIRS * (int)sizeof(SFp2);  // 100,352 B: two blocks per SM
 constexpr int M6_ITEMS_PER_BLOCK = 120;                                   // k_m6_accum: 4 warps x 5 groups x 6 lanes
 constexpr int M6_ACCUM_SMEM = 4 * 60 * (int)sizeof(SAccRec);
 constexpr size_t M6_LINE_RECS = (size_t)M6_STEPS * 3;                     // records per item in the line stream
@@ -299,34 +300,59 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_m6_prep(size_t n, size_
   args[c] = a;
 }
 
+// Two lanes per pair: lane h computes coefficient h of every program step (sop1), both read the pair's 14 records in
+// shared memory (record-major, 112-byte stride between pairs: conflict-free; the two lanes of a pair read the same words).
+// 64 pairs per 128-thread block, 100,352 B of shared memory: two blocks per SM, two warps per scheduler.
 template <class PkA, class HA>
-__global__ void __launch_bounds__(M6_LINES_TPB, 1) k_m6_lines(size_t n, size_t base, const M6Arg* __restrict__ args, const PkA* __restrict__ pk,
+__global__ void __launch_bounds__(M6_LINES_TPB, 2) k_m6_lines(size_t n, size_t base, const M6Arg* __restrict__ args, const PkA* __restrict__ pk,
                                                              const HA* __restrict__ h, const uint8_t* __restrict__ pre, SLineRec* __restrict__ lines) {
   extern __shared__ __align__(16) uint8_t m6_smem[];
-  size_t c = BLS_TID();
-  if (c >= n || pre[base + c] != ST_OK) return;
-  const G2Aff& q = m6_g2(pk, h, base + c);
-  SLineRec* out = lines + c * M6_LINE_RECS;
-  SopSpaces cx = m6_spaces_line(reinterpret_cast<SFp2*>(m6_smem) + threadIdx.x, M6_LINES_TPB, args + c, out);
-  {
+  const int hh = threadIdx.x & 1, pib = threadIdx.x >> 1;
+  const size_t c = (size_t)blockIdx.x * M6_LINES_PAIRS + pib;
+  const bool active = c < n && pre[base + (c < n ? c : 0)] == ST_OK;
+  const size_t cc = active ? c : 0;
+  const G2Aff& q = m6_g2(pk, h, base + cc);
+  SopSpaces cx = m6_spaces_line(reinterpret_cast<SFp2*>(m6_smem) + pib, M6_LINES_PAIRS, args + cc, lines + cc * M6_LINE_RECS);
+  if (active && hh == 0) {
     const G2Aff qv = q;
     m6_init_point(cx, qv);
   }
+  __syncwarp();
   const uint64_t e = K_X_ABS;
 #pragma unroll 1
   for (int i = 62; i >= 0; i--) {
-    m6_dbl_line(cx);
-    cx.line += 3;
-    if ((e >> i) & 1) {
-      const G2Aff qv = q;
-      m6_add_line(cx, qv);
+#pragma unroll 1
+    for (int pass = 0; pass < 1 + (int)((e >> i) & 1); pass++) {
+      if (pass == 1) {
+        if (active && hh == 0) {
+          const G2Aff qv = q;
+          m6_add_setup(cx, qv);
+        }
+        __syncwarp();
+      }
+      const M6Op* prog = pass == 0 ? K_M6_DBL : K_M6_ADD;
+      const int nops = pass == 0 ? K_M6_DBL_N : K_M6_ADD_N;
+#pragma unroll 1
+      for (int o = 0; o < nops; o++) {
+        const M6Op* op = prog + o;
+        int32_t res[NL], other[NL];
+        double vb = 0;
+        if (active) vb = m6_op_compute(res, op, cx, hh);
+        if (op->dst >= SOPX_LINE) {  // the sum run of a line record needs the partner's coefficient (uniform branch)
+#pragma unroll
+          for (int j = 0; j < NL; j++) other[j] = __shfl_xor_sync(0xffffffffu, res[j], 1);
+        }
+        __syncwarp();  // every lane has read its operands: results may now overwrite them
+        if (active) m6_op_store(op, cx, hh, res, other, vb);
+        __syncwarp();
+      }
       cx.line += 3;
     }
   }
 }
 
 #ifndef M6_ACC_BLOCKS
-#define M6_ACC_BLOCKS 2
+#define M6_ACC_BLOCKS 3
 #endif
 __global__ void __launch_bounds__(128, M6_ACC_BLOCKS) k_m6_accum(size_t n, size_t base, const uint8_t* __restrict__ pre, const SLineRec* __restrict__ lines,
                                                      Fp12* __restrict__ out) {

@@ -159,6 +159,18 @@ BLS_FN void m6_run(const M6Op* prog, int n, const SopSpaces& cx) {
   }
 }
 
+// Two lanes per pair (lane h computes coefficient h of every result): one program step in two halves, so that the caller
+// can put its barrier between "every operand has been read" and "the result is written" (results may alias operands).
+BLS_HD double m6_op_compute(int32_t* res, const M6Op* op, const SopSpaces& cx, int h) {
+  if (op->kind == 0) return sop1_compute(res, op->t, op->nt, op->fp, cx, h);
+  return sfp2_lin_half(res, sop_rec(cx, op->xr), op->lx, op->lfl, op->yr == RNONE ? nullptr : sop_rec(cx, op->yr), op->ly,
+                       op->zr == RNONE ? nullptr : sop_rec(cx, op->zr), op->lz, h);
+}
+BLS_HD void m6_op_store(const M6Op* op, const SopSpaces& cx, int h, const int32_t* res, const int32_t* other, double vb) {
+  if (op->dst >= SOPX_LINE) sop1_store_line(cx.line + (op->dst - SOPX_LINE), res, other, h, vb);
+  else sop1_store_rec(sop_rec(cx, op->dst), res, h, vb);
+}
+
 // the prepared G1 argument of one pair: px, -py, pz as Fp scalars in the c0 halves of three records (HBM, read-only)
 struct M6Arg {
   SFp2 px, npy, pz;
@@ -189,11 +201,14 @@ BLS_HD void m6_init_point(const SopSpaces& cx, const G2Aff& q) {
   sfp2_one(*sop_rec(cx, RZ));
 }
 BLS_HD void m6_dbl_line(const SopSpaces& cx) { m6_run(K_M6_DBL, K_M6_DBL_N, cx); }
-BLS_HD void m6_add_line(const SopSpaces& cx, const G2Aff& q) {
+BLS_HD void m6_add_setup(const SopSpaces& cx, const G2Aff& q) {
   SFp2* nqx = sop_rec(cx, RNQX);
   sfp2_from_fp2(*nqx, q.x);
   sfp2_neg(*nqx, *nqx);
   sfp2_from_fp2(*sop_rec(cx, RQY), q.y);
+}
+BLS_HD void m6_add_line(const SopSpaces& cx, const G2Aff& q) {
+  m6_add_setup(cx, q);
   m6_run(K_M6_ADD, K_M6_ADD_N, cx);
 }
 constexpr int M6_STEPS = 68;  // 63 doublings + 5 additions: line records per pair

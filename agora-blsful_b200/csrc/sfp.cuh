@@ -102,6 +102,17 @@ BLS_HD SFp2* sop_rec(const SopSpaces& c, uint32_t i) {
 struct alignas(16) SopI4 {
   int32_t x, y, z, w;
 };
+#if !defined(__CUDACC__)
+struct alignas(8) int2 {
+  int32_t x, y;
+};
+static inline int2 make_int2(int32_t a, int32_t b) {
+  int2 r;
+  r.x = a;
+  r.y = b;
+  return r;
+}
+#endif
 BLS_HD void sop_ld28(int32_t* t, const SFp2* p) {
   const SopI4* q = reinterpret_cast<const SopI4*>(p->w);  // 128-bit loads: the records are 16-byte aligned
 #pragma unroll
@@ -337,6 +348,168 @@ BLS_FN void sop2f(SFp2* dst, SLineRec* dst_line, const SopTerm* t, int nt, int f
 #if defined(BLS_TRACK)
   STRK(*dst, vsum / 2500.0 + 1.0, 134217728.0);
 #endif
+}
+
+// ---- sop1: ONE coefficient per lane (the lines kernel: two lanes per pair share one record file) -----------------------
+// Lane h (0: real, 1: imaginary) computes its coefficient of sum_t A_t B_t with two integer products per term,
+//   h = 0:  a0 b0 + (-a1) b1        h = 1:  a0 b1 + a1 b0        (fp_mode: a_h b0, one product per term)
+// and ONE reduction; nothing is exchanged between the two lanes and nothing waits in local memory (no Karatsuba: four
+// products per term instead of three, but the two lanes of a pair need 7 records of shared memory each instead of 14,
+// which is what lets the lines kernel keep two warps per scheduler busy).  Same software pipeline as sop2f.
+BLS_HD SopPrep sop1_prep_a(int sel, int xi, int neg, int sh) {  // sel 0: A'0 = a0 - [xi] a1 ; sel 1: A'1 = [xi] a0 + a1
+  SopPrep p;
+  p.m0 = -((sel ^ 1) | xi);
+  p.m1 = -(sel | xi);
+  p.n1 = -(sel ^ 1);
+  p.ng = -neg;
+  p.sh = sh;
+  return p;
+}
+BLS_HD SopPrep sop1_prep_b(int idx, int sh) {
+  SopPrep p;
+  p.m0 = -(idx ^ 1);
+  p.m1 = -idx;
+  p.n1 = 0;
+  p.ng = 0;
+  p.sh = sh;
+  return p;
+}
+// res[14] = lane h's coefficient (balanced limbs).  Returns the value bound of the result under BLS_TRACK (else 0).
+BLS_FN double sop1_compute(int32_t* res, const SopTerm* t, int nt, int fp_mode, const SopSpaces& cx, int h) {
+  const int lane_k = cx.k;
+  uint64_t T[2 * NL];
+  int32_t x[NL], y[NL];
+  SopI4 ra[7], rb[7];
+  double vout = 0;
+#if defined(BLS_TRACK)
+  double col = 0, vsum = 0;
+  BLS_REQ(nt >= 1 && nt <= SOP_MAX_TERMS, "sop1 term count");
+  for (int k = 0; k < nt; k++) {
+    const SopTerm m = t[k];
+    const SFp2 *pa = sop_rec(cx, m.a), *pb = sop_rec(cx, m.b);
+    const double xi = sop_term_xi(m.fl, lane_k) ? 2.0 : 1.0;
+    const double la = pa->lb * (double)(1 << m.sha) * xi, lb = pb->lb * (double)(1 << m.shb);
+    BLS_REQ(la < 1073741824.0 && lb < 1073741824.0 && m.sha < 4 && m.shb < 4, "sop1 operand limb overflow");
+    col += 14.0 * 2.0 * la * lb;
+    vsum += 2.0 * pa->vb * (double)(1 << m.sha) * xi * pb->vb * (double)(1 << m.shb);
+  }
+  {
+    const double lim = 9223372036854775808.0 - 15.0 * 72057594037927936.0;
+    BLS_REQ(col < lim, "sop1 column overflow");
+    BLS_REQ(vsum / 2500.0 + 1.0 < 16.0, "sop1 result value bound");
+  }
+  vout = vsum / 2500.0 + 1.0;
+#endif
+#pragma unroll
+  for (int i = 0; i < 2 * NL; i++) T[i] = 0;
+  const int per = fp_mode ? 1 : 2;
+  {
+    const SopTerm m = t[0];
+    sop_fetch(ra, sop_rec(cx, m.a));
+    sop_fetch(rb, sop_rec(cx, m.b));
+    sop_prep_apply(x, ra, sop1_prep_a(fp_mode ? h : 0, sop_term_xi(m.fl, lane_k), (m.fl & SOP_NEG) != 0, m.sha));
+    sop_prep_apply(y, rb, sop1_prep_b(fp_mode ? 0 : h, m.shb));
+  }
+  int k = 0, q = 0;
+  const int nsteps = per * nt;
+#pragma unroll 1
+  for (int s = 0; s < nsteps; s++) {
+    const int qw = (q + 1 == per);
+    const int q1 = qw ? 0 : q + 1;
+    const int k1 = qw ? (k + 1 == nt ? 0 : k + 1) : k;  // after the last step: a harmless refetch of term 0
+    const SopTerm m = t[k1];
+    sop_fetch(ra, sop_rec(cx, m.a));
+    sop_fetch(rb, sop_rec(cx, m.b));
+    sop_acc(T, x, y);
+    const int sel = fp_mode ? h : q1;
+    const int neg = (int)((m.fl & SOP_NEG) != 0) ^ (fp_mode ? 0 : (q1 & (h ^ 1)));
+    sop_prep_apply(x, ra, sop1_prep_a(sel, sop_term_xi(m.fl, lane_k), neg, m.sha));
+    sop_prep_apply(y, rb, sop1_prep_b(fp_mode ? 0 : (q1 ^ h), m.shb));
+    k = k1;
+    q = q1;
+  }
+  T[2 * NL - 1] = 0;
+  sop_redc(res, T);
+  return vout;
+}
+// lane h's half of a compact record (64-bit stores: the imaginary half starts at byte 56)
+BLS_HD void sop1_store_rec(SFp2* dst, const int32_t* res, int h, double vb) {
+  int2* q = reinterpret_cast<int2*>(dst->w + NL * h);
+#pragma unroll
+  for (int i = 0; i < 7; i++) q[i] = make_int2(res[2 * i], res[2 * i + 1]);
+  (void)vb;
+  STRK(*dst, vb, 134217728.0);
+}
+// lane h's run of an expanded line record; lane 0 also writes the sum run (`other` = the partner lane's coefficient)
+BLS_HD void sop1_store_line(SLineRec* dst, const int32_t* res, const int32_t* other, int h, double vb) {
+  SopI4* q = reinterpret_cast<SopI4*>(dst->w);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    int32_t e[4], f[4];
+#pragma unroll
+    for (int z = 0; z < 4; z++) {
+      const int j = 4 * i + z;
+      e[z] = j >= NL ? 0 : res[j];
+      f[z] = j >= NL ? 0 : res[j] + other[j];
+    }
+    SopI4 v, w;
+    v.x = e[0]; v.y = e[1]; v.z = e[2]; v.w = e[3];
+    w.x = f[0]; w.y = f[1]; w.z = f[2]; w.w = f[3];
+    q[4 * h + i] = v;
+    if (h == 0) q[8 + i] = w;
+  }
+  (void)vb;
+  STRK(*dst, vb, 134217728.0);
+}
+// lane h's half of  sx * [xi] x + sy * y + sz * z  (y, z optional), limbs renormalised
+BLS_FN double sfp2_lin_half(int32_t* res, const SFp2* x, int32_t sx, uint32_t flx, const SFp2* y, int32_t sy, const SFp2* z, int32_t sz, int h) {
+  int64_t v[NL];
+  double vb = 0;
+  {
+    int32_t t[2 * NL];
+    sop_ld28(t, x);
+#pragma unroll
+    for (int i = 0; i < NL; i++) {
+      const int32_t plain = t[NL * h + i];
+      const int32_t mixed = h ? t[i] + t[NL + i] : t[i] - t[NL + i];  // limbs < 2^30 (checked): no overflow
+      v[i] = (int64_t)sx * (int64_t)((flx & SOP_XI) ? mixed : plain);
+    }
+#if defined(BLS_TRACK)
+    vb = (sx < 0 ? -(double)sx : (double)sx) * x->vb * ((flx & SOP_XI) ? 2.0 : 1.0);
+    BLS_REQ(x->lb < 1073741824.0, "sfp2_lin_half limb");
+#endif
+  }
+  if (y != nullptr) {
+    int32_t t[2 * NL];
+    sop_ld28(t, y);
+#pragma unroll
+    for (int i = 0; i < NL; i++) v[i] += (int64_t)sy * (int64_t)t[NL * h + i];
+#if defined(BLS_TRACK)
+    vb += (sy < 0 ? -(double)sy : (double)sy) * y->vb;
+#endif
+  }
+  if (z != nullptr) {
+    int32_t t[2 * NL];
+    sop_ld28(t, z);
+#pragma unroll
+    for (int i = 0; i < NL; i++) v[i] += (int64_t)sz * (int64_t)t[NL * h + i];
+#if defined(BLS_TRACK)
+    vb += (sz < 0 ? -(double)sz : (double)sz) * z->vb;
+#endif
+  }
+  int64_t c = 0;
+#pragma unroll
+  for (int j = 0; j < NL - 1; j++) {
+    c += v[j];
+    const int64_t u = c + (1 << 27);
+    res[j] = (int32_t)((uint32_t)u & M28) - (1 << 27);
+    c = u >> 28;
+  }
+  res[NL - 1] = (int32_t)(c + v[NL - 1]);
+#if defined(BLS_TRACK)
+  BLS_REQ(vb < 1000.0, "sfp2_lin_half value bound");
+#endif
+  return vb;
 }
 
 // ---- sopw: the same unit over EXPANDED records (the accumulator kernel) -------------------------------------------------

@@ -169,7 +169,7 @@ void emu_sop2f(const uint8_t* in, const uint8_t* k48, uint8_t* out) {
 }
 // cooperative Miller loop of miller6.cuh, lanes emulated one after the other: f = prod_j ML(k_j * P_j, Q_j), j < n <= 6.
 // Mirrors the two device kernels: every pair's 68 line records first (k_m6_lines), then the shared accumulator (k_m6_accum).
-int emu_miller6(int n, const uint8_t* p48, const uint8_t* q96, const uint32_t* k, int nl, uint8_t* ml_out, uint8_t* fe_out) {
+int emu_miller6(int n, const uint8_t* p48, const uint8_t* q96, const uint32_t* k, int nl, int two_lane, uint8_t* ml_out, uint8_t* fe_out) {
   static SLineRec lines[6][M6_STEPS][3];
   const uint64_t e = K_X_ABS;
   for (int j = 0; j < n; j++) {
@@ -183,8 +183,23 @@ int emu_miller6(int n, const uint8_t* p48, const uint8_t* q96, const uint32_t* k
     m6_init_point(cx, q);
     int step = 0;
     for (int i = 62; i >= 0; i--) {
-      cx.line = lines[j][step++]; m6_dbl_line(cx);
-      if ((e >> i) & 1) { cx.line = lines[j][step++]; m6_add_line(cx, q); }
+      for (int pass = 0; pass < 2; pass++) {
+        if (pass == 1 && !((e >> i) & 1)) break;
+        cx.line = lines[j][step++];
+        if (pass == 1) m6_add_setup(cx, q);
+        const M6Op* prog = pass == 0 ? K_M6_DBL : K_M6_ADD;
+        const int nops = pass == 0 ? K_M6_DBL_N : K_M6_ADD_N;
+        if (two_lane) {  // k_m6_lines: two lanes per pair, emulated one after the other around the store barrier
+          for (int o = 0; o < nops; o++) {
+            int32_t r0[NL], r1[NL];
+            double v0 = m6_op_compute(r0, prog + o, cx, 0), v1 = m6_op_compute(r1, prog + o, cx, 1);
+            m6_op_store(prog + o, cx, 0, r0, r1, v0);
+            m6_op_store(prog + o, cx, 1, r1, r0, v1);
+          }
+        } else {
+          m6_run(prog, nops, cx);
+        }
+      }
     }
     if (step != M6_STEPS) return -2;
   }

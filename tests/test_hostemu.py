@@ -261,14 +261,14 @@ def test_sop2f_fused_unit(L):
 def test_miller6_cooperative(L):
     """csrc/miller6.cuh: six pairings, one shared accumulator spread over six lanes == the product of the pairings."""
     rnd = random.Random(77)
-    for n, nl in ((6, 2), (1, 0), (3, 2)):
+    for n, nl, two_lane in ((6, 2, 1), (1, 0, 0), (3, 2, 0), (2, 0, 1)):
         ps = [O.g1_mul(O.G1_GEN, rnd.randrange(1, O.R)) for _ in range(n)]
         qs = [O.g2_mul(O.G2_GEN, rnd.randrange(1, O.R)) for _ in range(n)]
         ks = [rnd.randrange(1, 2 ** 64) for _ in range(n)]
         karr = (ctypes.c_uint32 * (2 * n))(*[w for k in ks for w in (k & 0xFFFFFFFF, k >> 32)])
         ml, fe = buf(576), buf(576)
         assert L.emu_miller6(n, b"".join(O.g1_serialize(p) for p in ps), b"".join(O.g2_serialize(q) for q in qs),
-                             karr, nl, ml, fe) == 0
+                             karr, nl, two_lane, ml, fe) == 0
         want = O.F12_ONE
         for p, q, k in zip(ps, qs, ks):
             want = O.f12_mul(want, O.f12_pow(O.pairing(p, q), 3 * (k if nl else 1)))
