@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -35,7 +36,13 @@ thread_local std::string g_create_error;
 
 constexpr int TPB = 128;
 constexpr size_t MSM_MIN_ITEMS = 4096;  // below this the per-item scaling is as fast as the bucket method's fixed costs
-constexpr size_t M6_CHUNK = 1024 * 120;  // items per pass of the Miller kernels (a multiple of 6 and of 120): 2.8 GB of lines, twice
+// Items per pass of the Miller kernels (a multiple of 120).  Measured on B200 at n = 1M: every extra pass costs ~8 ms of
+// kernel ramp-up and tail (444 ms in one pass, 452 in three, 468 in six), and HBM is there to be used: 39 KB per item.
+inline size_t m6_chunk(int sm_count) {
+  if (const char* e = getenv("BLSGPU_M6_CHUNK")) return (size_t)atoll(e) / 120 * 120;  // tuning experiments only
+  (void)sm_count;
+  return (size_t)8736 * 120;  // 1,048,320 items = 41 GB of line records: a 1M batch goes through in one pass
+}
 inline unsigned blocks_for(size_t n, int tpb = TPB) { return (unsigned)((n + tpb - 1) / tpb); }
 
 // bump allocator over one device buffer, regrown between calls
@@ -61,6 +68,7 @@ struct blsgpu_ctx {
   std::vector<int> devices;
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
+  int sm_count = 148;
   // the Miller stage runs its two big kernels on two side streams so that one block of each shares every SM (kernels.cuh)
   cudaStream_t side[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_lines[2] = {nullptr, nullptr}, ev_accum[2] = {nullptr, nullptr};
@@ -189,6 +197,7 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
     // produced on side stream 0 while chunk c-1's accumulator consumes the other buffer on side stream 1: k_m6_lines is
     // limited to ONE block per SM by its shared-memory record file and leaves half of the registers and the multiplier
     // pipe's idle slots to one block of k_m6_accum - two kernels that cannot fill an SM alone fill it together.
+    const size_t M6_CHUNK = m6_chunk(ctx->sm_count);
     const size_t chunk = std::min(n, M6_CHUNK);
     const int nbuf = n > M6_CHUNK ? 2 : 1;
     M6Arg* d_args[2];
@@ -325,7 +334,8 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
 }
 
 template <class PkA, class SigA>
-size_t pipeline_bytes(size_t n) {
+size_t pipeline_bytes(size_t n, int sm_count) {
+  const size_t M6_CHUNK = m6_chunk(sm_count);
   typedef typename PtInfo<SigA>::Jac SigJ;
   size_t total = levels_total(make_levels(std::max<size_t>(n, 1)));
   size_t gtotal = levels_total(make_levels((std::max<size_t>(n, 1) + M6_GROUP - 1) / M6_GROUP));
@@ -370,10 +380,10 @@ int verify_dev(blsgpu_ctx* ctx, int msg_mode, const DstParam& dst, int format, s
   return BLSGPU_OK;
 }
 template <int IMPL>
-size_t verify_bytes(size_t n) {
+size_t verify_bytes(size_t n, int sm_count) {
   typedef typename ImplT<IMPL>::PkAff PkA;
   typedef typename ImplT<IMPL>::SigAff SigA;
-  return n * (sizeof(PkA) + 2 * sizeof(SigA) + 2) + 8 * 256 + pipeline_bytes<PkA, SigA>(n);
+  return n * (sizeof(PkA) + 2 * sizeof(SigA) + 2) + 8 * 256 + pipeline_bytes<PkA, SigA>(n, sm_count);
 }
 
 bool args_ok(int impl_id, int scheme, int format) {
@@ -420,6 +430,7 @@ int blsgpu_ctx_create(const int* devices, int ndev, blsgpu_ctx** out) {
   e = cudaSetDevice(devices[0]);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
   ctx->stream = ctx->own_stream;
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, devices[0]);
   int prio_lo = 0, prio_hi = 0;
   if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
   for (int i = 0; e == cudaSuccess && i < 2; i++) {
@@ -490,10 +501,10 @@ int blsgpu_verify_batch_dev(blsgpu_ctx* ctx, int impl_id, int scheme, int format
   make_dst(dst, impl_id, scheme, false);
   int mode = scheme == 1 ? 1 : 0;
   if (impl_id == 2) {
-    CKR(ensure_arena(ctx, verify_bytes<2>(n)));
+    CKR(ensure_arena(ctx, verify_bytes<2>(n, ctx->sm_count)));
     return verify_dev<2>(ctx, mode, dst, format, n, pks_dev, sigs_dev, msgs_dev, msg_off_dev, status_out_dev, 0);
   }
-  CKR(ensure_arena(ctx, verify_bytes<1>(n)));
+  CKR(ensure_arena(ctx, verify_bytes<1>(n, ctx->sm_count)));
   return verify_dev<1>(ctx, mode, dst, format, n, pks_dev, sigs_dev, msgs_dev, msg_off_dev, status_out_dev, 0);
 }
 
@@ -503,7 +514,7 @@ static int verify_host_common(blsgpu_ctx* ctx, int impl_id, int msg_mode, const 
   size_t pk_len = impl_id == 2 ? 48 : 96, sig_len = impl_id == 2 ? 96 : 48;
   size_t msg_bytes = msg_off ? (size_t)msg_off[n] : 0;
   size_t in_bytes = n * (pk_len + sig_len + 1) + msg_bytes + (n + 1) * 8 + 8 * 256;
-  CKR(ensure_arena(ctx, in_bytes + (impl_id == 2 ? verify_bytes<2>(n) : verify_bytes<1>(n))));
+  CKR(ensure_arena(ctx, in_bytes + (impl_id == 2 ? verify_bytes<2>(n, ctx->sm_count) : verify_bytes<1>(n, ctx->sm_count))));
   uint8_t *d_pks, *d_sigs, *d_msgs, *d_st;
   uint64_t* d_off;
   CKR(upload(ctx, d_pks, pks, n * pk_len));
@@ -559,7 +570,7 @@ static int aggregate_verify_impl(blsgpu_ctx* ctx, int scheme, int format, size_t
   const size_t pk_len = PtInfo<PkA>::LEN, sig_len = PtInfo<SigA>::LEN;
   size_t msg_bytes = (size_t)msg_off[n];
   size_t need = n * (pk_len + sizeof(PkA) + sizeof(SigA) + 2) + msg_bytes + (n + 1) * 8 + sig_len + sizeof(SigA) + 16 * 256 +
-                pipeline_bytes<PkA, SigA>(std::max<size_t>(n, 1));
+                pipeline_bytes<PkA, SigA>(std::max<size_t>(n, 1), ctx->sm_count);
   CKR(ensure_arena(ctx, need));
   uint8_t *d_pks, *d_msgs, *d_sigb;
   uint64_t* d_off;
@@ -993,7 +1004,7 @@ int verify_secure_impl(blsgpu_ctx* ctx, int scheme, int format, size_t q, const 
   SecurePlan pl = make_secure_plan(q, key_off, pks, Lp);
   const size_t M = pl.M, msg_bytes = (size_t)msg_off[q];
   size_t need = M * (Lp + sizeof(PkA) + 2) + q * (Ls + 2 * sizeof(SigA) + sizeof(PkA) + sizeof(PkJ) + 8) + msg_bytes + (q + 1) * 8 +
-                secure_plan_bytes(pl, sizeof(PkJ)) + verify_bytes<IMPL>(q) + 32 * 256;
+                secure_plan_bytes(pl, sizeof(PkJ)) + verify_bytes<IMPL>(q, ctx->sm_count) + 32 * 256;
   CKR(ensure_arena(ctx, need));
   stage_reset(ctx);
   uint8_t *d_pkb, *d_sigb, *d_msgs;
