@@ -186,37 +186,62 @@ BLS_HD uint32_t opaque32(uint32_t x) {
   return x;
 }
 
-// r = a*b/R mod p.  Operand scanning with the reduction interleaved; the 14 column accumulators shift down one place per
-// row (register renaming after unrolling), so every multiply-accumulate is ONE IMAD.WIDE.U32 with its 64-bit addend:
-// 14 (a_j b_i) + 1 + 13 (m p_j) per row, 406 in all, and ~6 ALU instructions per row for m and the carry.
+// r = a*b/R mod p.  One level of Karatsuba on the 14 x 14 limb product (7 + 7 limbs): three 7 x 7 products instead of
+// four, 147 multiply-accumulates instead of 196, then a 14-row Montgomery reduction (196 + 14): 357 IMAD in all where
+// the operand-scanning form needs 406.  The kernels built on this function run at ~90% of the IMAD.WIDE issue rate and a
+// fifth of the ALU rate, so trading 49 multiplies for ~110 additions is a net gain.  The middle product
+// (a_lo + a_hi)(b_lo + b_hi) may wrap modulo 2^64; (M - L - H) is exact because the true cross sum fits (same column bound
+// as before: 14 lb_a lb_b + 14 * 2^56 < 2^63).
 BLS_HD void fp_mul_inl(Fp& r, const Fp& a, const Fp& b) {
 #if defined(BLS_TRACK)
   BLS_REQ((double)a.lb * (double)b.lb * 14.0 + 14.0 * 72057594037927936.0 < 9.2e18, "fp_mul column overflow");
   BLS_REQ(a.vb * b.vb <= 2000.0, "fp_mul value bound");
+  BLS_REQ(a.lb < (1ull << 31) && b.lb < (1ull << 31), "fp_mul operand half sums");
 #endif
-  uint64_t t[NL];
+  constexpr int HL = NL / 2;
+  uint64_t L[2 * HL - 1], H[2 * HL - 1], M[2 * HL - 1];
+  uint32_t sa[HL], sb[HL];
 #pragma unroll
-  for (int j = 0; j < NL; j++) t[j] = 0;
+  for (int i = 0; i < HL; i++) {
+    sa[i] = a.l[i] + a.l[HL + i];
+    sb[i] = b.l[i] + b.l[HL + i];
+  }
+#pragma unroll
+  for (int i = 0; i < 2 * HL - 1; i++) L[i] = H[i] = M[i] = 0;
+#pragma unroll
+  for (int i = 0; i < HL; i++) {
+#pragma unroll
+    for (int j = 0; j < HL; j++) {
+      L[i + j] += (uint64_t)a.l[i] * b.l[j];
+      H[i + j] += (uint64_t)a.l[HL + i] * b.l[HL + j];
+      M[i + j] += (uint64_t)sa[i] * sb[j];
+    }
+  }
+  uint64_t t[2 * NL];
+#pragma unroll
+  for (int i = 0; i < 2 * HL - 1; i++) {
+    t[i] = L[i];
+    t[NL + i] = H[i];
+  }
+  t[2 * HL - 1] = 0;
+  t[2 * NL - 1] = 0;
+#pragma unroll
+  for (int i = 0; i < 2 * HL - 1; i++) t[HL + i] += M[i] - L[i] - H[i];
 #pragma unroll
   for (int i = 0; i < NL; i++) {
-    const uint32_t bi = b.l[i];
+    const uint32_t m = opaque32(((uint32_t)t[i] * K_PINV28) & M28);
 #pragma unroll
-    for (int j = 0; j < NL; j++) t[j] += (uint64_t)a.l[j] * bi;
-    const uint32_t m = opaque32(((uint32_t)t[0] * K_PINV28) & M28);
-    const uint64_t c = (t[0] + (uint64_t)m * p28(0)) >> 28;
-#pragma unroll
-    for (int j = 1; j < NL; j++) t[j - 1] = t[j] + (uint64_t)m * p28(j);
-    t[0] += c;
-    t[NL - 1] = 0;
+    for (int j = 0; j < NL; j++) t[i + j] += (uint64_t)m * p28(j);
+    t[i + 1] += t[i] >> 28;
   }
   uint64_t c = 0;
 #pragma unroll
   for (int j = 0; j < NL - 1; j++) {
-    c += t[j];
+    c += t[NL + j];
     r.l[j] = (uint32_t)c & M28;
     c >>= 28;
   }
-  r.l[NL - 1] = (uint32_t)(c + t[NL - 1]);
+  r.l[NL - 1] = (uint32_t)(c + t[2 * NL - 1]);
   r.l[NL] = r.l[NL + 1] = 0;
   TRK(r, 2.0, M28);
 }

@@ -267,7 +267,7 @@ constexpr int M6_LINES_TPB = 128;
 constexpr int M6_LINES_PAIRS = M6_LINES_TPB / 2;
 constexpr int M6_LINES_SMEM = M6_NREG * M6_LINES_PAIRS * (int)sizeof(SFp2);  // 100,352 B: two blocks per SM
 constexpr int M6_ITEMS_PER_BLOCK = 120;                                   // k_m6_accum: 4 warps x 5 groups x 6 lanes
-constexpr int M6_ACCUM_SMEM = 4 * 60 * (int)sizeof(SAccRec);
+constexpr int M6_ACCUM_SMEM = 4 * 30 * (int)sizeof(SAccRec);
 constexpr size_t M6_LINE_RECS = (size_t)M6_STEPS * 3;                     // records per item in the line stream
 
 __device__ __forceinline__ const G1Aff& m6_g1(const G1Aff* pk, const G2Aff* h, size_t i) { return pk[i]; }
@@ -360,8 +360,8 @@ __global__ void __launch_bounds__(128, M6_ACC_BLOCKS) k_m6_accum(size_t n, size_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane / 6, k = lane - 6 * g;
   const bool lane_on = g < 5;  // lanes 30, 31 only keep the warp's barriers company
-  SAccRec* F = reinterpret_cast<SAccRec*>(m6_smem) + warp * 60 + 6 * (lane_on ? g : 0);  // current value; F + 30: next
-  SAccRec* G = F + 30;
+  SAccRec* F = reinterpret_cast<SAccRec*>(m6_smem) + warp * 30 + 6 * (lane_on ? g : 0);  // updated in place (sopw's barrier)
+  const unsigned gsync = lane_on ? 63u << (6 * g) : 0xc0000000u;  // the lanes that share this F
   const size_t group = ((size_t)blockIdx.x * 4 + warp) * 5 + g;  // within the chunk (base is a multiple of 6)
   const size_t item = group * 6 + k;
   const bool active = lane_on && item < n && pre[base + item] == ST_OK;
@@ -376,37 +376,31 @@ __global__ void __launch_bounds__(128, M6_ACC_BLOCKS) k_m6_accum(size_t n, size_
   const SLineRec* gl = lines + group * 6 * M6_LINE_RECS;  // the group's six line streams
   const uint64_t e = K_X_ABS;
   int step = 0;
+  if (gmask != 0) {  // uniform within the group; every barrier below names the group's lanes only
 #pragma unroll 1
-  for (int i = 62; i >= 0; i--) {
-    if (i != 62) {
-      if (lane_on) m6_sqr_lane(G + k, F, k);
-      __syncwarp();
-      SAccRec* t = F; F = G; G = t;
-    }
-    const int nst = 1 + (int)((e >> i) & 1);
+    for (int i = 62; i >= 0; i--) {
+      if (i != 62) m6_sqr_lane(F + k, F, k, gsync);
+      const int nst = 1 + (int)((e >> i) & 1);
 #pragma unroll 1
-    for (int st = 0; st < nst; st++, step++) {
+      for (int st = 0; st < nst; st++, step++) {
 #pragma unroll 1
-      for (int j = 0; j < 6; j++) {
-        {
-          // the NEXT line of this group (336 B in HBM, used once by all six lanes) starts its way into L1 now: sop2f
-          // prefetches within a call, but the first operands of a call would otherwise wait for HBM
-          const int jn = j == 5 ? 0 : j + 1;
-          const int sn = j == 5 ? step + 1 : step;
-          if (k < 3 && sn < M6_STEPS) {
-            const SLineRec* nx = gl + (size_t)jn * M6_LINE_RECS + 3 * sn + k;
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(nx) + 128));
+        for (int j = 0; j < 6; j++) {
+          {
+            // the NEXT line of this group (576 B in HBM, used once by all six lanes) starts its way into L1 now
+            const int jn = j == 5 ? 0 : j + 1;
+            const int sn = j == 5 ? step + 1 : step;
+            if (k < 3 && sn < M6_STEPS) {
+              const SLineRec* nx = gl + (size_t)jn * M6_LINE_RECS + 3 * sn + k;
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(nx) + 128));
+            }
           }
+          if ((gmask >> j) & 1u) m6_mul_line_lane(F + k, F, gl + (size_t)j * M6_LINE_RECS + 3 * step, k, gsync);
         }
-        if ((gmask >> j) & 1u) {  // uniform within the group; the barrier below is outside
-          m6_mul_line_lane(G + k, F, gl + (size_t)j * M6_LINE_RECS + 3 * step, k);
-          SAccRec* t = F; F = G; G = t;
-        }
-        __syncwarp();
       }
     }
   }
+  __syncwarp();
   if (lane_on && group * 6 < n) m6_finish_lane(*fp12_coeff(out[base / 6 + group], k), F[k], k);
 }
 

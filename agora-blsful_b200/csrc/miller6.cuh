@@ -38,10 +38,12 @@ BLS_CONST SopTerm K_M6_MUL_LINE[3] = {
     {SOPX_FREL + 3, SOPX_JL + 2, 0, 0, SOP_XI_LT3, 0, 0, 0},
 };
 
-// F: the group's six coefficients (w^0..w^5), expanded records.  *out = coefficient k of f^2   (out is not one of F's records)
-BLS_HD void m6_sqr_lane(SAccRec* out, const SAccRec* F, int k) { sopw(out, K_M6_SQR[k], 4, F, nullptr, k); }
+// F: the group's six coefficients (w^0..w^5), expanded records.  *out = coefficient k of f^2   (on the device out may be F + k: see sopw)
+BLS_HD void m6_sqr_lane(SAccRec* out, const SAccRec* F, int k, unsigned sync_mask) { sopw(out, K_M6_SQR[k], 4, F, nullptr, k, sync_mask); }
 // *out = coefficient k of  f * (l0 + l2 w^2 + l3 w^3)   (line[0..2] = l0, l2, l3: the sparse shape of a Miller line)
-BLS_HD void m6_mul_line_lane(SAccRec* out, const SAccRec* F, const SLineRec* line, int k) { sopw(out, K_M6_MUL_LINE, 3, F, line, k); }
+BLS_HD void m6_mul_line_lane(SAccRec* out, const SAccRec* F, const SLineRec* line, int k, unsigned sync_mask) {
+  sopw(out, K_M6_MUL_LINE, 3, F, line, k, sync_mask);
+}
 
 // slot of coefficient k (of w^k) in the tower layout of fp12.cuh: w^0..w^5 = c0.c0, c1.c0, c0.c1, c1.c1, c0.c2, c1.c2
 BLS_HD Fp2* fp12_coeff(Fp12& f, int k) {

@@ -515,7 +515,7 @@ BLS_FN double sfp2_lin_half(int32_t* res, const SFp2* x, int32_t sx, uint32_t fl
 // ---- sopw: the same unit over EXPANDED records (the accumulator kernel) -------------------------------------------------
 // A operands: accumulator coefficients (SAccRec), absolute (SOPX_F) or relative to the lane (SOPX_FREL); B operands:
 // accumulator coefficients or the incoming line (SOPX_JL, SLineRec).  Terms use sha and the xi flags only.
-// Per integer product the loop body is: 8 loads for the NEXT product, 196 IMAD.WIDE, 14 shifts.
+// Per integer product the loop body is: 8 loads, 14 shifts, 196 IMAD.WIDE.
 BLS_HD const int32_t* sopw_run_a(const SAccRec* F, int lane_k, uint32_t i, int pass, int xi) {
   int jr = lane_k - ((int)i - SOPX_FREL);
   jr += jr < 0 ? 6 : 0;
@@ -545,7 +545,9 @@ BLS_HD void sopw_take(int32_t* x, const SopI4* r, int sh) {
 #pragma unroll
   for (int i = 0; i < NL; i++) x[i] = (int32_t)((uint32_t)t[i] << sh);
 }
-BLS_FN void sopw(SAccRec* dst, const SopTerm* t, int nt, const SAccRec* F, const SLineRec* jl, int lane_k) {
+// sync_mask: the lanes that share F (device: a barrier separates the last operand read from the stores, so dst may be the
+// lane's own coefficient of F - the accumulator is updated in place, one buffer)
+BLS_FN void sopw(SAccRec* dst, const SopTerm* t, int nt, const SAccRec* F, const SLineRec* jl, int lane_k, unsigned sync_mask) {
   uint64_t T[2 * NL];
   SopKeep keep;
   int32_t res[2 * NL], x[NL], y[NL];
@@ -574,60 +576,53 @@ BLS_FN void sopw(SAccRec* dst, const SopTerm* t, int nt, const SAccRec* F, const
 #endif
 #pragma unroll
   for (int i = 0; i < 2 * NL; i++) T[i] = 0;
-  {
-    const SopTerm m = t[0];
-    const int xi = sop_term_xi(m.fl, lane_k);
-    sopw_fetch(ra, sopw_run_a(F, lane_k, m.a, 0, xi));
-    sopw_fetch(rb, sopw_run_b(F, jl, m.b, 0));
-    sopw_take(x, ra, m.sha);
-    sopw_take(y, rb, 0);
-  }
-  int pass = 0, k = 0;
-  const int nsteps = 3 * nt;
+  // No software pipeline here: the operand runs are short (8 loads from shared memory / L1) and the kernel runs three
+  // blocks per SM, so other warps' multiplies cover them; the straight form needs no register rotation at all.
 #pragma unroll 1
-  for (int s = 0; s < nsteps; s++) {
-    const int wrap = (k + 1 == nt);
-    const int k1 = wrap ? 0 : k + 1, p1 = pass + wrap;
-    const int pn = p1 > 2 ? 2 : p1;  // after the last step: a harmless refetch
-    const SopTerm m = t[k1];
-    const int xi = sop_term_xi(m.fl, lane_k);
-    sopw_fetch(ra, sopw_run_a(F, lane_k, m.a, pn, xi));
-    sopw_fetch(rb, sopw_run_b(F, jl, m.b, pn));
-    sop_acc(T, x, y);
-    sopw_take(x, ra, m.sha + (xi & (pn == 2)));
-    sopw_take(y, rb, 0);
-    if (wrap) {  // a product sum is complete
-      if (pass == 0) {
-#pragma unroll
-        for (int i = 0; i < NL; i++) {
-          sop_keep_st(keep, i, T[2 * i], T[2 * i + 1]);
-          T[2 * i] = T[2 * i + 1] = 0;
-        }
-      } else {
-        // pass 1: U = P0 - P1, keep <- P0 + P1 ;  pass 2: U = P2 - keep
-#pragma unroll
-        for (int i = 0; i < NL; i++) {
-          uint64_t u0, u1;
-          sop_keep_ld(keep, i, u0, u1);
-          const uint64_t v0 = T[2 * i], v1 = T[2 * i + 1];
-          if (pass == 1) sop_keep_st(keep, i, u0 + v0, u1 + v1);
-          T[2 * i] = pass == 1 ? u0 - v0 : v0 - u0;
-          T[2 * i + 1] = pass == 1 ? u1 - v1 : v1 - u1;
-        }
-        T[2 * NL - 1] = 0;
-        int32_t c[NL];
-        sop_redc(c, T);
-#pragma unroll
-        for (int i = 0; i < NL; i++) {
-          if (pass == 1) res[i] = c[i]; else res[NL + i] = c[i];
-        }
-#pragma unroll
-        for (int i = 0; i < 2 * NL; i++) T[i] = 0;
-      }
+  for (int pass = 0; pass < 3; pass++) {
+#pragma unroll 1
+    for (int k = 0; k < nt; k++) {
+      const SopTerm m = t[k];
+      const int xi = sop_term_xi(m.fl, lane_k);
+      sopw_fetch(ra, sopw_run_a(F, lane_k, m.a, pass, xi));
+      sopw_fetch(rb, sopw_run_b(F, jl, m.b, pass));
+      sopw_take(x, ra, m.sha + (xi & (pass == 2)));
+      sopw_take(y, rb, 0);
+      sop_acc(T, x, y);
     }
-    k = k1;
-    pass = p1;
+    if (pass == 0) {
+#pragma unroll
+      for (int i = 0; i < NL; i++) {
+        sop_keep_st(keep, i, T[2 * i], T[2 * i + 1]);
+        T[2 * i] = T[2 * i + 1] = 0;
+      }
+    } else {
+      // pass 1: U = P0 - P1, keep <- P0 + P1 ;  pass 2: U = P2 - keep
+#pragma unroll
+      for (int i = 0; i < NL; i++) {
+        uint64_t u0, u1;
+        sop_keep_ld(keep, i, u0, u1);
+        const uint64_t v0 = T[2 * i], v1 = T[2 * i + 1];
+        if (pass == 1) sop_keep_st(keep, i, u0 + v0, u1 + v1);
+        T[2 * i] = pass == 1 ? u0 - v0 : v0 - u0;
+        T[2 * i + 1] = pass == 1 ? u1 - v1 : v1 - u1;
+      }
+      T[2 * NL - 1] = 0;
+      int32_t c[NL];
+      sop_redc(c, T);
+#pragma unroll
+      for (int i = 0; i < NL; i++) {
+        if (pass == 1) res[i] = c[i]; else res[NL + i] = c[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 2 * NL; i++) T[i] = 0;
+    }
   }
+#if defined(__CUDA_ARCH__)
+  __syncwarp(sync_mask);
+#else
+  (void)sync_mask;
+#endif
   SopI4* q = reinterpret_cast<SopI4*>(dst->w);
 #pragma unroll
   for (int h = 0; h < 4; h++) {
@@ -649,6 +644,9 @@ BLS_FN void sopw(SAccRec* dst, const SopTerm* t, int nt, const SAccRec* F, const
   }
 #if defined(BLS_TRACK)
   STRK(*dst, vsum / 2500.0 + 1.0, 134217728.0);
+#endif
+#if defined(__CUDA_ARCH__)
+  __syncwarp(sync_mask);
 #endif
 }
 

@@ -208,13 +208,13 @@ int emu_miller6(int n, const uint8_t* p48, const uint8_t* q96, const uint32_t* k
   int step = 0;
   for (int i = 62; i >= 0; i--) {
     if (i != 62) {
-      for (int c = 0; c < 6; c++) m6_sqr_lane(&T[c], F, c);
+      for (int c = 0; c < 6; c++) m6_sqr_lane(&T[c], F, c, 0);
       for (int c = 0; c < 6; c++) F[c] = T[c];
     }
     for (int pass = 0; pass < 2; pass++) {
       if (pass == 1 && !((e >> i) & 1)) break;
       for (int j = 0; j < n; j++) {
-        for (int c = 0; c < 6; c++) m6_mul_line_lane(&T[c], F, lines[j][step], c);
+        for (int c = 0; c < 6; c++) m6_mul_line_lane(&T[c], F, lines[j][step], c, 0);
         for (int c = 0; c < 6; c++) F[c] = T[c];
       }
       step++;
