@@ -45,7 +45,7 @@ _STATUS_TEXT = {
     ST_MISMATCHED_LENGTHS: "invalid inputs: Mismatched array lengths",
 }
 
-STAGES = ["decode_pk", "decode_sig", "hash_to_curve", "miller", "scale_sig", "reduce", "final", "bisect"]
+STAGES = ["decode_pk", "decode_sig", "hash_to_curve", "scale_sig", "miller", "reduce", "final", "bisect"]
 
 
 class BlsError(Exception):

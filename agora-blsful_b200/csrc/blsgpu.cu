@@ -71,6 +71,8 @@ struct blsgpu_ctx {
   int sm_count = 148;
   // the Miller stage runs its two big kernels on two side streams so that one block of each shares every SM (kernels.cuh)
   cudaStream_t side[2] = {nullptr, nullptr};
+  cudaStream_t aux = nullptr;  // the signature side of the batch equation (bucket sum, its Miller loop), concurrent with the Miller stage
+  cudaEvent_t ev_aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_lines[2] = {nullptr, nullptr}, ev_accum[2] = {nullptr, nullptr};
   Arena arena;
   std::string err;
@@ -185,6 +187,49 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
     CK(cudaMemcpyAsync(d_root, d_dig + ld.back().off, sizeof(Digest), cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_root + 1, ctx->salt, 32, cudaMemcpyHostToDevice, ctx->stream));
   }
+  // S = sum r_i sig_i.  Large batches: bucket multi-scalar multiplication for the total only (the per-group sums the
+  // bisection needs are computed if the batch fails) BEFORE the Miller stage, so that its Miller loop T = ML(-g, S) - one
+  // thread, pure latency - can run on the aux stream beside the Miller kernels.  Small batches: per-item scaling.
+  // (Running the bucket kernels themselves beside the Miller stage was measured: they evict Miller blocks, +70 ms at 1M.)
+  stage_mark(ctx, BLSGPU_STAGE_SCALE_SIG);
+  const bool use_msm = use_rlc && n >= MSM_MIN_ITEMS;
+  SigJ* d_msm_root = nullptr;
+  Fp12* d_T = ctx->arena.take<Fp12>(1);
+  if (use_msm) {
+    int rc = [&]() -> int {
+      int c = 4;
+      while (c < 16 && ((size_t)1 << (c + 4)) <= n) c++;  // ~16 signatures per bucket
+      const int nwin = (64 + c - 1) / c;
+      const size_t nb = (size_t)1 << c, nbuckets = nb * nwin, nchunks = nbuckets / MSM_CHUNK;
+      uint64_t* d_r = ctx->arena.take<uint64_t>(n);
+      uint32_t* d_cnt = ctx->arena.take<uint32_t>(3 * nbuckets);
+      uint32_t *d_off = d_cnt + nbuckets, *d_cur = d_off + nbuckets;
+      uint32_t* d_sorted = ctx->arena.take<uint32_t>((size_t)nwin * n);
+      SigJ* d_B = ctx->arena.take<SigJ>(nbuckets);
+      std::vector<Level> lm = make_levels(nchunks);
+      SigJ* d_V = ctx->arena.take<SigJ>(levels_total(lm));
+      CK(cudaMemsetAsync(d_cnt, 0, nbuckets * sizeof(uint32_t), ctx->stream));
+      LAUNCH(k_msm_count, blocks_for(n), TPB, n, (const uint8_t*)d_status, (const Digest*)d_root, c, nwin, d_r, d_cnt);
+      LAUNCH(k_msm_scan, (unsigned)nwin, 1024, c, (const uint32_t*)d_cnt, d_off, d_cur);
+      LAUNCH(k_msm_scatter, blocks_for(n), TPB, n, (const uint64_t*)d_r, c, nwin, (const uint32_t*)d_off, d_cur, d_sorted);
+      LAUNCH((k_msm_bucket<SigA>), blocks_for(nbuckets), TPB, n, nbuckets, d_sig, c, (const uint32_t*)d_cnt, (const uint32_t*)d_off,
+             (const uint32_t*)d_sorted, d_B);
+      LAUNCH((k_msm_chunk<SigJ>), blocks_for(nchunks), TPB, nchunks, c, (const SigJ*)d_B, d_V);
+      for (size_t k = 0; k + 1 < lm.size(); k++)
+        LAUNCH((k_reduce_jac<SigJ>), blocks_for(lm[k + 1].cnt), TPB, lm[k].cnt, d_V + lm[k].off, lm[k + 1].cnt, d_V + lm[k + 1].off);
+      d_msm_root = d_V + lm.back().off;
+      return BLSGPU_OK;
+    }();
+    CKR(rc);
+  }
+  CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  if (use_msm) {
+    // one thread's Miller loop (9 ms of latency, no throughput): on the aux stream, beside the Miller stage
+    CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+    k_probe_ml<SigJ><<<1, 32, 0, ctx->aux>>>((const SigJ*)d_msm_root, d_T);
+    CKR(check_launch(ctx, "k_probe_ml"));
+    CK(cudaEventRecord(ctx->ev_aux, ctx->aux));
+  }
   stage_mark(ctx, BLSGPU_STAGE_MILLER);
   {
     static bool attr_done = false;  // per template instance
@@ -193,10 +238,8 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
       CK(cudaFuncSetAttribute(k_m6_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_ACCUM_SMEM));
       attr_done = true;
     }
-    // The line stream is 22.8 KB per item: the batch goes through in chunks with two line buffers.  Chunk c's lines are
-    // produced on side stream 0 while chunk c-1's accumulator consumes the other buffer on side stream 1: k_m6_lines is
-    // limited to ONE block per SM by its shared-memory record file and leaves half of the registers and the multiplier
-    // pipe's idle slots to one block of k_m6_accum - two kernels that cannot fill an SM alone fill it together.
+    // The line stream is 39 KB per item.  Batches beyond one pass (m6_chunk) go through in chunks with two line buffers:
+    // chunk c's lines are produced on side stream 0 while chunk c-1's accumulator consumes the other buffer on side stream 1.
     const size_t M6_CHUNK = m6_chunk(ctx->sm_count);
     const size_t chunk = std::min(n, M6_CHUNK);
     const int nbuf = n > M6_CHUNK ? 2 : 1;
@@ -206,7 +249,6 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
       d_args[b] = ctx->arena.take<M6Arg>(chunk);
       d_lines[b] = ctx->arena.take<SLineRec>(chunk * M6_LINE_RECS);
     }
-    CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->side[0], ctx->ev_fork, 0));
     CK(cudaStreamWaitEvent(ctx->side[1], ctx->ev_fork, 0));
     size_t ci = 0;
@@ -230,34 +272,8 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_accum[(ci - 1) % nbuf], 0));
     if (ci >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_accum[(ci - 2) % nbuf], 0));
   }
-  stage_mark(ctx, BLSGPU_STAGE_SCALE_SIG);
-  // S = sum r_i sig_i.  Large batches: bucket multi-scalar multiplication for the total only (the per-group sums the
-  // bisection needs are computed if the batch fails).  Small batches: per-item scaling right away.
-  const bool use_msm = use_rlc && n >= MSM_MIN_ITEMS;
-  SigJ* d_msm_root = nullptr;
-  if (use_msm) {
-    int c = 4;
-    while (c < 16 && ((size_t)1 << (c + 4)) <= n) c++;  // ~16 signatures per bucket
-    const int nwin = (64 + c - 1) / c;
-    const size_t nb = (size_t)1 << c, nbuckets = nb * nwin, nchunks = nbuckets / MSM_CHUNK;
-    uint64_t* d_r = ctx->arena.take<uint64_t>(n);
-    uint32_t* d_cnt = ctx->arena.take<uint32_t>(3 * nbuckets);
-    uint32_t *d_off = d_cnt + nbuckets, *d_cur = d_off + nbuckets;
-    uint32_t* d_sorted = ctx->arena.take<uint32_t>((size_t)nwin * n);
-    SigJ* d_B = ctx->arena.take<SigJ>(nbuckets);
-    std::vector<Level> lm = make_levels(nchunks);
-    SigJ* d_V = ctx->arena.take<SigJ>(levels_total(lm));
-    CK(cudaMemsetAsync(d_cnt, 0, nbuckets * sizeof(uint32_t), ctx->stream));
-    LAUNCH(k_msm_count, blocks_for(n), TPB, n, (const uint8_t*)d_status, (const Digest*)d_root, c, nwin, d_r, d_cnt);
-    LAUNCH(k_msm_scan, (unsigned)nwin, 1024, c, (const uint32_t*)d_cnt, d_off, d_cur);
-    LAUNCH(k_msm_scatter, blocks_for(n), TPB, n, (const uint64_t*)d_r, c, nwin, (const uint32_t*)d_off, d_cur, d_sorted);
-    LAUNCH((k_msm_bucket<SigA>), blocks_for(nbuckets), TPB, n, nbuckets, d_sig, c, (const uint32_t*)d_cnt, (const uint32_t*)d_off,
-           (const uint32_t*)d_sorted, d_B);
-    LAUNCH((k_msm_chunk<SigJ>), blocks_for(nchunks), TPB, nchunks, c, (const SigJ*)d_B, d_V);
-    for (size_t k = 0; k + 1 < lm.size(); k++)
-      LAUNCH((k_reduce_jac<SigJ>), blocks_for(lm[k + 1].cnt), TPB, lm[k].cnt, d_V + lm[k].off, lm[k + 1].cnt, d_V + lm[k + 1].off);
-    d_msm_root = d_V + lm.back().off;
-  } else if (use_rlc) {
+  if (use_msm) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_aux, 0));  // T = ML(-g, S) ran beside the Miller stage
+  if (use_rlc && !use_msm) {
     LAUNCH((k_scale_sig<SigA>), blocks_for(n), TPB, n, d_sig, d_status, d_root, d_Sitem);
     LAUNCH((k_group_sum<SigJ>), blocks_for(ng), TPB, n, (const SigJ*)d_Sitem, ng, d_S);
   }
@@ -271,7 +287,8 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
   if (!use_rlc) LAUNCH((k_reduce_aff<SigA>), 1, 32, (size_t)1, d_sig, (size_t)1, d_S);  // S = the single aggregate signature
   const Fp12* rootF = d_F + lv.back().off;
   const SigJ* rootS = use_msm ? d_msm_root : use_rlc ? d_S + lv.back().off : d_S;
-  LAUNCH((k_probe<SigJ>), 1, 64, (size_t)1, (const uint32_t*)nullptr, rootF, rootS, d_ok);
+  if (use_msm) LAUNCH(k_probe_fin, 1, 32, rootF, (const Fp12*)d_T, d_ok);
+  else LAUNCH((k_probe<SigJ>), 1, 64, (size_t)1, (const uint32_t*)nullptr, rootF, rootS, d_ok);
   uint8_t ok = 0;
   CK(cudaMemcpyAsync(&ok, d_ok, 1, cudaMemcpyDeviceToHost, ctx->stream));
   stage_mark(ctx, BLSGPU_STAGE_BISECT);
@@ -441,6 +458,8 @@ int blsgpu_ctx_create(const int* devices, int ndev, blsgpu_ctx** out) {
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_accum[i], cudaEventDisableTiming);
   }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, prio_hi);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_aux, cudaEventDisableTiming);
   for (int i = 0; e == cudaSuccess && i <= BLSGPU_STAGE_COUNT; i++) e = cudaEventCreate(&ctx->ev[i]);
   if (e != cudaSuccess) {
     g_create_error = std::string("context setup: ") + cudaGetErrorString(e);
@@ -464,6 +483,8 @@ void blsgpu_ctx_destroy(blsgpu_ctx* ctx) {
     if (ctx->ev_accum[i]) cudaEventDestroy(ctx->ev_accum[i]);
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->aux) cudaStreamDestroy(ctx->aux);
+  if (ctx->ev_aux) cudaEventDestroy(ctx->ev_aux);
   delete ctx;
 }
 

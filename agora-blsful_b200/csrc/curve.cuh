@@ -281,6 +281,27 @@ BLS_HD void jac_mul_aff(Jac<F>& r, const Aff<F>& p, const uint32_t* k, int nlimb
   }
   r = acc;
 }
+// r = k P for a 64-bit k: fixed 4-bit windows over a 15-entry Jacobian table.  What matters on a GPU is that all lanes
+// of a warp add at the SAME 16 positions: a sparse signed-digit form (NAF) was measured and is twice as SLOW as plain
+// double-and-add here, because a warp executes an addition whenever any of its 32 lanes has a non-zero digit - and then
+// once more for the other sign.  60 doublings + 16 full additions + the table (7 doublings, 7 mixed additions).
+template <class F>
+BLS_HD void jac_mul_aff_w4_64(Jac<F>& r, const Aff<F>& p, uint64_t k) {
+  Jac<F> tbl[16];
+  jac_set_inf(tbl[0]);
+  jac_from_aff(tbl[1], p);
+  for (int i = 2; i < 16; i += 2) {
+    jac_dbl(tbl[i], tbl[i / 2]);
+    jac_add_mixed(tbl[i + 1], tbl[i], p);
+  }
+  Jac<F> acc = tbl[(k >> 60) & 15u];
+  for (int w = 14; w >= 0; w--) {
+    for (int d = 0; d < 4; d++) jac_dbl(acc, acc);
+    const uint32_t dg = (uint32_t)(k >> (4 * w)) & 15u;
+    if (dg) jac_add(acc, acc, tbl[dg]);
+  }
+  r = acc;
+}
 // [|x|]P, |x| = 0xd201000000010000 (Hamming weight 6), Jacobian base
 template <class F>
 BLS_HD void jac_mul_xabs(Jac<F>& r, const Jac<F>& p) {

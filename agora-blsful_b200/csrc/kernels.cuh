@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_m6_prep(size_t n, size_
     uint32_t sc[2];
     rlc_scalar(sc, root, i);
     G1Jac pj;
-    jac_mul_aff(pj, p, sc, 2);
+    jac_mul_aff_w4_64(pj, p, (uint64_t)sc[0] | ((uint64_t)sc[1] << 32));
     miller_prepare(mp, pj);
   } else {
     miller_prepare(mp, p);
@@ -631,6 +631,49 @@ __device__ __forceinline__ bool probe_node(const Fp12& F, const G1Jac& S) {
   Fp12 e;
   final_exponentiation(e, g);
   return fp12_is_one(e);
+}
+// The same probe in two halves, so that the signature side can run while the Miller kernels are still busy:
+//   k_probe_ml:   T = ML(-g, S)  (one if S is the identity)       k_probe_fin:  final_exponentiation(F * T) == 1 ?
+__device__ __forceinline__ void probe_ml(Fp12& t, const G2Jac& S) {
+  if (jac_is_inf(S)) {
+    fp12_one(t);
+    return;
+  }
+  G2Aff sa;
+  jac_to_aff(sa, S);
+  G1Aff ng;
+  pt_generator(ng);
+  fp_neg(ng.y, ng.y);
+  MillerG1 mp;
+  miller_prepare(mp, ng);
+  miller_loop(t, mp, sa);
+}
+__device__ __forceinline__ void probe_ml(Fp12& t, const G1Jac& S) {
+  if (jac_is_inf(S)) {
+    fp12_one(t);
+    return;
+  }
+  G2Aff ng;
+  pt_generator(ng);
+  fneg(ng.y, ng.y);
+  MillerG1 mp;
+  miller_prepare(mp, S);
+  miller_loop(t, mp, ng);
+}
+template <class J>
+__global__ void __launch_bounds__(32) k_probe_ml(const J* __restrict__ S, Fp12* __restrict__ T) {
+  if (BLS_TID() != 0) return;
+  J s = S[0];
+  Fp12 t;
+  probe_ml(t, s);
+  T[0] = t;
+}
+__global__ void __launch_bounds__(32) k_probe_fin(const Fp12* __restrict__ F, const Fp12* __restrict__ T, uint8_t* __restrict__ ok) {
+  if (BLS_TID() != 0) return;
+  Fp12 f = F[0], t = T[0], g, e;
+  fp12_mul(g, f, t);
+  final_exponentiation(e, g);
+  ok[0] = fp12_is_one(e) ? 1 : 0;
 }
 // node list: idx[c] indexes into F/S of one tree level (idx == nullptr: identity)
 template <class J>

@@ -149,8 +149,8 @@ int blsgpu_imad_peak(blsgpu_ctx* ctx, double* mac_per_s_out);
 #define BLSGPU_STAGE_DECODE_PK 0
 #define BLSGPU_STAGE_DECODE_SIG 1
 #define BLSGPU_STAGE_HASH 2
-#define BLSGPU_STAGE_MILLER 3
-#define BLSGPU_STAGE_SCALE_SIG 4
+#define BLSGPU_STAGE_SCALE_SIG 3 /* sum r_i sig_i (bucket multi-scalar multiplication) */
+#define BLSGPU_STAGE_MILLER 4    /* prep + lines + accumulator kernels */
 #define BLSGPU_STAGE_REDUCE 5
 #define BLSGPU_STAGE_FINAL 6
 #define BLSGPU_STAGE_BISECT 7

@@ -101,6 +101,10 @@ int emu_g2_mul(const uint8_t* in, const uint32_t* k, int nl, int format, uint8_t
   G2Aff p, q; if (g2_decompress(p, in, false)) return -1;
   G2Jac r; jac_mul_aff(r, p, k, nl); jac_to_aff(q, r); g2_compress(out, q); header_from_modern(out[0], format); return 0;
 }
+int emu_g1_mul_w4(const uint8_t* in, uint64_t k, uint8_t* out) {
+  G1Aff p, q; if (g1_decompress(p, in, false)) return -1;
+  G1Jac r; jac_mul_aff_w4_64(r, p, k); jac_to_aff(q, r); g1_compress(out, q); return 0;
+}
 int emu_g1_add(const uint8_t* a, const uint8_t* b, uint8_t* out) {
   G1Aff p, q, s; if (g1_decompress(p, a, false) || g1_decompress(q, b, false)) return -1;
   G1Jac x, y, r; jac_from_aff(x, p); jac_from_aff(y, q); jac_add(r, x, y);

@@ -273,3 +273,17 @@ def test_miller6_cooperative(L):
         for p, q, k in zip(ps, qs, ks):
             want = O.f12_mul(want, O.f12_pow(O.pairing(p, q), 3 * (k if nl else 1)))
         assert bf12(fe.raw) == want
+
+
+def test_windowed_scalar_multiplication(L):
+    """csrc/curve.cuh jac_mul_aff_w4_64 (the r_i * pk_i of the batch equation): zero digits, zero top window, all-ones."""
+    rnd = random.Random(9)
+    L.emu_g1_mul_w4.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_char_p]
+    pt = O.g1_mul(O.G1_GEN, 0xABCDEF)
+    ser = O.g1_serialize(pt)
+    ks = [1, 2, 3, 15, 16, 17, 2 ** 63, 2 ** 64 - 1, 2 ** 64 - 2, 0xF000000000000000, 0x000000000000F000, 0x1010101010101010]
+    ks += [rnd.randrange(1, 2 ** 64) for _ in range(12)]
+    for k in ks:
+        o = buf(48)
+        assert L.emu_g1_mul_w4(ser, k, o) == 0
+        assert o.raw == O.g1_serialize(O.g1_mul(pt, k)), hex(k)
