@@ -44,6 +44,8 @@ struct alignas(16) SLineRec {
 };
 struct alignas(16) SAccRec {
   int32_t w[64];
+  int32_t pad[4];  // 272-byte stride: the six lanes of a group (and the five groups of a warp) read DIFFERENT records of the
+                   // accumulator at the same run offset; a 256-byte stride would put them all on the same four banks
 #if defined(BLS_TRACK)
   double vb, lb;
 #endif
@@ -226,7 +228,8 @@ BLS_HD int sop_term_xi(uint32_t fl, int lane_k) {
 
 // dst may alias any operand: results are written after the last operand read.
 // dst_line: the result goes to that line record (expanded form) instead of *dst
-BLS_FN void sop2f(SFp2* dst, SLineRec* dst_line, const SopTerm* t, int nt, int fp_mode, const SopSpaces& cx) {
+BLS_FN void sop2f(SFp2* dst, SLineRec* dst_line, const SopTerm* t, int nt, int fp_mode, const SopSpaces& cx_) {
+  const SopSpaces cx = cx_;  // into registers once: the caller's copy lives in local memory
   const int lane_k = cx.k;
   uint64_t T[2 * NL];
   SopKeep keep;
@@ -375,15 +378,19 @@ BLS_HD SopPrep sop1_prep_b(int idx, int sh) {
   return p;
 }
 // res[14] = lane h's coefficient (balanced limbs).  Returns the value bound of the result under BLS_TRACK (else 0).
-BLS_FN double sop1_compute(int32_t* res, const SopTerm* t, int nt, int fp_mode, const SopSpaces& cx, int h) {
+// (inlined into its single call site: the result stays in registers; at most two terms: both are read up front so that no
+// product waits for a table load)
+BLS_HD double sop1_compute(int32_t* res, const SopTerm* t, int nt, int fp_mode, const SopSpaces& cx_, int h) {
+  const SopSpaces cx = cx_;  // into registers once: the caller's copy lives in local memory
   const int lane_k = cx.k;
+  const SopTerm tm0 = t[0], tm1 = t[nt > 1 ? 1 : 0];
   uint64_t T[2 * NL];
   int32_t x[NL], y[NL];
   SopI4 ra[7], rb[7];
   double vout = 0;
 #if defined(BLS_TRACK)
   double col = 0, vsum = 0;
-  BLS_REQ(nt >= 1 && nt <= SOP_MAX_TERMS, "sop1 term count");
+  BLS_REQ(nt >= 1 && nt <= 2, "sop1 term count");
   for (int k = 0; k < nt; k++) {
     const SopTerm m = t[k];
     const SFp2 *pa = sop_rec(cx, m.a), *pb = sop_rec(cx, m.b);
@@ -404,7 +411,7 @@ BLS_FN double sop1_compute(int32_t* res, const SopTerm* t, int nt, int fp_mode, 
   for (int i = 0; i < 2 * NL; i++) T[i] = 0;
   const int per = fp_mode ? 1 : 2;
   {
-    const SopTerm m = t[0];
+    const SopTerm m = tm0;
     sop_fetch(ra, sop_rec(cx, m.a));
     sop_fetch(rb, sop_rec(cx, m.b));
     sop_prep_apply(x, ra, sop1_prep_a(fp_mode ? h : 0, sop_term_xi(m.fl, lane_k), (m.fl & SOP_NEG) != 0, m.sha));
@@ -417,7 +424,7 @@ BLS_FN double sop1_compute(int32_t* res, const SopTerm* t, int nt, int fp_mode, 
     const int qw = (q + 1 == per);
     const int q1 = qw ? 0 : q + 1;
     const int k1 = qw ? (k + 1 == nt ? 0 : k + 1) : k;  // after the last step: a harmless refetch of term 0
-    const SopTerm m = t[k1];
+    const SopTerm m = k1 ? tm1 : tm0;
     sop_fetch(ra, sop_rec(cx, m.a));
     sop_fetch(rb, sop_rec(cx, m.b));
     sop_acc(T, x, y);
@@ -462,7 +469,7 @@ BLS_HD void sop1_store_line(SLineRec* dst, const int32_t* res, const int32_t* ot
   STRK(*dst, vb, 134217728.0);
 }
 // lane h's half of  sx * [xi] x + sy * y + sz * z  (y, z optional), limbs renormalised
-BLS_FN double sfp2_lin_half(int32_t* res, const SFp2* x, int32_t sx, uint32_t flx, const SFp2* y, int32_t sy, const SFp2* z, int32_t sz, int h) {
+BLS_HD double sfp2_lin_half(int32_t* res, const SFp2* x, int32_t sx, uint32_t flx, const SFp2* y, int32_t sy, const SFp2* z, int32_t sz, int h) {
   int64_t v[NL];
   double vb = 0;
   {
@@ -554,7 +561,7 @@ BLS_FN void sopw(SAccRec* dst, const SopTerm* t, int nt, const SAccRec* F, const
   SopI4 ra[4], rb[4];
 #if defined(BLS_TRACK)
   double col = 0, vsum = 0;
-  BLS_REQ(nt >= 1 && nt <= SOP_MAX_TERMS, "sopw term count");
+  BLS_REQ(nt >= 3 && nt <= 4, "sopw term count");
   for (int k = 0; k < nt; k++) {
     const SopTerm m = t[k];
     const double xi = sop_term_xi(m.fl, lane_k) ? 2.0 : 1.0;

@@ -8,7 +8,9 @@ no data-path collective, weak scaling): every rank verifies its own batch.
   value : sigs/s with the batch already resident in HBM (blsgpu_verify_batch_dev), CUDA events on the launching stream
   e2e   : sigs/s through the host-buffer C-ABI call (pinned host inputs, H2D + D2H inside the timed region)
   roofline : INT32 multiply-accumulate (IMAD.WIDE) rate of the dominant kernel against the rate measured on this
-             GPU by blsgpu_imad_peak (this path is integer-multiply bound; HBM traffic is ~2 KB per signature)
+             GPU by blsgpu_imad_peak.  The path is integer-multiply bound: the largest HBM stream (the Miller line
+             records, 39 KB per signature written once and read once) is ~80 GB per 1M batch = 12 ms at 6.5 TB/s,
+             against ~1 s of arithmetic.
   cpu_baseline : the CPU oracle restating the reference's per-signature core_verify, timed on a bounded sample
 
 `--impl reference` times the reference's CPU path (oracle restatement: blsful itself needs cargo + un-vendored crates).
@@ -224,19 +226,32 @@ def main():
     value = world * n * args.steps / (ms_total * 1e-3)
     e2e_value = world * n * e2e_steps / (ms_e2e * 1e-3)
 
-    # roofline of the dominant kernel (largest stage): algorithmic MACs / its CUDA-event duration
-    dom = max(stages, key=lambda k: stages[k])
+    # roofline of the dominant kernel: the largest single-kernel stage (the "miller" stage is three kernels, reported as
+    # a stage below; hash_to_curve / decode_* are one kernel each).  Algorithmic MACs / CUDA-event duration.
+    single = {k: v for k, v in stages.items() if k in ("decode_pk", "decode_sig", "hash_to_curve")}
+    dom = max(single, key=lambda k: single[k])
     dom_macs = n * FPMUL_PER_STAGE[dom] * MAC_PER_FPMUL
     achieved = dom_macs / (stages[dom] * 1e-3) / 1e9 if stages[dom] > 0 else 0.0
     whole = n * FPMUL_PER_SIG * MAC_PER_FPMUL / ((ms_total / args.steps) * 1e-3) / 1e9
+    per_stage = {k: {"ms": v, "fp_mul_per_sig": FPMUL_PER_STAGE[k],
+                     "frac": (n * FPMUL_PER_STAGE[k] * MAC_PER_FPMUL / (v * 1e-3) / peak_mac) if v > 0 else None}
+                 for k, v in stages.items()}
+    traffic = None
+    try:  # dram bytes per launch of the dominant kernel from the committed ncu capture of this round (profiles/)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
+        traffic = tr.get(dom, {}).get("dram_bytes_per_sig", None)
+        traffic = traffic * n if traffic is not None else None
+    except Exception:
+        pass
     roofline = {
-        "bound": "int32_imad", "kernel": dom, "achieved": achieved, "peak": peak_mac / 1e9, "unit": "GMAC/s",
-        "frac": achieved / (peak_mac / 1e9), "traffic": None,
+        "bound": "int32_imad (not hbm, not tensor: see DESIGN.md section 6)", "kernel": dom, "achieved": achieved,
+        "peak": peak_mac / 1e9, "unit": "GMAC/s", "frac": achieved / (peak_mac / 1e9), "traffic": traffic,
         "whole_step": {"achieved": whole, "frac": whole / (peak_mac / 1e9), "fp_mul_per_sig": FPMUL_PER_SIG},
         "peak_source": "measured live by blsgpu_imad_peak (8 independent IMAD.WIDE.U32 chains per thread with changing "
                        "operands on all SMs); MEASURED_PEAKS.json holds no INT32 figure; ncu counterpart: "
                        "sm__pipe_fmaheavy_cycles_active",
-        "stage_ms": stages,
+        "algorithmic_unit": "1 Fp-mul = 300 32x32->64 MACs (SURVEY.md 8d); the kernels execute 357 (Karatsuba, 28-bit radix)",
+        "stages": per_stage,
     }
 
     line = {
@@ -245,7 +260,7 @@ def main():
         "dtype": "u32 limbs (381-bit modular integers)", "data": "synthetic",
         "config": {"workload": f"Bls12381G2Impl Basic batch verify, {n} distinct 32-byte messages per GPU, compressed inputs "
                                "(48 B pk + 96 B sig), hash_to_curve + pairing, all valid",
-                   "sigs_per_gpu": n, "l2": "inputs (176 B/sig) exceed L2 at 1M; intermediates stream through HBM",
+                   "sigs_per_gpu": n, "l2": "inputs (176 B/sig) and the 39 KB/sig Miller line records exceed L2 at 1M: everything streams through HBM",
                    "miller_loops_per_s_per_gpu": n * args.steps / (ms_total * 1e-3)},
         "roofline": roofline, "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 176 + (n + 1) * 8), "d2h_bytes_per_step": int(n)},
