@@ -197,8 +197,16 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
   Fp12* d_T = ctx->arena.take<Fp12>(1);
   if (use_msm) {
     int rc = [&]() -> int {
+      // window width: >= ~16 signatures per bucket, and only widths whose TOP window (64 - (nwin-1) c bits) is not much
+      // narrower than the others - a 4-bit top window would put n/16 signatures into each of 16 buckets, one thread each
+      // (measured: 1.5 s at n = 500,000 with c = 15)
+      static const int widths[] = {16, 13, 11, 8, 5, 4};
       int c = 4;
-      while (c < 16 && ((size_t)1 << (c + 4)) <= n) c++;  // ~16 signatures per bucket
+      for (int w : widths)
+        if (((size_t)1 << (w + 4)) <= n) {
+          c = w;
+          break;
+        }
       const int nwin = (64 + c - 1) / c;
       const size_t nb = (size_t)1 << c, nbuckets = nb * nwin, nchunks = nbuckets / MSM_CHUNK;
       uint64_t* d_r = ctx->arena.take<uint64_t>(n);

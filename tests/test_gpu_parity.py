@@ -168,12 +168,11 @@ def test_verify_batch_bisection_finds_exact_bad_set(eng, B, impl):
                                  sigs[i * sl:(i + 1) * sl].tobytes(), m)
 
 
-@pytest.mark.parametrize("impl", [2, 1])
-def test_verify_batch_large_batch_bucket_msm_and_chunks(eng, B, impl):
+@pytest.mark.parametrize("impl,n", [(2, 4500), (1, 4500), (2, 33000)])
+def test_verify_batch_large_batch_bucket_msm_and_chunks(eng, B, impl, n):
     """Batches of >= 4096 items take the bucket multi-scalar multiplication for sum r_i sig_i; a failing batch falls back
     to per-group sums for the bisection.  Also covers identity / undecodable items inside cooperative groups of six."""
-    rnd = random.Random(50 + impl)
-    n = 4500
+    rnd = random.Random(50 + impl)  # n = 33000: 11-bit windows with a narrower (9-bit) top window
     k = np.frombuffer(b"".join(rnd.randrange(1, O.R).to_bytes(32, "big") for _ in range(n)), dtype=np.uint8)
     msgs = [hashlib.sha256(b"big%d" % i).digest() for i in range(n)]
     data, off = B.pack_messages(msgs)
