@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_miller(size_t n, const 
 //               memory; the lines come back from HBM one step ahead of their use (sop2f's prefetch)
 constexpr int M6_LINES_TPB = 128;
 constexpr int M6_LINES_PAIRS = M6_LINES_TPB / 2;
-constexpr int M6_LINES_SMEM = M6_NREG * M6_LINES_PAIRS * (int)sizeof(SFp2);  // 100,352 B: two blocks per SM
+constexpr int M6_LINES_SMEM = M6_NREG * M6_LINES_PAIRS * (int)sizeof(SFp2);  // 71,680 B: three blocks per SM
 constexpr int M6_ITEMS_PER_BLOCK = 120;                                   // k_m6_accum: 4 warps x 5 groups x 6 lanes
 constexpr int M6_ACCUM_SMEM = 4 * 30 * (int)sizeof(SAccRec);
 constexpr size_t M6_LINE_RECS = (size_t)M6_STEPS * 3;                     // records per item in the line stream
@@ -296,15 +296,16 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_m6_prep(size_t n, size_
     miller_prepare(mp, p);
   }
   M6Arg a;
-  m6_make_arg(a, mp);
+  const G2Aff q = m6_g2(pk, h, i);
+  m6_make_arg(a, mp, q);
   args[c] = a;
 }
 
 // Two lanes per pair: lane h computes coefficient h of every program step (sop1), both read the pair's 14 records in
 // shared memory (record-major, 112-byte stride between pairs: conflict-free; the two lanes of a pair read the same words).
-// 64 pairs per 128-thread block, 100,352 B of shared memory: two blocks per SM, two warps per scheduler.
+// 64 pairs per 128-thread block, 71,680 B of shared memory (10 records per pair): three blocks per SM.
 template <class PkA, class HA>
-__global__ void __launch_bounds__(M6_LINES_TPB, 2) k_m6_lines(size_t n, size_t base, const M6Arg* __restrict__ args, const PkA* __restrict__ pk,
+__global__ void __launch_bounds__(M6_LINES_TPB, 3) k_m6_lines(size_t n, size_t base, const M6Arg* __restrict__ args, const PkA* __restrict__ pk,
                                                              const HA* __restrict__ h, const uint8_t* __restrict__ pre, SLineRec* __restrict__ lines) {
   extern __shared__ __align__(16) uint8_t m6_smem[];
   const int hh = threadIdx.x & 1, pib = threadIdx.x >> 1;
@@ -323,13 +324,6 @@ __global__ void __launch_bounds__(M6_LINES_TPB, 2) k_m6_lines(size_t n, size_t b
   for (int i = 62; i >= 0; i--) {
 #pragma unroll 1
     for (int pass = 0; pass < 1 + (int)((e >> i) & 1); pass++) {
-      if (pass == 1) {
-        if (active && hh == 0) {
-          const G2Aff qv = q;
-          m6_add_setup(cx, qv);
-        }
-        __syncwarp();
-      }
       const M6Op* prog = pass == 0 ? K_M6_DBL : K_M6_ADD;
       const int nops = pass == 0 ? K_M6_DBL_N : K_M6_ADD_N;
 #pragma unroll 1

@@ -71,49 +71,51 @@ BLS_HD void m6_finish_lane(Fp2& out, const SAccRec& fa, int k) {
 // Running point T = (X : Y : Z) in HOMOGENEOUS projective coordinates on the twist y^2 = x^3 + 4 xi; the G1 argument
 // enters as three Fp scalars px = Xp Zp, -py = -Yp, pz = Zp^3 (affine: x, -y, 1), so a Jacobian r_i * pk_i needs no
 // inversion.  Lines are scaled by factors in proper subfields (erased by the final exponentiation):
-//   doubling:  B = Y^2, C = Z^2, J = X^2, G = xi C;   U = B - 36G, V = B + 36G
-//              X3 = 2XY U,  Y3 = V^2 - 48G 36G,  Z3 = 8 B YZ                    (4 x the textbook (X3:Y3:Z3))
-//              l0 = (12G - B) pz,  l2 = 3J px,  l3 = 2YZ (-py)
+//   doubling:  B = Y^2, C = Z^2, J = X^2, E = 12 xi C;   U = B - 3E, V = B + 3E
+//              X3 = 2XY U,  Y3 = V^2 - 12 E^2,  Z3 = 8 B YZ                     (4 x the textbook (X3:Y3:Z3))
+//              l0 = (E - B) pz,  l2 = 3J px,  l3 = 2YZ (-py)
 //   addition:  u = y2 Z - Y, v = x2 Z - X, A = u^2 Z - v^3 - 2 v^2 X
 //              X3 = v A,  Y3 = u (v^2 X - A) - v^3 Y,  Z3 = v^3 Z
 //              l0 = (v y2 - u x2) pz,  l2 = u px,  l3 = v (-py)
 // (derivation checked against the big-int oracle in tools/proto_lines.py; bounds by the BLS_TRACK build)
 enum : uint8_t {
-  RX = 0, RY, RZ, RNQX, RQY, RT0, RT1, RT2, RT3, RT4, RT5, RT6, RT7, RT8,
-  M6_NREG,                                            // 14 records per pair in the thread's record file
-  RPX = SOPX_P, RNPY = SOPX_P + 1, RPZ = SOPX_P + 2,  // the prepared G1 argument: read-only records (M6Arg)
-  RL0 = SOPX_LINE, RL2 = SOPX_LINE + 1, RL3 = SOPX_LINE + 2,  // the lane's line record (shared memory on the device)
+  RX = 0, RY, RZ, RT0, RT1, RT2, RT3, RT4, RT5, RT6,
+  M6_NREG,                                            // 10 records per pair in the thread's record file
+  RPX = SOPX_P, RNPY = SOPX_P + 1, RPZ = SOPX_P + 2,  // the prepared arguments: read-only records (M6Arg)
+  RNQX = SOPX_P + 3, RQY = SOPX_P + 4,
+  RL0 = SOPX_LINE, RL2 = SOPX_LINE + 1, RL3 = SOPX_LINE + 2,  // the line record being produced
   RNONE = SOPX_NONE
 };
 struct M6Op {
-  uint8_t kind;  // 0: sop2f, 1: sfp2_lin  (dst = lx * [xi] xr + ly * yr + lz * zr)
+  uint8_t kind;  // 0: sum of products, 1: sfp2_lin  (dst = lx * [xi] xr + ly * yr + lz * zr)
   uint8_t dst, nt, fp;
-  SopTerm t[2];
+  SopTerm t[3];
   int8_t lx, ly, lz;
   uint8_t xr, yr, zr, lfl, pad;
 };
 #define M6_T(a, b) {a, b, 0, 0, 0, 0, 0, 0}
 #define M6_TS(a, sha, b, shb, fl) {a, b, sha, shb, fl, 0, 0, 0}
-#define M6_SOP1(dst, t0) {0, dst, 1, 0, {t0, t0}, 0, 0, 0, RNONE, RNONE, RNONE, 0, 0}
-#define M6_SOP2(dst, t0, t1) {0, dst, 2, 0, {t0, t1}, 0, 0, 0, RNONE, RNONE, RNONE, 0, 0}
-#define M6_SOPFP(dst, t0) {0, dst, 1, 1, {t0, t0}, 0, 0, 0, RNONE, RNONE, RNONE, 0, 0}
-#define M6_LIN(dst, x, lx, fl, y, ly, z, lz) {1, dst, 0, 0, {M6_T(RNONE, RNONE), M6_T(RNONE, RNONE)}, lx, ly, lz, x, y, z, fl, 0}
+#define M6_SOP1(dst, t0) {0, dst, 1, 0, {t0, t0, t0}, 0, 0, 0, RNONE, RNONE, RNONE, 0, 0}
+#define M6_SOP2(dst, t0, t1) {0, dst, 2, 0, {t0, t1, t1}, 0, 0, 0, RNONE, RNONE, RNONE, 0, 0}
+#define M6_SOP3(dst, t0, t1, t2) {0, dst, 3, 0, {t0, t1, t2}, 0, 0, 0, RNONE, RNONE, RNONE, 0, 0}
+#define M6_SOPFP(dst, t0) {0, dst, 1, 1, {t0, t0, t0}, 0, 0, 0, RNONE, RNONE, RNONE, 0, 0}
+#define M6_SOPFP2(dst, t0, t1) {0, dst, 2, 1, {t0, t1, t1}, 0, 0, 0, RNONE, RNONE, RNONE, 0, 0}
+#define M6_LIN(dst, x, lx, fl, y, ly, z, lz) {1, dst, 0, 0, {M6_T(RNONE, RNONE), M6_T(RNONE, RNONE), M6_T(RNONE, RNONE)}, lx, ly, lz, x, y, z, fl, 0}
+// Ten records per pair (X, Y, Z and seven temporaries) is what lets THREE blocks of the lines kernel share an SM.
 BLS_CONST M6Op K_M6_DBL[] = {
     M6_SOP1(RT0, M6_T(RY, RY)),                                   // B
     M6_SOP1(RT1, M6_T(RZ, RZ)),                                   // C
     M6_SOP1(RT2, M6_T(RX, RX)),                                   // J
     M6_SOP1(RT3, M6_T(RX, RY)),                                   // XY
     M6_SOP1(RT4, M6_T(RY, RZ)),                                   // YZ
-    M6_LIN(RT5, RT1, -36, SOP_XI, RT0, 1, RNONE, 0),              // U = B - 36 xi C
-    M6_LIN(RT6, RT1, 36, SOP_XI, RT0, 1, RNONE, 0),               // V = B + 36 xi C
-    M6_LIN(RT7, RT1, 36, SOP_XI, RNONE, 0, RNONE, 0),             // F = 36 xi C
-    M6_LIN(RT8, RT1, -48, SOP_XI, RNONE, 0, RNONE, 0),            // E4 = -48 xi C
-    M6_LIN(RT1, RT1, 12, SOP_XI, RT0, -1, RNONE, 0),              // W = 12 xi C - B   (in place)
+    M6_LIN(RT1, RT1, 12, SOP_XI, RNONE, 0, RNONE, 0),             // E = 12 xi C       (in place)
+    M6_LIN(RT5, RT1, -3, 0, RT0, 1, RNONE, 0),                    // U = B - 3E
+    M6_LIN(RT6, RT1, 3, 0, RT0, 1, RNONE, 0),                     // V = B + 3E
     M6_LIN(RT2, RT2, 3, 0, RNONE, 0, RNONE, 0),                   // J3 = 3J           (in place)
     M6_SOP1(RX, M6_TS(RT3, 1, RT5, 0, 0)),                        // X3 = 2XY U
-    M6_SOP2(RY, M6_T(RT6, RT6), M6_T(RT8, RT7)),                  // Y3 = V^2 + E4 F
+    M6_SOP3(RY, M6_T(RT6, RT6), M6_TS(RT1, 2, RT1, 1, SOP_NEG), M6_TS(RT1, 2, RT1, 0, SOP_NEG)),  // Y3 = V^2 - 8E^2 - 4E^2
     M6_SOP1(RZ, M6_TS(RT0, 2, RT4, 1, 0)),                        // Z3 = 4B 2YZ
-    M6_SOPFP(RL0, M6_T(RT1, RPZ)),                                // l0 = W pz
+    M6_SOPFP2(RL0, M6_T(RT1, RPZ), M6_TS(RT0, 0, RPZ, 0, SOP_NEG)),  // l0 = (E - B) pz
     M6_SOPFP(RL2, M6_T(RT2, RPX)),                                // l2 = 3J px
     M6_SOPFP(RL3, M6_TS(RT4, 1, RNPY, 0, 0)),                     // l3 = 2YZ (-py)
 };
@@ -125,23 +127,24 @@ BLS_CONST M6Op K_M6_ADD[] = {
     M6_SOP1(RT2, M6_T(RT1, RT1)),                                 // vv
     M6_SOP1(RT3, M6_T(RT1, RT2)),                                 // vvv
     M6_SOP1(RT4, M6_T(RT2, RX)),                                  // Rr = vv X
-    M6_SOP1(RT5, M6_T(RT0, RT0)),                                 // uu
-    M6_SOP1(RT5, M6_T(RT5, RZ)),                                  // uu Z
-    M6_LIN(RT5, RT5, 1, 0, RT3, -1, RT4, -2),                     // A = uu Z - vvv - 2 Rr
-    M6_LIN(RT6, RT4, 1, 0, RT5, -1, RNONE, 0),                    // D = Rr - A
-    M6_SOP2(RT7, M6_T(RT1, RQY), M6_T(RT0, RNQX)),                // v y2 - u x2
-    M6_SOPFP(RL0, M6_T(RT7, RPZ)),                                // l0
+    M6_SOP2(RT2, M6_T(RT1, RQY), M6_T(RT0, RNQX)),                // v y2 - u x2       (vv is dead)
+    M6_SOPFP(RL0, M6_T(RT2, RPZ)),                                // l0
     M6_SOPFP(RL2, M6_T(RT0, RPX)),                                // l2 = u px
     M6_SOPFP(RL3, M6_T(RT1, RNPY)),                               // l3 = v (-py)
-    M6_SOP1(RX, M6_T(RT1, RT5)),                                  // X3 = v A
-    M6_SOP2(RY, M6_T(RT0, RT6), M6_TS(RT3, 0, RY, 0, SOP_NEG)),   // Y3 = u D - vvv Y
+    M6_SOP1(RT2, M6_T(RT0, RT0)),                                 // uu
+    M6_SOP1(RT2, M6_T(RT2, RZ)),                                  // uu Z
+    M6_LIN(RT2, RT2, 1, 0, RT3, -1, RT4, -2),                     // A = uu Z - vvv - 2 Rr
+    M6_SOP1(RX, M6_T(RT1, RT2)),                                  // X3 = v A
+    M6_SOP3(RY, M6_T(RT0, RT4), M6_TS(RT0, 0, RT2, 0, SOP_NEG), M6_TS(RT3, 0, RY, 0, SOP_NEG)),  // Y3 = u Rr - u A - vvv Y
     M6_SOP1(RZ, M6_T(RT3, RZ)),                                   // Z3 = vvv Z
 };
 #undef M6_T
 #undef M6_TS
 #undef M6_SOP1
 #undef M6_SOP2
+#undef M6_SOP3
 #undef M6_SOPFP
+#undef M6_SOPFP2
 #undef M6_LIN
 constexpr int K_M6_DBL_N = (int)(sizeof(K_M6_DBL) / sizeof(M6Op));
 constexpr int K_M6_ADD_N = (int)(sizeof(K_M6_ADD) / sizeof(M6Op));
@@ -173,16 +176,20 @@ BLS_HD void m6_op_store(const M6Op* op, const SopSpaces& cx, int h, const int32_
   else sop1_store_rec(sop_rec(cx, op->dst), res, h, vb);
 }
 
-// the prepared G1 argument of one pair: px, -py, pz as Fp scalars in the c0 halves of three records (HBM, read-only)
+// the prepared arguments of one pair (HBM, read-only): px, -py, pz as Fp scalars in the c0 halves of three records, and the
+// G2 point as (-x2, y2) for the addition steps
 struct M6Arg {
-  SFp2 px, npy, pz;
+  SFp2 px, npy, pz, nqx, qy;
 };
-// P prepared by miller_prepare (pairing.cuh)
-BLS_HD void m6_make_arg(M6Arg& a, const MillerG1& P) {
+// P prepared by miller_prepare (pairing.cuh), Q affine and not the identity
+BLS_HD void m6_make_arg(M6Arg& a, const MillerG1& P, const G2Aff& q) {
   sfp2_from_fp(a.px, P.px);
   sfp2_from_fp(a.npy, P.py);
   sfp2_neg(a.npy, a.npy);
   sfp2_from_fp(a.pz, P.pz);
+  sfp2_from_fp2(a.nqx, q.x);
+  sfp2_neg(a.nqx, a.nqx);
+  sfp2_from_fp2(a.qy, q.y);
 }
 // the spaces of one pair's line programs: record file `reg` (stride in records), argument, and the line record to produce
 BLS_HD SopSpaces m6_spaces_line(SFp2* reg, int stride, const M6Arg* arg, SLineRec* line) {
@@ -203,16 +210,7 @@ BLS_HD void m6_init_point(const SopSpaces& cx, const G2Aff& q) {
   sfp2_one(*sop_rec(cx, RZ));
 }
 BLS_HD void m6_dbl_line(const SopSpaces& cx) { m6_run(K_M6_DBL, K_M6_DBL_N, cx); }
-BLS_HD void m6_add_setup(const SopSpaces& cx, const G2Aff& q) {
-  SFp2* nqx = sop_rec(cx, RNQX);
-  sfp2_from_fp2(*nqx, q.x);
-  sfp2_neg(*nqx, *nqx);
-  sfp2_from_fp2(*sop_rec(cx, RQY), q.y);
-}
-BLS_HD void m6_add_line(const SopSpaces& cx, const G2Aff& q) {
-  m6_add_setup(cx, q);
-  m6_run(K_M6_ADD, K_M6_ADD_N, cx);
-}
+BLS_HD void m6_add_line(const SopSpaces& cx) { m6_run(K_M6_ADD, K_M6_ADD_N, cx); }
 constexpr int M6_STEPS = 68;  // 63 doublings + 5 additions: line records per pair
 
 }  // namespace bls

@@ -73,7 +73,7 @@ constexpr int SOP_MAX_TERMS = 8;
 
 // Operand references are one-byte indices into a few record spaces, so that a whole computation is a constant table
 // (no descriptor is ever built in local memory; the table is read through the constant cache):
-//   0..23   the thread's record file: reg[i * reg_stride]     24..31  read-only per-item records P[i - 24] (HBM)
+//   0..23   the pair's record file: reg[i * reg_stride]       24..31  read-only per-item records P[i - 24] (HBM)
 //   32..34  the line record being produced (destination of the line programs)
 //   48..53  accumulator coefficient F[i - 48]                  56..58  coefficient i - 56 of the line being multiplied in
 //   64..69  accumulator coefficient F[(k - (i - 64)) mod 6], k = the lane's coefficient index        255 none
@@ -378,19 +378,19 @@ BLS_HD SopPrep sop1_prep_b(int idx, int sh) {
   return p;
 }
 // res[14] = lane h's coefficient (balanced limbs).  Returns the value bound of the result under BLS_TRACK (else 0).
-// (inlined into its single call site: the result stays in registers; at most two terms: both are read up front so that no
+// (inlined into its single call site: the result stays in registers; at most three terms: all are read up front so that no
 // product waits for a table load)
 BLS_HD double sop1_compute(int32_t* res, const SopTerm* t, int nt, int fp_mode, const SopSpaces& cx_, int h) {
   const SopSpaces cx = cx_;  // into registers once: the caller's copy lives in local memory
   const int lane_k = cx.k;
-  const SopTerm tm0 = t[0], tm1 = t[nt > 1 ? 1 : 0];
+  const SopTerm tm0 = t[0], tm1 = t[nt > 1 ? 1 : 0], tm2 = t[nt > 2 ? 2 : 0];
   uint64_t T[2 * NL];
   int32_t x[NL], y[NL];
   SopI4 ra[7], rb[7];
   double vout = 0;
 #if defined(BLS_TRACK)
   double col = 0, vsum = 0;
-  BLS_REQ(nt >= 1 && nt <= 2, "sop1 term count");
+  BLS_REQ(nt >= 1 && nt <= 3, "sop1 term count");
   for (int k = 0; k < nt; k++) {
     const SopTerm m = t[k];
     const SFp2 *pa = sop_rec(cx, m.a), *pb = sop_rec(cx, m.b);
@@ -424,7 +424,7 @@ BLS_HD double sop1_compute(int32_t* res, const SopTerm* t, int nt, int fp_mode, 
     const int qw = (q + 1 == per);
     const int q1 = qw ? 0 : q + 1;
     const int k1 = qw ? (k + 1 == nt ? 0 : k + 1) : k;  // after the last step: a harmless refetch of term 0
-    const SopTerm m = k1 ? tm1 : tm0;
+    const SopTerm m = k1 == 0 ? tm0 : k1 == 1 ? tm1 : tm2;
     sop_fetch(ra, sop_rec(cx, m.a));
     sop_fetch(rb, sop_rec(cx, m.b));
     sop_acc(T, x, y);

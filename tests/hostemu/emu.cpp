@@ -181,7 +181,7 @@ int emu_miller6(int n, const uint8_t* p48, const uint8_t* q96, const uint32_t* k
     if (g1_decompress(p, p48 + 48 * j, false) || g2_decompress(q, q96 + 96 * j, false)) return -1;
     MillerG1 mp;
     if (nl) { G1Jac pj; jac_mul_aff(pj, p, k + nl * j, nl); miller_prepare(mp, pj); } else miller_prepare(mp, p);
-    M6Arg arg; m6_make_arg(arg, mp);
+    M6Arg arg; m6_make_arg(arg, mp, q);
     SFp2 reg[2 * M6_NREG];  // exercised with a record stride of 2
     SopSpaces cx = m6_spaces_line(reg, 2, &arg, nullptr);
     m6_init_point(cx, q);
@@ -190,7 +190,6 @@ int emu_miller6(int n, const uint8_t* p48, const uint8_t* q96, const uint32_t* k
       for (int pass = 0; pass < 2; pass++) {
         if (pass == 1 && !((e >> i) & 1)) break;
         cx.line = lines[j][step++];
-        if (pass == 1) m6_add_setup(cx, q);
         const M6Op* prog = pass == 0 ? K_M6_DBL : K_M6_ADD;
         const int nops = pass == 0 ? K_M6_DBL_N : K_M6_ADD_N;
         if (two_lane) {  // k_m6_lines: two lanes per pair, emulated one after the other around the store barrier
