@@ -31,6 +31,7 @@ class SerializationFormat:
 
 ST_OK, ST_INVALID_SIGNATURE, ST_SIG_IDENTITY, ST_PK_IDENTITY, ST_DESERIALIZE, ST_LEGACY_FORMAT = 0, 1, 2, 3, 4, 5
 ST_INVALID_LENGTH, ST_INVALID_COEFFICIENT, ST_DUPLICATE_MESSAGES, ST_SCHEME, ST_MISMATCHED_LENGTHS = 6, 7, 8, 9, 10
+ST_VSSS = 11
 
 _STATUS_TEXT = {
     ST_INVALID_SIGNATURE: "invalid signature",
@@ -43,6 +44,7 @@ _STATUS_TEXT = {
     ST_DUPLICATE_MESSAGES: "invalid inputs: duplicate messages detected",
     ST_SCHEME: "Invalid signature scheme",
     ST_MISMATCHED_LENGTHS: "invalid inputs: Mismatched array lengths",
+    ST_VSSS: "an error occurred during secret sharing",
 }
 
 STAGES = ["decode_pk", "decode_sig", "hash_to_curve", "scale_sig", "miller", "reduce", "final", "bisect"]
@@ -109,6 +111,7 @@ def load_library() -> ctypes.CDLL:
         "blsgpu_fp_mul_batch": (c.c_int, [vp, c.c_int, c.c_size_t, u8p, u8p, u8p]),
         "blsgpu_pairing_product_is_one": (c.c_int, [vp, c.c_size_t, u8p, u8p, c.POINTER(c.c_int)]),
         "blsgpu_testdata_sign": (c.c_int, [vp, c.c_int, c.c_int, c.c_size_t, u8p, u8p, u64p, u8p, u8p]),
+        "blsgpu_combine_shares_batch": (c.c_int, [vp, c.c_int, c.c_size_t, u64p, u8p, u8p, u8p]),
         "blsgpu_imad_peak": (c.c_int, [vp, c.POINTER(c.c_double)]),
         "blsgpu_last_stage_ms": (c.c_int, [vp, c.POINTER(c.c_float)]),
         "blsgpu_launch_count": (c.c_uint64, [vp]),
@@ -126,7 +129,7 @@ EXPORTED_SYMBOLS = [
     "blsgpu_verify_batch_dev", "blsgpu_pop_verify_batch", "blsgpu_aggregate_verify", "blsgpu_sum_points",
     "blsgpu_verify_secure_batch", "blsgpu_aggregate_secure_batch", "blsgpu_hash_to_curve_batch", "blsgpu_recode_points",
     "blsgpu_fp_mul_batch", "blsgpu_pairing_product_is_one", "blsgpu_testdata_sign", "blsgpu_imad_peak",
-    "blsgpu_last_stage_ms", "blsgpu_launch_count",
+    "blsgpu_combine_shares_batch", "blsgpu_last_stage_ms", "blsgpu_launch_count",
 ]
 
 
@@ -401,6 +404,26 @@ class Engine:
         self._check(self._lib.blsgpu_pairing_product_is_one(self._ctx, n, _ptr(a), _ptr(b), ctypes.byref(res)),
                     "blsgpu_pairing_product_is_one")
         return bool(res.value)
+
+    # ---- threshold shares ------------------------------------------------------------------------------------------
+    def combine_shares_batch(self, group: int, share_sets: Sequence[Sequence[bytes]]) -> Tuple[np.ndarray, List[bytes]]:
+        """Signature::from_shares / PublicKey::from_shares for many share sets (signature.rs:151-165, sig_core.rs:92-105).
+        A share is the reference's raw form: 32-byte big-endian identifier || compressed point (lib.rs:117-157)."""
+        length = 48 if group == 1 else 96
+        q = len(share_sets)
+        off = np.zeros(q + 1, dtype=np.uint64)
+        if q:
+            off[1:] = np.cumsum([len(s) for s in share_sets], dtype=np.uint64)
+        flat = [sh for ss in share_sets for sh in ss]
+        for sh in flat:
+            if len(sh) != 32 + length:
+                raise BlsError(ST_DESERIALIZE, "Invalid length for share")  # lib.rs:121-125
+        data = np.frombuffer(b"".join(flat), dtype=np.uint8) if flat else np.zeros(0, dtype=np.uint8)
+        out = np.zeros(q * length, dtype=np.uint8)
+        status = np.zeros(q, dtype=np.uint8)
+        rc = self._lib.blsgpu_combine_shares_batch(self._ctx, group, q, _ptr(off), _ptr(data), _ptr(out), _ptr(status))
+        self._check(rc, "blsgpu_combine_shares_batch")
+        return status, [out[j * length:(j + 1) * length].tobytes() for j in range(q)]
 
     def testdata_sign(self, impl_id: int, scheme: int, scalars: np.ndarray, msgs_data: np.ndarray, msg_off: np.ndarray):
         """Synthetic data only (see include/blsgpu.h): returns (pks, sigs) flat uint8 arrays."""

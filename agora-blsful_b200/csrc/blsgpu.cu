@@ -1183,3 +1183,106 @@ int blsgpu_aggregate_secure_batch(blsgpu_ctx* ctx, int impl_id, int format, size
   return impl_id == 2 ? aggregate_secure_impl<2>(ctx, format, q, key_off, pks, member_sigs, out_sigs, status_out)
                       : aggregate_secure_impl<1>(ctx, format, q, key_off, pks, member_sigs, out_sigs, status_out);
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Threshold-share combination.  Host side: splitting the records, the set-level rules of vsss-rs `combine` (at least two
+// shares, non-zero and distinct identifiers); device side: identifier parsing, Lagrange coefficients in Fr, the
+// lambda_i * value_i multiplications, segmented sums, encoding.
+template <class A>
+static int combine_shares_impl(blsgpu_ctx* ctx, size_t q, const uint64_t* share_off, const uint8_t* shares, uint8_t* out, uint8_t* status_out) {
+  typedef typename PtInfo<A>::Jac J;
+  const size_t L = PtInfo<A>::LEN, REC = 32 + L, M = (size_t)share_off[q];
+  std::vector<uint8_t> ids(M * 32), pts(M * L);
+  std::vector<uint32_t> set_of(M), c_start, c_cnt, s_start, s_cnt;
+  for (size_t j = 0; j < q; j++) {
+    const size_t lo = (size_t)share_off[j], hi = (size_t)share_off[j + 1];
+    s_start.push_back((uint32_t)c_start.size());
+    for (size_t i = lo; i < hi; i++) {
+      memcpy(&ids[i * 32], shares + i * REC, 32);
+      memcpy(&pts[i * L], shares + i * REC + 32, L);
+      set_of[i] = (uint32_t)j;
+    }
+    for (size_t i = lo; i < hi; i += 16) {
+      c_start.push_back((uint32_t)i);
+      c_cnt.push_back((uint32_t)std::min<size_t>(16, hi - i));
+    }
+    s_cnt.push_back((uint32_t)c_start.size() - s_start.back());
+  }
+  const size_t nc = c_start.size();
+  CKR(ensure_arena(ctx, M * (32 + L + 32 + sizeof(A) + sizeof(J) + 8) + (nc + q + 2) * (sizeof(J) + 8) + q * (sizeof(A) + L + 16) +
+                            (q + 1) * 8 + 32 * 256));
+  uint8_t *d_ids, *d_pts;
+  uint32_t *d_set, *d_cs, *d_cc, *d_ss, *d_sc;
+  uint64_t* d_off;
+  CKR(upload(ctx, d_ids, ids.data(), M * 32));
+  CKR(upload(ctx, d_pts, pts.data(), M * L));
+  CKR(upload(ctx, d_set, set_of.data(), M));
+  CKR(upload(ctx, d_off, share_off, q + 1));
+  CKR(upload(ctx, d_cs, c_start.data(), nc));
+  CKR(upload(ctx, d_cc, c_cnt.data(), nc));
+  CKR(upload(ctx, d_ss, s_start.data(), q));
+  CKR(upload(ctx, d_sc, s_cnt.data(), q));
+  uint32_t* d_raw = ctx->arena.take<uint32_t>(std::max<size_t>(M, 1) * 8);
+  uint8_t* d_idflag = ctx->arena.take<uint8_t>(std::max<size_t>(M, 1));
+  uint8_t* d_stpt = ctx->arena.take<uint8_t>(std::max<size_t>(M, 1));
+  uint8_t* d_dup = ctx->arena.take<uint8_t>(std::max<size_t>(M, 1));
+  uint8_t* d_bad = ctx->arena.take<uint8_t>(q);
+  A* d_p = ctx->arena.take<A>(std::max<size_t>(M, 1));
+  J* d_scaled = ctx->arena.take<J>(std::max<size_t>(M, 1));
+  J* d_part = ctx->arena.take<J>(std::max<size_t>(nc, 1));
+  J* d_sum = ctx->arena.take<J>(q);
+  A* d_res = ctx->arena.take<A>(q);
+  uint8_t* d_out = ctx->arena.take<uint8_t>(q * L);
+  std::vector<uint8_t> idflag(M), stpt(M), dup(M), bad(q, 0);
+  if (M) {
+    LAUNCH(k_share_ids, blocks_for(M), TPB, M, (const uint8_t*)d_ids, d_raw, d_idflag);
+    LAUNCH((k_decode<A>), blocks_for(M), TPB, M, (const uint8_t*)d_pts, 1, d_p, d_stpt);
+    CK(cudaMemcpyAsync(idflag.data(), d_idflag, M, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(stpt.data(), d_stpt, M, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  // parse errors first (every share is parsed before `combine` runs), then the set rules
+  for (size_t j = 0; j < q; j++) {
+    const size_t lo = (size_t)share_off[j], hi = (size_t)share_off[j + 1];
+    uint8_t s = BLSGPU_ST_OK;
+    for (size_t i = lo; i < hi && s == BLSGPU_ST_OK; i++)
+      if (idflag[i] == 1 || stpt[i] != BLSGPU_ST_OK) s = BLSGPU_ST_DESERIALIZE;
+    if (s == BLSGPU_ST_OK && hi - lo < 2) s = BLSGPU_ST_VSSS;
+    for (size_t i = lo; i < hi && s == BLSGPU_ST_OK; i++)
+      if (idflag[i] == 2) s = BLSGPU_ST_VSSS;
+    status_out[j] = s;
+    bad[j] = s != BLSGPU_ST_OK;
+  }
+  CK(cudaMemcpyAsync(d_bad, bad.data(), q, cudaMemcpyHostToDevice, ctx->stream));
+  if (M) {
+    LAUNCH((k_share_scale<A>), blocks_for(M), TPB, M, (const uint32_t*)d_set, (const uint64_t*)d_off, (const uint8_t*)d_bad,
+           (const uint32_t*)d_raw, (const A*)d_p, d_scaled, d_dup);
+    LAUNCH((k_seg_sum<J>), blocks_for(nc), TPB, nc, (const uint32_t*)d_cs, (const uint32_t*)d_cc, (const J*)d_scaled, d_part);
+    CK(cudaMemcpyAsync(dup.data(), d_dup, M, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  LAUNCH((k_seg_sum<J>), blocks_for(q), TPB, q, (const uint32_t*)d_ss, (const uint32_t*)d_sc, (const J*)d_part, d_sum);
+  LAUNCH((k_to_affine<A>), blocks_for(q), TPB, q, (const J*)d_sum, d_res);
+  LAUNCH((k_encode<A>), blocks_for(q), TPB, q, (const A*)d_res, 1, d_out);
+  CK(cudaMemcpyAsync(out, d_out, q * L, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (size_t j = 0; j < q; j++) {
+    if (status_out[j] == BLSGPU_ST_OK)
+      for (size_t i = (size_t)share_off[j]; i < (size_t)share_off[j + 1]; i++)
+        if (dup[i]) status_out[j] = BLSGPU_ST_VSSS;
+    if (status_out[j] != BLSGPU_ST_OK) memset(out + j * L, 0, L);
+  }
+  return BLSGPU_OK;
+}
+
+int blsgpu_combine_shares_batch(blsgpu_ctx* ctx, int group, size_t q, const uint64_t* share_off, const uint8_t* shares, uint8_t* out,
+                                uint8_t* status_out) {
+  if (!ctx) return BLSGPU_E_ARG;
+  if ((group != 1 && group != 2) || (q && (!share_off || !out || !status_out)) || (q && share_off[q] && !shares)) {
+    ctx->err = "blsgpu_combine_shares_batch: bad arguments";
+    return BLSGPU_E_ARG;
+  }
+  if (q == 0) return BLSGPU_OK;
+  CKR(set_device(ctx));
+  return group == 1 ? combine_shares_impl<G1Aff>(ctx, q, share_off, shares, out, status_out)
+                    : combine_shares_impl<G2Aff>(ctx, q, share_off, shares, out, status_out);
+}

@@ -6,6 +6,7 @@
 #include "h2c.cuh"
 #include "pairing.cuh"
 #include "miller6.cuh"
+#include "fr.cuh"
 
 namespace bls {
 
@@ -804,6 +805,49 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_seg_sum(size_t nseg, co
     jac_add(acc, acc, t);
   }
   out[c] = acc;
+}
+
+// ---- threshold-share combination (vsss-rs `combine` behind Signature::from_shares / PublicKey::from_shares) ------------
+// identifiers: 32 big-endian bytes -> raw words; flag 1: >= r (DeserializationError), 2: zero (VsssError)
+__global__ void __launch_bounds__(128) k_share_ids(size_t M, const uint8_t* __restrict__ ids_be, uint32_t* __restrict__ ids_raw, uint8_t* __restrict__ flag) {
+  size_t i = BLS_TID();
+  if (i >= M) return;
+  uint8_t b[32];
+  for (int k = 0; k < 32; k++) b[k] = ids_be[i * 32 + k];
+  uint32_t w[8];
+  fr_raw_from_be32(w, b);
+  uint32_t any = 0;
+  for (int k = 0; k < 8; k++) any |= w[k];
+  uint8_t f = fr_raw_ge_r(w) ? 1 : any == 0 ? 2 : 0;
+  if (f == 1)
+    for (int k = 0; k < 8; k++) w[k] = 0;
+  for (int k = 0; k < 8; k++) ids_raw[i * 8 + k] = w[k];
+  flag[i] = f;
+}
+// one thread per share: its Lagrange coefficient at zero within its set, then lambda * value; dup[i] = 1 on a duplicate
+// identifier.  Sets flagged bad by the host (bad[set] != 0) are skipped.
+template <class A>
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_share_scale(size_t M, const uint32_t* __restrict__ set_of, const uint64_t* __restrict__ share_off,
+                                                     const uint8_t* __restrict__ bad, const uint32_t* __restrict__ ids_raw,
+                                                     const A* __restrict__ points, typename PtInfo<A>::Jac* __restrict__ out,
+                                                     uint8_t* __restrict__ dup) {
+  size_t i = BLS_TID();
+  if (i >= M) return;
+  typename PtInfo<A>::Jac r;
+  jac_set_inf(r);
+  dup[i] = 0;
+  const uint32_t s = set_of[i];
+  if (!bad[s]) {
+    const uint64_t lo = share_off[s], hi = share_off[s + 1];
+    uint32_t lam[8];
+    if (!fr_lagrange_at_zero(lam, ids_raw + 8 * lo, (uint32_t)(hi - lo), (uint32_t)(i - lo))) {
+      dup[i] = 1;
+    } else {
+      A p = points[i];
+      jac_mul_aff(r, p, lam, 8);
+    }
+  }
+  out[i] = r;
 }
 
 // ---- building blocks ------------------------------------------------------------------------------------------------

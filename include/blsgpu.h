@@ -48,6 +48,7 @@ extern "C" {
 #define BLSGPU_ST_DUPLICATE_MESSAGES 8  /* InvalidInputs("duplicate messages detected at {a} and {b}")  src/traits/sig_basic.rs:51-56 */
 #define BLSGPU_ST_SCHEME 9              /* InvalidSignatureScheme / fewer than 2 signatures (binding side) src/aggregate_signature.rs:127-133 */
 #define BLSGPU_ST_MISMATCHED_LENGTHS 10 /* InvalidInputs("Mismatched array lengths")  src/secure_aggregation.rs:125-129 */
+#define BLSGPU_ST_VSSS 11               /* BlsError::VsssError (fewer than 2 shares, zero or duplicate identifier)  src/error.rs:24-26,60-64 */
 
 typedef struct blsgpu_ctx blsgpu_ctx;
 
@@ -143,6 +144,19 @@ int blsgpu_testdata_sign(blsgpu_ctx* ctx, int impl_id, int scheme, size_t n, con
 /* INT32 multiply-issue roofline probe: runs independent mad.wide.u32 chains on every SM and returns the measured
  * 32x32->64 multiply-accumulate rate (MAC/s) of the context's first device. */
 int blsgpu_imad_peak(blsgpu_ctx* ctx, double* mac_per_s_out);
+
+/* Threshold-share combination: Signature::from_shares / PublicKey::from_shares
+ * (reference src/signature.rs:151-165, src/public_key.rs, src/traits/sig_core.rs:92-105 -> vsss-rs `combine`):
+ * Lagrange interpolation at zero over the share identifiers, out_j = sum_i lambda_i * value_i for every share set j.
+ *   group      : 1 = G1 values (48-byte points), 2 = G2 values (96-byte points)
+ *   shares     : share_off[q] records of 32 + 48|96 bytes, the reference's raw share form (src/lib.rs:117-157):
+ *                32-byte big-endian identifier (a scalar < r) followed by the IETF compressed point
+ *   share_off  : q + 1 offsets in shares (records, not bytes) delimiting the sets
+ *   out        : q compressed points (zeroed for sets that fail);  status_out[q]: BLSGPU_ST_OK, BLSGPU_ST_DESERIALIZE
+ *                (identifier >= r or undecodable point) or BLSGPU_ST_VSSS (fewer than 2 shares, zero or duplicate identifier)
+ * The scheme-consistency rule (InvalidSignatureScheme, signature.rs:152-154) is decided by the caller-side binding. */
+int blsgpu_combine_shares_batch(blsgpu_ctx* ctx, int group, size_t q, const uint64_t* share_off, const uint8_t* shares,
+                                uint8_t* out, uint8_t* status_out);
 
 /* ---- metrics ---------------------------------------------------------------------------------------------------
  * Per-stage device times (CUDA events on the engine's stream) of the LAST verify call on the first device. */

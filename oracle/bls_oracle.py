@@ -826,3 +826,42 @@ def rlc_scalars(seed: bytes, n: int) -> List[int]:
         d = hashlib.sha256(seed + i.to_bytes(8, "little")).digest()
         out.append(int.from_bytes(d[:8], "little") | 1)
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# threshold shares on public data
+# ----------------------------------------------------------------------------------------------
+ERR_VSSS = 11  # BlsError::VsssError: every vsss_rs::Error maps to it (error.rs:24-26,60-64)
+
+
+def combine_shares(group: int, shares: Sequence[bytes]) -> Tuple[int, bytes]:
+    """Signature::from_shares / PublicKey::from_shares (signature.rs:151-165; sig_core.rs:92-105) = vsss-rs 5.0.0-rc2
+    `combine` (dependency absent from /root/reference, Cargo.toml:43; published algorithm: at least two shares, no zero
+    identifier, no duplicate identifier, then Lagrange interpolation at zero: sum_i value_i * prod_{j!=i} x_j/(x_j - x_i)).
+    A share is the raw form of InnerPointShareG1/G2 (lib.rs:117-157): 32-byte big-endian identifier (must be < r:
+    Scalar::from_be_bytes) followed by the IETF compressed point (from_compressed: curve + subgroup check)."""
+    deser, ser, add, mul = ((g1_deserialize, g1_serialize, g1_add, g1_mul) if group == 1
+                            else (g2_deserialize, g2_serialize, g2_add, g2_mul))
+    length = 48 if group == 1 else 96
+    ids, vals = [], []
+    for sh in shares:
+        if len(sh) != 32 + length:
+            return ERR_DESERIALIZE, b""
+        x = int.from_bytes(sh[:32], "big")
+        if x >= R:
+            return ERR_DESERIALIZE, b""
+        pt, st = _decode(deser, sh[32:], MODERN)
+        if st != OK:
+            return ERR_DESERIALIZE, b""
+        ids.append(x)
+        vals.append(pt)
+    if len(ids) < 2 or any(x == 0 for x in ids) or len(set(ids)) != len(ids):
+        return ERR_VSSS, b""
+    acc = None
+    for i, (xi, v) in enumerate(zip(ids, vals)):
+        lam = 1
+        for j, xj in enumerate(ids):
+            if j != i:
+                lam = lam * xj % R * pow((xj - xi) % R, -1, R) % R
+        acc = add(acc, mul(v, lam))
+    return OK, ser(acc, MODERN)

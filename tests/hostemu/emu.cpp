@@ -5,6 +5,7 @@
 #include "../../agora-blsful_b200/csrc/pairing.cuh"
 #include "../../agora-blsful_b200/csrc/h2c.cuh"
 #include "../../agora-blsful_b200/csrc/miller6.cuh"
+#include "../../agora-blsful_b200/csrc/fr.cuh"
 
 using namespace bls;
 
@@ -227,6 +228,26 @@ int emu_miller6(int n, const uint8_t* p48, const uint8_t* q96, const uint32_t* k
   for (int c = 0; c < 6; c++) m6_finish_lane(*fp12_coeff(f, c), F[c], c);
   fp12_out(ml_out, f);
   final_exponentiation(g, f); fp12_out(fe_out, g);
+  return 0;
+}
+// Fr: c = a*b mod r, d = a^-1 mod r (32-byte big-endian in and out), and the Lagrange coefficient at zero of share i
+int emu_fr_ops(const uint8_t* a32, const uint8_t* b32, uint8_t* mul_out, uint8_t* inv_out) {
+  uint32_t ra[8], rb[8], o[8];
+  fr_raw_from_be32(ra, a32); fr_raw_from_be32(rb, b32);
+  if (fr_raw_ge_r(ra) || fr_raw_ge_r(rb)) return -1;
+  Fr a, b, c; fr_from_raw(a, ra); fr_from_raw(b, rb);
+  fr_mul(c, a, b); fr_to_raw(o, c);
+  for (int w = 0; w < 8; w++) for (int k = 0; k < 4; k++) mul_out[31 - 4 * w - k] = (uint8_t)(o[w] >> (8 * k));
+  fr_inv(c, a); fr_to_raw(o, c);
+  for (int w = 0; w < 8; w++) for (int k = 0; k < 4; k++) inv_out[31 - 4 * w - k] = (uint8_t)(o[w] >> (8 * k));
+  return 0;
+}
+int emu_fr_lagrange(const uint8_t* ids32, int m, int i, uint8_t* out32) {
+  uint32_t ids[8 * 64], o[8];
+  if (m > 64) return -2;
+  for (int j = 0; j < m; j++) fr_raw_from_be32(ids + 8 * j, ids32 + 32 * j);
+  if (!fr_lagrange_at_zero(o, ids, (uint32_t)m, (uint32_t)i)) return 1;
+  for (int w = 0; w < 8; w++) for (int k = 0; k < 4; k++) out32[31 - 4 * w - k] = (uint8_t)(o[w] >> (8 * k));
   return 0;
 }
 }

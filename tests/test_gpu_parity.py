@@ -333,3 +333,43 @@ def test_secure_semantics_against_oracle(eng, B, impl, fmt):
         re = C.sig_ser(C.sig_deser(agg2[0], other), fmt)
         assert eng.verify_secure_batch(impl, 2, [pks], [re], [msg], fmt).tolist() == \
             [O.verify_secure(impl, 2, fmt, pks, re, msg)]
+
+
+def test_combine_shares_matches_oracle_and_golden_signature(eng, B, cpp):
+    """blsgpu_combine_shares_batch (Signature::from_shares / PublicKey::from_shares) against the oracle; one set is the
+    Shamir sharing of a golden secret key and must combine to the reference's golden signature bytes."""
+    rnd = random.Random(91)
+    msg = bytes.fromhex(cpp["message"])
+    s = cpp["signers"][1]
+    sk = int(s["sk"], 16)
+
+    def shamir(secret, t, ids):
+        coef = [secret] + [rnd.randrange(O.R) for _ in range(t - 1)]
+        return [sum(c * pow(x, k, O.R) for k, c in enumerate(coef)) % O.R for x in ids]
+
+    H = O.hash_to_curve_g2(msg, O.sig_dst(O.G2IMPL, O.BASIC))
+    ids = [3, 1, 7, 2 ** 200 + 11, O.R - 1]
+    sks = shamir(sk, 4, ids)
+    sig_sh = [x.to_bytes(32, "big") + O.g2_serialize(O.g2_mul(H, k)) for x, k in zip(ids, sks)]
+    pk_sh = [x.to_bytes(32, "big") + O.g1_serialize(O.g1_mul(O.G1_GEN, k)) for x, k in zip(ids, sks)]
+    big_ids = list(range(1, 41))  # more than one chunk of 16
+    big = [x.to_bytes(32, "big") + O.g2_serialize(O.g2_mul(O.G2_GEN, rnd.randrange(1, O.R))) for x in big_ids]
+    sets2 = [
+        sig_sh[:4], sig_sh, sig_sh[1:5], sig_sh[:2], big,
+        sig_sh[:1], [],                                                  # fewer than two shares
+        [bytes(32) + sig_sh[0][32:], sig_sh[1]],                         # zero identifier
+        [sig_sh[0], sig_sh[0][:32] + sig_sh[1][32:], sig_sh[2]],         # duplicate identifier
+        [O.R.to_bytes(32, "big") + sig_sh[0][32:], sig_sh[1]],           # identifier >= r
+        [sig_sh[0], sig_sh[1][:32] + bytes(96)],                         # undecodable point
+        [sig_sh[0], bytes(32) + bytes(96)],                              # zero identifier AND bad point: parse error first
+    ]
+    st, outs = eng.combine_shares_batch(2, sets2)
+    for ss, got_st, got in zip(sets2, st, outs):
+        want_st, want = O.combine_shares(2, ss)
+        assert got_st == want_st, (len(ss), got_st, want_st)
+        assert got == (want if want_st == 0 else bytes(96))
+    assert outs[0].hex() == s["sig"] and outs[1].hex() == s["sig"] and outs[2].hex() == s["sig"]
+    st, outs = eng.combine_shares_batch(1, [pk_sh[:4], pk_sh[::-1], pk_sh[:1]])
+    assert st.tolist() == [0, 0, 11] and outs[0].hex() == s["pk"] and outs[1].hex() == s["pk"]
+    # the combined signature verifies under the combined key
+    assert eng.verify_batch(2, 0, [outs[0]], [bytes.fromhex(s["sig"])], [msg]).tolist() == [0]

@@ -287,3 +287,31 @@ def test_windowed_scalar_multiplication(L):
         o = buf(48)
         assert L.emu_g1_mul_w4(ser, k, o) == 0
         assert o.raw == O.g1_serialize(O.g1_mul(pt, k)), hex(k)
+
+
+def test_fr_arithmetic_and_lagrange(L):
+    """csrc/fr.cuh: scalar-field Montgomery arithmetic and the Lagrange basis at zero used by share combination."""
+    rnd = random.Random(33)
+    R = O.R
+    b32 = lambda v: v.to_bytes(32, "big")
+    for it in range(40):
+        a, b = rnd.randrange(1, R), rnd.randrange(R)
+        if it == 0:
+            a, b = R - 1, R - 1
+        if it == 1:
+            a, b = 1, 0
+        m, inv = buf(32), buf(32)
+        assert L.emu_fr_ops(b32(a), b32(b), m, inv) == 0
+        assert int.from_bytes(m.raw, "big") == a * b % R
+        assert int.from_bytes(inv.raw, "big") == pow(a, -1, R)
+    assert L.emu_fr_ops(b32(R), b32(1), buf(32), buf(32)) == -1
+    for ids in ([1, 2, 3], [5, 1, 9, 2 ** 200 + 7, R - 1], list(range(1, 41))):
+        for i in range(len(ids)):
+            want = 1
+            for j, x in enumerate(ids):
+                if j != i:
+                    want = want * x % R * pow((x - ids[i]) % R, -1, R) % R
+            o = buf(32)
+            assert L.emu_fr_lagrange(b"".join(b32(x) for x in ids), len(ids), i, o) == 0
+            assert int.from_bytes(o.raw, "big") == want
+    assert L.emu_fr_lagrange(b32(4) + b32(7) + b32(4), 3, 0, buf(32)) == 1  # duplicate identifier

@@ -206,3 +206,38 @@ def test_verify_secure_edge_semantics():
         == O.ERR_INVALID_SIGNATURE
     assert O.aggregate_secure(O.G2IMPL, O.MODERN, [O.g1_serialize(O.G1_GEN)], [])[0] == O.ERR_MISMATCHED_LENGTHS
     assert O.aggregate_secure(O.G2IMPL, O.MODERN, [], []) == (O.OK, ident2)
+
+
+def _shamir_shares(secret, threshold, ids, seed):
+    import random
+    rnd = random.Random(seed)
+    coef = [secret] + [rnd.randrange(O.R) for _ in range(threshold - 1)]
+    return [sum(c * pow(x, k, O.R) for k, c in enumerate(coef)) % O.R for x in ids]
+
+
+def test_combine_shares_reproduces_the_golden_signature(cpp):
+    """Signature::from_shares / PublicKey::from_shares (signature.rs:151-165): Shamir shares of a golden secret key give
+    signature / public-key shares whose combination must be the reference's own golden sig / pk bytes
+    (tests/cpp_integration_test.rs:19-82) - an absolute pin for the Lagrange combination."""
+    msg = bytes.fromhex(cpp["message"])
+    s = cpp["signers"][0]
+    sk = int(s["sk"], 16)
+    ids = [1, 2, 5, 2 ** 130 + 3]
+    sks = _shamir_shares(sk, 3, ids, seed=4)
+    H = O.hash_to_curve_g2(msg, O.sig_dst(O.G2IMPL, O.BASIC))
+    sig_shares = [x.to_bytes(32, "big") + O.g2_serialize(O.g2_mul(H, k)) for x, k in zip(ids, sks)]
+    pk_shares = [x.to_bytes(32, "big") + O.g1_serialize(O.g1_mul(O.G1_GEN, k)) for x, k in zip(ids, sks)]
+    for subset in ([0, 1, 2], [3, 1, 0], [0, 1, 2, 3]):
+        st, sig = O.combine_shares(2, [sig_shares[i] for i in subset])
+        assert st == O.OK and sig.hex() == s["sig"]
+        st, pk = O.combine_shares(1, [pk_shares[i] for i in subset])
+        assert st == O.OK and pk.hex() == s["pk"]
+    # two shares of a degree-2 polynomial combine to something else (no error: the threshold is not known to combine)
+    st, sig = O.combine_shares(2, sig_shares[:2])
+    assert st == O.OK and sig.hex() != s["sig"]
+    # vsss errors: fewer than two shares, zero identifier, duplicate identifier; parse errors: identifier >= r, bad point
+    assert O.combine_shares(2, sig_shares[:1])[0] == O.ERR_VSSS
+    assert O.combine_shares(2, [bytes(32) + sig_shares[0][32:], sig_shares[1]])[0] == O.ERR_VSSS
+    assert O.combine_shares(2, [sig_shares[0], sig_shares[0][:32] + sig_shares[1][32:]])[0] == O.ERR_VSSS
+    assert O.combine_shares(2, [O.R.to_bytes(32, "big") + sig_shares[0][32:], sig_shares[1]])[0] == O.ERR_DESERIALIZE
+    assert O.combine_shares(2, [sig_shares[0], sig_shares[1][:32] + bytes(96)])[0] == O.ERR_DESERIALIZE
