@@ -112,6 +112,7 @@ def load_library() -> ctypes.CDLL:
         "blsgpu_pairing_product_is_one": (c.c_int, [vp, c.c_size_t, u8p, u8p, c.POINTER(c.c_int)]),
         "blsgpu_testdata_sign": (c.c_int, [vp, c.c_int, c.c_int, c.c_size_t, u8p, u8p, u64p, u8p, u8p]),
         "blsgpu_combine_shares_batch": (c.c_int, [vp, c.c_int, c.c_size_t, u64p, u8p, u8p, u8p]),
+        "blsgpu_verify_batch_wire": (c.c_int, [vp, c.c_int, c.c_size_t, u8p, u8p, u8p, u64p, u8p]),
         "blsgpu_imad_peak": (c.c_int, [vp, c.POINTER(c.c_double)]),
         "blsgpu_last_stage_ms": (c.c_int, [vp, c.POINTER(c.c_float)]),
         "blsgpu_launch_count": (c.c_uint64, [vp]),
@@ -129,7 +130,7 @@ EXPORTED_SYMBOLS = [
     "blsgpu_verify_batch_dev", "blsgpu_pop_verify_batch", "blsgpu_aggregate_verify", "blsgpu_sum_points",
     "blsgpu_verify_secure_batch", "blsgpu_aggregate_secure_batch", "blsgpu_hash_to_curve_batch", "blsgpu_recode_points",
     "blsgpu_fp_mul_batch", "blsgpu_pairing_product_is_one", "blsgpu_testdata_sign", "blsgpu_imad_peak",
-    "blsgpu_combine_shares_batch", "blsgpu_last_stage_ms", "blsgpu_launch_count",
+    "blsgpu_combine_shares_batch", "blsgpu_verify_batch_wire", "blsgpu_last_stage_ms", "blsgpu_launch_count",
 ]
 
 
@@ -404,6 +405,23 @@ class Engine:
         self._check(self._lib.blsgpu_pairing_product_is_one(self._ctx, n, _ptr(a), _ptr(b), ctypes.byref(res)),
                     "blsgpu_pairing_product_is_one")
         return bool(res.value)
+
+    def verify_batch_wire(self, impl_id: int, pks, tagged_sigs: Sequence[bytes], msgs: Sequence[bytes]) -> np.ndarray:
+        """Signature::try_from(&[u8]) + verify for serde_bare signatures (tag byte + point, signature.rs:112-126,285-286)."""
+        pk = _pack_points(pks, pk_len(impl_id), "public key")
+        n = pk.size // pk_len(impl_id)
+        rec = sig_len(impl_id) + 1
+        for t in tagged_sigs:
+            if len(t) != rec:
+                raise BlsError(ST_DESERIALIZE, "invalid byte sequence")
+        if len(tagged_sigs) != n or len(msgs) != n:
+            raise BlsError(ST_MISMATCHED_LENGTHS)
+        sg = np.frombuffer(b"".join(tagged_sigs), dtype=np.uint8) if n else np.zeros(0, dtype=np.uint8)
+        data, off = pack_messages(msgs)
+        status = np.zeros(n, dtype=np.uint8)
+        rc = self._lib.blsgpu_verify_batch_wire(self._ctx, impl_id, n, _ptr(pk), _ptr(sg), _ptr(data), _ptr(off), _ptr(status))
+        self._check(rc, "blsgpu_verify_batch_wire")
+        return status
 
     # ---- threshold shares ------------------------------------------------------------------------------------------
     def combine_shares_batch(self, group: int, share_sets: Sequence[Sequence[bytes]]) -> Tuple[np.ndarray, List[bytes]]:

@@ -1286,3 +1286,35 @@ int blsgpu_combine_shares_batch(blsgpu_ctx* ctx, int group, size_t q, const uint
   return group == 1 ? combine_shares_impl<G1Aff>(ctx, q, share_off, shares, out, status_out)
                     : combine_shares_impl<G2Aff>(ctx, q, share_off, shares, out, status_out);
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Wire-format front end: tagged signatures, schemes mixed in one call.  The host only regroups bytes by tag.
+int blsgpu_verify_batch_wire(blsgpu_ctx* ctx, int impl_id, size_t n, const uint8_t* pks, const uint8_t* tagged_sigs, const uint8_t* msgs,
+                             const uint64_t* msg_off, uint8_t* status_out) {
+  if (!ctx) return BLSGPU_E_ARG;
+  if ((impl_id != 1 && impl_id != 2) || (n && (!pks || !tagged_sigs || !msg_off || !status_out))) {
+    ctx->err = "blsgpu_verify_batch_wire: bad arguments";
+    return BLSGPU_E_ARG;
+  }
+  const size_t pk_len = impl_id == 2 ? 48 : 96, sig_len = impl_id == 2 ? 96 : 48, rec = sig_len + 1;
+  for (int scheme = 0; scheme < 3; scheme++) {
+    std::vector<size_t> idx;
+    for (size_t i = 0; i < n; i++)
+      if (tagged_sigs[i * rec] == (uint8_t)scheme) idx.push_back(i);
+    if (idx.empty()) continue;
+    std::vector<uint8_t> p(idx.size() * pk_len), g(idx.size() * sig_len), m, st(idx.size());
+    std::vector<uint64_t> off(idx.size() + 1, 0);
+    for (size_t k = 0; k < idx.size(); k++) {
+      const size_t i = idx[k];
+      memcpy(&p[k * pk_len], pks + i * pk_len, pk_len);
+      memcpy(&g[k * sig_len], tagged_sigs + i * rec + 1, sig_len);
+      m.insert(m.end(), msgs + msg_off[i], msgs + msg_off[i + 1]);
+      off[k + 1] = m.size();
+    }
+    CKR(blsgpu_verify_batch(ctx, impl_id, scheme, 1, idx.size(), p.data(), g.data(), m.data(), off.data(), st.data()));
+    for (size_t k = 0; k < idx.size(); k++) status_out[idx[k]] = st[k];
+  }
+  for (size_t i = 0; i < n; i++)
+    if (tagged_sigs[i * rec] > 2) status_out[i] = BLSGPU_ST_DESERIALIZE;
+  return BLSGPU_OK;
+}

@@ -145,6 +145,15 @@ int blsgpu_testdata_sign(blsgpu_ctx* ctx, int impl_id, int scheme, size_t n, con
  * 32x32->64 multiply-accumulate rate (MAC/s) of the context's first device. */
 int blsgpu_imad_peak(blsgpu_ctx* ctx, double* mac_per_s_out);
 
+/* Wire-format front end: the same check as blsgpu_verify_batch for signatures in the reference's
+ * serde_bare form, `Vec::<u8>::from(&Signature<C>)` / `Signature::try_from(&[u8])` (src/signature.rs:112-126): one tag
+ * byte {0 Basic, 1 MessageAugmentation, 2 ProofOfPossession} followed by the IETF compressed point (49 | 97 bytes,
+ * src/signature.rs:285-286).  The scheme of every item comes from its tag (items of different schemes may be mixed);
+ * an unknown tag gives BLSGPU_ST_DESERIALIZE (`InvalidInputs(serde error)`).  Public keys are their plain 48 | 96 bytes
+ * (the serde_bare form of PublicKey has no tag). */
+int blsgpu_verify_batch_wire(blsgpu_ctx* ctx, int impl_id, size_t n, const uint8_t* pks, const uint8_t* tagged_sigs,
+                             const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out);
+
 /* Threshold-share combination: Signature::from_shares / PublicKey::from_shares
  * (reference src/signature.rs:151-165, src/public_key.rs, src/traits/sig_core.rs:92-105 -> vsss-rs `combine`):
  * Lagrange interpolation at zero over the share identifiers, out_j = sum_i lambda_i * value_i for every share set j.

@@ -373,3 +373,30 @@ def test_combine_shares_matches_oracle_and_golden_signature(eng, B, cpp):
     assert st.tolist() == [0, 0, 11] and outs[0].hex() == s["pk"] and outs[1].hex() == s["pk"]
     # the combined signature verifies under the combined key
     assert eng.verify_batch(2, 0, [outs[0]], [bytes.fromhex(s["sig"])], [msg]).tolist() == [0]
+
+
+def test_verify_batch_wire_mixed_schemes(eng, B, cpp):
+    """blsgpu_verify_batch_wire: serde_bare tagged signatures (signature.rs:112-126), schemes mixed in one call; every
+    status equals the oracle's verify under the scheme named by the tag."""
+    rnd = random.Random(17)
+    for impl in (2, 1):
+        C = O.IMPLS[impl]
+        items = []
+        for i in range(14):
+            sk = rnd.randrange(1, O.R)
+            scheme = i % 3
+            msg = b"wire message %d" % i
+            pk = C.pk_ser(O.sk_to_pk(impl, sk), O.MODERN)
+            sig = C.sig_ser(O.sign(impl, scheme, sk, msg), O.MODERN)
+            tag = scheme
+            if i == 5:
+                tag = (scheme + 1) % 3      # valid point, wrong scheme tag: verifies under the tag's scheme -> invalid
+            if i == 7:
+                tag = 3                     # unknown tag
+            if i == 9:
+                sig = bytes([0xC0]) + bytes(len(sig) - 1)   # identity signature
+            items.append((pk, bytes([tag]) + sig, msg, tag))
+        st = eng.verify_batch_wire(impl, [x[0] for x in items], [x[1] for x in items], [x[2] for x in items])
+        want = [4 if t > 2 else O.verify(impl, t, O.MODERN, pk, ts[1:], m) for pk, ts, m, t in items]
+        assert st.tolist() == want
+        assert want[5] == 1 and want[7] == 4 and want[9] == 2 and want[0] == 0 and want[1] == 0 and want[2] == 0
