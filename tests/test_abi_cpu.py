@@ -6,6 +6,13 @@ import re
 import pytest
 
 
+@pytest.fixture(scope="module", autouse=True)
+def built_library():
+    """nvcc cross-compiles without a GPU: (re)build the library when it is missing or older than its sources."""
+    import __graft_entry__ as g
+    g.build_engine()
+
+
 def test_library_exports_every_declared_symbol():
     import blsful_b200 as B
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
