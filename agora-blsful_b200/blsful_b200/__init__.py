@@ -113,6 +113,7 @@ def load_library() -> ctypes.CDLL:
         "blsgpu_testdata_sign": (c.c_int, [vp, c.c_int, c.c_int, c.c_size_t, u8p, u8p, u64p, u8p, u8p]),
         "blsgpu_combine_shares_batch": (c.c_int, [vp, c.c_int, c.c_size_t, u64p, u8p, u8p, u8p]),
         "blsgpu_verify_batch_wire": (c.c_int, [vp, c.c_int, c.c_size_t, u8p, u8p, u8p, u64p, u8p]),
+        "blsgpu_pairing_check_batch": (c.c_int, [vp, c.c_size_t, u64p, u8p, u8p, u8p, u8p]),
         "blsgpu_imad_peak": (c.c_int, [vp, c.POINTER(c.c_double)]),
         "blsgpu_last_stage_ms": (c.c_int, [vp, c.POINTER(c.c_float)]),
         "blsgpu_launch_count": (c.c_uint64, [vp]),
@@ -130,7 +131,7 @@ EXPORTED_SYMBOLS = [
     "blsgpu_verify_batch_dev", "blsgpu_pop_verify_batch", "blsgpu_aggregate_verify", "blsgpu_sum_points",
     "blsgpu_verify_secure_batch", "blsgpu_aggregate_secure_batch", "blsgpu_hash_to_curve_batch", "blsgpu_recode_points",
     "blsgpu_fp_mul_batch", "blsgpu_pairing_product_is_one", "blsgpu_testdata_sign", "blsgpu_imad_peak",
-    "blsgpu_combine_shares_batch", "blsgpu_verify_batch_wire", "blsgpu_last_stage_ms", "blsgpu_launch_count",
+    "blsgpu_combine_shares_batch", "blsgpu_verify_batch_wire", "blsgpu_pairing_check_batch", "blsgpu_last_stage_ms", "blsgpu_launch_count",
 ]
 
 
@@ -422,6 +423,20 @@ class Engine:
         rc = self._lib.blsgpu_verify_batch_wire(self._ctx, impl_id, n, _ptr(pk), _ptr(sg), _ptr(data), _ptr(off), _ptr(status))
         self._check(rc, "blsgpu_verify_batch_wire")
         return status
+
+    def pairing_check_batch(self, pair_sets: Sequence[Sequence[Tuple[bytes, bytes]]]) -> Tuple[np.ndarray, np.ndarray]:
+        """For every set of (G1 bytes, G2 bytes) pairs: prod e(.,.) == 1 ?  (pairings.rs:50; sign_crypt.rs:69-77,192-207)."""
+        q = len(pair_sets)
+        off = np.zeros(q + 1, dtype=np.uint64)
+        if q:
+            off[1:] = np.cumsum([len(s) for s in pair_sets], dtype=np.uint64)
+        g1 = _pack_points([p[0] for s in pair_sets for p in s], 48, "G1 point")
+        g2 = _pack_points([p[1] for s in pair_sets for p in s], 96, "G2 point")
+        ok = np.zeros(q, dtype=np.uint8)
+        status = np.zeros(q, dtype=np.uint8)
+        rc = self._lib.blsgpu_pairing_check_batch(self._ctx, q, _ptr(off), _ptr(g1), _ptr(g2), _ptr(ok), _ptr(status))
+        self._check(rc, "blsgpu_pairing_check_batch")
+        return ok, status
 
     # ---- threshold shares ------------------------------------------------------------------------------------------
     def combine_shares_batch(self, group: int, share_sets: Sequence[Sequence[bytes]]) -> Tuple[np.ndarray, List[bytes]]:

@@ -1318,3 +1318,44 @@ int blsgpu_verify_batch_wire(blsgpu_ctx* ctx, int impl_id, size_t n, const uint8
     if (tagged_sigs[i * rec] > 2) status_out[i] = BLSGPU_ST_DESERIALIZE;
   return BLSGPU_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+int blsgpu_pairing_check_batch(blsgpu_ctx* ctx, size_t q, const uint64_t* pair_off, const uint8_t* g1_points, const uint8_t* g2_points,
+                               uint8_t* ok_out, uint8_t* status_out) {
+  if (!ctx) return BLSGPU_E_ARG;
+  if (q && (!pair_off || !ok_out || !status_out || (pair_off[q] && (!g1_points || !g2_points)))) {
+    ctx->err = "blsgpu_pairing_check_batch: bad arguments";
+    return BLSGPU_E_ARG;
+  }
+  if (q == 0) return BLSGPU_OK;
+  CKR(set_device(ctx));
+  const size_t M = (size_t)pair_off[q];
+  CKR(ensure_arena(ctx, M * (48 + 96 + sizeof(G1Aff) + sizeof(G2Aff) + sizeof(Fp12) + 2) + (q + 1) * 9 + 16 * 256));
+  uint8_t *d_a, *d_b;
+  uint64_t* d_off;
+  CKR(upload(ctx, d_a, g1_points, M * 48));
+  CKR(upload(ctx, d_b, g2_points, M * 96));
+  CKR(upload(ctx, d_off, pair_off, q + 1));
+  G1Aff* d_p = ctx->arena.take<G1Aff>(std::max<size_t>(M, 1));
+  G2Aff* d_q = ctx->arena.take<G2Aff>(std::max<size_t>(M, 1));
+  uint8_t* d_st = ctx->arena.take<uint8_t>(2 * std::max<size_t>(M, 1));
+  Fp12* d_F = ctx->arena.take<Fp12>(std::max<size_t>(M, 1));
+  uint8_t* d_ok = ctx->arena.take<uint8_t>(q);
+  std::vector<uint8_t> st(2 * M);
+  if (M) {
+    LAUNCH((k_decode<G1Aff>), blocks_for(M), TPB, M, (const uint8_t*)d_a, 1, d_p, d_st);
+    LAUNCH((k_decode<G2Aff>), blocks_for(M), TPB, M, (const uint8_t*)d_b, 1, d_q, d_st + M);
+    LAUNCH(k_miller_pairs, blocks_for(M), TPB, M, (const G1Aff*)d_p, (const G2Aff*)d_q, d_F);  // undecodable -> identity -> 1
+    CK(cudaMemcpyAsync(st.data(), d_st, 2 * M, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  LAUNCH(k_set_final_is_one, blocks_for(q, 64), 64, q, (const uint64_t*)d_off, (const Fp12*)d_F, d_ok);
+  CK(cudaMemcpyAsync(ok_out, d_ok, q, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (size_t j = 0; j < q; j++) {
+    status_out[j] = BLSGPU_ST_OK;
+    for (size_t i = (size_t)pair_off[j]; i < (size_t)pair_off[j + 1]; i++)
+      if (st[i] != BLSGPU_ST_OK || st[M + i] != BLSGPU_ST_OK) status_out[j] = BLSGPU_ST_DESERIALIZE;
+    if (status_out[j] != BLSGPU_ST_OK) ok_out[j] = 0;
+  }
+  return BLSGPU_OK;
+}

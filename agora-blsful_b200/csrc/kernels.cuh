@@ -891,6 +891,21 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_miller_pairs(size_t n, 
   }
   out[i] = f;
 }
+// per set: product of its Miller values, final exponentiation, == 1 ?   (one thread per set)
+__global__ void __launch_bounds__(64) k_set_final_is_one(size_t q, const uint64_t* __restrict__ off, const Fp12* __restrict__ F,
+                                                         uint8_t* __restrict__ ok) {
+  size_t j = BLS_TID();
+  if (j >= q) return;
+  Fp12 acc;
+  fp12_one(acc);
+  for (uint64_t i = off[j]; i < off[j + 1]; i++) {
+    Fp12 t = F[i];
+    fp12_mul(acc, acc, t);
+  }
+  Fp12 e;
+  final_exponentiation(e, acc);
+  ok[j] = fp12_is_one(e) ? 1 : 0;
+}
 __global__ void k_final_is_one(const Fp12* f, uint8_t* ok) {
   if (BLS_TID() != 0) return;
   Fp12 g = f[0], e;

@@ -154,6 +154,16 @@ int blsgpu_imad_peak(blsgpu_ctx* ctx, double* mac_per_s_out);
 int blsgpu_verify_batch_wire(blsgpu_ctx* ctx, int impl_id, size_t n, const uint8_t* pks, const uint8_t* tagged_sigs,
                              const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out);
 
+/* Batched pairing-product checks: for every set j, is  prod_i e(g1[i], g2[i]) == 1  over its
+ * pairs?  The building block of the reference's other public 2-pairing checks - `BlsSignCrypt::valid` / `verify_share`
+ * (src/traits/sign_crypt.rs:69-77,192-207: pairing(&[(w, -g), (w', u)]).is_identity()) and `ProofOfKnowledge::verify`
+ * (src/traits/sig_proof.rs:102-142) - whose hashed points come from blsgpu_hash_to_curve_batch.  Same pairing as
+ * `Pairing::pairing` (src/traits/pairings.rs:50, src/helpers.rs:41-63): identity points contribute 1.
+ *   pair_off[q+1] : offsets (in pairs) of the sets;  g1_points 48 B, g2_points 96 B each, IETF compressed
+ *   ok_out[q]     : 1 / 0;  status_out[q]: BLSGPU_ST_OK or BLSGPU_ST_DESERIALIZE (some point of the set undecodable) */
+int blsgpu_pairing_check_batch(blsgpu_ctx* ctx, size_t q, const uint64_t* pair_off, const uint8_t* g1_points,
+                               const uint8_t* g2_points, uint8_t* ok_out, uint8_t* status_out);
+
 /* Threshold-share combination: Signature::from_shares / PublicKey::from_shares
  * (reference src/signature.rs:151-165, src/public_key.rs, src/traits/sig_core.rs:92-105 -> vsss-rs `combine`):
  * Lagrange interpolation at zero over the share identifiers, out_j = sum_i lambda_i * value_i for every share set j.

@@ -400,3 +400,41 @@ def test_verify_batch_wire_mixed_schemes(eng, B, cpp):
         want = [4 if t > 2 else O.verify(impl, t, O.MODERN, pk, ts[1:], m) for pk, ts, m, t in items]
         assert st.tolist() == want
         assert want[5] == 1 and want[7] == 4 and want[9] == 2 and want[0] == 0 and want[1] == 0 and want[2] == 0
+
+
+def test_pairing_check_batch_against_oracle(eng, B):
+    """blsgpu_pairing_check_batch: the 2-pairing public checks of the reference (sign_crypt.rs:69-77,192-207) as sets of
+    pairs; compared with the oracle's pairing product, incl. identity points and an undecodable point."""
+    rnd = random.Random(23)
+    g1, g2 = O.G1_GEN, O.G2_GEN
+    a, b, c = (rnd.randrange(1, O.R) for _ in range(3))
+    s1, s2 = O.g1_serialize, O.g2_serialize
+    neg_g1 = O.g1_neg(g1)
+    sets = [
+        [(s1(O.g1_mul(g1, a)), s2(O.g2_mul(g2, b))), (s1(neg_g1), s2(O.g2_mul(g2, a * b % O.R)))],        # e(aG,bH) e(-G,abH) = 1
+        [(s1(O.g1_mul(g1, a)), s2(O.g2_mul(g2, b))), (s1(neg_g1), s2(O.g2_mul(g2, (a * b + 1) % O.R)))],  # != 1
+        [(s1(O.g1_mul(g1, a)), s2(O.g2_mul(g2, b))), (s1(O.g1_mul(g1, c)), s2(g2)),
+         (s1(neg_g1), s2(O.g2_mul(g2, (a * b + c) % O.R)))],                                                # three pairs
+        [(IDENT1, s2(g2)), (s1(g1), IDENT2)],                                                               # identities only: 1
+        [],                                                                                                 # empty product: 1
+        [(bytes(48), s2(g2)), (s1(g1), s2(g2))],                                                            # undecodable point
+    ]
+    ok, st = eng.pairing_check_batch(sets)
+    want = []
+    for ps in sets[:5]:
+        want.append(1 if O.pairing_product_is_one([(_g1(p), _g2(q)) for p, q in ps]) else 0)
+    assert ok.tolist() == want + [0]
+    assert st.tolist() == [0, 0, 0, 0, 0, 4]
+    assert want == [1, 0, 1, 1, 1]
+
+
+def _g1(b):
+    pt, st = O._decode(O.g1_deserialize, b, O.MODERN)
+    assert st == 0
+    return pt
+
+
+def _g2(b):
+    pt, st = O._decode(O.g2_deserialize, b, O.MODERN)
+    assert st == 0
+    return pt
