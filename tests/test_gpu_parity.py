@@ -438,3 +438,22 @@ def _g2(b):
     pt, st = O._decode(O.g2_deserialize, b, O.MODERN)
     assert st == 0
     return pt
+
+
+def test_verify_batch_in_several_miller_passes(eng, B, monkeypatch):
+    """Batches beyond one pass of the Miller kernels (1,048,320 items) go through in chunks with two line buffers on two
+    streams; the chunk size is overridden here so that a small batch takes the same path (5 passes, last one partial)."""
+    rnd = random.Random(61)
+    n = 5000
+    k = np.frombuffer(b"".join(rnd.randrange(1, O.R).to_bytes(32, "big") for _ in range(n)), dtype=np.uint8)
+    msgs = [hashlib.sha256(b"chunk%d" % i).digest() for i in range(n)]
+    data, off = B.pack_messages(msgs)
+    pks, sigs = eng.testdata_sign(2, 0, k, data, off)
+    monkeypatch.setenv("BLSGPU_M6_CHUNK", "1200")
+    assert eng.verify_batch_packed(2, 0, pks, sigs, data, off).tolist() == [0] * n
+    bad = sorted(rnd.sample(range(n), 4)) + [1199, 1200, 4999]
+    bad = sorted(set(bad))
+    s2 = sigs.copy().reshape(n, 96)
+    s2[bad] = s2[[(i + 3) % n for i in bad]]
+    st = eng.verify_batch_packed(2, 0, pks, s2.reshape(-1), data, off)
+    assert [i for i in range(n) if st[i]] == bad and all(st[i] == 1 for i in bad)
