@@ -114,6 +114,7 @@ def load_library() -> ctypes.CDLL:
         "blsgpu_combine_shares_batch": (c.c_int, [vp, c.c_int, c.c_size_t, u64p, u8p, u8p, u8p]),
         "blsgpu_verify_batch_wire": (c.c_int, [vp, c.c_int, c.c_size_t, u8p, u8p, u8p, u64p, u8p]),
         "blsgpu_pairing_check_batch": (c.c_int, [vp, c.c_size_t, u64p, u8p, u8p, u8p, u8p]),
+        "blsgpu_plan_msm": (c.c_int, [c.c_size_t, c.POINTER(c.c_int), c.POINTER(c.c_int), c.POINTER(c.c_int)]),
         "blsgpu_imad_peak": (c.c_int, [vp, c.POINTER(c.c_double)]),
         "blsgpu_last_stage_ms": (c.c_int, [vp, c.POINTER(c.c_float)]),
         "blsgpu_launch_count": (c.c_uint64, [vp]),
@@ -131,7 +132,7 @@ EXPORTED_SYMBOLS = [
     "blsgpu_verify_batch_dev", "blsgpu_pop_verify_batch", "blsgpu_aggregate_verify", "blsgpu_sum_points",
     "blsgpu_verify_secure_batch", "blsgpu_aggregate_secure_batch", "blsgpu_hash_to_curve_batch", "blsgpu_recode_points",
     "blsgpu_fp_mul_batch", "blsgpu_pairing_product_is_one", "blsgpu_testdata_sign", "blsgpu_imad_peak",
-    "blsgpu_combine_shares_batch", "blsgpu_verify_batch_wire", "blsgpu_pairing_check_batch", "blsgpu_last_stage_ms", "blsgpu_launch_count",
+    "blsgpu_combine_shares_batch", "blsgpu_verify_batch_wire", "blsgpu_pairing_check_batch", "blsgpu_plan_msm", "blsgpu_last_stage_ms", "blsgpu_launch_count",
 ]
 
 

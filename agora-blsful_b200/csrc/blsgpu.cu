@@ -143,6 +143,16 @@ bool make_dst(DstParam& d, int impl_id, int scheme, bool pop_proof) {
   return true;
 }
 
+// Window width of the bucket multi-scalar multiplication over 64-bit scalars: >= ~16 signatures per bucket, and only
+// widths whose TOP window (64 - (nwin - 1) c bits) is not much narrower than the others - a 4-bit top window would put
+// n/16 signatures into each of 16 buckets, one thread each (measured: 1.5 s at n = 500,000 with c = 15).
+int msm_window_bits(size_t n) {
+  static const int widths[] = {16, 13, 11, 8, 5, 4};
+  for (int w : widths)
+    if (((size_t)1 << (w + 4)) <= n) return w;
+  return 4;
+}
+
 std::vector<Level> make_levels(size_t n) {
   std::vector<Level> lv;
   size_t off = 0, cnt = n;
@@ -197,16 +207,7 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
   Fp12* d_T = ctx->arena.take<Fp12>(1);
   if (use_msm) {
     int rc = [&]() -> int {
-      // window width: >= ~16 signatures per bucket, and only widths whose TOP window (64 - (nwin-1) c bits) is not much
-      // narrower than the others - a 4-bit top window would put n/16 signatures into each of 16 buckets, one thread each
-      // (measured: 1.5 s at n = 500,000 with c = 15)
-      static const int widths[] = {16, 13, 11, 8, 5, 4};
-      int c = 4;
-      for (int w : widths)
-        if (((size_t)1 << (w + 4)) <= n) {
-          c = w;
-          break;
-        }
+      const int c = msm_window_bits(n);
       const int nwin = (64 + c - 1) / c;
       const size_t nb = (size_t)1 << c, nbuckets = nb * nwin, nchunks = nbuckets / MSM_CHUNK;
       uint64_t* d_r = ctx->arena.take<uint64_t>(n);
@@ -1357,5 +1358,14 @@ int blsgpu_pairing_check_batch(blsgpu_ctx* ctx, size_t q, const uint64_t* pair_o
       if (st[i] != BLSGPU_ST_OK || st[M + i] != BLSGPU_ST_OK) status_out[j] = BLSGPU_ST_DESERIALIZE;
     if (status_out[j] != BLSGPU_ST_OK) ok_out[j] = 0;
   }
+  return BLSGPU_OK;
+}
+
+int blsgpu_plan_msm(size_t n, int* window_bits_out, int* windows_out, int* top_window_bits_out) {
+  if (!window_bits_out || !windows_out || !top_window_bits_out) return BLSGPU_E_ARG;
+  const int c = msm_window_bits(n), nwin = (64 + c - 1) / c;
+  *window_bits_out = c;
+  *windows_out = nwin;
+  *top_window_bits_out = 64 - (nwin - 1) * c;
   return BLSGPU_OK;
 }

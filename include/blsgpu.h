@@ -177,6 +177,10 @@ int blsgpu_pairing_check_batch(blsgpu_ctx* ctx, size_t q, const uint64_t* pair_o
 int blsgpu_combine_shares_batch(blsgpu_ctx* ctx, int group, size_t q, const uint64_t* share_off, const uint8_t* shares,
                                 uint8_t* out, uint8_t* status_out);
 
+/* Host-only planning query (no device needed): the window layout the bucket multi-scalar multiplication of
+ * blsgpu_verify_batch uses for a batch of n signatures (64-bit scalars). */
+int blsgpu_plan_msm(size_t n, int* window_bits_out, int* windows_out, int* top_window_bits_out);
+
 /* ---- metrics ---------------------------------------------------------------------------------------------------
  * Per-stage device times (CUDA events on the engine's stream) of the LAST verify call on the first device. */
 #define BLSGPU_STAGE_DECODE_PK 0

@@ -38,3 +38,18 @@ def test_length_rules_are_enforced_host_side():
     with pytest.raises(B.BlsError) as e:
         B._pack_points([bytes(47)], 48, "public key")
     assert e.value.status == B.ST_INVALID_LENGTH
+
+
+def test_msm_window_plan_never_has_a_narrow_top_window():
+    """blsgpu_plan_msm (host-only): a narrow top window concentrates n / 2^bits signatures in each of its few buckets -
+    one thread each.  (n = 500,000 once took 1.5 s with a 4-bit top window.)"""
+    import ctypes
+    import blsful_b200 as B
+    lib = B.load_library()
+    for n in [4096, 4097, 5000, 33000, 65536, 100000, 262144, 500000, 524288, 999999, 1000000, 1048576, 4000000, 10 ** 8]:
+        c, w, top = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        assert lib.blsgpu_plan_msm(n, ctypes.byref(c), ctypes.byref(w), ctypes.byref(top)) == 0
+        c, w, top = c.value, w.value, top.value
+        assert (w - 1) * c + top == 64 and 0 < top <= c
+        assert n >> c >= 8 or c == 4          # enough signatures per bucket to amortise the bucket reduction
+        assert (n >> top) <= 16 * max(1, n >> c) or n < (1 << 16), (n, c, top)   # top-window buckets at most 16x larger
