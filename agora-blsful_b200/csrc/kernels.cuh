@@ -1,5 +1,7 @@
-// Device kernels of the batch verification engine.  One thread per item (signature, public key, tree node ...): the
-// work is ~10^4 field multiplications per item, integer-multiply bound, HBM traffic negligible.
+// Device kernels of the batch verification engine.  Decode, hash, bucket-sum and tree kernels: one thread per item
+// (signature, public key, bucket, tree node ...); the Miller stage: two lanes per pair for the lines, six lanes per group
+// of six pairs for the shared accumulator.  ~10^4 field multiplications per item, integer-multiply bound; the largest HBM
+// stream (39 KB of line records per item) is 1% of the run time (DESIGN.md sections 3-6).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -259,11 +261,12 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_miller(size_t n, const 
 
 // ---- cooperative Miller loop (miller6.cuh): groups of 6 consecutive items, F_g = prod_{i in g} ML(r_i * pk_i, H_i) -------
 // Three kernels, so that each keeps its working set on chip:
-//   k_m6_prep   one thread per item: the RLC scalar and r_i * pk_i, stored as the three Fp scalars the lines need (336 B)
-//   k_m6_lines  two lanes per item: the 68 line evaluations of the pair, record file in SHARED memory (14 records per
+//   k_m6_prep   one thread per item: the RLC scalar and r_i * pk_i, stored as the three Fp scalars the lines need, plus
+//               the G2 point as (-x2, y2) for the addition steps (M6Arg, 560 B)
+//   k_m6_lines  two lanes per item: the 68 line evaluations of the pair, record file in SHARED memory (10 records per
 //               pair, record-major: conflict-free 128-bit accesses), lines streamed to HBM (39 KB per item)
-//   k_m6_accum  six lanes per group: the shared Fp12 accumulator, one coefficient per lane, double-buffered in shared
-//               memory; the lines come back from HBM one step ahead of their use (sop2f's prefetch)
+//   k_m6_accum  six lanes per group: the shared Fp12 accumulator, one coefficient per lane, in shared memory (expanded
+//               records, updated in place behind a group barrier); the next line is prefetched into L1 from HBM
 constexpr int M6_LINES_TPB = 128;
 constexpr int M6_LINES_PAIRS = M6_LINES_TPB / 2;
 constexpr int M6_LINES_SMEM = M6_NREG * M6_LINES_PAIRS * (int)sizeof(SFp2);  // 71,680 B: three blocks per SM
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_m6_prep(size_t n, size_
   args[c] = a;
 }
 
-// Two lanes per pair: lane h computes coefficient h of every program step (sop1), both read the pair's 14 records in
+// Two lanes per pair: lane h computes coefficient h of every program step (sop1), both read the pair's 10 records in
 // shared memory (record-major, 112-byte stride between pairs: conflict-free; the two lanes of a pair read the same words).
 // 64 pairs per 128-thread block, 71,680 B of shared memory (10 records per pair): three blocks per SM.
 template <class PkA, class HA>

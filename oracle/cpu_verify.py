@@ -2,8 +2,10 @@
 (core_verify, reference src/traits/sig_core.rs:120-146: hash_to_curve, two Miller loops, one final exponentiation per
 signature, no batching) restated by the oracle and run on the host cores.
 
-Uses the C restatement (oracle/c -> oracle/_build/liboracle.so) when it has been built, otherwise the big-int Python
-oracle.  blsful itself cannot be built here (no cargo, un-vendored blstrs_plus/blst), so kind is always "port"."""
+Uses the C++ restatement (oracle/c -> oracle/_build/liboracle.so: the reference's call sequence over the engine's
+field / curve / pairing headers compiled for the host, validated against the big-int oracle by tests/test_c_oracle.py)
+when it has been built, otherwise the big-int Python oracle.  blsful itself cannot be built here (no cargo, un-vendored
+blstrs_plus/blst), so kind is always "port"."""
 import json
 import multiprocessing as mp
 import os
@@ -58,13 +60,14 @@ def _run(total, impl, procs):
 
 
 def _auto_sample(procs):
-    # ~10-30 s of CPU work: C restatement ~2-3 ms/verify, Python big-int ~2 s/verify
-    return (4000 if _c_oracle() is not None else 4) * procs
+    # ~10-30 s of CPU work: C++ restatement ~11 ms/verify, Python big-int ~1 s/verify
+    return (1000 if _c_oracle() is not None else 4) * procs
 
 
 def time_verify_sample(sample=0, impl=2):
     procs = os.cpu_count() or 1
-    kind = "C restatement (oracle/c, 64-bit limbs, no asm)" if _c_oracle() is not None else "Python big-int oracle"
+    kind = ("C++ restatement (oracle/c: per-signature core_verify over the engine's host-compiled field/curve headers, "
+            "g++ -O3, no asm)") if _c_oracle() is not None else "Python big-int oracle"
     n1 = max(1, (sample or _auto_sample(1)) // (1 if sample else 4))
     dt1 = _run(n1, impl, 1)
     nall = sample or _auto_sample(procs)
@@ -83,6 +86,6 @@ def reference_arm(n_per_step=0, steps=3, warmup=1):
     for _ in range(steps):
         _run(n, 2, procs)
     dt = time.perf_counter() - t0
-    kind = "C restatement (oracle/c)" if _c_oracle() is not None else "Python big-int oracle"
+    kind = "C++ restatement (oracle/c, g++ -O3, no asm)" if _c_oracle() is not None else "Python big-int oracle"
     return {"value": n * steps / dt, "ms_per_step": dt / steps * 1e3, "n_per_step": n, "cores": procs, "kind": "port",
             "sample": f"{n} per-signature verifies per step on {procs} processes; {kind}; blsful+blst cannot be built here"}
