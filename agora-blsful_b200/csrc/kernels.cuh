@@ -225,7 +225,7 @@ __device__ __forceinline__ void rlc_scalar(uint32_t k[2], const Digest* root, si
   if ((k[0] | k[1]) == 0) k[0] = 1;
 }
 
-// ---- per-item Miller loop  f_i = ML(r_i * pk_i, H_i)  (G2Impl)  |  ML(r_i * H_i, pk_i)  (G1Impl) ---------------------
+// ---- per-item Miller loop (exact per-item checks of failing groups): ML(pk_i, H_i) (G2Impl) | ML(H_i, pk_i) (G1Impl) ------
 __device__ __forceinline__ void miller_item(Fp12& f, const G1Aff& pk, const G2Aff& h, const uint32_t* k, bool scale) {
   MillerG1 mp;
   if (scale) {
@@ -240,25 +240,6 @@ __device__ __forceinline__ void miller_item(Fp12& f, const G1Aff& pk, const G2Af
 __device__ __forceinline__ void miller_item(Fp12& f, const G2Aff& pk, const G1Aff& h, const uint32_t* k, bool scale) {
   miller_item(f, h, pk, k, scale);
 }
-template <class PkA, class HA>
-__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_miller(size_t n, const PkA* __restrict__ pk, const HA* __restrict__ h,
-                                                const uint8_t* __restrict__ pre, const Digest* __restrict__ root, int use_rlc,
-                                                Fp12* __restrict__ out) {
-  size_t i = BLS_TID();
-  if (i >= n) return;
-  Fp12 f;
-  if (pre[i] != ST_OK) {
-    fp12_one(f);
-  } else {
-    uint32_t k[2] = {1, 0};
-    if (use_rlc) rlc_scalar(k, root, i);
-    PkA p = pk[i];
-    HA q = h[i];
-    miller_item(f, p, q, k, use_rlc != 0);
-  }
-  out[i] = f;
-}
-
 // ---- cooperative Miller loop (miller6.cuh): groups of 6 consecutive items, F_g = prod_{i in g} ML(r_i * pk_i, H_i) -------
 // Three kernels, so that each keeps its working set on chip:
 //   k_m6_prep   one thread per item: the RLC scalar and r_i * pk_i, stored as the three Fp scalars the lines need, plus
