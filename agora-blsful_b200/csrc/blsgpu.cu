@@ -370,6 +370,24 @@ size_t pipeline_bytes(size_t n, int sm_count) {
          n * (8 + 4 * 16) + ((size_t)16 << 16) * (12 + 2 * sizeof(SigJ)) + (1 << 20) + (n + 64) * 8 + 16 * 256 + 4096;
 }
 
+// hash_to_curve of n framed messages into affine points: k_hash leaves Jacobian points in scratch that is handed back to
+// the arena at once (later takes on the same stream may reuse it), k_to_affine_batch normalises them 16 per inversion
+template <class HA, class PkA>
+int hash_points(blsgpu_ctx* ctx, size_t n, const uint8_t* d_msgs, const uint64_t* d_moff, int msg_mode, const PkA* d_pk,
+                const uint8_t* d_pre, const DstParam& dst, HA* d_h) {
+  typedef typename PtInfo<HA>::Jac HJ;
+  size_t mark = ctx->arena.off;
+  HJ* d_hj = ctx->arena.take<HJ>(n);
+  if (ctx->arena.off > ctx->arena.cap) {
+    ctx->err = "hash_points: arena too small";
+    return BLSGPU_E_ALLOC;
+  }
+  LAUNCH((k_hash<HA, PkA>), blocks_for(n), TPB, n, d_msgs, d_moff, msg_mode, d_pk, d_pre, dst, d_hj);
+  LAUNCH((k_to_affine_batch<HA>), blocks_for((n + TO_AFFINE_BATCH - 1) / TO_AFFINE_BATCH), TPB, n, (const HJ*)d_hj, d_h);
+  ctx->arena.off = mark;
+  return BLSGPU_OK;
+}
+
 // verify over decoded points: per-item pre-status, hash_to_curve of the framed message, pairing pipeline
 template <int IMPL>
 int verify_points(blsgpu_ctx* ctx, int msg_mode, const DstParam& dst, size_t n, const typename ImplT<IMPL>::PkAff* d_pk,
@@ -380,7 +398,7 @@ int verify_points(blsgpu_ctx* ctx, int msg_mode, const DstParam& dst, size_t n, 
   SigA* d_h = ctx->arena.take<SigA>(n);
   LAUNCH((k_prestatus<PkA, SigA>), blocks_for(n), TPB, n, d_stpk, d_stsig, d_pk, d_sig, d_status_out);
   stage_mark(ctx, BLSGPU_STAGE_HASH);
-  LAUNCH((k_hash<SigA, PkA>), blocks_for(n), TPB, n, d_msgs, d_moff, msg_mode, d_pk, (const uint8_t*)d_status_out, dst, d_h);
+  CKR((hash_points<SigA, PkA>(ctx, n, d_msgs, d_moff, msg_mode, d_pk, (const uint8_t*)d_status_out, dst, d_h)));
   CKR((run_pairing_pipeline<PkA, SigA>(ctx, n, d_pk, d_sig, d_h, d_status_out, true, nullptr)));
   return BLSGPU_OK;
 }
@@ -671,8 +689,8 @@ static int aggregate_verify_impl(blsgpu_ctx* ctx, int scheme, int format, size_t
   make_dst(dst, IMPL, scheme, false);
   uint8_t* d_status = ctx->arena.take<uint8_t>(n);
   CK(cudaMemsetAsync(d_status, 0, n, ctx->stream));
-  LAUNCH((k_hash<SigA, PkA>), blocks_for(n), TPB, n, (const uint8_t*)d_msgs, (const uint64_t*)d_off, scheme == 1 ? 1 : 0, (const PkA*)d_pk,
-         (const uint8_t*)nullptr, dst, d_h);
+  CKR((hash_points<SigA, PkA>(ctx, n, (const uint8_t*)d_msgs, (const uint64_t*)d_off, scheme == 1 ? 1 : 0, (const PkA*)d_pk,
+                              (const uint8_t*)nullptr, dst, d_h)));
   CKR((run_pairing_pipeline<PkA, SigA>(ctx, n, d_pk, d_sig, d_h, d_status, false, &ok)));
   *status_out = ok ? BLSGPU_ST_OK : BLSGPU_ST_INVALID_SIGNATURE;
   return BLSGPU_OK;
@@ -759,15 +777,15 @@ template <class A>
 static int hash_batch_impl(blsgpu_ctx* ctx, size_t n, const uint8_t* msgs, const uint64_t* msg_off, const DstParam& dst, uint8_t* out) {
   const size_t L = PtInfo<A>::LEN;
   size_t msg_bytes = (size_t)msg_off[n];
-  CKR(ensure_arena(ctx, msg_bytes + (n + 1) * 8 + n * (sizeof(A) + L) + 8 * 256));
+  CKR(ensure_arena(ctx, msg_bytes + (n + 1) * 8 + n * (sizeof(A) + L + sizeof(typename PtInfo<A>::Jac)) + 8 * 256));
   uint8_t* d_msgs;
   uint64_t* d_off;
   CKR(upload(ctx, d_msgs, msgs, msg_bytes));
   CKR(upload(ctx, d_off, msg_off, n + 1));
   A* d_h = ctx->arena.take<A>(n);
   uint8_t* d_out = ctx->arena.take<uint8_t>(n * L);
-  LAUNCH((k_hash<A, G1Aff>), blocks_for(n), TPB, n, (const uint8_t*)d_msgs, (const uint64_t*)d_off, 0, (const G1Aff*)nullptr,
-         (const uint8_t*)nullptr, dst, d_h);
+  CKR((hash_points<A, G1Aff>(ctx, n, (const uint8_t*)d_msgs, (const uint64_t*)d_off, 0, (const G1Aff*)nullptr, (const uint8_t*)nullptr,
+                             dst, d_h)));
   LAUNCH((k_encode<A>), blocks_for(n), TPB, n, (const A*)d_h, 1, d_out);
   CK(cudaMemcpyAsync(out, d_out, n * L, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));

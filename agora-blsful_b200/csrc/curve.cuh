@@ -245,6 +245,39 @@ BLS_HD void jac_to_aff(Aff<F>& r, const Jac<F>& p) {
   r.inf = 0;
 }
 
+// cnt (<= K) Jacobian points -> affine with ONE field inversion (Montgomery's simultaneous inversion: prefix products
+// forward, one inverse, peel backward).  Points at infinity take part with 1 in place of their Z.
+template <class F, int K>
+BLS_HD void jac_to_aff_batch(Aff<F>* out, const Jac<F>* in, int cnt) {
+  F pre[K], acc, z;
+  fone(acc);
+  for (int j = 0; j < cnt; j++) {
+    pre[j] = acc;
+    z = in[j].Z;
+    if (!fis_zero(z)) fmul(acc, acc, z);
+  }
+  finv(acc, acc);  // 1 / (product of the non-zero Z)
+  for (int j = cnt - 1; j >= 0; j--) {
+    Jac<F> p = in[j];
+    Aff<F> a;
+    if (fis_zero(p.Z)) {
+      fzero(a.x);
+      fzero(a.y);
+      a.inf = 1;
+    } else {
+      F zi, zi2;
+      fmul(zi, acc, pre[j]);  // 1 / Z_j
+      fmul(acc, acc, p.Z);    // inverse of the product of the Z before j
+      fsqr(zi2, zi);
+      fmul(a.x, p.X, zi2);
+      fmul(zi2, zi2, zi);
+      fmul(a.y, p.Y, zi2);
+      a.inf = 0;
+    }
+    out[j] = a;
+  }
+}
+
 // projective equality
 template <class F>
 BLS_HD bool jac_eq(const Jac<F>& a, const Jac<F>& b) {

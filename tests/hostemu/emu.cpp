@@ -106,6 +106,23 @@ int emu_g1_mul_w4(const uint8_t* in, uint64_t k, uint8_t* out) {
   G1Aff p, q; if (g1_decompress(p, in, false)) return -1;
   G1Jac r; jac_mul_aff_w4_64(r, p, k); jac_to_aff(q, r); g1_compress(out, q); return 0;
 }
+// cnt points (compressed; identity allowed), each scaled by k to give it a non-trivial Z, normalised with one shared inversion
+int emu_to_aff_batch(int g2, const uint8_t* in, int cnt, uint64_t k, uint8_t* out) {
+  uint32_t kl[2] = {(uint32_t)k, (uint32_t)(k >> 32)};
+  if (cnt > 16) return -3;
+  if (g2) {
+    G2Jac j[16]; G2Aff a[16];
+    for (int i = 0; i < cnt; i++) { G2Aff p; if (g2_decompress(p, in + 96 * i, false)) return -1; jac_mul_aff(j[i], p, kl, 2); }
+    jac_to_aff_batch<Fp2, 16>(a, j, cnt);
+    for (int i = 0; i < cnt; i++) g2_compress(out + 96 * i, a[i]);
+  } else {
+    G1Jac j[16]; G1Aff a[16];
+    for (int i = 0; i < cnt; i++) { G1Aff p; if (g1_decompress(p, in + 48 * i, false)) return -1; jac_mul_aff(j[i], p, kl, 2); }
+    jac_to_aff_batch<Fp, 16>(a, j, cnt);
+    for (int i = 0; i < cnt; i++) g1_compress(out + 48 * i, a[i]);
+  }
+  return 0;
+}
 int emu_g1_add(const uint8_t* a, const uint8_t* b, uint8_t* out) {
   G1Aff p, q, s; if (g1_decompress(p, a, false) || g1_decompress(q, b, false)) return -1;
   G1Jac x, y, r; jac_from_aff(x, p); jac_from_aff(y, q); jac_add(r, x, y);

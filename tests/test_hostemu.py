@@ -289,6 +289,21 @@ def test_windowed_scalar_multiplication(L):
         assert o.raw == O.g1_serialize(O.g1_mul(pt, k)), hex(k)
 
 
+def test_shared_inversion_normalisation(L):
+    """csrc/curve.cuh jac_to_aff_batch (hash_to_curve outputs, 16 per inversion): ragged counts, identities anywhere."""
+    rnd = random.Random(5)
+    L.emu_to_aff_batch.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_char_p]
+    for g2 in (0, 1):
+        gen, mul, ser, ln = (O.G2_GEN, O.g2_mul, O.g2_serialize, 96) if g2 else (O.G1_GEN, O.g1_mul, O.g1_serialize, 48)
+        for cnt, inf_at in [(1, ()), (1, (0,)), (2, (1,)), (5, (0, 4)), (16, ()), (16, (0, 7, 15)), (3, (0, 1, 2))]:
+            pts = [None if i in inf_at else mul(gen, rnd.randrange(1, O.R)) for i in range(cnt)]
+            k = rnd.randrange(2, 2 ** 64)
+            o = buf(ln * cnt)
+            assert L.emu_to_aff_batch(g2, b"".join(ser(p) for p in pts), cnt, k, o) == 0
+            want = b"".join(ser(None if p is None else mul(p, k)) for p in pts)
+            assert o.raw == want, (g2, cnt, inf_at)
+
+
 def test_fr_arithmetic_and_lagrange(L):
     """csrc/fr.cuh: scalar-field Montgomery arithmetic and the Lagrange basis at zero used by share combination."""
     rnd = random.Random(33)
