@@ -9,6 +9,7 @@
 #include <cstring>
 #include <string>
 #include <unordered_map>
+#include <thread>
 #include <vector>
 
 #include "../../include/blsgpu.h"
@@ -66,6 +67,7 @@ struct Level {
 
 struct blsgpu_ctx {
   std::vector<int> devices;
+  std::vector<blsgpu_ctx*> peers;  // one single-device context per further device (devices[1..]); see verify_host_common
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
   int sm_count = 148;
@@ -241,12 +243,9 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
   }
   stage_mark(ctx, BLSGPU_STAGE_MILLER);
   {
-    static bool attr_done = false;  // per template instance
-    if (!attr_done) {
-      CK(cudaFuncSetAttribute(k_m6_lines<PkA, SigA>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_LINES_SMEM));
-      CK(cudaFuncSetAttribute(k_m6_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_ACCUM_SMEM));
-      attr_done = true;
-    }
+    // per device and per call (microseconds): a context per device may run this from several host threads
+    CK(cudaFuncSetAttribute(k_m6_lines<PkA, SigA>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_LINES_SMEM));
+    CK(cudaFuncSetAttribute(k_m6_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_ACCUM_SMEM));
     // The line stream is 39 KB per item.  Batches beyond one pass (m6_chunk) go through in chunks with two line buffers:
     // chunk c's lines are produced on side stream 0 while chunk c-1's accumulator consumes the other buffer on side stream 1.
     const size_t M6_CHUNK = m6_chunk(ctx->sm_count);
@@ -494,12 +493,23 @@ int blsgpu_ctx_create(const int* devices, int ndev, blsgpu_ctx** out) {
     return BLSGPU_E_CUDA;
   }
   stage_reset(ctx);
+  for (int i = 1; i < ndev; i++) {
+    blsgpu_ctx* peer = nullptr;
+    int r = blsgpu_ctx_create(devices + i, 1, &peer);
+    if (r != BLSGPU_OK) {
+      blsgpu_ctx_destroy(ctx);
+      return r;
+    }
+    ctx->peers.push_back(peer);
+  }
+  cudaSetDevice(devices[0]);
   *out = ctx;
   return BLSGPU_OK;
 }
 
 void blsgpu_ctx_destroy(blsgpu_ctx* ctx) {
   if (!ctx) return;
+  for (blsgpu_ctx* peer : ctx->peers) blsgpu_ctx_destroy(peer);
   cudaSetDevice(ctx->devices[0]);
   if (ctx->arena.base) cudaFree(ctx->arena.base);
   for (int i = 0; i <= BLSGPU_STAGE_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
@@ -526,6 +536,7 @@ int blsgpu_ctx_set_stream(blsgpu_ctx* ctx, void* cuda_stream) {
 int blsgpu_ctx_set_rlc_salt(blsgpu_ctx* ctx, const uint8_t salt[32]) {
   if (!ctx || !salt) return BLSGPU_E_ARG;
   memcpy(ctx->salt, salt, 32);
+  for (blsgpu_ctx* peer : ctx->peers) memcpy(peer->salt, salt, 32);
   return BLSGPU_OK;
 }
 
@@ -534,7 +545,12 @@ int blsgpu_last_stage_ms(const blsgpu_ctx* ctx, float ms_out[BLSGPU_STAGE_COUNT]
   for (int i = 0; i < BLSGPU_STAGE_COUNT; i++) ms_out[i] = ctx->stage_ms[i];
   return BLSGPU_OK;
 }
-uint64_t blsgpu_launch_count(const blsgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t blsgpu_launch_count(const blsgpu_ctx* ctx) {
+  if (!ctx) return 0;
+  uint64_t total = ctx->launches;
+  for (const blsgpu_ctx* peer : ctx->peers) total += peer->launches;
+  return total;
+}
 
 int blsgpu_verify_batch_dev(blsgpu_ctx* ctx, int impl_id, int scheme, int format, size_t n, const uint8_t* pks_dev,
                             const uint8_t* sigs_dev, const uint8_t* msgs_dev, const uint64_t* msg_off_dev, uint8_t* status_out_dev) {
@@ -556,8 +572,46 @@ int blsgpu_verify_batch_dev(blsgpu_ctx* ctx, int impl_id, int scheme, int format
   return verify_dev<1>(ctx, mode, dst, format, n, pks_dev, sigs_dev, msgs_dev, msg_off_dev, status_out_dev, 0);
 }
 
+static int verify_host_one(blsgpu_ctx* ctx, int impl_id, int msg_mode, const DstParam& dst, int format, size_t n, const uint8_t* pks,
+                           const uint8_t* sigs, const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out);
+
+// A context created on several devices shards a host-buffer batch into contiguous slices, one per device, each driven by
+// its own host thread and verified exactly like a batch of its own (own random linear combination, own bisection): the
+// per-item results are independent, so there is no collective and no combine step.  Below
+// SHARD_MIN_ITEMS per device the first device takes the whole batch.
+constexpr size_t SHARD_MIN_ITEMS = 4096;
 static int verify_host_common(blsgpu_ctx* ctx, int impl_id, int msg_mode, const DstParam& dst, int format, size_t n, const uint8_t* pks,
                               const uint8_t* sigs, const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out) {
+  const size_t ndev = 1 + ctx->peers.size();
+  if (ndev == 1 || n < ndev * SHARD_MIN_ITEMS)
+    return verify_host_one(ctx, impl_id, msg_mode, dst, format, n, pks, sigs, msgs, msg_off, status_out);
+  const size_t pk_len = impl_id == 2 ? 48 : 96, sig_len = impl_id == 2 ? 96 : 48;
+  std::vector<int> rc(ndev, BLSGPU_OK);
+  auto slice = [&](size_t d) {
+    const size_t s = n * d / ndev, e = n * (d + 1) / ndev;
+    blsgpu_ctx* c = d == 0 ? ctx : ctx->peers[d - 1];
+    std::vector<uint64_t> off;  // the slice's offsets, rebased to its first message
+    if (msg_off) {
+      off.resize(e - s + 1);
+      for (size_t i = s; i <= e; i++) off[i - s] = msg_off[i] - msg_off[s];
+    }
+    rc[d] = verify_host_one(c, impl_id, msg_mode, dst, format, e - s, pks + s * pk_len, sigs + s * sig_len,
+                            msg_off ? msgs + msg_off[s] : nullptr, msg_off ? off.data() : nullptr, status_out + s);
+  };
+  std::vector<std::thread> workers;
+  for (size_t d = 1; d < ndev; d++) workers.emplace_back(slice, d);
+  slice(0);
+  for (std::thread& w : workers) w.join();
+  for (size_t d = 0; d < ndev; d++)
+    if (rc[d] != BLSGPU_OK) {
+      if (d) ctx->err = "device " + std::to_string(ctx->devices[d]) + ": " + ctx->peers[d - 1]->err;
+      return rc[d];
+    }
+  return BLSGPU_OK;
+}
+
+static int verify_host_one(blsgpu_ctx* ctx, int impl_id, int msg_mode, const DstParam& dst, int format, size_t n, const uint8_t* pks,
+                           const uint8_t* sigs, const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out) {
   CKR(set_device(ctx));
   size_t pk_len = impl_id == 2 ? 48 : 96, sig_len = impl_id == 2 ? 96 : 48;
   size_t msg_bytes = msg_off ? (size_t)msg_off[n] : 0;

@@ -20,6 +20,11 @@
 #pragma once
 #include "fp2.cuh"
 
+// 1: sop_acc multiplies with one Karatsuba level over the limbs (Miller stage 366 -> 357 ms at 1M); 0: schoolbook
+#if !defined(SOP_KARATSUBA)
+#define SOP_KARATSUBA 1
+#endif
+
 namespace bls {
 
 struct alignas(16) SFp2 {
@@ -127,13 +132,46 @@ BLS_HD void sop_ld28(int32_t* t, const SFp2* p) {
   }
 }
 
-// T[i+j] += a[i] * b[j]   (196 signed IMAD.WIDE; columns wrap modulo 2^64 by design)
+// T[i+j] += a[i] * b[j]   (signed IMAD.WIDE; columns wrap modulo 2^64 by design)
 BLS_HD void sop_acc(uint64_t* T, const int32_t* a, const int32_t* b) {
+#if SOP_KARATSUBA
+  // One Karatsuba level over the limbs (7 + 7): 147 multiplies instead of 196.  The identity holds modulo 2^64, so T is
+  // bit-identical to the schoolbook columns; |a_i| + |a_{7+i}| < 2^31 because every caller keeps operand limbs < 2^30.
+  constexpr int H = NL / 2;
+  uint64_t C[2 * H - 1];
+#pragma unroll
+  for (int part = 0; part < 2; part++) {  // low x low -> columns 0..12, high x high -> 14..26, both leave the middle
+#pragma unroll
+    for (int i = 0; i < 2 * H - 1; i++) C[i] = 0;
+#pragma unroll
+    for (int i = 0; i < H; i++) {
+#pragma unroll
+      for (int j = 0; j < H; j++) C[i + j] += (uint64_t)((int64_t)a[part * H + i] * (int64_t)b[part * H + j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 2 * H - 1; i++) {
+      T[2 * part * H + i] += C[i];
+      T[H + i] -= C[i];
+    }
+  }
+  int32_t sa[H], sb[H];
+#pragma unroll
+  for (int i = 0; i < H; i++) {
+    sa[i] = a[i] + a[H + i];
+    sb[i] = b[i] + b[H + i];
+  }
+#pragma unroll
+  for (int i = 0; i < H; i++) {
+#pragma unroll
+    for (int j = 0; j < H; j++) T[H + i + j] += (uint64_t)((int64_t)sa[i] * (int64_t)sb[j]);
+  }
+#else
 #pragma unroll
   for (int i = 0; i < NL; i++) {
 #pragma unroll
     for (int j = 0; j < NL; j++) T[i + j] += (uint64_t)((int64_t)a[i] * (int64_t)b[j]);
   }
+#endif
 }
 
 // Montgomery reduction of 27 signed columns (T[27] must be 0 on entry) -> 14 balanced limbs.  210 IMAD.

@@ -52,8 +52,11 @@ extern "C" {
 
 typedef struct blsgpu_ctx blsgpu_ctx;
 
-/* Create a context on the given CUDA devices (ndev >= 1).  Large batches are sharded contiguously across the devices
- * with no collective: each device folds its slice into one partial Fp12 product + one partial point sum. */
+/* Create a context on the given CUDA devices (ndev >= 1).  With several devices, blsgpu_verify_batch and
+ * blsgpu_pop_verify_batch shard a batch of at least 4096 items per device into contiguous slices, one per device, each
+ * driven by its own host thread and verified as a batch of its own (per-item results are independent, so there is no
+ * collective and no combine step); every other entry point, the *_dev variants and blsgpu_ctx_set_stream use the first
+ * device.  One context per device in one process (or one process per device) works just as well. */
 int blsgpu_ctx_create(const int* devices, int ndev, blsgpu_ctx** out);
 void blsgpu_ctx_destroy(blsgpu_ctx* ctx);
 /* Text of the last engine error on this context (or of the last failed blsgpu_ctx_create when ctx is NULL). */

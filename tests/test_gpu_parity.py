@@ -457,3 +457,34 @@ def test_verify_batch_in_several_miller_passes(eng, B, monkeypatch):
     s2[bad] = s2[[(i + 3) % n for i in bad]]
     st = eng.verify_batch_packed(2, 0, pks, s2.reshape(-1), data, off)
     assert [i for i in range(n) if st[i]] == bad and all(st[i] == 1 for i in bad)
+
+
+def test_context_on_two_devices_shards_the_batch(eng, B):
+    """blsgpu_ctx_create with several devices: contiguous slices, one host thread per device, no collective.
+    The status vector must equal the single-device one, with bad items in every slice and ragged message lengths."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n = 2 * 4096 + 37
+    rnd = random.Random(77)
+    k = np.frombuffer(b"".join(rnd.randrange(1, O.R).to_bytes(32, "big") for _ in range(n)), dtype=np.uint8)
+    msgs = [hashlib.sha256(b"two%d" % i).digest()[:1 + i % 32] for i in range(n)]
+    data, off = B.pack_messages(msgs)
+    pks, sigs = eng.testdata_sign(2, 1, k, data, off)       # MessageAugmentation: the pk prefix travels with each slice
+    sigs = sigs.copy()
+    bad = [0, 5, 4100, 4101, n - 1]
+    for i in bad:
+        sigs[i * 96:(i + 1) * 96] = sigs[(i + 9) % n * 96:((i + 9) % n + 1) * 96].copy()
+    want = eng.verify_batch_packed(2, 1, pks, sigs, data, off).tolist()
+    assert [i for i, s in enumerate(want) if s] == bad
+    e2 = B.Engine([0, 1])
+    try:
+        before = e2.launch_count()
+        assert e2.verify_batch_packed(2, 1, pks, sigs, data, off).tolist() == want
+        assert e2.launch_count() - before > 2 * 20            # both devices launched their own pipeline
+        # a batch too small to shard stays on the first device
+        before = e2.launch_count()
+        assert e2.verify_batch_packed(2, 1, pks[:48 * 64], sigs[:96 * 64], data, off[:65]).tolist() == want[:64]
+        assert 0 < e2.launch_count() - before < 2 * 20 + 40
+    finally:
+        e2.close()
