@@ -369,6 +369,14 @@ size_t pipeline_bytes(size_t n, int sm_count) {
          n * (8 + 4 * 16) + ((size_t)16 << 16) * (12 + 2 * sizeof(SigJ)) + (1 << 20) + (n + 64) * 8 + 16 * 256 + 4096;
 }
 
+// compressed bytes -> affine points + per-item status: decompression (square root), then the subgroup check
+template <class A>
+int decode_points(blsgpu_ctx* ctx, size_t n, const uint8_t* d_in, int format, A* d_out, uint8_t* d_st) {
+  LAUNCH((k_decode<A>), blocks_for(n), TPB, n, d_in, format, d_out, d_st);
+  LAUNCH((k_subgroup_check<A>), blocks_for(n), TPB, n, d_out, d_st);
+  return BLSGPU_OK;
+}
+
 // hash_to_curve of n framed messages into affine points: k_hash leaves Jacobian points in scratch that is handed back to
 // the arena at once (later takes on the same stream may reuse it), k_to_affine_batch normalises them 16 per inversion
 template <class HA, class PkA>
@@ -382,6 +390,7 @@ int hash_points(blsgpu_ctx* ctx, size_t n, const uint8_t* d_msgs, const uint64_t
     return BLSGPU_E_ALLOC;
   }
   LAUNCH((k_hash<HA, PkA>), blocks_for(n), TPB, n, d_msgs, d_moff, msg_mode, d_pk, d_pre, dst, d_hj);
+  LAUNCH((k_clear_cofactor<HA>), blocks_for(n), TPB, n, d_hj);
   LAUNCH((k_to_affine_batch<HA>), blocks_for((n + TO_AFFINE_BATCH - 1) / TO_AFFINE_BATCH), TPB, n, (const HJ*)d_hj, d_h);
   ctx->arena.off = mark;
   return BLSGPU_OK;
@@ -415,9 +424,9 @@ int verify_dev(blsgpu_ctx* ctx, int msg_mode, const DstParam& dst, int format, s
   uint8_t* d_stsig = ctx->arena.take<uint8_t>(n);
   stage_reset(ctx);
   stage_mark(ctx, BLSGPU_STAGE_DECODE_PK);
-  LAUNCH((k_decode<PkA>), blocks_for(n), TPB, n, d_pks, format, d_pk, d_stpk);
+  CKR((decode_points<PkA>(ctx, n, d_pks, format, d_pk, d_stpk)));
   stage_mark(ctx, BLSGPU_STAGE_DECODE_SIG);
-  LAUNCH((k_decode<SigA>), blocks_for(n), TPB, n, d_sigs, format, d_sig, d_stsig);
+  CKR((decode_points<SigA>(ctx, n, d_sigs, format, d_sig, d_stsig)));
   CKR((verify_points<IMPL>(ctx, msg_mode, dst, n, d_pk, d_sig, d_stpk, d_stsig, d_msgs, d_moff, d_status_out)));
   stage_collect(ctx);
   return BLSGPU_OK;
@@ -686,8 +695,8 @@ static int aggregate_verify_impl(blsgpu_ctx* ctx, int scheme, int format, size_t
   uint8_t* d_stpk = ctx->arena.take<uint8_t>(n + 1);
   uint8_t* d_stsig = d_stpk + n;
   stage_reset(ctx);
-  if (n) LAUNCH((k_decode<PkA>), blocks_for(n), TPB, n, (const uint8_t*)d_pks, format, d_pk, d_stpk);
-  LAUNCH((k_decode<SigA>), 1, 32, (size_t)1, (const uint8_t*)d_sigb, format, d_sig, d_stsig);
+  if (n) CKR((decode_points<PkA>(ctx, n, (const uint8_t*)d_pks, format, d_pk, d_stpk)));
+  CKR((decode_points<SigA>(ctx, (size_t)1, (const uint8_t*)d_sigb, format, d_sig, d_stsig)));
   std::vector<uint8_t> st(n + 1);
   CK(cudaMemcpyAsync(st.data(), d_stpk, n + 1, cudaMemcpyDeviceToHost, ctx->stream));
   std::vector<uint32_t> inf(n + 1, 0);
@@ -783,7 +792,7 @@ static int sum_points_impl(blsgpu_ctx* ctx, int format, size_t n, const uint8_t*
   *bad_index_out = -1;
   std::vector<uint8_t> st(n);
   if (n) {
-    LAUNCH((k_decode<A>), blocks_for(n), TPB, n, (const uint8_t*)d_in, format, d_pts, d_st);
+    CKR((decode_points<A>(ctx, n, (const uint8_t*)d_in, format, d_pts, d_st)));
     CK(cudaMemcpyAsync(st.data(), d_st, n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     for (size_t i = 0; i < n; i++)
@@ -871,7 +880,7 @@ static int recode_impl(blsgpu_ctx* ctx, int fin, int fout, size_t n, const uint8
   A* d_pts = ctx->arena.take<A>(n);
   uint8_t* d_st = ctx->arena.take<uint8_t>(n);
   uint8_t* d_out = ctx->arena.take<uint8_t>(n * L);
-  LAUNCH((k_decode<A>), blocks_for(n), TPB, n, (const uint8_t*)d_in, fin, d_pts, d_st);
+  CKR((decode_points<A>(ctx, n, (const uint8_t*)d_in, fin, d_pts, d_st)));
   LAUNCH((k_encode<A>), blocks_for(n), TPB, n, (const A*)d_pts, fout, d_out);
   CK(cudaMemcpyAsync(out, d_out, n * L, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(status_out, d_st, n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -932,8 +941,8 @@ int blsgpu_pairing_product_is_one(blsgpu_ctx* ctx, size_t n, const uint8_t* g1_p
   uint8_t* d_st = ctx->arena.take<uint8_t>(2 * n);
   Fp12* d_F = ctx->arena.take<Fp12>(levels_total(lv));
   uint8_t* d_ok = ctx->arena.take<uint8_t>(1);
-  LAUNCH((k_decode<G1Aff>), blocks_for(n), TPB, n, (const uint8_t*)d_a, 1, d_p, d_st);
-  LAUNCH((k_decode<G2Aff>), blocks_for(n), TPB, n, (const uint8_t*)d_b, 1, d_q, d_st + n);
+  CKR((decode_points<G1Aff>(ctx, n, (const uint8_t*)d_a, 1, d_p, d_st)));
+  CKR((decode_points<G2Aff>(ctx, n, (const uint8_t*)d_b, 1, d_q, d_st + n)));
   std::vector<uint8_t> st(2 * n);
   CK(cudaMemcpyAsync(st.data(), d_st, 2 * n, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -1124,8 +1133,8 @@ int verify_secure_impl(blsgpu_ctx* ctx, int scheme, int format, size_t q, const 
   PkA* d_agg = ctx->arena.take<PkA>(q);
   uint8_t* d_setst = ctx->arena.take<uint8_t>(q);
   uint8_t* d_status = ctx->arena.take<uint8_t>(q);
-  if (M) LAUNCH((k_decode<PkA>), blocks_for(M), TPB, M, (const uint8_t*)d_pkb, format, d_pk, d_stpk);
-  LAUNCH((k_decode<SigA>), blocks_for(q), TPB, q, (const uint8_t*)d_sigb, format, d_sig, d_stsig);
+  if (M) CKR((decode_points<PkA>(ctx, M, (const uint8_t*)d_pkb, format, d_pk, d_stpk)));
+  CKR((decode_points<SigA>(ctx, q, (const uint8_t*)d_sigb, format, d_sig, d_stsig)));
   CKR((secure_weighted_sums<PkA>(ctx, pl, key_off, d_pkb, (int)Lp, pl.ord, d_pk, d_sum, d_zero)));
   LAUNCH((k_to_affine<PkA>), blocks_for(q), TPB, q, (const PkJ*)d_sum, d_agg);
   std::vector<uint8_t> stpk(M), stsig(q), zero(M);
@@ -1188,8 +1197,8 @@ int aggregate_secure_impl(blsgpu_ctx* ctx, int format, size_t q, const uint64_t*
   SigA* d_agg = ctx->arena.take<SigA>(q);
   uint8_t* d_out = ctx->arena.take<uint8_t>(q * Ls);
   if (M) {
-    LAUNCH((k_decode<PkA>), blocks_for(M), TPB, M, (const uint8_t*)d_pkb, format, d_pk, d_stpk);
-    LAUNCH((k_decode<SigA>), blocks_for(M), TPB, M, (const uint8_t*)d_sigb, format, d_sig, d_stsig);
+    CKR((decode_points<PkA>(ctx, M, (const uint8_t*)d_pkb, format, d_pk, d_stpk)));
+    CKR((decode_points<SigA>(ctx, M, (const uint8_t*)d_sigb, format, d_sig, d_stsig)));
   }
   // sum_i t_i * sig[first original index whose key bytes equal sorted key i]   (secure_aggregation.rs:138-153)
   CKR((secure_weighted_sums<SigA>(ctx, pl, key_off, d_pkb, (int)Lp, pl.first, d_sig, d_sum, d_zero)));
@@ -1309,7 +1318,7 @@ static int combine_shares_impl(blsgpu_ctx* ctx, size_t q, const uint64_t* share_
   std::vector<uint8_t> idflag(M), stpt(M), dup(M), bad(q, 0);
   if (M) {
     LAUNCH(k_share_ids, blocks_for(M), TPB, M, (const uint8_t*)d_ids, d_raw, d_idflag);
-    LAUNCH((k_decode<A>), blocks_for(M), TPB, M, (const uint8_t*)d_pts, 1, d_p, d_stpt);
+    CKR((decode_points<A>(ctx, M, (const uint8_t*)d_pts, 1, d_p, d_stpt)));
     CK(cudaMemcpyAsync(idflag.data(), d_idflag, M, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(stpt.data(), d_stpt, M, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1416,8 +1425,8 @@ int blsgpu_pairing_check_batch(blsgpu_ctx* ctx, size_t q, const uint64_t* pair_o
   uint8_t* d_ok = ctx->arena.take<uint8_t>(q);
   std::vector<uint8_t> st(2 * M);
   if (M) {
-    LAUNCH((k_decode<G1Aff>), blocks_for(M), TPB, M, (const uint8_t*)d_a, 1, d_p, d_st);
-    LAUNCH((k_decode<G2Aff>), blocks_for(M), TPB, M, (const uint8_t*)d_b, 1, d_q, d_st + M);
+    CKR((decode_points<G1Aff>(ctx, M, (const uint8_t*)d_a, 1, d_p, d_st)));
+    CKR((decode_points<G2Aff>(ctx, M, (const uint8_t*)d_b, 1, d_q, d_st + M)));
     LAUNCH(k_miller_pairs, blocks_for(M), TPB, M, (const G1Aff*)d_p, (const G2Aff*)d_q, d_F);  // undecodable -> identity -> 1
     CK(cudaMemcpyAsync(st.data(), d_st, 2 * M, cudaMemcpyDeviceToHost, ctx->stream));
   }

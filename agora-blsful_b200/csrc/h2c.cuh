@@ -271,23 +271,37 @@ BLS_FN void g2_clear_cofactor(G2Jac& r, const G2Jac& p) {
   jac_add(r, t3, n);  // - P
 }
 
-// msg' = prefix || msg
-BLS_FN void hash_to_g2(G2Jac& r, const uint8_t* prefix, uint32_t prefix_len, const uint8_t* msg, uint32_t msg_len,
-                       const uint8_t* dst, uint32_t dst_len) {
+// msg' = prefix || msg.  The batch kernels run hash_to_curve as two launches - everything up to Q0 + Q1 (hash_map_g2: a
+// point of E2, not yet of G2), then clear_cofactor - so that neither carries the other's stack frame (kernels.cuh k_hash /
+// k_clear_cofactor).
+BLS_FN void hash_field_g2(Fp2* u, const uint8_t* prefix, uint32_t prefix_len, const uint8_t* msg, uint32_t msg_len,
+                          const uint8_t* dst, uint32_t dst_len) {
   uint8_t ub[256];
   expand_message_xmd(ub, 256, prefix, prefix_len, msg, msg_len, dst, dst_len);
-  Fp2 u0, u1, xn, xd, y;
-  fp_from_be64_mod(u0.c0, ub);
-  fp_from_be64_mod(u0.c1, ub + 64);
-  fp_from_be64_mod(u1.c0, ub + 128);
-  fp_from_be64_mod(u1.c1, ub + 192);
+  fp_from_be64_mod(u[0].c0, ub);
+  fp_from_be64_mod(u[0].c1, ub + 64);
+  fp_from_be64_mod(u[1].c0, ub + 128);
+  fp_from_be64_mod(u[1].c1, ub + 192);
+}
+BLS_FN void map_to_curve_g2(G2Jac& r, const Fp2& u) {
+  Fp2 xn, xd, y;
+  sswu_g2(xn, xd, y, u);
+  iso3_map(r, xn, xd, y);
+}
+BLS_FN void hash_map_g2(G2Jac& r, const uint8_t* prefix, uint32_t prefix_len, const uint8_t* msg, uint32_t msg_len,
+                       const uint8_t* dst, uint32_t dst_len) {
+  Fp2 u[2];
+  hash_field_g2(u, prefix, prefix_len, msg, msg_len, dst, dst_len);
   G2Jac q0, q1;
-  sswu_g2(xn, xd, y, u0);
-  iso3_map(q0, xn, xd, y);
-  sswu_g2(xn, xd, y, u1);
-  iso3_map(q1, xn, xd, y);
-  jac_add(q0, q0, q1);
-  g2_clear_cofactor(r, q0);
+  map_to_curve_g2(q0, u[0]);
+  map_to_curve_g2(q1, u[1]);
+  jac_add(r, q0, q1);
+}
+BLS_FN void hash_to_g2(G2Jac& r, const uint8_t* prefix, uint32_t prefix_len, const uint8_t* msg, uint32_t msg_len,
+                       const uint8_t* dst, uint32_t dst_len) {
+  G2Jac q;
+  hash_map_g2(q, prefix, prefix_len, msg, msg_len, dst, dst_len);
+  g2_clear_cofactor(r, q);
 }
 
 // ------------------------------------------------------------------------------------------------ G1 suite
@@ -374,23 +388,38 @@ BLS_FN void iso11_map(G1Jac& r, const Fp& xn, const Fp& xd, const Fp& y) {
   fp_mul(r.Y, t, y);
 }
 
-BLS_FN void hash_to_g1(G1Jac& r, const uint8_t* prefix, uint32_t prefix_len, const uint8_t* msg, uint32_t msg_len,
-                       const uint8_t* dst, uint32_t dst_len) {
+BLS_FN void hash_field_g1(Fp* u, const uint8_t* prefix, uint32_t prefix_len, const uint8_t* msg, uint32_t msg_len,
+                          const uint8_t* dst, uint32_t dst_len) {
   uint8_t ub[128];
   expand_message_xmd(ub, 128, prefix, prefix_len, msg, msg_len, dst, dst_len);
-  Fp u0, u1, xn, xd, y;
-  fp_from_be64_mod(u0, ub);
-  fp_from_be64_mod(u1, ub + 64);
+  fp_from_be64_mod(u[0], ub);
+  fp_from_be64_mod(u[1], ub + 64);
+}
+BLS_FN void map_to_curve_g1(G1Jac& r, const Fp& u) {
+  Fp xn, xd, y;
+  sswu_g1(xn, xd, y, u);
+  iso11_map(r, xn, xd, y);
+}
+BLS_FN void hash_map_g1(G1Jac& r, const uint8_t* prefix, uint32_t prefix_len, const uint8_t* msg, uint32_t msg_len,
+                       const uint8_t* dst, uint32_t dst_len) {
+  Fp u[2];
+  hash_field_g1(u, prefix, prefix_len, msg, msg_len, dst, dst_len);
   G1Jac q0, q1;
-  sswu_g1(xn, xd, y, u0);
-  iso11_map(q0, xn, xd, y);
-  sswu_g1(xn, xd, y, u1);
-  iso11_map(q1, xn, xd, y);
-  jac_add(q0, q0, q1);
-  // h_eff = 1 - x = 1 + |x|
+  map_to_curve_g1(q0, u[0]);
+  map_to_curve_g1(q1, u[1]);
+  jac_add(r, q0, q1);
+}
+// h_eff = 1 - x = 1 + |x|
+BLS_FN void g1_clear_cofactor(G1Jac& r, const G1Jac& q) {
   G1Jac t;
-  jac_mul_xabs(t, q0);
-  jac_add(r, t, q0);
+  jac_mul_xabs(t, q);
+  jac_add(r, t, q);
+}
+BLS_FN void hash_to_g1(G1Jac& r, const uint8_t* prefix, uint32_t prefix_len, const uint8_t* msg, uint32_t msg_len,
+                       const uint8_t* dst, uint32_t dst_len) {
+  G1Jac q;
+  hash_map_g1(q, prefix, prefix_len, msg, msg_len, dst, dst_len);
+  g1_clear_cofactor(r, q);
 }
 
 }  // namespace bls

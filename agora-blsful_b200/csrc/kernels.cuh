@@ -74,6 +74,17 @@ __device__ __forceinline__ void hash_to_group(G1Jac& r, const uint8_t* pre, uint
   hash_to_g1(r, pre, pl, m, ml, dst, dl);
 }
 
+__device__ __forceinline__ void hash_map_to_curve(G2Jac& r, const uint8_t* pre, uint32_t pl, const uint8_t* m, uint32_t ml,
+                                                  const uint8_t* dst, uint32_t dl) {
+  hash_map_g2(r, pre, pl, m, ml, dst, dl);
+}
+__device__ __forceinline__ void hash_map_to_curve(G1Jac& r, const uint8_t* pre, uint32_t pl, const uint8_t* m, uint32_t ml,
+                                                  const uint8_t* dst, uint32_t dl) {
+  hash_map_g1(r, pre, pl, m, ml, dst, dl);
+}
+__device__ __forceinline__ void clear_cofactor(G2Jac& r, const G2Jac& q) { g2_clear_cofactor(r, q); }
+__device__ __forceinline__ void clear_cofactor(G1Jac& r, const G1Jac& q) { g1_clear_cofactor(r, q); }
+
 struct DstParam {
   uint8_t b[64];
   uint32_t len;
@@ -88,6 +99,12 @@ struct Digest {
 #define BLS_MIN_BLOCKS 1
 #endif
 
+// k_subgroup_check and k_clear_cofactor are pure curve arithmetic and take a 128-register cap (four blocks per SM) with a
+// handful of spilled words; measured at 1M: decode 174 -> 171 ms, hash_to_curve 268 -> 257 ms.  The same cap on every
+// kernel gains nothing more and slows the bucket kernels.
+#if !defined(BLS_SPLIT_MIN_BLOCKS)
+#define BLS_SPLIT_MIN_BLOCKS 4
+#endif
 // ---- decode: compressed bytes -> affine Montgomery points, curve + subgroup check --------------------------------
 template <class A>
 __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_decode(size_t n, const uint8_t* __restrict__ in, int format, A* __restrict__ out,
@@ -107,10 +124,25 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_decode(size_t n, const 
   }
   uint8_t s = header_to_modern(b[0], format);
   A p;
-  if (s == ST_OK) s = pt_decompress(p, b, true);
+  if (s == ST_OK) s = pt_decompress(p, b, false);  // on the curve; k_subgroup_check decides membership
   if (s != ST_OK) pt_set_inf(p);
   out[i] = p;
   st[i] = s;
+}
+
+// second half of the decode: the endomorphism subgroup check (G1: phi(P) + [x^2]P = O, G2: psi(P) = [x]P) on the decoded
+// points, a launch of its own for the same reason as k_clear_cofactor (neither half carries the other's stack frame)
+__device__ __forceinline__ bool pt_in_subgroup(const G1Aff& p) { return g1_in_subgroup(p); }
+__device__ __forceinline__ bool pt_in_subgroup(const G2Aff& p) { return g2_in_subgroup(p); }
+template <class A>
+__global__ void __launch_bounds__(128, BLS_SPLIT_MIN_BLOCKS) k_subgroup_check(size_t n, A* __restrict__ pts, uint8_t* __restrict__ st) {
+  size_t i = BLS_TID();
+  if (i >= n || st[i] != ST_OK) return;
+  A p = pts[i];
+  if (p.inf || pt_in_subgroup(p)) return;
+  pt_set_inf(p);
+  pts[i] = p;
+  st[i] = ST_DESERIALIZE;
 }
 
 // affine points -> compressed bytes in `format`
@@ -189,8 +221,22 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_hash(size_t n, const ui
     m = msgs + o0;
     mlen = (uint32_t)(o1 - o0);
   }
-  hash_to_group(hj, prefix, plen, m, mlen, dst.b, dst.len);
-  out[i] = hj;  // Jacobian: k_to_affine_batch normalises TO_AFFINE_BATCH points per field inversion
+  hash_map_to_curve(hj, prefix, plen, m, mlen, dst.b, dst.len);
+  out[i] = hj;  // on the curve, not yet in the subgroup: k_clear_cofactor, then k_to_affine_batch, finish the hash
+}
+
+// second half of hash_to_curve, in place: the h_eff multiplication (G2: psi method, two 64-bit multiplications; G1: 1 + |x|).
+// A launch of its own so that neither half carries the other's stack frame (as one kernel: 9.2 KB of frame per thread and
+// 276 ms at 1M; as two: 267 ms.  A third launch for hash_to_field, with map_to_curve per field element, gained nothing.)
+// The result stays Jacobian: k_to_affine_batch normalises TO_AFFINE_BATCH points per field inversion.
+template <class HA>
+__global__ void __launch_bounds__(128, BLS_SPLIT_MIN_BLOCKS) k_clear_cofactor(size_t n, typename PtInfo<HA>::Jac* __restrict__ pts) {
+  size_t i = BLS_TID();
+  if (i >= n) return;
+  typename PtInfo<HA>::Jac q = pts[i], r;
+  if (jac_is_inf(q)) return;  // items skipped by k_hash
+  clear_cofactor(r, q);
+  pts[i] = r;
 }
 
 // ---- deterministic random-linear-combination scalars ----------------------------------------------------------------
