@@ -48,6 +48,9 @@ _STATUS_TEXT = {
 }
 
 STAGES = ["decode_pk", "decode_sig", "hash_to_curve", "scale_sig", "miller", "reduce", "final", "bisect"]
+# BLSGPU_KERNEL_* of include/blsgpu.h, in index order
+KERNELS = ["k_decode_pk", "k_subgroup_check_pk", "k_decode_sig", "k_subgroup_check_sig", "k_hash", "k_clear_cofactor",
+           "k_to_affine_batch", "k_m6_prep", "k_m6_lines", "k_m6_accum"]
 
 
 class BlsError(Exception):
@@ -117,6 +120,7 @@ def load_library() -> ctypes.CDLL:
         "blsgpu_plan_msm": (c.c_int, [c.c_size_t, c.POINTER(c.c_int), c.POINTER(c.c_int), c.POINTER(c.c_int)]),
         "blsgpu_imad_peak": (c.c_int, [vp, c.POINTER(c.c_double)]),
         "blsgpu_last_stage_ms": (c.c_int, [vp, c.POINTER(c.c_float)]),
+        "blsgpu_last_kernel_ms": (c.c_int, [vp, c.POINTER(c.c_float), c.POINTER(c.c_int)]),
         "blsgpu_launch_count": (c.c_uint64, [vp]),
     }
     for name, (res, args) in sigs.items():
@@ -132,7 +136,7 @@ EXPORTED_SYMBOLS = [
     "blsgpu_verify_batch_dev", "blsgpu_pop_verify_batch", "blsgpu_aggregate_verify", "blsgpu_sum_points",
     "blsgpu_verify_secure_batch", "blsgpu_aggregate_secure_batch", "blsgpu_hash_to_curve_batch", "blsgpu_recode_points",
     "blsgpu_fp_mul_batch", "blsgpu_pairing_product_is_one", "blsgpu_testdata_sign", "blsgpu_imad_peak",
-    "blsgpu_combine_shares_batch", "blsgpu_verify_batch_wire", "blsgpu_pairing_check_batch", "blsgpu_plan_msm", "blsgpu_last_stage_ms", "blsgpu_launch_count",
+    "blsgpu_combine_shares_batch", "blsgpu_verify_batch_wire", "blsgpu_pairing_check_batch", "blsgpu_plan_msm", "blsgpu_last_stage_ms", "blsgpu_last_kernel_ms", "blsgpu_launch_count",
 ]
 
 
@@ -479,6 +483,13 @@ class Engine:
         arr = (ctypes.c_float * len(STAGES))()
         self._check(self._lib.blsgpu_last_stage_ms(self._ctx, arr), "blsgpu_last_stage_ms")
         return {name: float(arr[i]) for i, name in enumerate(STAGES)}
+
+    def last_kernel_ms(self) -> dict:
+        """{kernel: (total ms, launches)} of the hot kernels of the last verify call (CUDA events on their own streams)."""
+        ms = (ctypes.c_float * len(KERNELS))()
+        cnt = (ctypes.c_int * len(KERNELS))()
+        self._check(self._lib.blsgpu_last_kernel_ms(self._ctx, ms, cnt), "blsgpu_last_kernel_ms")
+        return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(KERNELS)}
 
     def launch_count(self) -> int:
         return int(self._lib.blsgpu_launch_count(self._ctx))

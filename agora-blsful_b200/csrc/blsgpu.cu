@@ -82,6 +82,15 @@ struct blsgpu_ctx {
   cudaEvent_t ev[BLSGPU_STAGE_COUNT + 1];
   bool ev_valid[BLSGPU_STAGE_COUNT + 1];
   float stage_ms[BLSGPU_STAGE_COUNT];
+  // per-kernel CUDA-event pairs of the hot kernels, recorded on the stream each kernel is launched on (blsgpu_last_kernel_ms)
+  struct KernelMark {
+    int id;
+    cudaEvent_t begin, end;
+  };
+  std::vector<KernelMark> kmarks;
+  size_t kmarks_used = 0;
+  float kernel_ms[BLSGPU_KERNEL_COUNT];
+  int kernel_launches[BLSGPU_KERNEL_COUNT];
   uint64_t launches = 0;
 };
 
@@ -114,6 +123,17 @@ int check_launch(blsgpu_ctx* ctx, const char* what) {
     CKR(check_launch(ctx, #name));                              \
   } while (0)
 
+#define LAUNCH_TIMED(kid, name, grid, block, ...)               \
+  do {                                                          \
+    const size_t km_ = kernel_begin(ctx, (kid), ctx->stream);   \
+    name<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__);     \
+    kernel_end(ctx, km_, ctx->stream);                          \
+    CKR(check_launch(ctx, #name));                              \
+  } while (0)
+
+size_t kernel_begin(blsgpu_ctx* ctx, int id, cudaStream_t stream);
+void kernel_end(blsgpu_ctx* ctx, size_t k, cudaStream_t stream);
+
 void stage_mark(blsgpu_ctx* ctx, int idx) {
   cudaEventRecord(ctx->ev[idx], ctx->stream);
   ctx->ev_valid[idx] = true;
@@ -121,9 +141,38 @@ void stage_mark(blsgpu_ctx* ctx, int idx) {
 void stage_reset(blsgpu_ctx* ctx) {
   for (int i = 0; i <= BLSGPU_STAGE_COUNT; i++) ctx->ev_valid[i] = false;
   for (int i = 0; i < BLSGPU_STAGE_COUNT; i++) ctx->stage_ms[i] = 0.f;
+  ctx->kmarks_used = 0;
+  for (int i = 0; i < BLSGPU_KERNEL_COUNT; i++) {
+    ctx->kernel_ms[i] = 0.f;
+    ctx->kernel_launches[i] = 0;
+  }
+}
+// event pair around ONE launch of a hot kernel, on the stream it is launched on; id < 0: not timed
+size_t kernel_begin(blsgpu_ctx* ctx, int id, cudaStream_t stream) {
+  if (id < 0) return (size_t)-1;
+  if (ctx->kmarks_used == ctx->kmarks.size()) {
+    blsgpu_ctx::KernelMark m{id, nullptr, nullptr};
+    if (cudaEventCreate(&m.begin) != cudaSuccess || cudaEventCreate(&m.end) != cudaSuccess) return (size_t)-1;
+    ctx->kmarks.push_back(m);
+  }
+  const size_t k = ctx->kmarks_used++;
+  ctx->kmarks[k].id = id;
+  cudaEventRecord(ctx->kmarks[k].begin, stream);
+  return k;
+}
+void kernel_end(blsgpu_ctx* ctx, size_t k, cudaStream_t stream) {
+  if (k != (size_t)-1) cudaEventRecord(ctx->kmarks[k].end, stream);
 }
 void stage_collect(blsgpu_ctx* ctx) {
   if (ctx->ev_valid[BLSGPU_STAGE_COUNT]) cudaEventSynchronize(ctx->ev[BLSGPU_STAGE_COUNT]);
+  for (size_t k = 0; k < ctx->kmarks_used; k++) {
+    float ms = 0.f;
+    const blsgpu_ctx::KernelMark& m = ctx->kmarks[k];
+    if (cudaEventSynchronize(m.end) == cudaSuccess && cudaEventElapsedTime(&ms, m.begin, m.end) == cudaSuccess) {
+      ctx->kernel_ms[m.id] += ms;
+      ctx->kernel_launches[m.id]++;
+    }
+  }
   for (int i = 0; i < BLSGPU_STAGE_COUNT; i++) {
     if (ctx->ev_valid[i] && ctx->ev_valid[i + 1]) {
       float ms = 0.f;
@@ -264,15 +313,21 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
       const size_t cn = std::min(M6_CHUNK, n - base);
       const int b = (int)(ci % nbuf);
       if (ci >= (size_t)nbuf) CK(cudaStreamWaitEvent(ctx->side[0], ctx->ev_accum[b], 0));  // the buffer's previous reader is done
+      size_t km = kernel_begin(ctx, BLSGPU_KERNEL_M6_PREP, ctx->side[0]);
       k_m6_prep<PkA, SigA><<<blocks_for(cn), TPB, 0, ctx->side[0]>>>(cn, base, d_pk, d_h, (const uint8_t*)d_status, (const Digest*)d_root,
                                                                       use_rlc ? 1 : 0, d_args[b]);
+      kernel_end(ctx, km, ctx->side[0]);
       CKR(check_launch(ctx, "k_m6_prep"));
+      km = kernel_begin(ctx, BLSGPU_KERNEL_M6_LINES, ctx->side[0]);
       k_m6_lines<PkA, SigA><<<blocks_for(cn, M6_LINES_PAIRS), M6_LINES_TPB, M6_LINES_SMEM, ctx->side[0]>>>(
           cn, base, d_args[b], d_pk, d_h, d_status, d_lines[b]);
+      kernel_end(ctx, km, ctx->side[0]);
       CKR(check_launch(ctx, "k_m6_lines"));
       CK(cudaEventRecord(ctx->ev_lines[b], ctx->side[0]));
       CK(cudaStreamWaitEvent(ctx->side[1], ctx->ev_lines[b], 0));
+      km = kernel_begin(ctx, BLSGPU_KERNEL_M6_ACCUM, ctx->side[1]);
       k_m6_accum<<<blocks_for(cn, M6_ITEMS_PER_BLOCK), 128, M6_ACCUM_SMEM, ctx->side[1]>>>(cn, base, d_status, d_lines[b], d_F);
+      kernel_end(ctx, km, ctx->side[1]);
       CKR(check_launch(ctx, "k_m6_accum"));
       CK(cudaEventRecord(ctx->ev_accum[b], ctx->side[1]));
     }
@@ -371,9 +426,9 @@ size_t pipeline_bytes(size_t n, int sm_count) {
 
 // compressed bytes -> affine points + per-item status: decompression (square root), then the subgroup check
 template <class A>
-int decode_points(blsgpu_ctx* ctx, size_t n, const uint8_t* d_in, int format, A* d_out, uint8_t* d_st) {
-  LAUNCH((k_decode<A>), blocks_for(n), TPB, n, d_in, format, d_out, d_st);
-  LAUNCH((k_subgroup_check<A>), blocks_for(n), TPB, n, d_out, d_st);
+int decode_points(blsgpu_ctx* ctx, size_t n, const uint8_t* d_in, int format, A* d_out, uint8_t* d_st, int kid = -1) {
+  LAUNCH_TIMED(kid, (k_decode<A>), blocks_for(n), TPB, n, d_in, format, d_out, d_st);
+  LAUNCH_TIMED(kid < 0 ? -1 : kid + 1, (k_subgroup_check<A>), blocks_for(n), TPB, n, d_out, d_st);
   return BLSGPU_OK;
 }
 
@@ -389,9 +444,10 @@ int hash_points(blsgpu_ctx* ctx, size_t n, const uint8_t* d_msgs, const uint64_t
     ctx->err = "hash_points: arena too small";
     return BLSGPU_E_ALLOC;
   }
-  LAUNCH((k_hash<HA, PkA>), blocks_for(n), TPB, n, d_msgs, d_moff, msg_mode, d_pk, d_pre, dst, d_hj);
-  LAUNCH((k_clear_cofactor<HA>), blocks_for(n), TPB, n, d_hj);
-  LAUNCH((k_to_affine_batch<HA>), blocks_for((n + TO_AFFINE_BATCH - 1) / TO_AFFINE_BATCH), TPB, n, (const HJ*)d_hj, d_h);
+  LAUNCH_TIMED(BLSGPU_KERNEL_HASH_MAP, (k_hash<HA, PkA>), blocks_for(n), TPB, n, d_msgs, d_moff, msg_mode, d_pk, d_pre, dst, d_hj);
+  LAUNCH_TIMED(BLSGPU_KERNEL_CLEAR_COFACTOR, (k_clear_cofactor<HA>), blocks_for(n), TPB, n, d_hj);
+  LAUNCH_TIMED(BLSGPU_KERNEL_TO_AFFINE, (k_to_affine_batch<HA>), blocks_for((n + TO_AFFINE_BATCH - 1) / TO_AFFINE_BATCH), TPB, n,
+               (const HJ*)d_hj, d_h);
   ctx->arena.off = mark;
   return BLSGPU_OK;
 }
@@ -424,9 +480,9 @@ int verify_dev(blsgpu_ctx* ctx, int msg_mode, const DstParam& dst, int format, s
   uint8_t* d_stsig = ctx->arena.take<uint8_t>(n);
   stage_reset(ctx);
   stage_mark(ctx, BLSGPU_STAGE_DECODE_PK);
-  CKR((decode_points<PkA>(ctx, n, d_pks, format, d_pk, d_stpk)));
+  CKR((decode_points<PkA>(ctx, n, d_pks, format, d_pk, d_stpk, BLSGPU_KERNEL_DECODE_PK)));
   stage_mark(ctx, BLSGPU_STAGE_DECODE_SIG);
-  CKR((decode_points<SigA>(ctx, n, d_sigs, format, d_sig, d_stsig)));
+  CKR((decode_points<SigA>(ctx, n, d_sigs, format, d_sig, d_stsig, BLSGPU_KERNEL_DECODE_SIG)));
   CKR((verify_points<IMPL>(ctx, msg_mode, dst, n, d_pk, d_sig, d_stpk, d_stsig, d_msgs, d_moff, d_status_out)));
   stage_collect(ctx);
   return BLSGPU_OK;
@@ -522,6 +578,10 @@ void blsgpu_ctx_destroy(blsgpu_ctx* ctx) {
   cudaSetDevice(ctx->devices[0]);
   if (ctx->arena.base) cudaFree(ctx->arena.base);
   for (int i = 0; i <= BLSGPU_STAGE_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
+  for (const blsgpu_ctx::KernelMark& m : ctx->kmarks) {
+    cudaEventDestroy(m.begin);
+    cudaEventDestroy(m.end);
+  }
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   for (int i = 0; i < 2; i++) {
     if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
@@ -552,6 +612,14 @@ int blsgpu_ctx_set_rlc_salt(blsgpu_ctx* ctx, const uint8_t salt[32]) {
 int blsgpu_last_stage_ms(const blsgpu_ctx* ctx, float ms_out[BLSGPU_STAGE_COUNT]) {
   if (!ctx || !ms_out) return BLSGPU_E_ARG;
   for (int i = 0; i < BLSGPU_STAGE_COUNT; i++) ms_out[i] = ctx->stage_ms[i];
+  return BLSGPU_OK;
+}
+int blsgpu_last_kernel_ms(const blsgpu_ctx* ctx, float ms_out[BLSGPU_KERNEL_COUNT], int launches_out[BLSGPU_KERNEL_COUNT]) {
+  if (!ctx || !ms_out) return BLSGPU_E_ARG;
+  for (int i = 0; i < BLSGPU_KERNEL_COUNT; i++) {
+    ms_out[i] = ctx->kernel_ms[i];
+    if (launches_out) launches_out[i] = ctx->kernel_launches[i];
+  }
   return BLSGPU_OK;
 }
 uint64_t blsgpu_launch_count(const blsgpu_ctx* ctx) {

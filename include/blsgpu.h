@@ -196,6 +196,22 @@ int blsgpu_plan_msm(size_t n, int* window_bits_out, int* windows_out, int* top_w
 #define BLSGPU_STAGE_BISECT 7
 #define BLSGPU_STAGE_COUNT 8
 int blsgpu_last_stage_ms(const blsgpu_ctx* ctx, float ms_out[BLSGPU_STAGE_COUNT]);
+
+/* Device time of the hot kernels of the last blsgpu_verify_batch[_dev] call on this context (first device): one CUDA-event
+ * pair around every launch, recorded on the stream the kernel is launched on; ms_out = total per kernel, launches_out
+ * (may be NULL) = how many launches that total covers (more than one only when the Miller stage runs in several passes). */
+#define BLSGPU_KERNEL_DECODE_PK 0      /* k_decode<pk group>: decompression (square root) */
+#define BLSGPU_KERNEL_SUBGROUP_PK 1    /* k_subgroup_check<pk group> */
+#define BLSGPU_KERNEL_DECODE_SIG 2     /* k_decode<sig group> */
+#define BLSGPU_KERNEL_SUBGROUP_SIG 3   /* k_subgroup_check<sig group> */
+#define BLSGPU_KERNEL_HASH_MAP 4       /* k_hash: expand_message, hash_to_field, 2 x (SSWU + isogeny), point addition */
+#define BLSGPU_KERNEL_CLEAR_COFACTOR 5 /* k_clear_cofactor */
+#define BLSGPU_KERNEL_TO_AFFINE 6      /* k_to_affine_batch (16 points per inversion) */
+#define BLSGPU_KERNEL_M6_PREP 7        /* k_m6_prep: r_i * pk_i and the line scalars */
+#define BLSGPU_KERNEL_M6_LINES 8       /* k_m6_lines: 68 line evaluations per pairing */
+#define BLSGPU_KERNEL_M6_ACCUM 9       /* k_m6_accum: the shared Fp12 accumulators */
+#define BLSGPU_KERNEL_COUNT 10
+int blsgpu_last_kernel_ms(const blsgpu_ctx* ctx, float ms_out[BLSGPU_KERNEL_COUNT], int launches_out[BLSGPU_KERNEL_COUNT]);
 /* number of kernel launches issued by this context since creation */
 uint64_t blsgpu_launch_count(const blsgpu_ctx* ctx);
 
