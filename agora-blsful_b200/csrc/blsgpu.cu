@@ -50,11 +50,13 @@ inline unsigned blocks_for(size_t n, int tpb = TPB) { return (unsigned)((n + tpb
 struct Arena {
   uint8_t* base = nullptr;
   size_t cap = 0, off = 0;
+  bool over = false;  // a take ran past the capacity the entry point sized: every later launch is refused (ARENA_OK)
   template <class T>
   T* take(size_t count) {
     size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
     T* p = reinterpret_cast<T*>(base + off);
     off += bytes;
+    if (off > cap) over = true;
     return p;
   }
 };
@@ -98,6 +100,7 @@ namespace {
 
 int ensure_arena(blsgpu_ctx* ctx, size_t bytes) {
   ctx->arena.off = 0;
+  ctx->arena.over = false;
   if (ctx->arena.cap >= bytes) return BLSGPU_OK;
   if (ctx->arena.base) CK(cudaFree(ctx->arena.base));
   ctx->arena.base = nullptr;
@@ -117,14 +120,23 @@ int check_launch(blsgpu_ctx* ctx, const char* what) {
   }
   return BLSGPU_OK;
 }
+#define ARENA_OK()                                                          \
+  do {                                                                      \
+    if (ctx->arena.over) {                                                  \
+      ctx->err = "internal: device scratch arena sized too small";          \
+      return BLSGPU_E_ALLOC;                                                \
+    }                                                                       \
+  } while (0)
 #define LAUNCH(name, grid, block, ...)                          \
   do {                                                          \
+    ARENA_OK();                                                 \
     name<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__);     \
     CKR(check_launch(ctx, #name));                              \
   } while (0)
 
 #define LAUNCH_TIMED(kid, name, grid, block, ...)               \
   do {                                                          \
+    ARENA_OK();                                                 \
     const size_t km_ = kernel_begin(ctx, (kid), ctx->stream);   \
     name<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__);     \
     kernel_end(ctx, km_, ctx->stream);                          \
@@ -306,6 +318,7 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
       d_args[b] = ctx->arena.take<M6Arg>(chunk);
       d_lines[b] = ctx->arena.take<SLineRec>(chunk * M6_LINE_RECS);
     }
+    ARENA_OK();
     CK(cudaStreamWaitEvent(ctx->side[0], ctx->ev_fork, 0));
     CK(cudaStreamWaitEvent(ctx->side[1], ctx->ev_fork, 0));
     size_t ci = 0;
@@ -420,7 +433,8 @@ size_t pipeline_bytes(size_t n, int sm_count) {
   size_t total = levels_total(make_levels(std::max<size_t>(n, 1)));
   size_t gtotal = levels_total(make_levels((std::max<size_t>(n, 1) + M6_GROUP - 1) / M6_GROUP));
   return gtotal * (sizeof(Fp12) + sizeof(SigJ)) + n * (sizeof(SigJ) + sizeof(Fp12) + sizeof(SigJ)) +
-         2 * std::min(std::max<size_t>(n, 1), M6_CHUNK) * (sizeof(M6Arg) + M6_LINE_RECS * sizeof(SLineRec) + 512) + total * sizeof(Digest) +
+         (n > M6_CHUNK ? 2 : 1) * std::min(std::max<size_t>(n, 1), M6_CHUNK) * (sizeof(M6Arg) + M6_LINE_RECS * sizeof(SLineRec) + 512) +
+         total * sizeof(Digest) +
          n * (8 + 4 * 16) + ((size_t)16 << 16) * (12 + 2 * sizeof(SigJ)) + (1 << 20) + (n + 64) * 8 + 16 * 256 + 4096;
 }
 

@@ -488,3 +488,20 @@ def test_context_on_two_devices_shards_the_batch(eng, B):
         assert 0 < e2.launch_count() - before < 2 * 20 + 40
     finally:
         e2.close()
+
+
+def test_kernel_event_timings_cover_the_hot_kernels(eng, B, cpp):
+    """blsgpu_last_kernel_ms: one CUDA-event pair per launch of each hot kernel of the last verify call (what bench.py's
+    per-kernel roofline reads)."""
+    n = 600
+    rnd = random.Random(3)
+    k = np.frombuffer(b"".join(rnd.randrange(1, O.R).to_bytes(32, "big") for _ in range(n)), dtype=np.uint8)
+    data, off = B.pack_messages([b"t%d" % i for i in range(n)])
+    pks, sigs = eng.testdata_sign(2, 0, k, data, off)
+    assert eng.verify_batch_packed(2, 0, pks, sigs, data, off).tolist() == [0] * n
+    km = eng.last_kernel_ms()
+    assert list(km) == B.KERNELS
+    for name, (ms, launches) in km.items():
+        assert launches == 1 and 0 < ms < 1000, (name, ms, launches)
+    stages = eng.last_stage_ms()
+    assert km["k_hash"][0] + km["k_clear_cofactor"][0] + km["k_to_affine_batch"][0] <= stages["hash_to_curve"] * 1.05 + 0.05
