@@ -119,6 +119,7 @@ def load_library() -> ctypes.CDLL:
         "blsgpu_pairing_check_batch": (c.c_int, [vp, c.c_size_t, u64p, u8p, u8p, u8p, u8p]),
         "blsgpu_plan_msm": (c.c_int, [c.c_size_t, c.POINTER(c.c_int), c.POINTER(c.c_int), c.POINTER(c.c_int)]),
         "blsgpu_imad_peak": (c.c_int, [vp, c.POINTER(c.c_double)]),
+        "blsgpu_verify_share_batch": (c.c_int, [vp, c.c_int, c.c_int, c.c_size_t, vp, vp, vp, vp, vp]),
         "blsgpu_last_stage_ms": (c.c_int, [vp, c.POINTER(c.c_float)]),
         "blsgpu_last_kernel_ms": (c.c_int, [vp, c.POINTER(c.c_float), c.POINTER(c.c_int)]),
         "blsgpu_launch_count": (c.c_uint64, [vp]),
@@ -136,7 +137,7 @@ EXPORTED_SYMBOLS = [
     "blsgpu_verify_batch_dev", "blsgpu_pop_verify_batch", "blsgpu_aggregate_verify", "blsgpu_sum_points",
     "blsgpu_verify_secure_batch", "blsgpu_aggregate_secure_batch", "blsgpu_hash_to_curve_batch", "blsgpu_recode_points",
     "blsgpu_fp_mul_batch", "blsgpu_pairing_product_is_one", "blsgpu_testdata_sign", "blsgpu_imad_peak",
-    "blsgpu_combine_shares_batch", "blsgpu_verify_batch_wire", "blsgpu_pairing_check_batch", "blsgpu_plan_msm", "blsgpu_last_stage_ms", "blsgpu_last_kernel_ms", "blsgpu_launch_count",
+    "blsgpu_combine_shares_batch", "blsgpu_verify_batch_wire", "blsgpu_pairing_check_batch", "blsgpu_plan_msm", "blsgpu_verify_share_batch", "blsgpu_last_stage_ms", "blsgpu_last_kernel_ms", "blsgpu_launch_count",
 ]
 
 
@@ -462,6 +463,25 @@ class Engine:
         rc = self._lib.blsgpu_combine_shares_batch(self._ctx, group, q, _ptr(off), _ptr(data), _ptr(out), _ptr(status))
         self._check(rc, "blsgpu_combine_shares_batch")
         return status, [out[j * length:(j + 1) * length].tobytes() for j in range(q)]
+
+    def verify_share_batch(self, impl_id: int, scheme: int, pk_shares: Sequence[bytes], sig_shares: Sequence[bytes],
+                           msgs: Sequence[bytes]) -> np.ndarray:
+        """n x PublicKeyShare::verify / SignatureShare::verify (public_key_share.rs:55-71, signature_share.rs:98-101) on raw
+        share records: 32-byte big-endian identifier || compressed point (lib.rs:117-157).  Returns BLSGPU_ST_* per item."""
+        n = len(pk_shares)
+        if len(sig_shares) != n or len(msgs) != n:
+            raise BlsError(ST_MISMATCHED_LENGTHS)
+        for sh, ln in [(s, 32 + pk_len(impl_id)) for s in pk_shares] + [(s, 32 + sig_len(impl_id)) for s in sig_shares]:
+            if len(sh) != ln:
+                raise BlsError(ST_DESERIALIZE, "Invalid length for share")  # lib.rs:121-125
+        pk = np.frombuffer(b"".join(pk_shares), dtype=np.uint8) if n else np.zeros(0, dtype=np.uint8)
+        sg = np.frombuffer(b"".join(sig_shares), dtype=np.uint8) if n else np.zeros(0, dtype=np.uint8)
+        data, off = pack_messages(msgs)
+        status = np.zeros(n, dtype=np.uint8)
+        rc = self._lib.blsgpu_verify_share_batch(self._ctx, impl_id, scheme, n, _ptr(pk), _ptr(sg), _ptr(data), _ptr(off),
+                                                 _ptr(status))
+        self._check(rc, "blsgpu_verify_share_batch")
+        return status
 
     def testdata_sign(self, impl_id: int, scheme: int, scalars: np.ndarray, msgs_data: np.ndarray, msg_off: np.ndarray):
         """Synthetic data only (see include/blsgpu.h): returns (pks, sigs) flat uint8 arrays."""

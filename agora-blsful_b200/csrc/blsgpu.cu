@@ -1484,6 +1484,33 @@ int blsgpu_verify_batch_wire(blsgpu_ctx* ctx, int impl_id, size_t n, const uint8
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Share verification on raw share records: strip (and validate) the identifiers on the host, verify the values.
+int blsgpu_verify_share_batch(blsgpu_ctx* ctx, int impl_id, int scheme, size_t n, const uint8_t* pk_shares, const uint8_t* sig_shares,
+                              const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out) {
+  if (!ctx) return BLSGPU_E_ARG;
+  if (!args_ok(impl_id, scheme, 1) || (n && (!pk_shares || !sig_shares || !msg_off || !status_out))) {
+    ctx->err = "blsgpu_verify_share_batch: bad arguments";
+    return BLSGPU_E_ARG;
+  }
+  if (n == 0) return BLSGPU_OK;
+  static const uint8_t R_BE[32] = {0x73, 0xed, 0xa7, 0x53, 0x29, 0x9d, 0x7d, 0x48, 0x33, 0x39, 0xd8, 0x08, 0x09, 0xa1, 0xd8, 0x05,
+                                   0x53, 0xbd, 0xa4, 0x02, 0xff, 0xfe, 0x5b, 0xfe, 0xff, 0xff, 0xff, 0xff, 0x00, 0x00, 0x00, 0x01};
+  const size_t pk_len = impl_id == 2 ? 48 : 96, sig_len = impl_id == 2 ? 96 : 48;
+  std::vector<uint8_t> p(n * pk_len), g(n * sig_len), bad_id(n, 0);
+  for (size_t i = 0; i < n; i++) {
+    const uint8_t* pr = pk_shares + i * (32 + pk_len);
+    const uint8_t* sr = sig_shares + i * (32 + sig_len);
+    bad_id[i] = memcmp(pr, R_BE, 32) >= 0 || memcmp(sr, R_BE, 32) >= 0;  // Scalar::from_be_bytes rejects values >= r
+    memcpy(&p[i * pk_len], pr + 32, pk_len);
+    memcpy(&g[i * sig_len], sr + 32, sig_len);
+  }
+  CKR(blsgpu_verify_batch(ctx, impl_id, scheme, 1, n, p.data(), g.data(), msgs, msg_off, status_out));
+  for (size_t i = 0; i < n; i++)
+    if (bad_id[i]) status_out[i] = BLSGPU_ST_DESERIALIZE;
+  return BLSGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 int blsgpu_pairing_check_batch(blsgpu_ctx* ctx, size_t q, const uint64_t* pair_off, const uint8_t* g1_points, const uint8_t* g2_points,
                                uint8_t* ok_out, uint8_t* status_out) {
   if (!ctx) return BLSGPU_E_ARG;

@@ -180,6 +180,15 @@ int blsgpu_pairing_check_batch(blsgpu_ctx* ctx, size_t q, const uint64_t* pair_o
 int blsgpu_combine_shares_batch(blsgpu_ctx* ctx, int group, size_t q, const uint64_t* share_off, const uint8_t* shares,
                                 uint8_t* out, uint8_t* status_out);
 
+/* Share verification on the raw share records: n x PublicKeyShare::verify /
+ * SignatureShare::verify (reference src/public_key_share.rs:55-71, src/signature_share.rs:98-101), which run the scheme's
+ * verify on the share VALUES and ignore the identifiers.  Records are the reference's raw share form (src/lib.rs:117-157,
+ * 219-259): 32-byte big-endian identifier || IETF compressed point, i.e. pk_shares: n x (32 + 48|96) bytes,
+ * sig_shares: n x (32 + 96|48) bytes for impl 2 | 1.  An identifier that is not a canonical scalar (>= r) fails the
+ * record's TryFrom (lib.rs:126-133) -> BLSGPU_ST_DESERIALIZE; everything else is blsgpu_verify_batch's status. */
+int blsgpu_verify_share_batch(blsgpu_ctx* ctx, int impl_id, int scheme, size_t n, const uint8_t* pk_shares,
+                              const uint8_t* sig_shares, const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out);
+
 /* Host-only planning query (no device needed): the window layout the bucket multi-scalar multiplication of
  * blsgpu_verify_batch uses for a batch of n signatures (64-bit scalars). */
 int blsgpu_plan_msm(size_t n, int* window_bits_out, int* windows_out, int* top_window_bits_out);

@@ -663,6 +663,20 @@ def verify(impl: int, scheme: int, fmt: int, pk_bytes: bytes, sig_bytes: bytes, 
     return core_verify(impl, pk, sig, scheme_message(impl, scheme, pk, msg), sig_dst(impl, scheme))
 
 
+def verify_share(impl: int, scheme: int, pk_share: bytes, sig_share: bytes, msg: bytes) -> int:
+    """PublicKeyShare::verify / SignatureShare::verify (public_key_share.rs:55-71, signature_share.rs:98-101) fed from the
+    raw share records of lib.rs:117-157 / 219-259 (32-byte big-endian identifier || compressed point): both records must
+    parse (identifier a canonical scalar < r, lib.rs:126-133; the point through from_compressed), then the scheme's
+    verify runs on the share VALUES - the identifiers play no part in it."""
+    C = IMPLS[impl]
+    pl, sl = (48, 96) if impl == G2IMPL else (96, 48)
+    if len(pk_share) != 32 + pl or len(sig_share) != 32 + sl:
+        return ERR_DESERIALIZE
+    if int.from_bytes(pk_share[:32], "big") >= R or int.from_bytes(sig_share[:32], "big") >= R:
+        return ERR_DESERIALIZE
+    return verify(impl, scheme, MODERN, pk_share[32:], sig_share[32:], msg)
+
+
 def pop_verify(impl: int, fmt: int, pk_bytes: bytes, sig_bytes: bytes) -> int:
     """sig_pop.rs:61-70 / proof_of_possession.rs:77-81."""
     C = IMPLS[impl]

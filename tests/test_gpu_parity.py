@@ -375,6 +375,34 @@ def test_combine_shares_matches_oracle_and_golden_signature(eng, B, cpp):
     assert eng.verify_batch(2, 0, [outs[0]], [bytes.fromhex(s["sig"])], [msg]).tolist() == [0]
 
 
+def test_verify_share_batch_against_oracle(eng, B, cpp):
+    """blsgpu_verify_share_batch (PublicKeyShare::verify on raw share records): Shamir shares of a golden key verify,
+    identifiers are ignored by the check but must be canonical scalars, every other outcome is verify's."""
+    rnd = random.Random(17)
+    msg = bytes.fromhex(cpp["message"])
+    sk = int(cpp["signers"][0]["sk"], 16)
+    coef = [sk] + [rnd.randrange(O.R) for _ in range(2)]
+    ids = [1, 2 ** 130 + 5, O.R - 1]
+    sks = [sum(c * pow(x, k, O.R) for k, c in enumerate(coef)) % O.R for x in ids]
+    for impl, scheme in [(2, 0), (1, 1)]:
+        C = O.IMPLS[impl]
+        pkv = [C.pk_ser(C.pk_mul(C.pk_gen, k), O.MODERN) for k in sks]
+        sgv = [C.sig_ser(O.sign(impl, scheme, k, msg), O.MODERN) for k in sks]
+        pk_sh = [x.to_bytes(32, "big") + v for x, v in zip(ids, pkv)]
+        sg_sh = [x.to_bytes(32, "big") + v for x, v in zip(ids, sgv)]
+        cases = list(zip(pk_sh, sg_sh))
+        cases.append((pk_sh[0], sg_sh[1]))                                         # another share's signature
+        cases.append((pk_sh[0], (7).to_bytes(32, "big") + sgv[0]))                 # identifiers differ: not looked at
+        cases.append((O.R.to_bytes(32, "big") + pkv[0], sg_sh[0]))                 # identifier >= r
+        cases.append((pk_sh[0], (2 ** 256 - 1).to_bytes(32, "big") + sgv[0]))
+        cases.append((pk_sh[0][:32] + bytes(len(pkv[0])), sg_sh[0]))               # undecodable value
+        cases.append((pk_sh[0], sg_sh[0][:32] + bytes([0xC0]) + bytes(len(sgv[0]) - 1)))   # identity signature share
+        got = eng.verify_share_batch(impl, scheme, [c[0] for c in cases], [c[1] for c in cases], [msg] * len(cases))
+        want = [O.verify_share(impl, scheme, a, b, msg) for a, b in cases]
+        assert got.tolist() == want, (impl, scheme)
+        assert want[:3] == [0] * 3 and want[3] == 1 and want[4] == 0 and want[5:8] == [4, 4, 4] and want[8] == 2
+
+
 def test_verify_batch_wire_mixed_schemes(eng, B, cpp):
     """blsgpu_verify_batch_wire: serde_bare tagged signatures (signature.rs:112-126), schemes mixed in one call; every
     status equals the oracle's verify under the scheme named by the tag."""

@@ -241,3 +241,18 @@ def test_combine_shares_reproduces_the_golden_signature(cpp):
     assert O.combine_shares(2, [sig_shares[0], sig_shares[0][:32] + sig_shares[1][32:]])[0] == O.ERR_VSSS
     assert O.combine_shares(2, [O.R.to_bytes(32, "big") + sig_shares[0][32:], sig_shares[1]])[0] == O.ERR_DESERIALIZE
     assert O.combine_shares(2, [sig_shares[0], sig_shares[1][:32] + bytes(96)])[0] == O.ERR_DESERIALIZE
+
+
+def test_verify_share_on_golden_triple(golden_dir):
+    """oracle verify_share (PublicKeyShare::verify on raw share records): the share VALUES decide, identifiers only have
+    to be canonical scalars (lib.rs:126-133).  Pinned on the reference's golden pk/sig pair (cpp_integration_test.rs)."""
+    import json, os
+    g = json.load(open(os.path.join(golden_dir, "cpp_integration.json")))
+    msg = bytes.fromhex(g["message"])
+    s0, s1 = g["signers"][0], g["signers"][1]
+    pk = (5).to_bytes(32, "big") + bytes.fromhex(s0["pk"])
+    sg = (9).to_bytes(32, "big") + bytes.fromhex(s0["sig"])
+    assert O.verify_share(2, 0, pk, sg, msg) == 0
+    assert O.verify_share(2, 0, pk, (9).to_bytes(32, "big") + bytes.fromhex(s1["sig"]), msg) == 1
+    assert O.verify_share(2, 0, O.R.to_bytes(32, "big") + pk[32:], sg, msg) == 4
+    assert O.verify_share(2, 0, pk, sg[:-1], msg) == 4
