@@ -133,7 +133,28 @@ def run_reference(args, rank, world):
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line: anything libraries print there (NCCL's version banner under NCCL_DEBUG, for
+    one) is sent to stderr instead; emit() writes the result to the real stdout."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
@@ -147,6 +168,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="signatures for the cpu_baseline leg (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    _claim_stdout()
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -283,7 +305,7 @@ def main():
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(args.cpu_sample)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
