@@ -101,6 +101,7 @@ def load_library() -> ctypes.CDLL:
         "blsgpu_ctx_destroy": (None, [vp]),
         "blsgpu_last_error": (c.c_char_p, [vp]),
         "blsgpu_ctx_set_rlc_salt": (c.c_int, [vp, u8p]),
+        "blsgpu_ctx_set_rlc_bits": (c.c_int, [vp, c.c_int]),
         "blsgpu_ctx_set_stream": (c.c_int, [vp, vp]),
         "blsgpu_verify_batch": (c.c_int, [vp, c.c_int, c.c_int, c.c_int, c.c_size_t, u8p, u8p, u8p, u64p, u8p]),
         "blsgpu_verify_batch_dev": (c.c_int, [vp, c.c_int, c.c_int, c.c_int, c.c_size_t, u8p, u8p, u8p, u64p, u8p]),
@@ -117,7 +118,7 @@ def load_library() -> ctypes.CDLL:
         "blsgpu_combine_shares_batch": (c.c_int, [vp, c.c_int, c.c_size_t, u64p, u8p, u8p, u8p]),
         "blsgpu_verify_batch_wire": (c.c_int, [vp, c.c_int, c.c_size_t, u8p, u8p, u8p, u64p, u8p]),
         "blsgpu_pairing_check_batch": (c.c_int, [vp, c.c_size_t, u64p, u8p, u8p, u8p, u8p]),
-        "blsgpu_plan_msm": (c.c_int, [c.c_size_t, c.POINTER(c.c_int), c.POINTER(c.c_int), c.POINTER(c.c_int)]),
+        "blsgpu_plan_msm": (c.c_int, [c.c_size_t, c.c_int, c.POINTER(c.c_int), c.POINTER(c.c_int), c.POINTER(c.c_int)]),
         "blsgpu_imad_peak": (c.c_int, [vp, c.POINTER(c.c_double)]),
         "blsgpu_verify_share_batch": (c.c_int, [vp, c.c_int, c.c_int, c.c_size_t, vp, vp, vp, vp, vp]),
         "blsgpu_last_stage_ms": (c.c_int, [vp, c.POINTER(c.c_float)]),
@@ -132,7 +133,8 @@ def load_library() -> ctypes.CDLL:
 
 
 EXPORTED_SYMBOLS = [
-    "blsgpu_ctx_create", "blsgpu_ctx_destroy", "blsgpu_last_error", "blsgpu_ctx_set_rlc_salt", "blsgpu_ctx_set_stream",
+    "blsgpu_ctx_create", "blsgpu_ctx_destroy", "blsgpu_last_error", "blsgpu_ctx_set_rlc_salt", "blsgpu_ctx_set_rlc_bits",
+    "blsgpu_ctx_set_stream",
     "blsgpu_verify_batch",
     "blsgpu_verify_batch_dev", "blsgpu_pop_verify_batch", "blsgpu_aggregate_verify", "blsgpu_sum_points",
     "blsgpu_verify_secure_batch", "blsgpu_aggregate_secure_batch", "blsgpu_hash_to_curve_batch", "blsgpu_recode_points",
@@ -227,6 +229,17 @@ class Engine:
     def set_stream(self, cuda_stream: int) -> None:
         """Run on a caller-owned CUDA stream (e.g. torch.cuda.Stream().cuda_stream); 0 restores the engine's own."""
         self._check(self._lib.blsgpu_ctx_set_stream(self._ctx, cuda_stream or None), "blsgpu_ctx_set_stream")
+
+    def set_rlc_salt(self, salt: bytes) -> None:
+        """Pins the salt of the batch-check scalars (tests / reproducible runs only; the default is fresh OS randomness per call)."""
+        if len(salt) != 32:
+            raise ValueError("salt must be 32 bytes")
+        buf = np.frombuffer(bytes(salt), dtype=np.uint8)
+        self._check(self._lib.blsgpu_ctx_set_rlc_salt(self._ctx, _ptr(buf)), "blsgpu_ctx_set_rlc_salt")
+
+    def set_rlc_bits(self, bits: int) -> None:
+        """64- (default) or 128-bit random-linear-combination scalars."""
+        self._check(self._lib.blsgpu_ctx_set_rlc_bits(self._ctx, bits), "blsgpu_ctx_set_rlc_bits")
 
     def _check(self, rc: int, what: str):
         if rc != 0:

@@ -2,6 +2,7 @@
 // No CPU arithmetic lives here: every field/curve/pairing operation runs on the device; the host only stages buffers,
 // launches kernels, walks the bisection tree and applies the reference's host-side rules (duplicate messages, sorting).
 #include <cuda_runtime.h>
+#include <sys/random.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -39,11 +40,10 @@ constexpr int TPB = 128;
 constexpr size_t MSM_MIN_ITEMS = 4096;  // below this the per-item scaling is as fast as the bucket method's fixed costs
 // Items per pass of the Miller kernels (a multiple of 120).  Measured on B200 at n = 1M: every extra pass costs ~8 ms of
 // kernel ramp-up and tail (444 ms in one pass, 452 in three, 468 in six), and HBM is there to be used: 39 KB per item.
-inline size_t m6_chunk(int sm_count) {
-  if (const char* e = getenv("BLSGPU_M6_CHUNK")) return (size_t)atoll(e) / 120 * 120;  // tuning experiments only
-  (void)sm_count;
-  return (size_t)8736 * 120;  // 1,048,320 items = 41 GB of line records: a 1M batch goes through in one pass
-}
+// The pass size of a call is planned from the memory that is actually free (plan_m6_chunk below): a context next to
+// other tenants, or on a smaller device, takes more passes instead of failing with BLSGPU_E_ALLOC.
+constexpr size_t M6_CHUNK_MAX = (size_t)8736 * 120;  // 1,048,320 items = 41 GB of line records: a 1M batch in one pass
+constexpr size_t M6_CHUNK_MIN = 120;
 inline unsigned blocks_for(size_t n, int tpb = TPB) { return (unsigned)((n + tpb - 1) / tpb); }
 
 // bump allocator over one device buffer, regrown between calls
@@ -80,7 +80,10 @@ struct blsgpu_ctx {
   cudaEvent_t ev_fork = nullptr, ev_lines[2] = {nullptr, nullptr}, ev_accum[2] = {nullptr, nullptr};
   Arena arena;
   std::string err;
-  uint8_t salt[32];
+  uint8_t salt[32];        // salt of the current call's random-linear-combination scalars
+  bool salt_pinned = false;  // blsgpu_ctx_set_rlc_salt: reproducible scalars (tests); otherwise fresh OS randomness per call
+  int rlc_bits = 64;       // width of the scalars: 64 | 128
+  size_t m6_chunk = M6_CHUNK_MAX;  // items per pass of the Miller kernels for the current call (plan_m6_chunk)
   cudaEvent_t ev[BLSGPU_STAGE_COUNT + 1];
   bool ev_valid[BLSGPU_STAGE_COUNT + 1];
   float stage_ms[BLSGPU_STAGE_COUNT];
@@ -102,12 +105,56 @@ int ensure_arena(blsgpu_ctx* ctx, size_t bytes) {
   ctx->arena.off = 0;
   ctx->arena.over = false;
   if (ctx->arena.cap >= bytes) return BLSGPU_OK;
-  if (ctx->arena.base) CK(cudaFree(ctx->arena.base));
+  if (ctx->arena.base) CK(cudaFree(ctx->arena.base));  // the device may not hold the old and the new arena at once
   ctx->arena.base = nullptr;
   ctx->arena.cap = 0;
   size_t want = bytes + (bytes >> 3) + (1 << 20);
-  CK(cudaMalloc(&ctx->arena.base, want));
+  if (cudaMalloc(&ctx->arena.base, want) != cudaSuccess) {
+    (void)cudaGetLastError();
+    want = bytes;  // no head-room available: the exact size
+    ctx->arena.base = nullptr;
+    CK(cudaMalloc(&ctx->arena.base, want));
+  }
   ctx->arena.cap = want;
+  return BLSGPU_OK;
+}
+
+// Pass size of the Miller kernels for a call over n items whose other scratch is `other_bytes`: as many items per pass as
+// fit into ~85% of the memory this context may use (what is free now plus its own arena), at most M6_CHUNK_MAX, at least
+// M6_CHUNK_MIN, a multiple of 120.  BLSGPU_M6_CHUNK overrides it (experiments and the multi-pass test), same clamps.
+constexpr size_t M6_ITEM_BYTES = sizeof(M6Arg) + (size_t)M6_LINE_RECS * sizeof(SLineRec) + 512;
+void plan_m6_chunk(blsgpu_ctx* ctx, size_t n, size_t other_bytes) {
+  size_t chunk = M6_CHUNK_MAX;
+  const char* e = getenv("BLSGPU_M6_CHUNK");
+  if (e != nullptr && atoll(e) > 0) {
+    chunk = (size_t)atoll(e);
+  } else {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+      const size_t usable = (free_b + ctx->arena.cap) / 20 * 17;
+      const size_t room = usable > other_bytes ? usable - other_bytes : 0;
+      const size_t one_pass = std::max<size_t>(n, 1) * M6_ITEM_BYTES;
+      if (one_pass > room) chunk = room / (2 * M6_ITEM_BYTES);  // several passes run on two line buffers
+    } else {
+      (void)cudaGetLastError();
+    }
+  }
+  chunk = std::min(chunk, M6_CHUNK_MAX) / 120 * 120;
+  ctx->m6_chunk = std::max(chunk, M6_CHUNK_MIN);
+}
+
+// The salt of this call's random-linear-combination scalars: 32 bytes from the OS CSPRNG unless the caller pinned one.
+int fresh_salt(blsgpu_ctx* ctx) {
+  if (ctx->salt_pinned) return BLSGPU_OK;
+  size_t got = 0;
+  while (got < 32) {
+    ssize_t r = getrandom(ctx->salt + got, 32 - got, 0);
+    if (r <= 0) {
+      ctx->err = "getrandom failed: no randomness for the batch-check scalars";
+      return BLSGPU_E_CUDA;
+    }
+    got += (size_t)r;
+  }
   return BLSGPU_OK;
 }
 
@@ -206,12 +253,13 @@ bool make_dst(DstParam& d, int impl_id, int scheme, bool pop_proof) {
   return true;
 }
 
-// Window width of the bucket multi-scalar multiplication over 64-bit scalars: >= ~16 signatures per bucket, and only
-// widths whose TOP window (64 - (nwin - 1) c bits) is not much narrower than the others - a 4-bit top window would put
+// Window width of the bucket multi-scalar multiplication over rbits-bit scalars: >= ~16 signatures per bucket, and only
+// widths whose TOP window (rbits - (nwin - 1) c bits) is not much narrower than the others - a 4-bit top window would put
 // n/16 signatures into each of 16 buckets, one thread each (measured: 1.5 s at n = 500,000 with c = 15).
-int msm_window_bits(size_t n) {
-  static const int widths[] = {16, 13, 11, 8, 5, 4};
-  for (int w : widths)
+int msm_window_bits(size_t n, int rbits = 64) {
+  static const int widths64[] = {16, 13, 11, 8, 5, 4};    // top windows of 16, 12, 9, 8, 4, 4 bits
+  static const int widths128[] = {16, 13, 10, 8, 5, 4};   // top windows of 16, 11, 8, 8, 3, 4 bits
+  for (int w : (rbits == 128 ? widths128 : widths64))
     if (((size_t)1 << (w + 4)) <= n) return w;
   return 4;
 }
@@ -252,7 +300,9 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
   uint8_t* d_ok = ctx->arena.take<uint8_t>(std::max<size_t>(n, 16));
   uint32_t* d_idx = ctx->arena.take<uint32_t>(std::max<size_t>(n, 16));
 
+  const int rbits = use_rlc ? ctx->rlc_bits : 0;
   if (use_rlc) {
+    CKR(fresh_salt(ctx));
     std::vector<Level> ld = make_levels(n);
     LAUNCH((k_leaf_digest<PkA, SigA>), blocks_for(n), TPB, n, d_pk, d_sig, d_h, d_dig);
     for (size_t k = 0; k + 1 < ld.size(); k++)
@@ -270,10 +320,10 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
   Fp12* d_T = ctx->arena.take<Fp12>(1);
   if (use_msm) {
     int rc = [&]() -> int {
-      const int c = msm_window_bits(n);
-      const int nwin = (64 + c - 1) / c;
+      const int c = msm_window_bits(n, rbits);
+      const int nwin = (rbits + c - 1) / c;
       const size_t nb = (size_t)1 << c, nbuckets = nb * nwin, nchunks = nbuckets / MSM_CHUNK;
-      uint64_t* d_r = ctx->arena.take<uint64_t>(n);
+      RlcScalar* d_r = ctx->arena.take<RlcScalar>(n);
       uint32_t* d_cnt = ctx->arena.take<uint32_t>(3 * nbuckets);
       uint32_t *d_off = d_cnt + nbuckets, *d_cur = d_off + nbuckets;
       uint32_t* d_sorted = ctx->arena.take<uint32_t>((size_t)nwin * n);
@@ -281,9 +331,9 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
       std::vector<Level> lm = make_levels(nchunks);
       SigJ* d_V = ctx->arena.take<SigJ>(levels_total(lm));
       CK(cudaMemsetAsync(d_cnt, 0, nbuckets * sizeof(uint32_t), ctx->stream));
-      LAUNCH(k_msm_count, blocks_for(n), TPB, n, (const uint8_t*)d_status, (const Digest*)d_root, c, nwin, d_r, d_cnt);
+      LAUNCH(k_msm_count, blocks_for(n), TPB, n, (const uint8_t*)d_status, (const Digest*)d_root, rbits, c, nwin, d_r, d_cnt);
       LAUNCH(k_msm_scan, (unsigned)nwin, 1024, c, (const uint32_t*)d_cnt, d_off, d_cur);
-      LAUNCH(k_msm_scatter, blocks_for(n), TPB, n, (const uint64_t*)d_r, c, nwin, (const uint32_t*)d_off, d_cur, d_sorted);
+      LAUNCH(k_msm_scatter, blocks_for(n), TPB, n, (const RlcScalar*)d_r, c, nwin, (const uint32_t*)d_off, d_cur, d_sorted);
       LAUNCH((k_msm_bucket<SigA>), blocks_for(nbuckets), TPB, n, nbuckets, d_sig, c, (const uint32_t*)d_cnt, (const uint32_t*)d_off,
              (const uint32_t*)d_sorted, d_B);
       LAUNCH((k_msm_chunk<SigJ>), blocks_for(nchunks), TPB, nchunks, c, (const SigJ*)d_B, d_V);
@@ -309,7 +359,7 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
     CK(cudaFuncSetAttribute(k_m6_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_ACCUM_SMEM));
     // The line stream is 39 KB per item.  Batches beyond one pass (m6_chunk) go through in chunks with two line buffers:
     // chunk c's lines are produced on side stream 0 while chunk c-1's accumulator consumes the other buffer on side stream 1.
-    const size_t M6_CHUNK = m6_chunk(ctx->sm_count);
+    const size_t M6_CHUNK = ctx->m6_chunk;  // planned by the entry point together with the arena size (plan_m6_chunk)
     const size_t chunk = std::min(n, M6_CHUNK);
     const int nbuf = n > M6_CHUNK ? 2 : 1;
     M6Arg* d_args[2];
@@ -328,7 +378,7 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
       if (ci >= (size_t)nbuf) CK(cudaStreamWaitEvent(ctx->side[0], ctx->ev_accum[b], 0));  // the buffer's previous reader is done
       size_t km = kernel_begin(ctx, BLSGPU_KERNEL_M6_PREP, ctx->side[0]);
       k_m6_prep<PkA, SigA><<<blocks_for(cn), TPB, 0, ctx->side[0]>>>(cn, base, d_pk, d_h, (const uint8_t*)d_status, (const Digest*)d_root,
-                                                                      use_rlc ? 1 : 0, d_args[b]);
+                                                                      rbits, d_args[b]);
       kernel_end(ctx, km, ctx->side[0]);
       CKR(check_launch(ctx, "k_m6_prep"));
       km = kernel_begin(ctx, BLSGPU_KERNEL_M6_LINES, ctx->side[0]);
@@ -350,7 +400,7 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
   }
   if (use_msm) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_aux, 0));  // T = ML(-g, S) ran beside the Miller stage
   if (use_rlc && !use_msm) {
-    LAUNCH((k_scale_sig<SigA>), blocks_for(n), TPB, n, d_sig, d_status, d_root, d_Sitem);
+    LAUNCH((k_scale_sig<SigA>), blocks_for(n), TPB, n, d_sig, d_status, d_root, rbits, d_Sitem);
     LAUNCH((k_group_sum<SigJ>), blocks_for(ng), TPB, n, (const SigJ*)d_Sitem, ng, d_S);
   }
   stage_mark(ctx, BLSGPU_STAGE_REDUCE);
@@ -376,7 +426,7 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
   }
   if (!ok && use_msm) {
     // the batch failed: now the bisection needs the per-group sums of r_i sig_i
-    LAUNCH((k_scale_sig<SigA>), blocks_for(n), TPB, n, d_sig, d_status, d_root, d_Sitem);
+    LAUNCH((k_scale_sig<SigA>), blocks_for(n), TPB, n, d_sig, d_status, d_root, rbits, d_Sitem);
     LAUNCH((k_group_sum<SigJ>), blocks_for(ng), TPB, n, (const SigJ*)d_Sitem, ng, d_S);
     for (size_t k = 0; k + 1 < lv.size(); k++)
       LAUNCH((k_reduce_jac<SigJ>), blocks_for(lv[k + 1].cnt), TPB, lv[k].cnt, d_S + lv[k].off, lv[k + 1].cnt, d_S + lv[k + 1].off);
@@ -426,16 +476,29 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
   return BLSGPU_OK;
 }
 
+// device scratch of run_pairing_pipeline for n items, without the Miller line buffers
 template <class PkA, class SigA>
-size_t pipeline_bytes(size_t n, int sm_count) {
-  const size_t M6_CHUNK = m6_chunk(sm_count);
+size_t pipeline_other_bytes(size_t n) {
   typedef typename PtInfo<SigA>::Jac SigJ;
   size_t total = levels_total(make_levels(std::max<size_t>(n, 1)));
   size_t gtotal = levels_total(make_levels((std::max<size_t>(n, 1) + M6_GROUP - 1) / M6_GROUP));
-  return gtotal * (sizeof(Fp12) + sizeof(SigJ)) + n * (sizeof(SigJ) + sizeof(Fp12) + sizeof(SigJ)) +
-         (n > M6_CHUNK ? 2 : 1) * std::min(std::max<size_t>(n, 1), M6_CHUNK) * (sizeof(M6Arg) + M6_LINE_RECS * sizeof(SLineRec) + 512) +
-         total * sizeof(Digest) +
-         n * (8 + 4 * 16) + ((size_t)16 << 16) * (12 + 2 * sizeof(SigJ)) + (1 << 20) + (n + 64) * 8 + 16 * 256 + 4096;
+  return gtotal * (sizeof(Fp12) + sizeof(SigJ)) + n * (sizeof(SigJ) + sizeof(Fp12) + sizeof(SigJ)) + total * sizeof(Digest) +
+         n * (16 + 4 * 32) + ((size_t)32 << 16) * (12 + 2 * sizeof(SigJ)) + (1 << 20) + (n + 64) * 8 + 16 * 256 + 4096;
+}
+size_t m6_line_bytes(size_t n, size_t chunk) { return (n > chunk ? 2 : 1) * std::min(std::max<size_t>(n, 1), chunk) * M6_ITEM_BYTES; }
+// Plans the pass size of the Miller kernels for this call and sizes the arena: `head_bytes` is what the entry point takes
+// from the arena besides the pipeline's own scratch.  If the allocation fails the pass size is halved (more passes) until
+// it fits or reaches the minimum.
+template <class PkA, class SigA>
+int ensure_pipeline_arena(blsgpu_ctx* ctx, size_t n, size_t head_bytes) {
+  const size_t other = head_bytes + pipeline_other_bytes<PkA, SigA>(n);
+  plan_m6_chunk(ctx, n, other);
+  for (;;) {
+    const int r = ensure_arena(ctx, other + m6_line_bytes(n, ctx->m6_chunk));
+    if (r != BLSGPU_E_ALLOC || ctx->m6_chunk <= M6_CHUNK_MIN || n <= M6_CHUNK_MIN) return r;
+    (void)cudaGetLastError();
+    ctx->m6_chunk = std::max(M6_CHUNK_MIN, std::min(ctx->m6_chunk, n) / 2 / 120 * 120);
+  }
 }
 
 // compressed bytes -> affine points + per-item status: decompression (square root), then the subgroup check
@@ -501,12 +564,32 @@ int verify_dev(blsgpu_ctx* ctx, int msg_mode, const DstParam& dst, int format, s
   stage_collect(ctx);
   return BLSGPU_OK;
 }
+// what verify_dev takes from the arena before the pipeline's own scratch
 template <int IMPL>
-size_t verify_bytes(size_t n, int sm_count) {
+size_t verify_head_bytes(size_t n) {
   typedef typename ImplT<IMPL>::PkAff PkA;
   typedef typename ImplT<IMPL>::SigAff SigA;
-  return n * (sizeof(PkA) + 2 * sizeof(SigA) + 2) + 8 * 256 + pipeline_bytes<PkA, SigA>(n, sm_count);
+  return n * (sizeof(PkA) + 2 * sizeof(SigA) + 2) + 8 * 256;
 }
+template <int IMPL>
+int ensure_verify_arena(blsgpu_ctx* ctx, size_t n, size_t head_bytes) {
+  return ensure_pipeline_arena<typename ImplT<IMPL>::PkAff, typename ImplT<IMPL>::SigAff>(ctx, n, head_bytes + verify_head_bytes<IMPL>(n));
+}
+
+// host offset arrays: n + 1 non-decreasing entries, every record shorter than 2^32 bytes (the kernels keep lengths in 32 bits)
+bool offsets_ok(const uint64_t* off, size_t n) {
+  if (!off) return false;
+  for (size_t i = 0; i < n; i++)
+    if (off[i + 1] < off[i] || off[i + 1] - off[i] > 0xffffffffull) return false;
+  return true;
+}
+#define CHECK_OFFSETS(off, n, what)                                                                    \
+  do {                                                                                                 \
+    if (!offsets_ok((off), (n))) {                                                                     \
+      ctx->err = std::string(what) + ": offsets must be non-decreasing with records below 2^32 bytes"; \
+      return BLSGPU_E_ARG;                                                                             \
+    }                                                                                                  \
+  } while (0)
 
 bool args_ok(int impl_id, int scheme, int format) {
   return (impl_id == 1 || impl_id == 2) && scheme >= 0 && scheme <= 2 && (format == 0 || format == 1);
@@ -515,6 +598,7 @@ bool args_ok(int impl_id, int scheme, int format) {
 template <class T>
 int upload(blsgpu_ctx* ctx, T*& d, const T* h, size_t count) {
   d = ctx->arena.take<T>(std::max<size_t>(count, 1));
+  ARENA_OK();
   if (count) CK(cudaMemcpyAsync(d, h, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
   return BLSGPU_OK;
 }
@@ -547,8 +631,7 @@ int blsgpu_ctx_create(const int* devices, int ndev, blsgpu_ctx** out) {
     }
   blsgpu_ctx* ctx = new blsgpu_ctx();
   ctx->devices.assign(devices, devices + ndev);
-  memset(ctx->salt, 0, 32);
-  memcpy(ctx->salt, "blsgpu-rlc-v1", 13);
+  memset(ctx->salt, 0, 32);  // every batch check draws its own salt (fresh_salt) unless blsgpu_ctx_set_rlc_salt pinned one
   e = cudaSetDevice(devices[0]);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
   ctx->stream = ctx->own_stream;
@@ -619,7 +702,18 @@ int blsgpu_ctx_set_stream(blsgpu_ctx* ctx, void* cuda_stream) {
 int blsgpu_ctx_set_rlc_salt(blsgpu_ctx* ctx, const uint8_t salt[32]) {
   if (!ctx || !salt) return BLSGPU_E_ARG;
   memcpy(ctx->salt, salt, 32);
-  for (blsgpu_ctx* peer : ctx->peers) memcpy(peer->salt, salt, 32);
+  ctx->salt_pinned = true;
+  for (blsgpu_ctx* peer : ctx->peers) {
+    memcpy(peer->salt, salt, 32);
+    peer->salt_pinned = true;
+  }
+  return BLSGPU_OK;
+}
+
+int blsgpu_ctx_set_rlc_bits(blsgpu_ctx* ctx, int bits) {
+  if (!ctx || (bits != 64 && bits != 128)) return BLSGPU_E_ARG;
+  ctx->rlc_bits = bits;
+  for (blsgpu_ctx* peer : ctx->peers) peer->rlc_bits = bits;
   return BLSGPU_OK;
 }
 
@@ -656,10 +750,10 @@ int blsgpu_verify_batch_dev(blsgpu_ctx* ctx, int impl_id, int scheme, int format
   make_dst(dst, impl_id, scheme, false);
   int mode = scheme == 1 ? 1 : 0;
   if (impl_id == 2) {
-    CKR(ensure_arena(ctx, verify_bytes<2>(n, ctx->sm_count)));
+    CKR(ensure_verify_arena<2>(ctx, n, 0));
     return verify_dev<2>(ctx, mode, dst, format, n, pks_dev, sigs_dev, msgs_dev, msg_off_dev, status_out_dev, 0);
   }
-  CKR(ensure_arena(ctx, verify_bytes<1>(n, ctx->sm_count)));
+  CKR(ensure_verify_arena<1>(ctx, n, 0));
   return verify_dev<1>(ctx, mode, dst, format, n, pks_dev, sigs_dev, msgs_dev, msg_off_dev, status_out_dev, 0);
 }
 
@@ -707,7 +801,7 @@ static int verify_host_one(blsgpu_ctx* ctx, int impl_id, int msg_mode, const Dst
   size_t pk_len = impl_id == 2 ? 48 : 96, sig_len = impl_id == 2 ? 96 : 48;
   size_t msg_bytes = msg_off ? (size_t)msg_off[n] : 0;
   size_t in_bytes = n * (pk_len + sig_len + 1) + msg_bytes + (n + 1) * 8 + 8 * 256;
-  CKR(ensure_arena(ctx, in_bytes + (impl_id == 2 ? verify_bytes<2>(n, ctx->sm_count) : verify_bytes<1>(n, ctx->sm_count))));
+  CKR(impl_id == 2 ? ensure_verify_arena<2>(ctx, n, in_bytes) : ensure_verify_arena<1>(ctx, n, in_bytes));
   uint8_t *d_pks, *d_sigs, *d_msgs, *d_st;
   uint64_t* d_off;
   CKR(upload(ctx, d_pks, pks, n * pk_len));
@@ -736,6 +830,11 @@ int blsgpu_verify_batch(blsgpu_ctx* ctx, int impl_id, int scheme, int format, si
     return BLSGPU_E_ARG;
   }
   if (n == 0) return BLSGPU_OK;
+  CHECK_OFFSETS(msg_off, n, "blsgpu_verify_batch");
+  if (msg_off[n] > msg_off[0] && !msgs) {
+    ctx->err = "blsgpu_verify_batch: msgs is null";
+    return BLSGPU_E_ARG;
+  }
   DstParam dst;
   make_dst(dst, impl_id, scheme, false);
   return verify_host_common(ctx, impl_id, scheme == 1 ? 1 : 0, dst, format, n, pks, sigs, msgs, msg_off, status_out);
@@ -762,9 +861,9 @@ static int aggregate_verify_impl(blsgpu_ctx* ctx, int scheme, int format, size_t
   typedef typename ImplT<IMPL>::SigAff SigA;
   const size_t pk_len = PtInfo<PkA>::LEN, sig_len = PtInfo<SigA>::LEN;
   size_t msg_bytes = (size_t)msg_off[n];
-  size_t need = n * (pk_len + sizeof(PkA) + sizeof(SigA) + 2) + msg_bytes + (n + 1) * 8 + sig_len + sizeof(SigA) + 16 * 256 +
-                pipeline_bytes<PkA, SigA>(std::max<size_t>(n, 1), ctx->sm_count);
-  CKR(ensure_arena(ctx, need));
+  size_t head = n * (pk_len + sizeof(PkA) + sizeof(SigA) + 2) + msg_bytes + (n + 1) * 8 + sig_len + sizeof(SigA) + 16 * 256 +
+                std::max<size_t>(n, 1) * sizeof(typename PtInfo<SigA>::Jac);
+  CKR((ensure_pipeline_arena<PkA, SigA>(ctx, std::max<size_t>(n, 1), head)));
   uint8_t *d_pks, *d_msgs, *d_sigb;
   uint64_t* d_off;
   CKR(upload(ctx, d_pks, pks, n * pk_len));
@@ -850,6 +949,7 @@ int blsgpu_aggregate_verify(blsgpu_ctx* ctx, int impl_id, int scheme, int format
     ctx->err = "blsgpu_aggregate_verify: bad arguments";
     return BLSGPU_E_ARG;
   }
+  CHECK_OFFSETS(msg_off, n, "blsgpu_aggregate_verify");
   CKR(set_device(ctx));
   return impl_id == 2 ? aggregate_verify_impl<2>(ctx, scheme, format, n, pks, msgs, msg_off, sig, status_out, index_out)
                       : aggregate_verify_impl<1>(ctx, scheme, format, n, pks, msgs, msg_off, sig, status_out, index_out);
@@ -945,6 +1045,7 @@ int blsgpu_hash_to_curve_batch(blsgpu_ctx* ctx, int group, size_t n, const uint8
     return BLSGPU_E_ARG;
   }
   if (n == 0) return BLSGPU_OK;
+  CHECK_OFFSETS(msg_off, n, "blsgpu_hash_to_curve_batch");
   CKR(set_device(ctx));
   DstParam d;
   memset(d.b, 0, sizeof d.b);
@@ -1047,11 +1148,13 @@ int blsgpu_pairing_product_is_one(blsgpu_ctx* ctx, size_t n, const uint8_t* g1_p
 int blsgpu_testdata_sign(blsgpu_ctx* ctx, int impl_id, int scheme, size_t n, const uint8_t* scalars32, const uint8_t* msgs,
                          const uint64_t* msg_off, uint8_t* out_pks, uint8_t* out_sigs) {
   if (!ctx) return BLSGPU_E_ARG;
-  if (!args_ok(impl_id, scheme, 1) || (n && (!scalars32 || !msg_off || !out_pks || !out_sigs))) {
+  const bool pop_proof = scheme == 3;  // proof of possession: message = the key's own bytes, BLS_POP_ DST
+  if (!args_ok(impl_id, pop_proof ? 2 : scheme, 1) || (n && (!scalars32 || !msg_off || !out_pks || !out_sigs))) {
     ctx->err = "blsgpu_testdata_sign: bad arguments";
     return BLSGPU_E_ARG;
   }
   if (n == 0) return BLSGPU_OK;
+  CHECK_OFFSETS(msg_off, n, "blsgpu_testdata_sign");
   CKR(set_device(ctx));
   size_t pk_len = impl_id == 2 ? 48 : 96, sig_len = impl_id == 2 ? 96 : 48;
   size_t msg_bytes = (size_t)msg_off[n];
@@ -1064,8 +1167,8 @@ int blsgpu_testdata_sign(blsgpu_ctx* ctx, int impl_id, int scheme, size_t n, con
   uint8_t* d_pk = ctx->arena.take<uint8_t>(n * pk_len);
   uint8_t* d_sig = ctx->arena.take<uint8_t>(n * sig_len);
   DstParam dst;
-  make_dst(dst, impl_id, scheme, false);
-  int mode = scheme == 1 ? 1 : 0;
+  make_dst(dst, impl_id, pop_proof ? 2 : scheme, pop_proof);
+  int mode = pop_proof ? 2 : scheme == 1 ? 1 : 0;
   if (impl_id == 2)
     LAUNCH((k_testdata_sign<G1Aff, G2Aff>), blocks_for(n), TPB, n, (const uint8_t*)d_k, (const uint8_t*)d_m, (const uint64_t*)d_off, mode, dst,
            d_pk, d_sig);
@@ -1196,9 +1299,9 @@ int verify_secure_impl(blsgpu_ctx* ctx, int scheme, int format, size_t q, const 
   const size_t Lp = PtInfo<PkA>::LEN, Ls = PtInfo<SigA>::LEN;
   SecurePlan pl = make_secure_plan(q, key_off, pks, Lp);
   const size_t M = pl.M, msg_bytes = (size_t)msg_off[q];
-  size_t need = M * (Lp + sizeof(PkA) + 2) + q * (Ls + 2 * sizeof(SigA) + sizeof(PkA) + sizeof(PkJ) + 8) + msg_bytes + (q + 1) * 8 +
-                secure_plan_bytes(pl, sizeof(PkJ)) + verify_bytes<IMPL>(q, ctx->sm_count) + 32 * 256;
-  CKR(ensure_arena(ctx, need));
+  size_t head = M * (Lp + sizeof(PkA) + 2) + q * (Ls + 2 * sizeof(SigA) + sizeof(PkA) + sizeof(PkJ) + 8) + msg_bytes + (q + 1) * 8 +
+                secure_plan_bytes(pl, sizeof(PkJ)) + 32 * 256;
+  CKR(ensure_verify_arena<IMPL>(ctx, q, head));
   stage_reset(ctx);
   uint8_t *d_pkb, *d_sigb, *d_msgs;
   uint64_t* d_moff;
@@ -1324,6 +1427,7 @@ int blsgpu_verify_secure_batch(blsgpu_ctx* ctx, int impl_id, int scheme, int for
       ctx->err = "blsgpu_verify_secure_batch: key_off must be non-decreasing and below 2^32";
       return BLSGPU_E_ARG;
     }
+  CHECK_OFFSETS(msg_off, q, "blsgpu_verify_secure_batch");
   CKR(set_device(ctx));
   return impl_id == 2 ? verify_secure_impl<2>(ctx, scheme, format, q, key_off, pks, sigs, msgs, msg_off, status_out)
                       : verify_secure_impl<1>(ctx, scheme, format, q, key_off, pks, sigs, msgs, msg_off, status_out);
@@ -1446,6 +1550,7 @@ int blsgpu_combine_shares_batch(blsgpu_ctx* ctx, int group, size_t q, const uint
     return BLSGPU_E_ARG;
   }
   if (q == 0) return BLSGPU_OK;
+  CHECK_OFFSETS(share_off, q, "blsgpu_combine_shares_batch");
   CKR(set_device(ctx));
   return group == 1 ? combine_shares_impl<G1Aff>(ctx, q, share_off, shares, out, status_out)
                     : combine_shares_impl<G2Aff>(ctx, q, share_off, shares, out, status_out);
@@ -1460,6 +1565,7 @@ int blsgpu_verify_batch_wire(blsgpu_ctx* ctx, int impl_id, size_t n, const uint8
     ctx->err = "blsgpu_verify_batch_wire: bad arguments";
     return BLSGPU_E_ARG;
   }
+  CHECK_OFFSETS(msg_off, n, "blsgpu_verify_batch_wire");
   const size_t pk_len = impl_id == 2 ? 48 : 96, sig_len = impl_id == 2 ? 96 : 48, rec = sig_len + 1;
   for (int scheme = 0; scheme < 3; scheme++) {
     std::vector<size_t> idx;
@@ -1519,6 +1625,7 @@ int blsgpu_pairing_check_batch(blsgpu_ctx* ctx, size_t q, const uint64_t* pair_o
     return BLSGPU_E_ARG;
   }
   if (q == 0) return BLSGPU_OK;
+  CHECK_OFFSETS(pair_off, q, "blsgpu_pairing_check_batch");
   CKR(set_device(ctx));
   const size_t M = (size_t)pair_off[q];
   CKR(ensure_arena(ctx, M * (48 + 96 + sizeof(G1Aff) + sizeof(G2Aff) + sizeof(Fp12) + 2) + (q + 1) * 9 + 16 * 256));
@@ -1551,11 +1658,11 @@ int blsgpu_pairing_check_batch(blsgpu_ctx* ctx, size_t q, const uint64_t* pair_o
   return BLSGPU_OK;
 }
 
-int blsgpu_plan_msm(size_t n, int* window_bits_out, int* windows_out, int* top_window_bits_out) {
-  if (!window_bits_out || !windows_out || !top_window_bits_out) return BLSGPU_E_ARG;
-  const int c = msm_window_bits(n), nwin = (64 + c - 1) / c;
+int blsgpu_plan_msm(size_t n, int scalar_bits, int* window_bits_out, int* windows_out, int* top_window_bits_out) {
+  if (!window_bits_out || !windows_out || !top_window_bits_out || (scalar_bits != 64 && scalar_bits != 128)) return BLSGPU_E_ARG;
+  const int c = msm_window_bits(n, scalar_bits), nwin = (scalar_bits + c - 1) / c;
   *window_bits_out = c;
   *windows_out = nwin;
-  *top_window_bits_out = 64 - (nwin - 1) * c;
+  *top_window_bits_out = scalar_bits - (nwin - 1) * c;
   return BLSGPU_OK;
 }

@@ -314,12 +314,12 @@ BLS_HD void jac_mul_aff(Jac<F>& r, const Aff<F>& p, const uint32_t* k, int nlimb
   }
   r = acc;
 }
-// r = k P for a 64-bit k: fixed 4-bit windows over a 15-entry Jacobian table.  What matters on a GPU is that all lanes
+// r = k P for a 64- or 128-bit k: fixed 4-bit windows over a 15-entry Jacobian table.  What matters on a GPU is that all lanes
 // of a warp add at the SAME 16 positions: a sparse signed-digit form (NAF) was measured and is twice as SLOW as plain
 // double-and-add here, because a warp executes an addition whenever any of its 32 lanes has a non-zero digit - and then
-// once more for the other sign.  60 doublings + 16 full additions + the table (7 doublings, 7 mixed additions).
+// once more for the other sign.  64-bit k: 60 doublings + 16 full additions + the table (7 doublings, 7 mixed additions).
 template <class F>
-BLS_HD void jac_mul_aff_w4_64(Jac<F>& r, const Aff<F>& p, uint64_t k) {
+BLS_HD void jac_mul_aff_w4(Jac<F>& r, const Aff<F>& p, const uint32_t* k, int nwin) {  // k: nwin 4-bit windows, little-endian words
   Jac<F> tbl[16];
   jac_set_inf(tbl[0]);
   jac_from_aff(tbl[1], p);
@@ -327,13 +327,18 @@ BLS_HD void jac_mul_aff_w4_64(Jac<F>& r, const Aff<F>& p, uint64_t k) {
     jac_dbl(tbl[i], tbl[i / 2]);
     jac_add_mixed(tbl[i + 1], tbl[i], p);
   }
-  Jac<F> acc = tbl[(k >> 60) & 15u];
-  for (int w = 14; w >= 0; w--) {
+  Jac<F> acc = tbl[(k[(nwin - 1) >> 3] >> (4 * ((nwin - 1) & 7))) & 15u];
+  for (int w = nwin - 2; w >= 0; w--) {
     for (int d = 0; d < 4; d++) jac_dbl(acc, acc);
-    const uint32_t dg = (uint32_t)(k >> (4 * w)) & 15u;
+    const uint32_t dg = (k[w >> 3] >> (4 * (w & 7))) & 15u;
     if (dg) jac_add(acc, acc, tbl[dg]);
   }
   r = acc;
+}
+template <class F>
+BLS_HD void jac_mul_aff_w4_64(Jac<F>& r, const Aff<F>& p, uint64_t k) {
+  const uint32_t w[2] = {(uint32_t)k, (uint32_t)(k >> 32)};
+  jac_mul_aff_w4(r, p, w, 16);
 }
 // [|x|]P, |x| = 0xd201000000010000 (Hamming weight 6), Jacobian base
 template <class F>

@@ -106,17 +106,34 @@ struct Digest {
 #define BLS_SPLIT_MIN_BLOCKS 4
 #endif
 // ---- decode: compressed bytes -> affine Montgomery points, curve + subgroup check --------------------------------
+// Input staging: the block's 128 records (48 | 96 bytes each, contiguous) are fetched with coalesced 16-byte loads into
+// shared memory and every thread then picks up its own record; a base pointer that is not 16-byte aligned (possible only
+// through blsgpu_verify_batch_dev with caller-owned device buffers) takes the byte-wise path.
 template <class A>
 __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_decode(size_t n, const uint8_t* __restrict__ in, int format, A* __restrict__ out,
                                                 uint8_t* __restrict__ st) {
+  constexpr int L = PtInfo<A>::LEN;
+  __shared__ __align__(16) uint8_t stage[128 * L];
+  const size_t first = (size_t)blockIdx.x * blockDim.x;
+  const size_t cnt = first < n ? (n - first < blockDim.x ? n - first : blockDim.x) : 0;
+  const uint8_t* src = in + first * L;
+  if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+    const uint4* v = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(stage);
+    const size_t quads = cnt * L / 16, tail = cnt * L - quads * 16;
+    for (size_t q = threadIdx.x; q < quads; q += blockDim.x) d[q] = v[q];
+    if (threadIdx.x < tail) stage[quads * 16 + threadIdx.x] = src[quads * 16 + threadIdx.x];
+  } else {
+    for (size_t b = threadIdx.x; b < cnt * L; b += blockDim.x) stage[b] = src[b];
+  }
+  __syncthreads();
   size_t i = BLS_TID();
   if (i >= n) return;
-  constexpr int L = PtInfo<A>::LEN;
   uint8_t b[L];
-  const uint32_t* src = reinterpret_cast<const uint32_t*>(in + i * L);  // 48 | 96 byte records: 4-byte aligned
+  const uint32_t* rec = reinterpret_cast<const uint32_t*>(stage + threadIdx.x * L);
 #pragma unroll
   for (int k = 0; k < L / 4; k++) {
-    uint32_t w = src[k];
+    uint32_t w = rec[k];
     b[4 * k] = (uint8_t)w;
     b[4 * k + 1] = (uint8_t)(w >> 8);
     b[4 * k + 2] = (uint8_t)(w >> 16);
@@ -239,17 +256,28 @@ __global__ void __launch_bounds__(128, BLS_SPLIT_MIN_BLOCKS) k_clear_cofactor(si
   pts[i] = r;
 }
 
-// ---- deterministic random-linear-combination scalars ----------------------------------------------------------------
-// leaf_i = SHA256(limbs of pk_i, sig_i, H_i); root = 16-ary SHA-256 tree over the leaves; r_i = LE64(SHA256(root||salt||i)).
+// ---- random-linear-combination scalars --------------------------------------------------------------------------------
+// leaf_i = SHA256(coordinates and identity flags of pk_i, sig_i, H_i); root = 16-ary SHA-256 tree over the leaves;
+// r_i = the first rbits (64 | 128) bits of SHA256(root || salt || i), little-endian, forced non-zero.  The salt is 32
+// bytes of OS randomness drawn per call (blsgpu.cu: fresh_salt) unless the caller pinned it for a reproducible run, so
+// the scalars are unpredictable to whoever chose the batch; binding them to the inputs as well keeps them from being
+// reused across different batches under a pinned salt.  Only explicit fields are hashed (never struct padding).
+template <class P>
+__device__ __forceinline__ void digest_point(Sha256& s, const P& p) {
+  sha256_update(s, reinterpret_cast<const uint8_t*>(&p.x), sizeof(p.x));
+  sha256_update(s, reinterpret_cast<const uint8_t*>(&p.y), sizeof(p.y));
+  const uint8_t f = p.inf ? 1 : 0;
+  sha256_update(s, &f, 1);
+}
 template <class PkA, class SigA>
 __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_leaf_digest(size_t n, const PkA* pk, const SigA* sig, const SigA* h, Digest* out) {
   size_t i = BLS_TID();
   if (i >= n) return;
   Sha256 s;
   sha256_init(s);
-  sha256_update(s, reinterpret_cast<const uint8_t*>(&pk[i]), sizeof(PkA));
-  sha256_update(s, reinterpret_cast<const uint8_t*>(&sig[i]), sizeof(SigA));
-  sha256_update(s, reinterpret_cast<const uint8_t*>(&h[i]), sizeof(SigA));
+  digest_point(s, pk[i]);
+  digest_point(s, sig[i]);
+  digest_point(s, h[i]);
   Digest d;
   sha256_final(s, d.b);
   out[i] = d;
@@ -267,19 +295,26 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_digest_reduce(size_t n_
   sha256_final(s, d.b);
   out[j] = d;
 }
-__device__ __forceinline__ void rlc_scalar(uint32_t k[2], const Digest* root, size_t i) {
+constexpr int RLC_MAX_WORDS = 4;  // 128-bit scalars at most
+// k[0 .. rbits/32) = the scalar, remaining words zero
+__device__ __forceinline__ void rlc_scalar(uint32_t k[RLC_MAX_WORDS], const Digest* root, size_t i, int rbits) {
   Sha256 s;
   sha256_init(s);
   sha256_update(s, root[0].b, 32);  // root[0] = tree root
-  sha256_update(s, root[1].b, 32);  // root[1] = context salt
+  sha256_update(s, root[1].b, 32);  // root[1] = salt of this call
   uint8_t ib[8];
   for (int b = 0; b < 8; b++) ib[b] = (uint8_t)((uint64_t)i >> (8 * b));
   sha256_update(s, ib, 8);
   uint8_t d[32];
   sha256_final(s, d);
-  k[0] = (uint32_t)d[0] | ((uint32_t)d[1] << 8) | ((uint32_t)d[2] << 16) | ((uint32_t)d[3] << 24);
-  k[1] = (uint32_t)d[4] | ((uint32_t)d[5] << 8) | ((uint32_t)d[6] << 16) | ((uint32_t)d[7] << 24);
-  if ((k[0] | k[1]) == 0) k[0] = 1;
+  uint32_t any = 0;
+#pragma unroll
+  for (int w = 0; w < RLC_MAX_WORDS; w++) {
+    const uint32_t v = (uint32_t)d[4 * w] | ((uint32_t)d[4 * w + 1] << 8) | ((uint32_t)d[4 * w + 2] << 16) | ((uint32_t)d[4 * w + 3] << 24);
+    k[w] = 32 * w < rbits ? v : 0u;
+    any |= k[w];
+  }
+  if (any == 0) k[0] = 1;
 }
 
 // ---- per-item Miller loop (exact per-item checks of failing groups): ML(pk_i, H_i) (G2Impl) | ML(H_i, pk_i) (G1Impl) ------
@@ -320,7 +355,7 @@ __device__ __forceinline__ const G2Aff& m6_g2(const G2Aff* pk, const G1Aff* h, s
 // items [base, base + n) of the batch -> args[0..n)
 template <class PkA, class HA>
 __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_m6_prep(size_t n, size_t base, const PkA* __restrict__ pk, const HA* __restrict__ h,
-                                                 const uint8_t* __restrict__ pre, const Digest* __restrict__ root, int use_rlc,
+                                                 const uint8_t* __restrict__ pre, const Digest* __restrict__ root, int rbits,
                                                  M6Arg* __restrict__ args) {
   size_t c = BLS_TID();
   if (c >= n) return;
@@ -328,11 +363,11 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_m6_prep(size_t n, size_
   if (pre[i] != ST_OK) return;
   G1Aff p = m6_g1(pk, h, i);
   MillerG1 mp;
-  if (use_rlc) {
-    uint32_t sc[2];
-    rlc_scalar(sc, root, i);
+  if (rbits) {  // 0: no random linear combination (aggregate verify), else the scalar width
+    uint32_t sc[RLC_MAX_WORDS];
+    rlc_scalar(sc, root, i, rbits);
     G1Jac pj;
-    jac_mul_aff_w4_64(pj, p, (uint64_t)sc[0] | ((uint64_t)sc[1] << 32));
+    jac_mul_aff_w4(pj, p, sc, rbits / 4);
     miller_prepare(mp, pj);
   } else {
     miller_prepare(mp, p);
@@ -443,17 +478,18 @@ __global__ void __launch_bounds__(128, M6_ACC_BLOCKS) k_m6_accum(size_t n, size_
 // S_i = r_i * sig_i
 template <class SigA>
 __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_scale_sig(size_t n, const SigA* __restrict__ sig, const uint8_t* __restrict__ pre,
-                                                   const Digest* __restrict__ root, typename PtInfo<SigA>::Jac* __restrict__ out) {
+                                                   const Digest* __restrict__ root, int rbits,
+                                                   typename PtInfo<SigA>::Jac* __restrict__ out) {
   size_t i = BLS_TID();
   if (i >= n) return;
   typename PtInfo<SigA>::Jac s;
   if (pre[i] != ST_OK) {
     jac_set_inf(s);
   } else {
-    uint32_t k[2];
-    rlc_scalar(k, root, i);
+    uint32_t k[RLC_MAX_WORDS];
+    rlc_scalar(k, root, i, rbits);
     SigA a = sig[i];
-    jac_mul_aff(s, a, k, 2);
+    jac_mul_aff(s, a, k, rbits / 32);
   }
   out[i] = s;
 }
@@ -468,20 +504,28 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_scale_sig(size_t n, con
 //   k_msm_bucket  one thread per (window, digit): B = sum of its signatures
 //   k_msm_chunk   one thread per 16 buckets: 2^(c w) * sum_j j B_j over the chunk (running sums), then a flat tree sum
 constexpr int MSM_CHUNK = 16;
-__global__ void __launch_bounds__(128) k_msm_count(size_t n, const uint8_t* __restrict__ pre, const Digest* __restrict__ root, int c, int nwin,
-                                                   uint64_t* __restrict__ r_out, uint32_t* __restrict__ counts) {
+struct RlcScalar {  // little-endian 64-bit halves (hi = 0 for 64-bit scalars)
+  uint64_t lo, hi;
+};
+__device__ __forceinline__ uint32_t msm_digit(const RlcScalar& r, int c, int w) {  // c <= 16
+  const int bit = c * w;
+  const uint64_t v = bit >= 64 ? r.hi >> (bit - 64) : bit == 0 ? r.lo : (r.lo >> bit) | (r.hi << (64 - bit));
+  return (uint32_t)v & ((1u << c) - 1u);
+}
+__global__ void __launch_bounds__(128) k_msm_count(size_t n, const uint8_t* __restrict__ pre, const Digest* __restrict__ root, int rbits, int c,
+                                                   int nwin, RlcScalar* __restrict__ r_out, uint32_t* __restrict__ counts) {
   size_t i = BLS_TID();
   if (i >= n) return;
-  uint64_t r = 0;
+  RlcScalar r = {0, 0};
   if (pre[i] == ST_OK) {
-    uint32_t k[2];
-    rlc_scalar(k, root, i);
-    r = (uint64_t)k[0] | ((uint64_t)k[1] << 32);
+    uint32_t k[RLC_MAX_WORDS];
+    rlc_scalar(k, root, i, rbits);
+    r.lo = (uint64_t)k[0] | ((uint64_t)k[1] << 32);
+    r.hi = (uint64_t)k[2] | ((uint64_t)k[3] << 32);
   }
   r_out[i] = r;
-  const uint32_t mask = (1u << c) - 1u;
   for (int w = 0; w < nwin; w++) {
-    const uint32_t d = (uint32_t)(r >> (c * w)) & mask;
+    const uint32_t d = msm_digit(r, c, w);
     if (d) atomicAdd(&counts[((size_t)w << c) + d], 1u);
   }
 }
@@ -512,14 +556,13 @@ __global__ void __launch_bounds__(1024) k_msm_scan(int c, const uint32_t* __rest
     run += cnt[j];
   }
 }
-__global__ void __launch_bounds__(128) k_msm_scatter(size_t n, const uint64_t* __restrict__ r_in, int c, int nwin, const uint32_t* __restrict__ offsets,
+__global__ void __launch_bounds__(128) k_msm_scatter(size_t n, const RlcScalar* __restrict__ r_in, int c, int nwin, const uint32_t* __restrict__ offsets,
                                                      uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
   size_t i = BLS_TID();
   if (i >= n) return;
-  const uint64_t r = r_in[i];
-  const uint32_t mask = (1u << c) - 1u;
+  const RlcScalar r = r_in[i];
   for (int w = 0; w < nwin; w++) {
-    const uint32_t d = (uint32_t)(r >> (c * w)) & mask;
+    const uint32_t d = msm_digit(r, c, w);
     if (d) {
       const size_t b = ((size_t)w << c) + d;
       const uint32_t pos = offsets[b] + atomicAdd(&cursor[b], 1u);

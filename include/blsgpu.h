@@ -64,8 +64,15 @@ const char* blsgpu_last_error(const blsgpu_ctx* ctx);
 /* Run the engine on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL restores the context's own stream).
  * Lets the caller bracket calls with its own CUDA events (bench.py does). */
 int blsgpu_ctx_set_stream(blsgpu_ctx* ctx, void* cuda_stream);
-/* 32-byte salt mixed into the (deterministic) random-linear-combination scalars of the batch checks. */
+/* Random-linear-combination scalars of the batch checks.  r_i = first `bits` bits of SHA-256(digest of the decoded batch ||
+ * salt || i).  By DEFAULT the salt is 32 bytes drawn from the OS CSPRNG (getrandom) for EVERY call, so the scalars cannot be
+ * predicted or ground offline by whoever chose the batch: a batch holding an invalid signature is accepted with
+ * probability <= 2^-bits per call (the statuses themselves do not depend on the salt otherwise).
+ * blsgpu_ctx_set_rlc_salt PINS the salt for this context - a determinism hook for tests and reproducible benchmarks only:
+ * with a salt known to the adversary the check degrades to a Fiat-Shamir argument with a 2^bits offline work factor.
+ * blsgpu_ctx_set_rlc_bits selects 64-bit (default) or 128-bit scalars (r_i * pk_i and the bucket sum cost twice as much). */
 int blsgpu_ctx_set_rlc_salt(blsgpu_ctx* ctx, const uint8_t salt[32]);
+int blsgpu_ctx_set_rlc_bits(blsgpu_ctx* ctx, int bits);
 
 /* ---- Signature::verify over a slice --------------------------------------------------------------------------
  * Replaces n calls of Signature::<C>::verify(&pk, msg)   (reference src/signature.rs:130-138 ->
@@ -78,7 +85,9 @@ int blsgpu_ctx_set_rlc_salt(blsgpu_ctx* ctx, const uint8_t salt[32]);
 int blsgpu_verify_batch(blsgpu_ctx* ctx, int impl_id, int scheme, int format, size_t n, const uint8_t* pks,
                         const uint8_t* sigs, const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out);
 /* Same with every input already resident in device memory of the context's first device (benchmark "value" leg);
- * status_out_dev receives n bytes on the device. */
+ * status_out_dev receives n bytes on the device.  msg_off_dev holds n + 1 non-decreasing offsets with messages shorter
+ * than 2^32 bytes (the host entry points check this, here it is the caller's contract); pks_dev / sigs_dev need no
+ * particular alignment (16-byte aligned buffers take the vectorised staging path). */
 int blsgpu_verify_batch_dev(blsgpu_ctx* ctx, int impl_id, int scheme, int format, size_t n, const uint8_t* pks_dev,
                             const uint8_t* sigs_dev, const uint8_t* msgs_dev, const uint64_t* msg_off_dev,
                             uint8_t* status_out_dev);
@@ -141,7 +150,7 @@ int blsgpu_pairing_product_is_one(blsgpu_ctx* ctx, size_t n, const uint8_t* g1_p
                                   int* is_one_out);
 /* Synthetic-data helper for benchmarks and tests (NOT part of the verification path, not a signing API: it takes no
  * secret-key type and is variable-time): out_pk[i] = [k_i] G, out_sig[i] = [k_i] H(msg_i) for 32-byte big-endian
- * scalars k_i, framed for (impl_id, scheme). */
+ * scalars k_i, framed for (impl_id, scheme); scheme 3 produces proofs of possession (message = the key's bytes, POP_DST). */
 int blsgpu_testdata_sign(blsgpu_ctx* ctx, int impl_id, int scheme, size_t n, const uint8_t* scalars32,
                          const uint8_t* msgs, const uint64_t* msg_off, uint8_t* out_pks, uint8_t* out_sigs);
 /* INT32 multiply-issue roofline probe: runs independent mad.wide.u32 chains on every SM and returns the measured
@@ -190,8 +199,8 @@ int blsgpu_verify_share_batch(blsgpu_ctx* ctx, int impl_id, int scheme, size_t n
                               const uint8_t* sig_shares, const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out);
 
 /* Host-only planning query (no device needed): the window layout the bucket multi-scalar multiplication of
- * blsgpu_verify_batch uses for a batch of n signatures (64-bit scalars). */
-int blsgpu_plan_msm(size_t n, int* window_bits_out, int* windows_out, int* top_window_bits_out);
+ * blsgpu_verify_batch uses for a batch of n signatures with scalar_bits-bit (64 | 128) scalars. */
+int blsgpu_plan_msm(size_t n, int scalar_bits, int* window_bits_out, int* windows_out, int* top_window_bits_out);
 
 /* ---- metrics ---------------------------------------------------------------------------------------------------
  * Per-stage device times (CUDA events on the engine's stream) of the LAST verify call on the first device. */

@@ -1,91 +1,77 @@
 """CPU timing legs for bench.py (test infrastructure): the reference's per-signature verification path
-(core_verify, reference src/traits/sig_core.rs:120-146: hash_to_curve, two Miller loops, one final exponentiation per
-signature, no batching) restated by the oracle and run on the host cores.
+(`Signature::verify` -> core_verify, reference src/signature.rs:130-138, src/traits/sig_core.rs:120-146: parse both points
+with curve + subgroup checks, hash_to_curve, two Miller loops, ONE final exponentiation per signature, nothing batched)
+executed by the 64-bit-limb C oracle (oracle/c64/bls64.c -> oracle/_build/libbls64.so: portable C, `unsigned __int128`,
+no assembly, its own source - not the engine's headers) on the host cores, one pthread per core.
 
-Uses the C++ restatement (oracle/c -> oracle/_build/liboracle.so: the reference's call sequence over the engine's
-field / curve / pairing headers compiled for the host, validated against the big-int oracle by tests/test_c_oracle.py)
-when it has been built, otherwise the big-int Python oracle.  blsful itself cannot be built here (no cargo, un-vendored
-blstrs_plus/blst), so kind is always "port"."""
-import json
-import multiprocessing as mp
+blsful itself cannot be built here (no cargo; blstrs_plus / blst are un-vendored, Cargo.toml:20-28), so `kind` is always
+"port".  Expect blst's hand-written assembly to be a few times faster per core than this portable C."""
 import os
 import time
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-ROOT = os.path.dirname(HERE)
+import numpy as np
+
+KIND_TEXT = ("C oracle oracle/c64/bls64.c: the reference's per-signature Signature::verify call sequence (decode + subgroup checks, "
+             "hash_to_curve, 2 Miller loops, 1 final exponentiation), 6x64-bit limbs, gcc -O3, no asm; blsful+blst cannot be built here")
 
 
-def _golden_triples():
-    g = json.load(open(os.path.join(ROOT, "tests", "golden", "cpp_integration.json")))
-    msg = bytes.fromhex(g["message"])
-    return [(bytes.fromhex(s["pk"]), bytes.fromhex(s["sig"]), msg) for s in g["signers"]]
+def _c64():
+    from oracle import c64_oracle
+    if not c64_oracle.available():
+        c64_oracle.build()
+    return c64_oracle
 
 
-def _c_oracle():
-    try:
-        from oracle import c_oracle
-        return c_oracle if c_oracle.available() else None
-    except Exception:
-        return None
+def synth_triples(n, seed=2024):
+    """n distinct (pk 48 B, 32-byte message, sig 96 B) Bls12381G2Impl/Basic triples made by the C oracle itself
+    (pk = [sk]G, sig = [sk]H(msg)); signing is outside every timed region."""
+    C = _c64()
+    rng = np.random.default_rng(seed)
+    dst = b"BLS_SIG_BLS12381G2_XMD:SHA-256_SSWU_RO_NUL_"
+    g1 = C.generator(1)
+    pks, sigs, msgs = [], [], []
+    for i in range(n):
+        sk = int.from_bytes(rng.bytes(31), "big") | 1
+        m = i.to_bytes(8, "little") + rng.bytes(24)
+        pks.append(C.point_mul(1, g1, sk))
+        sigs.append(C.point_mul(2, C.hash_to_curve(2, m, dst), sk))
+        msgs.append(m)
+    off = np.arange(n + 1, dtype=np.uint64) * 32
+    return (np.frombuffer(b"".join(pks), dtype=np.uint8), np.frombuffer(b"".join(sigs), dtype=np.uint8),
+            np.frombuffer(b"".join(msgs), dtype=np.uint8), off)
 
 
-def _verify_chunk(args):
-    count, impl = args
-    tr = _golden_triples()
-    co = _c_oracle()
-    ok = 0
-    for i in range(count):
-        pk, sig, msg = tr[i % len(tr)]
-        if co is not None:
-            st = co.verify(impl, 0, 1, pk, sig, msg)
-        else:
-            from oracle import bls_oracle as O
-            st = O.verify(impl, O.BASIC, O.MODERN, pk, sig, msg)
-        ok += st == 0
-    return ok
-
-
-def _run(total, impl, procs):
-    per = [total // procs + (1 if i < total % procs else 0) for i in range(procs)]
-    per = [p for p in per if p]
+def _time_verify(batch, threads):
+    C = _c64()
+    pks, sigs, msgs, off = batch
     t0 = time.perf_counter()
-    if len(per) == 1:
-        ok = _verify_chunk((per[0], impl))
-    else:
-        with mp.get_context("fork").Pool(len(per)) as pool:
-            ok = sum(pool.map(_verify_chunk, [(p, impl) for p in per]))
+    st = C.verify_many(2, 0, 1, pks, sigs, msgs, off, threads=threads)
     dt = time.perf_counter() - t0
-    assert ok == total, "reference vectors must verify"
+    assert int(st.max()) == 0, "the sample must verify"
     return dt
 
 
-def _auto_sample(procs):
-    # ~10-30 s of CPU work: C++ restatement ~11 ms/verify, Python big-int ~1 s/verify
-    return (1000 if _c_oracle() is not None else 4) * procs
-
-
-def time_verify_sample(sample=0, impl=2):
-    procs = os.cpu_count() or 1
-    kind = ("C++ restatement (oracle/c: per-signature core_verify over the engine's host-compiled field/curve headers, "
-            "g++ -O3, no asm)") if _c_oracle() is not None else "Python big-int oracle"
-    n1 = max(1, (sample or _auto_sample(1)) // (1 if sample else 4))
-    dt1 = _run(n1, impl, 1)
-    nall = sample or _auto_sample(procs)
-    dtall = _run(nall, impl, procs)
-    return {"value": nall / dtall, "unit": "sigs/s", "cores": procs, "kind": "port",
-            "sample": f"{nall} Signature::verify calls over the reference's 3 golden triples on {procs} processes; {kind}",
+def time_verify_sample(batch, threads=0):
+    """cpu_baseline leg: `batch` = (pks, sigs, msgs, off) is a bounded sample of the benchmark's own workload."""
+    procs = threads or (os.cpu_count() or 1)
+    n = batch[3].size - 1
+    n1 = max(1, min(n, 64))
+    dt1 = _time_verify((batch[0][:48 * n1], batch[1][:96 * n1], batch[2][:int(batch[3][n1])], batch[3][:n1 + 1]), 1)
+    dt = _time_verify(batch, procs)
+    return {"value": n / dt, "unit": "sigs/s", "cores": procs, "kind": "port",
+            "sample": f"the first {n} signatures of the benchmark batch, one Signature::verify each, {procs} threads; {KIND_TEXT}",
             "single_core_sigs_per_s": n1 / dt1}
 
 
 def reference_arm(n_per_step=0, steps=3, warmup=1):
+    """`bench.py --impl reference`: per step, n_per_step distinct triples through the per-signature path on every core."""
     procs = os.cpu_count() or 1
-    n = n_per_step or max(procs, _auto_sample(procs) // max(1, steps + warmup))
+    n = n_per_step or 1024   # configs[0]: Signature::verify over 1,024 distinct (pk, 32-byte msg, sig) triples
+    batch = synth_triples(n)
     for _ in range(warmup):
-        _run(n, 2, procs)
-    t0 = time.perf_counter()
+        _time_verify(batch, procs)
+    dt = 0.0
     for _ in range(steps):
-        _run(n, 2, procs)
-    dt = time.perf_counter() - t0
-    kind = "C++ restatement (oracle/c, g++ -O3, no asm)" if _c_oracle() is not None else "Python big-int oracle"
+        dt += _time_verify(batch, procs)
     return {"value": n * steps / dt, "ms_per_step": dt / steps * 1e3, "n_per_step": n, "cores": procs, "kind": "port",
-            "sample": f"{n} per-signature verifies per step on {procs} processes; {kind}; blsful+blst cannot be built here"}
+            "sample": f"{n} distinct triples per step, one Signature::verify each, {procs} threads; {KIND_TEXT}"}

@@ -46,10 +46,11 @@ def test_msm_window_plan_never_has_a_narrow_top_window():
     import ctypes
     import blsful_b200 as B
     lib = B.load_library()
-    for n in [4096, 4097, 5000, 33000, 65536, 100000, 262144, 500000, 524288, 999999, 1000000, 1048576, 4000000, 10 ** 8]:
+    for bits, n in [(b, n) for b in (64, 128) for n in [4096, 4097, 5000, 33000, 65536, 100000, 262144, 500000, 524288, 999999,
+                                                           1000000, 1048576, 4000000, 10 ** 8]]:
         c, w, top = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
-        assert lib.blsgpu_plan_msm(n, ctypes.byref(c), ctypes.byref(w), ctypes.byref(top)) == 0
+        assert lib.blsgpu_plan_msm(n, bits, ctypes.byref(c), ctypes.byref(w), ctypes.byref(top)) == 0
         c, w, top = c.value, w.value, top.value
-        assert (w - 1) * c + top == 64 and 0 < top <= c
+        assert (w - 1) * c + top == bits and 0 < top <= c
         assert n >> c >= 8 or c == 4          # enough signatures per bucket to amortise the bucket reduction
         assert (n >> top) <= 16 * max(1, n >> c) or n < (1 << 16), (n, c, top)   # top-window buckets at most 16x larger

@@ -1,0 +1,315 @@
+"""GPU parity tests, second set (round 2): the rejection paths of the decoders on the device, the Legacy format through
+every batch entry point, proofs of possession, the random-linear-combination modes.  Every expectation comes from the
+big-int oracle (oracle/bls_oracle.py) or from the reference's golden vectors; everything goes through the C ABI."""
+import hashlib
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import bls_oracle as O
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import blsful_b200 as B
+    e = B.Engine([0])
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def B():
+    import blsful_b200
+    return blsful_b200
+
+
+@pytest.fixture(scope="module")
+def cpp(golden_dir):
+    return json.load(open(os.path.join(golden_dir, "cpp_integration.json")))
+
+
+def ident(length):
+    return bytes([0xC0]) + bytes(length - 1)
+
+
+# ---- adversarial encodings (module-level so that several tests share the search) ------------------------------------
+def _g1_outside_subgroup():
+    x = 1
+    while True:
+        y = O.fp_sqrt((x ** 3 + 4) % O.P)
+        if y is not None and not O.g1_in_subgroup((x, y)):
+            return (x, y)
+        x += 1
+
+
+def _g2_outside_subgroup():
+    k = 1
+    while True:
+        x = (k, 1)
+        y = O.f2_sqrt(O.f2_add(O.f2_mul(O.f2_sqr(x), x), O.B2))
+        if y is not None and not O.g2_in_subgroup((x, y)):
+            return (x, y)
+        k += 1
+
+
+def _g1_off_curve_x():
+    x = 1
+    while O.fp_sqrt((x ** 3 + 4) % O.P) is not None:
+        x += 1
+    return x
+
+
+def _g2_off_curve_x():
+    k = 1
+    while O.f2_sqrt(O.f2_add(O.f2_mul(O.f2_sqr((k, 2)), (k, 2)), O.B2)) is not None:
+        k += 1
+    return (k, 2)
+
+
+@pytest.fixture(scope="module")
+def bad_points():
+    p1, p2 = _g1_outside_subgroup(), _g2_outside_subgroup()
+    assert O.g1_on_curve(p1) and O.g2_on_curve(p2)
+    x1, x2 = _g1_off_curve_x(), _g2_off_curve_x()
+    e1 = bytearray(x1.to_bytes(48, "big")); e1[0] |= 0x80
+    e2 = bytearray(x2[1].to_bytes(48, "big") + x2[0].to_bytes(48, "big")); e2[0] |= 0x80
+    return {
+        1: {"outside": O.g1_compress_modern(p1), "off_curve": bytes(e1)},
+        2: {"outside": O.g2_compress_modern(p2), "off_curve": bytes(e2)},
+    }
+
+
+def test_hash_to_curve_hello_full_known_answer(eng, cpp):
+    """The reference's golden triples pin H("hello") completely: sig = sk * H, so H = sk^-1 * sig for every signer
+    (cpp_integration_test.rs:19-82).  All 96 bytes are compared (round 1 compared a 16-byte prefix)."""
+    msg = bytes.fromhex(cpp["message"])
+    got = eng.hash_to_curve_batch(2, [msg], O.sig_dst(O.G2IMPL, O.BASIC))[0]
+    for s in cpp["signers"]:
+        sk = int(s["sk"], 16)
+        h = O.g2_mul(O.g2_deserialize(bytes.fromhex(s["sig"])), pow(sk, -1, O.R))
+        assert got == O.g2_serialize(h)
+    assert got.hex() == ("8dbf4d3c426badac1e66421c7d65dc017c05fb7631833f3c9a72f531bedf7995f2309d2fd6831018c83de0c27b6a10c8"
+                         "10946937ad15674b2f3976d10f50ae5a66a07f5da23a4f177870702d0dbf8463225a493a8c221032e15d445afeac748a")
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_decoder_rejects_points_outside_the_subgroup_and_off_the_curve(eng, B, bad_points, group):
+    """k_subgroup_check's REJECT path and the square-root failure of k_decode, for both groups and both formats
+    (from_compressed: legacy.rs:107,117,151,161 -> DeserializationError)."""
+    deser, ser = (O.g1_deserialize, O.g1_serialize) if group == 1 else (O.g2_deserialize, O.g2_serialize)
+    good = ser(O.g1_mul(O.G1_GEN, 5) if group == 1 else O.g2_mul(O.G2_GEN, 5))
+    enc = [bad_points[group]["outside"], bad_points[group]["off_curve"], good]
+    enc += [bytes([e[0] ^ 0x20]) + e[1:] for e in enc]           # the other y
+    for fin in (O.MODERN, O.LEGACY):
+        cases = enc if fin == O.MODERN else [O.modern_to_legacy(e) for e in enc]
+        st, outs = eng.recode_points(group, cases, fin, O.MODERN)
+        want = []
+        for c in cases:
+            try:
+                deser(c, fin); want.append(0)
+            except O.BlsError as ex:
+                want.append(ex.code)
+        assert st.tolist() == want
+        assert want == [4, 4, 0, 4, 4, 0]
+        # many copies in one launch: every lane of whole warps takes the reject path, mixed with accepting lanes
+        many = (cases * 700)[:4099]
+        st, _ = eng.recode_points(group, many, fin, O.MODERN)
+        assert st.tolist() == (want * 700)[:4099]
+
+
+@pytest.mark.parametrize("impl,fmt", [(2, 1), (2, 0), (1, 1), (1, 0)])
+def test_verify_batch_with_adversarial_encodings_inside_a_large_batch(eng, B, bad_points, impl, fmt):
+    """>= 4096 items (bucket path, cooperative groups of six) with out-of-subgroup / off-curve public keys and signatures,
+    in the given serialization format: statuses equal the oracle's, neighbours are unaffected."""
+    rnd = random.Random(900 + impl * 10 + fmt)
+    n = 4200
+    C = O.IMPLS[impl]
+    pl, sl = B.pk_len(impl), B.sig_len(impl)
+    pkg, sgg = (1, 2) if impl == 2 else (2, 1)
+    k = np.frombuffer(b"".join(rnd.randrange(1, O.R).to_bytes(32, "big") for _ in range(n)), dtype=np.uint8)
+    msgs = [hashlib.sha256(b"adv%d" % i).digest() for i in range(n)]
+    data, off = B.pack_messages(msgs)
+    pks, sigs = eng.testdata_sign(impl, 0, k, data, off)
+    if fmt == O.LEGACY:
+        st, p = eng.recode_points(pkg, pks, O.MODERN, O.LEGACY); assert int(st.max()) == 0
+        pks = np.frombuffer(b"".join(p), dtype=np.uint8)
+        st, s = eng.recode_points(sgg, sigs, O.MODERN, O.LEGACY); assert int(st.max()) == 0
+        sigs = np.frombuffer(b"".join(s), dtype=np.uint8)
+    pks, sigs = pks.copy(), sigs.copy()
+    conv = (lambda e: e) if fmt == O.MODERN else O.modern_to_legacy
+    plant = {
+        5: ("pk", conv(bad_points[pkg]["outside"])), 6: ("sig", conv(bad_points[sgg]["outside"])),
+        7: ("pk", conv(bad_points[pkg]["off_curve"])), 8: ("sig", conv(bad_points[sgg]["off_curve"])),
+        4100: ("sig", conv(bad_points[sgg]["outside"])), 4101: ("pk", conv(bad_points[pkg]["outside"])),
+        2000: ("sig", ident(sl)), 2001: ("pk", ident(pl)),
+        2002: ("sig", bytes([sigs[2002 * sl] ^ (0x20 if fmt == O.MODERN else 0x80)]) + sigs[2002 * sl + 1:2003 * sl].tobytes()),  # -sig
+    }
+    for i, (which, enc) in plant.items():
+        if which == "pk":
+            pks[i * pl:(i + 1) * pl] = np.frombuffer(enc, dtype=np.uint8)
+        else:
+            sigs[i * sl:(i + 1) * sl] = np.frombuffer(enc, dtype=np.uint8)
+    st = eng.verify_batch_packed(impl, 0, pks, sigs, data, off, fmt)
+    want = [0] * n
+    for i in plant:
+        want[i] = O.verify(impl, O.BASIC, fmt, pks[i * pl:(i + 1) * pl].tobytes(), sigs[i * sl:(i + 1) * sl].tobytes(), msgs[i])
+    assert st.tolist() == want
+    assert [want[i] for i in (5, 6, 7, 8, 4100, 4101, 2000, 2001, 2002)] == [4, 4, 4, 4, 4, 4, 2, 3, 1]
+    for i in (0, 4, 9, 4099, n - 1):   # untouched neighbours, checked one by one
+        assert O.verify(impl, O.BASIC, fmt, pks[i * pl:(i + 1) * pl].tobytes(), sigs[i * sl:(i + 1) * sl].tobytes(), msgs[i]) == 0
+
+
+@pytest.mark.parametrize("impl", [2, 1])
+def test_legacy_format_through_every_batch_entry_point(eng, B, impl):
+    """format = Legacy through verify_batch, aggregate_verify and sum_points (legacy_test.rs:70-171,
+    legacy_comprehensive_test.rs): results equal the oracle's under the same format, including the cross-format traps
+    of legacy.rs:39-67 (a Modern encoding with y-flag 0 decodes as -P under Legacy; one with y-flag 1 is a
+    LegacyFormatError; a Legacy encoding with sign 0 fails the Modern decoder)."""
+    rnd = random.Random(300 + impl)
+    C = O.IMPLS[impl]
+    n = 6
+    sks = [rnd.randrange(1, O.R) for _ in range(n)]
+    msgs = [b"legacy message %d" % i for i in range(n)]
+    pk_pts = [O.sk_to_pk(impl, sk) for sk in sks]
+    for scheme in (0, 1, 2):
+        m = n if scheme == 0 else 2
+        sig_pts = [O.sign(impl, scheme, sk, mm) for sk, mm in zip(sks[:m], msgs[:m])]
+        pk_m, sg_m = [C.pk_ser(p, O.MODERN) for p in pk_pts[:m]], [C.sig_ser(s, O.MODERN) for s in sig_pts]
+        pk_l, sg_l = [C.pk_ser(p, O.LEGACY) for p in pk_pts[:m]], [C.sig_ser(s, O.LEGACY) for s in sig_pts]
+        assert eng.verify_batch(impl, scheme, pk_l, sg_l, msgs[:m], O.LEGACY).tolist() == [0] * m
+        assert O.verify(impl, scheme, O.LEGACY, pk_l[0], sg_l[0], msgs[0]) == 0
+        if scheme != 0:
+            continue
+        # Modern bytes handed to the Legacy decoder and the reverse: whatever the oracle says, item by item
+        seen = set()
+        for fmt, pk_x, sg_x in ((O.LEGACY, pk_m, sg_m), (O.MODERN, pk_l, sg_l), (O.LEGACY, pk_l, sg_m), (O.LEGACY, pk_m, sg_l)):
+            got = eng.verify_batch(impl, scheme, pk_x, sg_x, msgs, fmt).tolist()
+            want = [O.verify(impl, scheme, fmt, p, s, mm) for p, s, mm in zip(pk_x, sg_x, msgs)]
+            assert got == want, (impl, scheme, fmt)
+            seen |= set(want)
+        assert seen >= {1, 4, 5} or seen >= {4, 5}
+    # aggregate_verify and sum_points in Legacy
+    sig_pts = [O.sign(impl, 0, sk, m) for sk, m in zip(sks[:6], msgs[:6])]
+    sg_l = [C.sig_ser(s, O.LEGACY) for s in sig_pts]
+    pk_l = [C.pk_ser(p, O.LEGACY) for p in pk_pts[:6]]
+    grp_sig, grp_pk = (2, 1) if impl == 2 else (1, 2)
+    agg = eng.sum_points(grp_sig, sg_l, O.LEGACY)
+    want_st, want_agg, _ = O.sum_points(grp_sig, O.LEGACY, sg_l)
+    assert want_st == 0 and agg == want_agg
+    assert eng.sum_points(grp_pk, pk_l, O.LEGACY) == O.sum_points(grp_pk, O.LEGACY, pk_l)[1]
+    assert eng.aggregate_verify_status(impl, 0, pk_l, msgs[:6], agg, O.LEGACY)[0] == \
+        O.aggregate_verify(impl, O.BASIC, O.LEGACY, pk_l, msgs[:6], agg)[0] == 0
+    # the Modern bytes of the same aggregate under Legacy: the oracle decides (sign flip or format error)
+    agg_m = C.sig_ser(C.sig_deser(agg, O.LEGACY), O.MODERN)
+    assert eng.aggregate_verify_status(impl, 0, pk_l, msgs[:6], agg_m, O.LEGACY)[0] == \
+        O.aggregate_verify(impl, O.BASIC, O.LEGACY, pk_l, msgs[:6], agg_m)[0] != 0
+    with pytest.raises(B.BlsError) as e:
+        eng.sum_points(grp_sig, [C.sig_ser(s, O.MODERN) for s in sig_pts], O.LEGACY)
+    assert e.value.status == O.sum_points(grp_sig, O.LEGACY, [C.sig_ser(s, O.MODERN) for s in sig_pts])[0]
+
+
+@pytest.mark.parametrize("impl,fmt", [(2, 1), (2, 0), (1, 1), (1, 0)])
+def test_pop_verify_batch_against_oracle(eng, B, bad_points, impl, fmt):
+    """blsgpu_pop_verify_batch = n x ProofOfPossession::verify (proof_of_possession.rs:77-81 -> pop_verify,
+    sig_pop.rs:61-70: core_verify(pk, proof, pk.to_bytes(), POP_DST)); the message is ALWAYS the Modern key bytes."""
+    rnd = random.Random(40 + impl * 10 + fmt)
+    C = O.IMPLS[impl]
+    pl, sl = B.pk_len(impl), B.sig_len(impl)
+    pkg, sgg = (1, 2) if impl == 2 else (2, 1)
+    sks = [rnd.randrange(1, O.R) for _ in range(9)]
+    pk_pts = [O.sk_to_pk(impl, sk) for sk in sks]
+    pops = [C.sig_mul(C.hash(C.pk_ser(p, O.MODERN), O.pop_dst(impl)), sk) for p, sk in zip(pk_pts, sks)]
+    pk_b = [C.pk_ser(p, fmt) for p in pk_pts]
+    pop_b = [C.sig_ser(s, fmt) for s in pops]
+    conv = (lambda e: e) if fmt == O.MODERN else O.modern_to_legacy
+    cases = list(zip(pk_b, pop_b))
+    cases += [
+        (pk_b[0], pop_b[1]),                                              # another key's proof
+        (pk_b[1], C.sig_ser(O.sign(impl, O.POP, sks[1], C.pk_ser(pk_pts[1], O.MODERN)), fmt)),  # a SIGNATURE over the key bytes: wrong DST
+        (ident(pl), pop_b[2]), (pk_b[2], ident(sl)), (ident(pl), ident(sl)),  # identity key / proof / both (proof checked first)
+        (bytes(pl), pop_b[3]), (pk_b[3], bytes(sl)),                      # undecodable
+        (conv(bad_points[pkg]["outside"]), pop_b[4]), (pk_b[4], conv(bad_points[sgg]["outside"])),
+        (conv(bad_points[pkg]["off_curve"]), pop_b[5]),
+        (C.pk_ser(pk_pts[6], 1 - fmt), pop_b[6]),                         # the key in the OTHER format
+    ]
+    got = eng.pop_verify_batch(impl, [c[0] for c in cases], [c[1] for c in cases], fmt)
+    want = [O.pop_verify(impl, fmt, a, b) for a, b in cases]
+    assert got.tolist() == want, (impl, fmt)
+    assert want[:9] == [0] * 9 and want[9] == 1 and want[10] == 1 and want[11:14] == [3, 2, 2] and want[14:19] == [4] * 5
+    # a batch large enough for the bucket path: proofs from the synthetic-data helper (scheme 3 = proof of possession),
+    # pinned to the oracle on a sample, then planted failures
+    n = 4200
+    k = np.frombuffer(b"".join(rnd.randrange(1, O.R).to_bytes(32, "big") for _ in range(n)), dtype=np.uint8)
+    none, off0 = np.zeros(0, dtype=np.uint8), np.zeros(n + 1, dtype=np.uint64)
+    pks, proofs = eng.testdata_sign(impl, 3, k, none, off0)
+    for i in (0, 1, n - 1):
+        ki = int.from_bytes(k[i * 32:(i + 1) * 32].tobytes(), "big")
+        pk_pt = C.pk_mul(C.pk_gen, ki)
+        assert pks[i * pl:(i + 1) * pl].tobytes() == C.pk_ser(pk_pt, O.MODERN)
+        assert proofs[i * sl:(i + 1) * sl].tobytes() == C.sig_ser(C.sig_mul(C.hash(C.pk_ser(pk_pt, O.MODERN), O.pop_dst(impl)), ki), O.MODERN)
+    if fmt == O.LEGACY:
+        st, p = eng.recode_points(pkg, pks, O.MODERN, O.LEGACY); assert int(st.max()) == 0
+        pks = np.frombuffer(b"".join(p), dtype=np.uint8)
+        st, p = eng.recode_points(sgg, proofs, O.MODERN, O.LEGACY); assert int(st.max()) == 0
+        proofs = np.frombuffer(b"".join(p), dtype=np.uint8)
+    assert eng.pop_verify_batch(impl, pks, proofs, fmt).tolist() == [0] * n
+    pr2 = proofs.copy().reshape(n, sl)
+    bad = [17, 2048, 4199]
+    pr2[bad] = pr2[[b - 1 for b in bad]]
+    st = eng.pop_verify_batch(impl, pks, pr2.reshape(-1), fmt)
+    assert [i for i in range(n) if st[i]] == bad and all(st[i] == 1 for i in bad)
+    assert O.pop_verify(impl, fmt, pks[17 * pl:18 * pl].tobytes(), pr2[17].tobytes()) == 1
+
+
+def test_rlc_salt_is_random_by_default_and_statuses_do_not_depend_on_it(eng, B):
+    """Default: a fresh OS-random salt per call.  Pinned salt: reproducible.  128-bit scalars: same statuses.
+    (The accept/reject vector is a property of the inputs; only the scalars of the batch equation change.)"""
+    rnd = random.Random(1234)
+    n = 4500
+    k = np.frombuffer(b"".join(rnd.randrange(1, O.R).to_bytes(32, "big") for _ in range(n)), dtype=np.uint8)
+    data, off = B.pack_messages([hashlib.sha256(b"salt%d" % i).digest() for i in range(n)])
+    pks, sigs = eng.testdata_sign(2, 0, k, data, off)
+    bad = [3, 700, 4499]
+    s2 = sigs.copy().reshape(n, 96)
+    s2[bad] = s2[[b + 1 if b + 1 < n else 0 for b in bad]]
+    want = [1 if i in bad else 0 for i in range(n)]
+    e2 = B.Engine([0])
+    try:
+        for bits in (64, 128):
+            e2.set_rlc_bits(bits)
+            for rep in range(2):      # unpinned: two calls draw two salts
+                assert e2.verify_batch_packed(2, 0, pks, s2.reshape(-1), data, off).tolist() == want
+            assert e2.verify_batch_packed(2, 0, pks, sigs, data, off).tolist() == [0] * n
+            small = e2.verify_batch_packed(2, 0, pks[:48 * 100], s2.reshape(-1)[:96 * 100], data, off[:101])   # per-item scaling path
+            assert small.tolist() == want[:100]
+        e2.set_rlc_salt(bytes(range(32)))
+        assert e2.verify_batch_packed(2, 0, pks, s2.reshape(-1), data, off).tolist() == want
+        e2.set_rlc_bits(64)
+        with pytest.raises(B.EngineError):
+            e2.set_rlc_bits(96)
+        for impl in (1,):
+            pk1, sg1 = e2.testdata_sign(impl, 0, k[:32 * 300], data, off[:301])
+            e2.set_rlc_bits(128)
+            assert e2.verify_batch_packed(impl, 0, pk1, sg1, data, off[:301]).tolist() == [0] * 300
+    finally:
+        e2.close()
+
+
+def test_bad_offsets_and_chunk_overrides_are_refused_or_clamped(eng, B, monkeypatch):
+    n = 300
+    rnd = random.Random(2)
+    k = np.frombuffer(b"".join(rnd.randrange(1, O.R).to_bytes(32, "big") for _ in range(n)), dtype=np.uint8)
+    data, off = B.pack_messages([b"o%d" % i for i in range(n)])
+    pks, sigs = eng.testdata_sign(2, 0, k, data, off)
+    bad_off = off.copy(); bad_off[10], bad_off[11] = off[11], off[10] - 1   # decreasing
+    with pytest.raises(B.EngineError):
+        eng.verify_batch_packed(2, 0, pks, sigs, data, bad_off)
+    for chunk in ("0", "7", "junk", "119"):   # used to loop forever (chunk 0) - now clamped to one group-multiple pass size
+        monkeypatch.setenv("BLSGPU_M6_CHUNK", chunk)
+        assert eng.verify_batch_packed(2, 0, pks, sigs, data, off).tolist() == [0] * n
+    monkeypatch.delenv("BLSGPU_M6_CHUNK")
