@@ -32,6 +32,7 @@ class SerializationFormat:
 ST_OK, ST_INVALID_SIGNATURE, ST_SIG_IDENTITY, ST_PK_IDENTITY, ST_DESERIALIZE, ST_LEGACY_FORMAT = 0, 1, 2, 3, 4, 5
 ST_INVALID_LENGTH, ST_INVALID_COEFFICIENT, ST_DUPLICATE_MESSAGES, ST_SCHEME, ST_MISMATCHED_LENGTHS = 6, 7, 8, 9, 10
 ST_VSSS = 11
+ST_INVALID_PROOF, ST_COMMITMENT_IDENTITY, ST_PROOF_IDENTITY, ST_ZERO_CHALLENGE = 12, 13, 14, 15
 
 _STATUS_TEXT = {
     ST_INVALID_SIGNATURE: "invalid signature",
@@ -45,6 +46,10 @@ _STATUS_TEXT = {
     ST_SCHEME: "Invalid signature scheme",
     ST_MISMATCHED_LENGTHS: "invalid inputs: Mismatched array lengths",
     ST_VSSS: "an error occurred during secret sharing",
+    ST_INVALID_PROOF: "invalid proof",
+    ST_COMMITMENT_IDENTITY: "invalid inputs: commitment is the identity point",
+    ST_PROOF_IDENTITY: "invalid inputs: proof is the identity point",
+    ST_ZERO_CHALLENGE: "invalid inputs: y is the zero",
 }
 
 STAGES = ["decode_pk", "decode_sig", "hash_to_curve", "scale_sig", "miller", "reduce", "final", "bisect"]
@@ -118,6 +123,10 @@ def load_library() -> ctypes.CDLL:
         "blsgpu_combine_shares_batch": (c.c_int, [vp, c.c_int, c.c_size_t, u64p, u8p, u8p, u8p]),
         "blsgpu_verify_batch_wire": (c.c_int, [vp, c.c_int, c.c_size_t, u8p, u8p, u8p, u64p, u8p]),
         "blsgpu_pairing_check_batch": (c.c_int, [vp, c.c_size_t, u64p, u8p, u8p, u8p, u8p]),
+        "blsgpu_signcrypt_valid_batch": (c.c_int, [vp, c.c_int, c.c_int, c.c_size_t, u8p, u8p, u8p, u64p, u8p, u8p]),
+        "blsgpu_signcrypt_verify_share_batch": (c.c_int, [vp, c.c_int, c.c_int, c.c_size_t, u8p, u8p, u8p, u8p, u8p, u64p, u8p, u8p]),
+        "blsgpu_pok_verify_batch": (c.c_int, [vp, c.c_int, c.c_int, c.c_size_t, u8p, u8p, u8p, u8p, u8p, u64p, u8p]),
+        "blsgpu_verify_batch_records": (c.c_int, [vp, c.c_int, c.c_int, c.c_int, c.c_size_t, u8p, u64p, u8p, u64p, u8p, u64p, u8p]),
         "blsgpu_plan_msm": (c.c_int, [c.c_size_t, c.c_int, c.POINTER(c.c_int), c.POINTER(c.c_int), c.POINTER(c.c_int)]),
         "blsgpu_imad_peak": (c.c_int, [vp, c.POINTER(c.c_double)]),
         "blsgpu_verify_share_batch": (c.c_int, [vp, c.c_int, c.c_int, c.c_size_t, vp, vp, vp, vp, vp]),
@@ -139,7 +148,8 @@ EXPORTED_SYMBOLS = [
     "blsgpu_verify_batch_dev", "blsgpu_pop_verify_batch", "blsgpu_aggregate_verify", "blsgpu_sum_points",
     "blsgpu_verify_secure_batch", "blsgpu_aggregate_secure_batch", "blsgpu_hash_to_curve_batch", "blsgpu_recode_points",
     "blsgpu_fp_mul_batch", "blsgpu_pairing_product_is_one", "blsgpu_testdata_sign", "blsgpu_imad_peak",
-    "blsgpu_combine_shares_batch", "blsgpu_verify_batch_wire", "blsgpu_pairing_check_batch", "blsgpu_plan_msm", "blsgpu_verify_share_batch", "blsgpu_last_stage_ms", "blsgpu_last_kernel_ms", "blsgpu_launch_count",
+    "blsgpu_combine_shares_batch", "blsgpu_verify_batch_wire", "blsgpu_pairing_check_batch",
+    "blsgpu_signcrypt_valid_batch", "blsgpu_signcrypt_verify_share_batch", "blsgpu_pok_verify_batch", "blsgpu_verify_batch_records", "blsgpu_plan_msm", "blsgpu_verify_share_batch", "blsgpu_last_stage_ms", "blsgpu_last_kernel_ms", "blsgpu_launch_count",
 ]
 
 
@@ -456,6 +466,70 @@ class Engine:
         rc = self._lib.blsgpu_pairing_check_batch(self._ctx, q, _ptr(off), _ptr(g1), _ptr(g2), _ptr(ok), _ptr(status))
         self._check(rc, "blsgpu_pairing_check_batch")
         return ok, status
+
+    # ---- the other public 2-pairing checks ------------------------------------------------------------
+    def signcrypt_valid_batch(self, impl_id: int, scheme: int, us, ws, vs: Sequence[bytes]) -> Tuple[np.ndarray, np.ndarray]:
+        """n x SignCryptCiphertext::is_valid (sign_crypt_ciphertext.rs:86-101): returns (valid[n], parse status[n])."""
+        u = _pack_points(us, pk_len(impl_id), "U")
+        w = _pack_points(ws, sig_len(impl_id), "W")
+        n = u.size // pk_len(impl_id)
+        if w.size // sig_len(impl_id) != n or len(vs) != n:
+            raise BlsError(ST_MISMATCHED_LENGTHS)
+        data, off = pack_messages(vs)
+        ok, st = np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.uint8)
+        rc = self._lib.blsgpu_signcrypt_valid_batch(self._ctx, impl_id, scheme, n, _ptr(u), _ptr(w), _ptr(data), _ptr(off), _ptr(ok), _ptr(st))
+        self._check(rc, "blsgpu_signcrypt_valid_batch")
+        return ok, st
+
+    def signcrypt_verify_share_batch(self, impl_id: int, scheme: int, shares, pk_shares, us, ws, vs: Sequence[bytes]):
+        """n x SignDecryptionShare::verify (sign_decryption_share.rs:45-61; the reference passes scheme = Basic)."""
+        L = pk_len(impl_id)
+        sh, pk, u = (_pack_points(x, L, "share") for x in (shares, pk_shares, us))
+        w = _pack_points(ws, sig_len(impl_id), "W")
+        n = sh.size // L
+        if pk.size // L != n or u.size // L != n or w.size // sig_len(impl_id) != n or len(vs) != n:
+            raise BlsError(ST_MISMATCHED_LENGTHS)
+        data, off = pack_messages(vs)
+        ok, st = np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.uint8)
+        rc = self._lib.blsgpu_signcrypt_verify_share_batch(self._ctx, impl_id, scheme, n, _ptr(sh), _ptr(pk), _ptr(u), _ptr(w), _ptr(data),
+                                                           _ptr(off), _ptr(ok), _ptr(st))
+        self._check(rc, "blsgpu_signcrypt_verify_share_batch")
+        return ok, st
+
+    def pok_verify_batch(self, impl_id: int, scheme: int, commitments, proofs, pks, ys: Sequence[bytes], msgs: Sequence[bytes]) -> np.ndarray:
+        """n x ProofOfKnowledge::verify (proof_of_knowledge.rs:132-165); ys: 32-byte big-endian challenge scalars."""
+        cm = _pack_points(commitments, sig_len(impl_id), "commitment")
+        pr = _pack_points(proofs, sig_len(impl_id), "proof")
+        pk = _pack_points(pks, pk_len(impl_id), "public key")
+        n = pk.size // pk_len(impl_id)
+        if cm.size // sig_len(impl_id) != n or pr.size // sig_len(impl_id) != n or len(ys) != n or len(msgs) != n:
+            raise BlsError(ST_MISMATCHED_LENGTHS)
+        for y in ys:
+            if len(y) != 32:
+                raise BlsError(ST_INVALID_LENGTH, "challenge scalar")
+        yb = np.frombuffer(b"".join(ys), dtype=np.uint8) if n else np.zeros(0, dtype=np.uint8)
+        data, off = pack_messages(msgs)
+        st = np.zeros(n, dtype=np.uint8)
+        rc = self._lib.blsgpu_pok_verify_batch(self._ctx, impl_id, scheme, n, _ptr(cm), _ptr(pr), _ptr(pk), _ptr(yb), _ptr(data), _ptr(off), _ptr(st))
+        self._check(rc, "blsgpu_pok_verify_batch")
+        return st
+
+    def verify_batch_records(self, impl_id: int, fmt: int, scheme_or_tagged: int, pk_records: Sequence[bytes],
+                             sig_records: Sequence[bytes], msgs: Sequence[bytes]) -> np.ndarray:
+        """Ragged network records (any lengths): PublicKey::from_bytes_with_mode + Signature::from_bytes_with_mode (scheme >= 0)
+        or Signature::try_from on the serde_bare form (scheme_or_tagged < 0), then verify.  Length / tag / header errors
+        come back as per-item statuses."""
+        n = len(pk_records)
+        if len(sig_records) != n or len(msgs) != n:
+            raise BlsError(ST_MISMATCHED_LENGTHS)
+        pk, pko = pack_messages(pk_records)
+        sg, sgo = pack_messages(sig_records)
+        data, off = pack_messages(msgs)
+        st = np.zeros(n, dtype=np.uint8)
+        rc = self._lib.blsgpu_verify_batch_records(self._ctx, impl_id, fmt, scheme_or_tagged, n, _ptr(pk), _ptr(pko), _ptr(sg), _ptr(sgo),
+                                                   _ptr(data), _ptr(off), _ptr(st))
+        self._check(rc, "blsgpu_verify_batch_records")
+        return st
 
     # ---- threshold shares ------------------------------------------------------------------------------------------
     def combine_shares_batch(self, group: int, share_sets: Sequence[Sequence[bytes]]) -> Tuple[np.ndarray, List[bytes]]:

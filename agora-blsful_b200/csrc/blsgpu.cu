@@ -1658,6 +1658,235 @@ int blsgpu_pairing_check_batch(blsgpu_ctx* ctx, size_t q, const uint64_t* pair_o
   return BLSGPU_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The reference's other public 2-pairing checks, pairs assembled on the device.
+
+// SignCryptCiphertext::is_valid -> BlsSignCrypt::valid(u, v, w, dst)  ==  core_verify(pk = u, sig = w, msg = u.to_bytes() || v, dst)
+// as a boolean: both check  pairing([(w, -g), (hash_to_point(u_bytes || v), u)]) == 1  and reject identity u / w.
+int blsgpu_signcrypt_valid_batch(blsgpu_ctx* ctx, int impl_id, int scheme, size_t n, const uint8_t* u_points, const uint8_t* w_points,
+                                 const uint8_t* v_bytes, const uint64_t* v_off, uint8_t* ok_out, uint8_t* status_out) {
+  if (!ctx) return BLSGPU_E_ARG;
+  if (!args_ok(impl_id, scheme, 1) || (n && (!u_points || !w_points || !v_off || !ok_out || !status_out))) {
+    ctx->err = "blsgpu_signcrypt_valid_batch: bad arguments";
+    return BLSGPU_E_ARG;
+  }
+  if (n == 0) return BLSGPU_OK;
+  CHECK_OFFSETS(v_off, n, "blsgpu_signcrypt_valid_batch");
+  DstParam dst;
+  make_dst(dst, impl_id, scheme, false);
+  CKR(verify_host_common(ctx, impl_id, 1, dst, 1, n, u_points, w_points, v_bytes, v_off, status_out));
+  for (size_t i = 0; i < n; i++) {
+    ok_out[i] = status_out[i] == BLSGPU_ST_OK;
+    if (status_out[i] != BLSGPU_ST_DESERIALIZE) status_out[i] = BLSGPU_ST_OK;  // only parse errors are errors; the rest is `false`
+  }
+  return BLSGPU_OK;
+}
+
+namespace {
+static const uint8_t R_ORDER_BE[32] = {0x73, 0xed, 0xa7, 0x53, 0x29, 0x9d, 0x7d, 0x48, 0x33, 0x39, 0xd8, 0x08, 0x09, 0xa1, 0xd8, 0x05,
+                                       0x53, 0xbd, 0xa4, 0x02, 0xff, 0xfe, 0x5b, 0xfe, 0xff, 0xff, 0xff, 0xff, 0x00, 0x00, 0x00, 0x01};
+
+// prod over the two pairs of every item == 1 ?  (one thread per pair / per item: these checks are low-volume)
+int pair2_check(blsgpu_ctx* ctx, size_t n, const G1Aff* d_g1, const G2Aff* d_g2, uint8_t* d_ok) {
+  Fp12* d_F = ctx->arena.take<Fp12>(2 * n);
+  uint64_t* d_off = ctx->arena.take<uint64_t>(n + 1);
+  LAUNCH(k_pair_offsets, blocks_for(n + 1), TPB, n, d_off);
+  LAUNCH(k_miller_pairs, blocks_for(2 * n), TPB, 2 * n, d_g1, d_g2, d_F);
+  LAUNCH(k_set_final_is_one, blocks_for(n, 64), 64, n, (const uint64_t*)d_off, (const Fp12*)d_F, d_ok);
+  return BLSGPU_OK;
+}
+
+template <int IMPL>
+int pok_verify_impl(blsgpu_ctx* ctx, int scheme, size_t n, const uint8_t* commitments, const uint8_t* proofs, const uint8_t* pks,
+                    const uint8_t* ys, const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out) {
+  typedef typename ImplT<IMPL>::PkAff PkA;
+  typedef typename ImplT<IMPL>::SigAff SigA;
+  typedef typename PtInfo<SigA>::Jac SigJ;
+  const size_t Lp = PtInfo<PkA>::LEN, Ls = PtInfo<SigA>::LEN, msg_bytes = (size_t)msg_off[n];
+  std::vector<uint8_t> yflag(n);
+  for (size_t i = 0; i < n; i++) {
+    const uint8_t* y = ys + 32 * i;
+    bool zero = true;
+    for (int b = 0; b < 32; b++) zero = zero && y[b] == 0;
+    yflag[i] = memcmp(y, R_ORDER_BE, 32) >= 0 ? 1 : zero ? 2 : 0;  // Scalar parsing rejects values >= r
+  }
+  CKR(ensure_arena(ctx, n * (2 * Ls + Lp + 32 + 4 * sizeof(SigA) + sizeof(PkA) + sizeof(SigJ) + 2 * (sizeof(G1Aff) + sizeof(G2Aff) + sizeof(Fp12)) + 16) +
+                            msg_bytes + (n + 1) * 16 + 40 * 256));
+  uint8_t *d_cmb, *d_prb, *d_pkb, *d_y, *d_yf, *d_msgs;
+  uint64_t* d_moff;
+  CKR(upload(ctx, d_cmb, commitments, n * Ls));
+  CKR(upload(ctx, d_prb, proofs, n * Ls));
+  CKR(upload(ctx, d_pkb, pks, n * Lp));
+  CKR(upload(ctx, d_y, ys, n * 32));
+  CKR(upload(ctx, d_yf, yflag.data(), n));
+  CKR(upload(ctx, d_msgs, msgs, msg_bytes));
+  CKR(upload(ctx, d_moff, msg_off, n + 1));
+  SigA* d_cm = ctx->arena.take<SigA>(n);
+  SigA* d_pr = ctx->arena.take<SigA>(n);
+  SigA* d_a = ctx->arena.take<SigA>(n);
+  PkA* d_pk = ctx->arena.take<PkA>(n);
+  uint8_t* d_st = ctx->arena.take<uint8_t>(4 * n);
+  uint8_t *d_stcm = d_st, *d_stpr = d_st + n, *d_stpk = d_st + 2 * n, *d_status = d_st + 3 * n;
+  uint8_t* d_ok = ctx->arena.take<uint8_t>(n);
+  G1Aff* d_g1 = ctx->arena.take<G1Aff>(2 * n);
+  G2Aff* d_g2 = ctx->arena.take<G2Aff>(2 * n);
+  CKR((decode_points<SigA>(ctx, n, (const uint8_t*)d_cmb, 1, d_cm, d_stcm)));
+  CKR((decode_points<SigA>(ctx, n, (const uint8_t*)d_prb, 1, d_pr, d_stpr)));
+  CKR((decode_points<PkA>(ctx, n, (const uint8_t*)d_pkb, 1, d_pk, d_stpk)));
+  LAUNCH((k_pok_prestatus<PkA, SigA>), blocks_for(n), TPB, n, (const uint8_t*)d_stcm, (const uint8_t*)d_stpr, (const uint8_t*)d_stpk,
+         (const uint8_t*)d_yf, (const SigA*)d_cm, (const SigA*)d_pr, (const PkA*)d_pk, d_status);
+  DstParam dst;
+  make_dst(dst, IMPL, scheme, false);
+  CKR((hash_points<SigA, PkA>(ctx, n, (const uint8_t*)d_msgs, (const uint64_t*)d_moff, 0, (const PkA*)d_pk, (const uint8_t*)d_status, dst, d_a)));
+  LAUNCH((k_pok_pairs<PkA, SigA>), blocks_for(n), TPB, n, (const uint8_t*)d_status, (const SigA*)d_a, (const SigA*)d_cm, (const SigA*)d_pr,
+         (const PkA*)d_pk, (const uint8_t*)d_y, d_g1, d_g2);
+  CKR(pair2_check(ctx, n, d_g1, d_g2, d_ok));
+  LAUNCH(k_pok_finish, blocks_for(n), TPB, n, (const uint8_t*)d_ok, d_status);
+  CK(cudaMemcpyAsync(status_out, d_status, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return BLSGPU_OK;
+}
+
+template <int IMPL>
+int signcrypt_share_impl(blsgpu_ctx* ctx, int scheme, size_t n, const uint8_t* shares, const uint8_t* pks, const uint8_t* us, const uint8_t* ws,
+                         const uint8_t* v_bytes, const uint64_t* v_off, uint8_t* ok_out, uint8_t* status_out) {
+  typedef typename ImplT<IMPL>::PkAff PkA;
+  typedef typename ImplT<IMPL>::SigAff SigA;
+  typedef typename PtInfo<SigA>::Jac SigJ;
+  const size_t Lp = PtInfo<PkA>::LEN, Ls = PtInfo<SigA>::LEN, v_total = (size_t)v_off[n];
+  CKR(ensure_arena(ctx, n * (3 * Lp + Ls + 3 * sizeof(PkA) + 2 * sizeof(SigA) + sizeof(SigJ) + 2 * (sizeof(G1Aff) + sizeof(G2Aff) + sizeof(Fp12)) + 24) +
+                            v_total + (n + 1) * 16 + 40 * 256));
+  uint8_t *d_shb, *d_pkb, *d_ub, *d_wb, *d_v;
+  uint64_t* d_voff;
+  CKR(upload(ctx, d_shb, shares, n * Lp));
+  CKR(upload(ctx, d_pkb, pks, n * Lp));
+  CKR(upload(ctx, d_ub, us, n * Lp));
+  CKR(upload(ctx, d_wb, ws, n * Ls));
+  CKR(upload(ctx, d_v, v_bytes, v_total));
+  CKR(upload(ctx, d_voff, v_off, n + 1));
+  PkA* d_sh = ctx->arena.take<PkA>(n);
+  PkA* d_pk = ctx->arena.take<PkA>(n);
+  PkA* d_u = ctx->arena.take<PkA>(n);
+  SigA* d_w = ctx->arena.take<SigA>(n);
+  SigA* d_wt = ctx->arena.take<SigA>(n);
+  uint8_t* d_st = ctx->arena.take<uint8_t>(6 * n);
+  uint8_t *d_s0 = d_st, *d_s1 = d_st + n, *d_s2 = d_st + 2 * n, *d_s3 = d_st + 3 * n, *d_flag = d_st + 4 * n, *d_ok = d_st + 5 * n;
+  G1Aff* d_g1 = ctx->arena.take<G1Aff>(2 * n);
+  G2Aff* d_g2 = ctx->arena.take<G2Aff>(2 * n);
+  CKR((decode_points<PkA>(ctx, n, (const uint8_t*)d_shb, 1, d_sh, d_s0)));
+  CKR((decode_points<PkA>(ctx, n, (const uint8_t*)d_pkb, 1, d_pk, d_s1)));
+  CKR((decode_points<PkA>(ctx, n, (const uint8_t*)d_ub, 1, d_u, d_s2)));
+  CKR((decode_points<SigA>(ctx, n, (const uint8_t*)d_wb, 1, d_w, d_s3)));
+  std::vector<uint8_t> st(4 * n);
+  CK(cudaMemcpyAsync(st.data(), d_st, 4 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (size_t i = 0; i < n; i++) {
+    uint8_t s = st[i];
+    for (int k = 1; k < 4 && s == BLSGPU_ST_OK; k++) s = st[k * n + i];
+    status_out[i] = s;
+  }
+  CK(cudaMemcpyAsync(d_s0, status_out, n, cudaMemcpyHostToDevice, ctx->stream));  // d_s0 now holds the combined parse status
+  DstParam dst;
+  make_dst(dst, IMPL, scheme, false);
+  // W' = hash_to_point(u.to_bytes() || v): the pk-prefix framing with u in the key's place (compute_w, sign_crypt.rs:151-158)
+  CKR((hash_points<SigA, PkA>(ctx, n, (const uint8_t*)d_v, (const uint64_t*)d_voff, 1, (const PkA*)d_u, (const uint8_t*)d_s0, dst, d_wt)));
+  LAUNCH((k_signcrypt_share_pairs<PkA, SigA>), blocks_for(n), TPB, n, (const uint8_t*)d_s0, (const SigA*)d_wt, (const PkA*)d_sh, (const PkA*)d_pk,
+         (const SigA*)d_w, d_g1, d_g2, d_flag);
+  CKR(pair2_check(ctx, n, d_g1, d_g2, d_ok));
+  LAUNCH(k_and_flags, blocks_for(n), TPB, n, (const uint8_t*)d_flag, d_ok);
+  CK(cudaMemcpyAsync(ok_out, d_ok, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return BLSGPU_OK;
+}
+}  // namespace
+
+int blsgpu_pok_verify_batch(blsgpu_ctx* ctx, int impl_id, int scheme, size_t n, const uint8_t* commitments, const uint8_t* proofs,
+                            const uint8_t* pks, const uint8_t* challenges32, const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out) {
+  if (!ctx) return BLSGPU_E_ARG;
+  if (!args_ok(impl_id, scheme, 1) || (n && (!commitments || !proofs || !pks || !challenges32 || !msg_off || !status_out))) {
+    ctx->err = "blsgpu_pok_verify_batch: bad arguments";
+    return BLSGPU_E_ARG;
+  }
+  if (n == 0) return BLSGPU_OK;
+  CHECK_OFFSETS(msg_off, n, "blsgpu_pok_verify_batch");
+  CKR(set_device(ctx));
+  return impl_id == 2 ? pok_verify_impl<2>(ctx, scheme, n, commitments, proofs, pks, challenges32, msgs, msg_off, status_out)
+                      : pok_verify_impl<1>(ctx, scheme, n, commitments, proofs, pks, challenges32, msgs, msg_off, status_out);
+}
+
+int blsgpu_signcrypt_verify_share_batch(blsgpu_ctx* ctx, int impl_id, int scheme, size_t n, const uint8_t* shares, const uint8_t* pk_shares,
+                                        const uint8_t* u_points, const uint8_t* w_points, const uint8_t* v_bytes, const uint64_t* v_off,
+                                        uint8_t* ok_out, uint8_t* status_out) {
+  if (!ctx) return BLSGPU_E_ARG;
+  if (!args_ok(impl_id, scheme, 1) || (n && (!shares || !pk_shares || !u_points || !w_points || !v_off || !ok_out || !status_out))) {
+    ctx->err = "blsgpu_signcrypt_verify_share_batch: bad arguments";
+    return BLSGPU_E_ARG;
+  }
+  if (n == 0) return BLSGPU_OK;
+  CHECK_OFFSETS(v_off, n, "blsgpu_signcrypt_verify_share_batch");
+  CKR(set_device(ctx));
+  return impl_id == 2 ? signcrypt_share_impl<2>(ctx, scheme, n, shares, pk_shares, u_points, w_points, v_bytes, v_off, ok_out, status_out)
+                      : signcrypt_share_impl<1>(ctx, scheme, n, shares, pk_shares, u_points, w_points, v_bytes, v_off, ok_out, status_out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Wire front end on ragged records: length rules, tags and the Legacy / Modern header validation
+// happen here, so callers hand over network buffers as they arrived.
+int blsgpu_verify_batch_records(blsgpu_ctx* ctx, int impl_id, int format, int scheme_or_tagged, size_t n, const uint8_t* pk_bytes,
+                                const uint64_t* pk_off, const uint8_t* sig_bytes, const uint64_t* sig_off, const uint8_t* msgs,
+                                const uint64_t* msg_off, uint8_t* status_out) {
+  if (!ctx) return BLSGPU_E_ARG;
+  const bool tagged = scheme_or_tagged < 0;
+  if ((impl_id != 1 && impl_id != 2) || (format != 0 && format != 1) || scheme_or_tagged > 2 ||
+      (n && (!pk_off || !sig_off || !msg_off || !status_out))) {
+    ctx->err = "blsgpu_verify_batch_records: bad arguments";
+    return BLSGPU_E_ARG;
+  }
+  if (n == 0) return BLSGPU_OK;
+  CHECK_OFFSETS(pk_off, n, "blsgpu_verify_batch_records");
+  CHECK_OFFSETS(sig_off, n, "blsgpu_verify_batch_records");
+  CHECK_OFFSETS(msg_off, n, "blsgpu_verify_batch_records");
+  const size_t pk_len = impl_id == 2 ? 48 : 96, sig_len = impl_id == 2 ? 96 : 48;
+  // InvalidLength (public_key.rs:159-164, signature.rs:236-241) and the serde_bare tag (signature.rs:120-126) per record;
+  // well-formed records are regrouped by scheme and go through blsgpu_verify_batch in `format`
+  std::vector<int8_t> scheme_of(n, -1);
+  for (size_t i = 0; i < n; i++) {
+    const size_t pl = (size_t)(pk_off[i + 1] - pk_off[i]), sl = (size_t)(sig_off[i + 1] - sig_off[i]);
+    status_out[i] = BLSGPU_ST_OK;
+    if (pl != pk_len) {
+      status_out[i] = BLSGPU_ST_INVALID_LENGTH;
+    } else if (tagged) {
+      // serde_bare: a short or long buffer and an unknown tag are both `InvalidInputs(serde error)`
+      if (sl != sig_len + 1 || sig_bytes[sig_off[i]] > 2) status_out[i] = BLSGPU_ST_DESERIALIZE;
+      else scheme_of[i] = (int8_t)sig_bytes[sig_off[i]];
+    } else if (sl != sig_len) {
+      status_out[i] = BLSGPU_ST_INVALID_LENGTH;
+    } else {
+      scheme_of[i] = (int8_t)scheme_or_tagged;
+    }
+  }
+  for (int scheme = 0; scheme < 3; scheme++) {
+    std::vector<size_t> idx;
+    for (size_t i = 0; i < n; i++)
+      if (scheme_of[i] == scheme) idx.push_back(i);
+    if (idx.empty()) continue;
+    std::vector<uint8_t> p(idx.size() * pk_len), g(idx.size() * sig_len), m, st(idx.size());
+    std::vector<uint64_t> off(idx.size() + 1, 0);
+    for (size_t k = 0; k < idx.size(); k++) {
+      const size_t i = idx[k];
+      memcpy(&p[k * pk_len], pk_bytes + pk_off[i], pk_len);
+      memcpy(&g[k * sig_len], sig_bytes + sig_off[i] + (tagged ? 1 : 0), sig_len);
+      if (msg_off[i + 1] > msg_off[i]) m.insert(m.end(), msgs + msg_off[i], msgs + msg_off[i + 1]);
+      off[k + 1] = m.size();
+    }
+    // the tagged (serde) form always carries the IETF encoding; raw records are in the caller's format
+    CKR(blsgpu_verify_batch(ctx, impl_id, scheme, tagged ? 1 : format, idx.size(), p.data(), g.data(), m.empty() ? p.data() : m.data(), off.data(),
+                            st.data()));
+    for (size_t k = 0; k < idx.size(); k++) status_out[idx[k]] = st[k];
+  }
+  return BLSGPU_OK;
+}
+
 int blsgpu_plan_msm(size_t n, int scalar_bits, int* window_bits_out, int* windows_out, int* top_window_bits_out) {
   if (!window_bits_out || !windows_out || !top_window_bits_out || (scalar_bits != 64 && scalar_bits != 128)) return BLSGPU_E_ARG;
   const int c = msm_window_bits(n, scalar_bits), nwin = (scalar_bits + c - 1) / c;

@@ -426,7 +426,12 @@ enum : uint8_t {
   ST_INVALID_COEFFICIENT = 7,
   ST_DUPLICATE_MESSAGES = 8,
   ST_SCHEME = 9,
-  ST_MISMATCHED_LENGTHS = 10
+  ST_MISMATCHED_LENGTHS = 10,
+  ST_VSSS = 11,
+  ST_INVALID_PROOF = 12,
+  ST_COMMITMENT_IDENTITY = 13,
+  ST_PROOF_IDENTITY = 14,
+  ST_ZERO_CHALLENGE = 15
 };
 
 BLS_HD bool bytes_all_zero(const uint8_t* b, int n) {

@@ -997,6 +997,113 @@ __global__ void k_final_is_one(const Fp12* f, uint8_t* ok) {
   ok[0] = fp12_is_one(e) ? 1 : 0;
 }
 
+// ---- the reference's other public 2-pairing checks ---------------------------------------------
+// Every item becomes two (G1, G2) pairs at 2i, 2i + 1; k_miller_pairs + k_set_final_is_one decide prod e(.,.) == 1 per item.
+__device__ __forceinline__ void put_pair(G1Aff* g1, G2Aff* g2, size_t idx, const G1Aff& a, const G2Aff& b) {
+  g1[idx] = a;
+  g2[idx] = b;
+}
+__device__ __forceinline__ void put_pair(G1Aff* g1, G2Aff* g2, size_t idx, const G2Aff& b, const G1Aff& a) { put_pair(g1, g2, idx, a, b); }
+// 32 big-endian bytes -> 8 little-endian words
+__device__ __forceinline__ void scalar_words_be32(uint32_t k[8], const uint8_t* b) {
+  for (int w = 0; w < 8; w++) {
+    const uint8_t* q = b + 28 - 4 * w;
+    k[w] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
+  }
+}
+// ProofOfKnowledge::verify (reference src/traits/sig_proof.rs:102-142): status before the pairing, in the reference's order.
+// yflag: 0 fine, 1 not a canonical scalar (parse error), 2 zero
+template <class PkA, class SigA>
+__global__ void k_pok_prestatus(size_t n, const uint8_t* st_cm, const uint8_t* st_pr, const uint8_t* st_pk, const uint8_t* yflag,
+                                const SigA* cm, const SigA* pr, const PkA* pk, uint8_t* out) {
+  size_t i = BLS_TID();
+  if (i >= n) return;
+  uint8_t s = st_cm[i];
+  if (s == ST_OK) s = st_pr[i];
+  if (s == ST_OK) s = st_pk[i];
+  if (s == ST_OK && yflag[i] == 1) s = ST_DESERIALIZE;
+  if (s == ST_OK && cm[i].inf) s = ST_COMMITMENT_IDENTITY;
+  if (s == ST_OK && pr[i].inf) s = ST_PROOF_IDENTITY;
+  if (s == ST_OK && pk[i].inf) s = ST_PK_IDENTITY;
+  if (s == ST_OK && yflag[i] == 2) s = ST_ZERO_CHALLENGE;
+  out[i] = s;
+}
+// pairs of item i: (proof, g), (commitment + [y] a, pk)   with a = hash_to_point(msg)   (sig_proof.rs:130-136)
+template <class PkA, class SigA>
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_pok_pairs(size_t n, const uint8_t* __restrict__ pre, const SigA* __restrict__ a,
+                                                   const SigA* __restrict__ cm, const SigA* __restrict__ pr, const PkA* __restrict__ pk,
+                                                   const uint8_t* __restrict__ y_be32, G1Aff* __restrict__ g1, G2Aff* __restrict__ g2) {
+  size_t i = BLS_TID();
+  if (i >= n) return;
+  PkA gen, key;
+  SigA proof, target;
+  if (pre[i] != ST_OK) {  // identity pairs: the product is 1, the status already says why the item failed
+    pt_set_inf(gen);
+    pt_set_inf(key);
+    pt_set_inf(proof);
+    pt_set_inf(target);
+  } else {
+    uint32_t k[8];
+    scalar_words_be32(k, y_be32 + 32 * i);
+    SigA h = a[i], c = cm[i];
+    typename PtInfo<SigA>::Jac t;
+    jac_mul_aff(t, h, k, 8);
+    jac_add_mixed(t, t, c);
+    jac_to_aff(target, t);
+    pt_generator(gen);
+    key = pk[i];
+    proof = pr[i];
+  }
+  put_pair(g1, g2, 2 * i, gen, proof);
+  put_pair(g1, g2, 2 * i + 1, key, target);
+}
+// BlsSignCrypt::verify_share (reference src/traits/sign_crypt.rs:192-207): pairs (-W', share), (w, pk); flag = 0 if share, pk
+// or w is the identity (the check is then false without a pairing)
+template <class PkA, class SigA>
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_signcrypt_share_pairs(size_t n, const uint8_t* __restrict__ pre, const SigA* __restrict__ wt,
+                                                               const PkA* __restrict__ share, const PkA* __restrict__ pk,
+                                                               const SigA* __restrict__ w, G1Aff* __restrict__ g1, G2Aff* __restrict__ g2,
+                                                               uint8_t* __restrict__ flag) {
+  size_t i = BLS_TID();
+  if (i >= n) return;
+  PkA s, k;
+  SigA h, ww;
+  uint8_t f = 0;
+  if (pre[i] == ST_OK) {
+    s = share[i];
+    k = pk[i];
+    ww = w[i];
+    h = wt[i];
+    f = !(s.inf || k.inf || ww.inf);
+  }
+  if (!f) {
+    pt_set_inf(s);
+    pt_set_inf(k);
+    pt_set_inf(h);
+    pt_set_inf(ww);
+  } else {
+    aff_neg(h, h);
+  }
+  put_pair(g1, g2, 2 * i, s, h);
+  put_pair(g1, g2, 2 * i + 1, k, ww);
+  flag[i] = f;
+}
+__global__ void k_pair_offsets(size_t q, uint64_t* off) {  // off[j] = 2 j, j = 0..q
+  size_t j = BLS_TID();
+  if (j <= q) off[j] = 2 * j;
+}
+// status / ok from the pairing results: PoK: ok ? OK : INVALID_PROOF (keeping earlier statuses)
+__global__ void k_pok_finish(size_t n, const uint8_t* ok, uint8_t* status) {
+  size_t i = BLS_TID();
+  if (i >= n) return;
+  if (status[i] == ST_OK && !ok[i]) status[i] = ST_INVALID_PROOF;
+}
+__global__ void k_and_flags(size_t n, const uint8_t* flag, uint8_t* ok) {
+  size_t i = BLS_TID();
+  if (i >= n) return;
+  ok[i] = ok[i] && flag[i];
+}
+
 // synthetic data: pk = [k]G, sig = [k]H(frame(msg))
 template <class PkA, class SigA>
 __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_testdata_sign(size_t n, const uint8_t* scalars, const uint8_t* msgs, const uint64_t* msg_off,

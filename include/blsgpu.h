@@ -49,6 +49,10 @@ extern "C" {
 #define BLSGPU_ST_SCHEME 9              /* InvalidSignatureScheme / fewer than 2 signatures (binding side) src/aggregate_signature.rs:127-133 */
 #define BLSGPU_ST_MISMATCHED_LENGTHS 10 /* InvalidInputs("Mismatched array lengths")  src/secure_aggregation.rs:125-129 */
 #define BLSGPU_ST_VSSS 11               /* BlsError::VsssError (fewer than 2 shares, zero or duplicate identifier)  src/error.rs:24-26,60-64 */
+#define BLSGPU_ST_INVALID_PROOF 12      /* BlsError::InvalidProof                src/traits/sig_proof.rs:140 */
+#define BLSGPU_ST_COMMITMENT_IDENTITY 13 /* InvalidInputs("commitment is the identity point")  sig_proof.rs:110-114 */
+#define BLSGPU_ST_PROOF_IDENTITY 14     /* InvalidInputs("proof is the identity point")  sig_proof.rs:115-119 */
+#define BLSGPU_ST_ZERO_CHALLENGE 15     /* InvalidInputs("y is the zero")        sig_proof.rs:125-127 */
 
 typedef struct blsgpu_ctx blsgpu_ctx;
 
@@ -175,6 +179,42 @@ int blsgpu_verify_batch_wire(blsgpu_ctx* ctx, int impl_id, size_t n, const uint8
  *   ok_out[q]     : 1 / 0;  status_out[q]: BLSGPU_ST_OK or BLSGPU_ST_DESERIALIZE (some point of the set undecodable) */
 int blsgpu_pairing_check_batch(blsgpu_ctx* ctx, size_t q, const uint64_t* pair_off, const uint8_t* g1_points,
                                const uint8_t* g2_points, uint8_t* ok_out, uint8_t* status_out);
+
+/* ---- the reference's other public 2-pairing checks, pairs assembled on the device ---------------
+ * SignCryptCiphertext::is_valid (reference src/sign_crypt_ciphertext.rs:86-101 -> BlsSignCrypt::valid, src/traits/sign_crypt.rs:69-77):
+ * W' = hash_to_point(U.to_bytes() || V, DST(scheme)); valid iff pairing([(W, -g), (W', U)]) is the identity and U, W are not.
+ * U: public-key group (48 | 96 B), W: signature group (96 | 48 B), IETF compressed; v_bytes/v_off: the ciphertext bodies.
+ *   ok_out[i] 1 | 0;  status_out[i]: BLSGPU_ST_OK or BLSGPU_ST_DESERIALIZE (an undecodable point: the reference fails at parse time) */
+int blsgpu_signcrypt_valid_batch(blsgpu_ctx* ctx, int impl_id, int scheme, size_t n, const uint8_t* u_points, const uint8_t* w_points,
+                                 const uint8_t* v_bytes, const uint64_t* v_off, uint8_t* ok_out, uint8_t* status_out);
+/* SignDecryptionShare::verify (reference src/sign_decryption_share.rs:45-61 -> BlsSignCrypt::verify_share,
+ * src/traits/sign_crypt.rs:192-207): ok iff share, pk_share and W are not the identity and
+ * pairing([(-W', share), (W, pk_share)]) is the identity.  The reference always passes the Basic DST here (scheme = 0).
+ *   shares, pk_shares, u_points: public-key group; w_points: signature group */
+int blsgpu_signcrypt_verify_share_batch(blsgpu_ctx* ctx, int impl_id, int scheme, size_t n, const uint8_t* shares, const uint8_t* pk_shares,
+                                        const uint8_t* u_points, const uint8_t* w_points, const uint8_t* v_bytes, const uint64_t* v_off,
+                                        uint8_t* ok_out, uint8_t* status_out);
+/* ProofOfKnowledge::verify (reference src/proof_of_knowledge.rs:132-165 -> BlsSignatureProof::verify,
+ * src/traits/sig_proof.rs:102-142): a = hash_to_point(msg, DST(scheme)); OK iff pairing([(proof, g), (commitment + a*y, pk)])
+ * is the identity.  commitments, proofs: signature group; pks: public-key group; challenges32: n x 32-byte big-endian
+ * scalars y (ProofCommitmentChallenge; the timestamp variant's y = compute_y(u, t) is computed by the caller,
+ * sig_proof.rs:37-46).  status_out[i]: OK, DESERIALIZE (a point, or y >= r), COMMITMENT_IDENTITY, PROOF_IDENTITY, PK_IDENTITY,
+ * ZERO_CHALLENGE (checked in that order), INVALID_PROOF. */
+int blsgpu_pok_verify_batch(blsgpu_ctx* ctx, int impl_id, int scheme, size_t n, const uint8_t* commitments, const uint8_t* proofs,
+                            const uint8_t* pks, const uint8_t* challenges32, const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out);
+
+/* Wire front end on RAGGED records: network buffers as they arrived, each record delimited by
+ * offsets; the length rules, the serde tag and the Legacy / Modern header validation are applied per record:
+ *   public keys   : PublicKey::from_bytes_with_mode (reference src/public_key.rs:146-179): 48 | 96 bytes in `format`, else
+ *                   BLSGPU_ST_INVALID_LENGTH
+ *   signatures    : scheme_or_tagged >= 0: raw bytes in `format` under that scheme = Signature::from_bytes_with_mode
+ *                   (src/signature.rs:209-253), wrong length -> INVALID_LENGTH;
+ *                   scheme_or_tagged < 0: the serde_bare form, tag byte + IETF point (src/signature.rs:112-126,285-286), wrong
+ *                   length or unknown tag -> BLSGPU_ST_DESERIALIZE
+ * Everything else is blsgpu_verify_batch's status (header rules of src/impls/legacy.rs:39-82 included). */
+int blsgpu_verify_batch_records(blsgpu_ctx* ctx, int impl_id, int format, int scheme_or_tagged, size_t n, const uint8_t* pk_bytes,
+                                const uint64_t* pk_off, const uint8_t* sig_bytes, const uint64_t* sig_off, const uint8_t* msgs,
+                                const uint64_t* msg_off, uint8_t* status_out);
 
 /* Threshold-share combination: Signature::from_shares / PublicKey::from_shares
  * (reference src/signature.rs:151-165, src/public_key.rs, src/traits/sig_core.rs:92-105 -> vsss-rs `combine`):

@@ -879,3 +879,82 @@ def combine_shares(group: int, shares: Sequence[bytes]) -> Tuple[int, bytes]:
                 lam = lam * xj % R * pow((xj - xi) % R, -1, R) % R
         acc = add(acc, mul(v, lam))
     return OK, ser(acc, MODERN)
+
+
+# ----------------------------------------------------------------------------------------------
+# the other public 2-pairing checks
+# ----------------------------------------------------------------------------------------------
+ERR_INVALID_PROOF = 12          # BlsError::InvalidProof (sig_proof.rs:140) / InvalidDecryptionShare (sign_decryption_share.rs:58)
+ERR_COMMITMENT_IDENTITY = 13    # InvalidInputs("commitment is the identity point")   sig_proof.rs:110-114
+ERR_PROOF_IDENTITY = 14         # InvalidInputs("proof is the identity point")        sig_proof.rs:115-119
+ERR_ZERO_CHALLENGE = 15         # InvalidInputs("y is the zero")                      sig_proof.rs:125-127
+
+
+def signcrypt_valid(impl: int, scheme: int, u_bytes: bytes, v: bytes, w_bytes: bytes) -> Tuple[int, bool]:
+    """SignCryptCiphertext::is_valid (sign_crypt_ciphertext.rs:86-101) -> BlsSignCrypt::valid (sign_crypt.rs:69-77):
+    W' = hash_to_point(U.to_bytes() || V, DST(scheme)) (compute_w, :151-158); valid iff
+    pairing([(W, -g), (W', U)]) is the identity and neither U nor W is.  U lives in the public-key group, W in the signature
+    group.  Returns (parse status, valid)."""
+    C = IMPLS[impl]
+    u, st = _decode(C.pk_deser, u_bytes, MODERN)
+    if st != OK:
+        return st, False
+    w, st = _decode(C.sig_deser, w_bytes, MODERN)
+    if st != OK:
+        return st, False
+    if u is None or w is None:
+        return OK, False
+    w_tick = C.hash(C.pk_ser(u, MODERN) + bytes(v), sig_dst(impl, scheme))
+    return OK, pairing_product_is_one([C.pair(w, C.pk_neg(C.pk_gen)), C.pair(w_tick, u)])
+
+
+def signcrypt_verify_share(impl: int, scheme: int, share_bytes: bytes, pk_bytes: bytes, u_bytes: bytes, v: bytes,
+                           w_bytes: bytes) -> Tuple[int, bool]:
+    """BlsSignCrypt::verify_share (sign_crypt.rs:192-207) behind SignDecryptionShare::verify (sign_decryption_share.rs:45-61,
+    which always passes the Basic DST): hash = -compute_w(u, v, dst); ok iff share, pk, w are not the identity and
+    pairing([(hash, share), (w, pk)]) is the identity.  share, pk, u: public-key group; w: signature group."""
+    C = IMPLS[impl]
+    pts = []
+    for fn, b in ((C.pk_deser, share_bytes), (C.pk_deser, pk_bytes), (C.pk_deser, u_bytes), (C.sig_deser, w_bytes)):
+        p, st = _decode(fn, b, MODERN)
+        if st != OK:
+            return st, False
+        pts.append(p)
+    share, pk, u, w = pts
+    if share is None or pk is None or w is None:
+        return OK, False
+    h = C.hash(C.pk_ser(u, MODERN) + bytes(v), sig_dst(impl, scheme))
+    sig_neg = g2_neg if impl == G2IMPL else g1_neg
+    return OK, pairing_product_is_one([C.pair(sig_neg(h), share), C.pair(w, pk)])
+
+
+def pok_verify(impl: int, scheme: int, commitment_bytes: bytes, proof_bytes: bytes, pk_bytes: bytes, y_be32: bytes,
+               msg: bytes) -> int:
+    """ProofOfKnowledge::verify (proof_of_knowledge.rs:132-165) -> BlsSignatureProof::verify (sig_proof.rs:102-142):
+    reject identity commitment / proof / pk and y = 0 (in that order), a = hash_to_point(msg, DST(scheme)), accept iff
+    pairing([(proof, g), (commitment + a*y, pk)]) is the identity.  commitment, proof: signature group; y: a scalar < r."""
+    C = IMPLS[impl]
+    cm, st = _decode(C.sig_deser, commitment_bytes, MODERN)
+    if st != OK:
+        return st
+    pr, st = _decode(C.sig_deser, proof_bytes, MODERN)
+    if st != OK:
+        return st
+    pk, st = _decode(C.pk_deser, pk_bytes, MODERN)
+    if st != OK:
+        return st
+    y = int.from_bytes(y_be32, "big")
+    if len(y_be32) != 32 or y >= R:
+        return ERR_DESERIALIZE
+    if cm is None:
+        return ERR_COMMITMENT_IDENTITY
+    if pr is None:
+        return ERR_PROOF_IDENTITY
+    if pk is None:
+        return ERR_PK_IDENTITY
+    if y == 0:
+        return ERR_ZERO_CHALLENGE
+    a = C.hash(bytes(msg), sig_dst(impl, scheme))
+    t = C.sig_add(cm, C.sig_mul(a, y))
+    ok = pairing_product_is_one([C.pair(pr, C.pk_gen), C.pair(t, pk)])
+    return OK if ok else ERR_INVALID_PROOF

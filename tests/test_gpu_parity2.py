@@ -313,3 +313,107 @@ def test_bad_offsets_and_chunk_overrides_are_refused_or_clamped(eng, B, monkeypa
         monkeypatch.setenv("BLSGPU_M6_CHUNK", chunk)
         assert eng.verify_batch_packed(2, 0, pks, sigs, data, off).tolist() == [0] * n
     monkeypatch.delenv("BLSGPU_M6_CHUNK")
+
+
+# ---- the other public 2-pairing checks, pairs assembled on the device -------------------------------------
+@pytest.mark.parametrize("impl", [2, 1])
+def test_signcrypt_valid_and_share_checks_against_oracle(eng, B, impl):
+    """blsgpu_signcrypt_valid_batch / blsgpu_signcrypt_verify_share_batch against the oracle's restatement of
+    BlsSignCrypt::valid / verify_share (sign_crypt.rs:69-77,192-207); ciphertexts built as `seal` builds them (:36-61)."""
+    rnd = random.Random(70 + impl)
+    C = O.IMPLS[impl]
+    pl, sl = B.pk_len(impl), B.sig_len(impl)
+    items = []
+    for i in range(4):
+        scheme = i % 3
+        r = rnd.randrange(1, O.R)
+        u = C.pk_mul(C.pk_gen, r)
+        v = bytes(rnd.randrange(256) for _ in range(32 + 5 * i))
+        w = C.sig_mul(C.hash(C.pk_ser(u, O.MODERN) + v, O.sig_dst(impl, scheme)), r)
+        items.append((scheme, C.pk_ser(u, O.MODERN), v, C.sig_ser(w, O.MODERN), r))
+    for scheme in (0, 1, 2):
+        sel = [it for it in items if it[0] == scheme] + [items[0]]          # the last one is valid only under scheme 0
+        cases = [(it[1], it[2], it[3]) for it in sel]
+        cases += [(sel[0][1], sel[0][2] + b"!", sel[0][3]), (ident(pl), sel[0][2], sel[0][3]), (sel[0][1], sel[0][2], ident(sl)),
+                  (bytes(pl), sel[0][2], sel[0][3])]
+        ok, st = eng.signcrypt_valid_batch(impl, scheme, [c[0] for c in cases], [c[2] for c in cases], [c[1] for c in cases])
+        want = [O.signcrypt_valid(impl, scheme, u, v, w) for u, v, w in cases]
+        assert list(zip(st.tolist(), [bool(x) for x in ok])) == want, (impl, scheme)
+    # decryption shares: share = U * sk_i, pk_share = g * sk_i   (create_decryption_share, sign_crypt.rs:166-184)
+    scheme, ub, v, wb, r = items[0]
+    u = C.pk_deser(ub, O.MODERN)
+    sks = [rnd.randrange(1, O.R) for _ in range(2)]
+    sh = [C.pk_ser(C.pk_mul(u, sk), O.MODERN) for sk in sks]
+    pk = [C.pk_ser(C.pk_mul(C.pk_gen, sk), O.MODERN) for sk in sks]
+    cases = [(sh[0], pk[0]), (sh[1], pk[1]), (sh[0], pk[1]), (ident(pl), pk[0]), (sh[0], ident(pl)), (bytes(pl), pk[0])]
+    ok, st = eng.signcrypt_verify_share_batch(impl, 0, [c[0] for c in cases], [c[1] for c in cases], [ub] * 6, [wb] * 6, [v] * 6)
+    want = [O.signcrypt_verify_share(impl, 0, a, b, ub, v, wb) for a, b in cases]
+    assert list(zip(st.tolist(), [bool(x) for x in ok])) == want
+    assert [w[1] for w in want] == [True, True, False, False, False, False] and want[5][0] == 4
+    ok, st = eng.signcrypt_verify_share_batch(impl, 0, [sh[0]], [pk[0]], [ub], [ident(sl)], [v])
+    assert (int(st[0]), bool(ok[0])) == O.signcrypt_verify_share(impl, 0, sh[0], pk[0], ub, v, ident(sl)) == (0, False)
+
+
+@pytest.mark.parametrize("impl", [2, 1])
+def test_pok_verify_batch_against_oracle(eng, B, impl):
+    """blsgpu_pok_verify_batch against the oracle's restatement of BlsSignatureProof::verify (sig_proof.rs:102-142); proofs
+    built as generate_proof builds them (:49-74): U = a*x, V = -(sig*(x+y))."""
+    rnd = random.Random(80 + impl)
+    C = O.IMPLS[impl]
+    pl, sl = B.pk_len(impl), B.sig_len(impl)
+    cases = []
+    for i in range(3):
+        scheme = i % 3
+        sk, x, y = (rnd.randrange(1, O.R) for _ in range(3))
+        msg = b"pok message %d" % i
+        a = C.hash(msg, O.sig_dst(impl, scheme))
+        U = C.sig_ser(C.sig_mul(a, x), O.MODERN)
+        V = C.sig_ser(C.sig_mul(a, (-(sk * (x + y))) % O.R), O.MODERN)
+        cases.append((scheme, U, V, C.pk_ser(C.pk_mul(C.pk_gen, sk), O.MODERN), y.to_bytes(32, "big"), msg))
+    s0 = cases[0]
+    extra = [
+        (0, s0[1], s0[2], s0[3], (int.from_bytes(s0[4], "big") + 1).to_bytes(32, "big"), s0[5]),   # wrong challenge
+        (0, s0[1], s0[2], s0[3], s0[4], s0[5] + b"?"),                                               # wrong message
+        (0, ident(sl), s0[2], s0[3], s0[4], s0[5]), (0, s0[1], ident(sl), s0[3], s0[4], s0[5]), (0, s0[1], s0[2], ident(pl), s0[4], s0[5]),
+        (0, s0[1], s0[2], s0[3], bytes(32), s0[5]), (0, s0[1], s0[2], s0[3], O.R.to_bytes(32, "big"), s0[5]),
+        (0, ident(sl), ident(sl), ident(pl), bytes(32), s0[5]),                                      # first check wins
+        (0, bytes(sl), s0[2], s0[3], s0[4], s0[5]),
+    ]
+    for scheme in (0, 1, 2):
+        sel = [c for c in cases if c[0] == scheme] + (extra if scheme == 0 else [cases[0]])
+        got = eng.pok_verify_batch(impl, scheme, [c[1] for c in sel], [c[2] for c in sel], [c[3] for c in sel], [c[4] for c in sel],
+                                   [c[5] for c in sel])
+        want = [O.pok_verify(impl, scheme, c[1], c[2], c[3], c[4], c[5]) for c in sel]
+        assert got.tolist() == want, (impl, scheme)
+        if scheme == 0:
+            assert want == [0, 12, 12, 13, 14, 3, 15, 4, 13, 4]
+
+
+@pytest.mark.parametrize("impl", [2, 1])
+def test_verify_batch_records_lengths_tags_and_formats(eng, B, impl):
+    """blsgpu_verify_batch_records: ragged network records.  Length rules (public_key.rs:159-164, signature.rs:236-241),
+    serde tags (signature.rs:112-126) and the Legacy / Modern header rules (legacy.rs:39-82), each against the oracle."""
+    rnd = random.Random(90 + impl)
+    C = O.IMPLS[impl]
+    pl, sl = B.pk_len(impl), B.sig_len(impl)
+    sks = [rnd.randrange(1, O.R) for _ in range(3)]
+    msgs = [b"rec-%d" % i for i in range(3)]
+    pk_pts = [O.sk_to_pk(impl, sk) for sk in sks]
+    for fmt in (O.MODERN, O.LEGACY):
+        pk = [C.pk_ser(p, fmt) for p in pk_pts]
+        sg = [C.sig_ser(O.sign(impl, 0, sk, m), fmt) for sk, m in zip(sks, msgs)]
+        other_pk = C.pk_ser(pk_pts[1], 1 - fmt)
+        recs = [(pk[0], sg[0], msgs[0]), (pk[1], sg[1], msgs[1]), (pk[2][:-1], sg[2], msgs[2]), (pk[2], sg[2] + b"\0", msgs[2]),
+                (b"", sg[0], msgs[0]), (pk[0], b"", msgs[0]), (other_pk, sg[1], msgs[1]), (pk[2], sg[2], b"")]
+        got = eng.verify_batch_records(impl, fmt, 0, [r[0] for r in recs], [r[1] for r in recs], [r[2] for r in recs])
+        want = [6 if len(p) != pl or len(s) != sl else O.verify(impl, 0, fmt, p, s, m) for p, s, m in recs]
+        assert got.tolist() == want, (impl, fmt)
+        assert want[:6] == [0, 0, 6, 6, 6, 6] and want[6] != 0 and want[7] == 1
+    # the serde_bare form: tag + IETF point; schemes mixed; short / long / unknown tag are serde errors
+    pk = [C.pk_ser(p, O.MODERN) for p in pk_pts]
+    tagged = [bytes([sch]) + C.sig_ser(O.sign(impl, sch, sk, m), O.MODERN) for sch, sk, m in zip((0, 1, 2), sks, msgs)]
+    recs = list(zip(pk, tagged, msgs)) + [(pk[0], tagged[0][:-1], msgs[0]), (pk[0], bytes([3]) + tagged[0][1:], msgs[0]),
+                                          (pk[0], bytes([1]) + tagged[0][1:], msgs[0]), (pk[0][:5], tagged[0], msgs[0])]
+    got = eng.verify_batch_records(impl, O.MODERN, -1, [r[0] for r in recs], [r[1] for r in recs], [r[2] for r in recs])
+    assert got.tolist() == [0, 0, 0, 4, 4, O.verify(impl, 1, O.MODERN, pk[0], tagged[0][1:], msgs[0]), 6]
+    assert got[5] == 1
