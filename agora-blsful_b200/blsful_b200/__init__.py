@@ -110,6 +110,9 @@ def load_library() -> ctypes.CDLL:
         "blsgpu_ctx_set_stream": (c.c_int, [vp, vp]),
         "blsgpu_verify_batch": (c.c_int, [vp, c.c_int, c.c_int, c.c_int, c.c_size_t, u8p, u8p, u8p, u64p, u8p]),
         "blsgpu_verify_batch_dev": (c.c_int, [vp, c.c_int, c.c_int, c.c_int, c.c_size_t, u8p, u8p, u8p, u64p, u8p]),
+        "blsgpu_miller_partial": (c.c_int, [vp, c.c_int, c.c_int, c.c_int, c.c_size_t, u8p, u8p, u8p, u64p, u8p, u8p]),
+        "blsgpu_final_exp_is_one": (c.c_int, [vp, c.c_int, c.c_size_t, u8p, u8p, c.POINTER(c.c_int)]),
+        "blsgpu_partial_finish": (c.c_int, [vp, c.c_int, u8p]),
         "blsgpu_pop_verify_batch": (c.c_int, [vp, c.c_int, c.c_int, c.c_size_t, u8p, u8p, u8p]),
         "blsgpu_aggregate_verify": (c.c_int, [vp, c.c_int, c.c_int, c.c_int, c.c_size_t, u8p, u8p, u64p, u8p, u8p, i64p]),
         "blsgpu_sum_points": (c.c_int, [vp, c.c_int, c.c_int, c.c_size_t, u8p, u8p, u8p, i64p]),
@@ -145,6 +148,7 @@ EXPORTED_SYMBOLS = [
     "blsgpu_ctx_create", "blsgpu_ctx_destroy", "blsgpu_last_error", "blsgpu_ctx_set_rlc_salt", "blsgpu_ctx_set_rlc_bits",
     "blsgpu_ctx_set_stream",
     "blsgpu_verify_batch",
+    "blsgpu_miller_partial", "blsgpu_final_exp_is_one", "blsgpu_partial_finish",
     "blsgpu_verify_batch_dev", "blsgpu_pop_verify_batch", "blsgpu_aggregate_verify", "blsgpu_sum_points",
     "blsgpu_verify_secure_batch", "blsgpu_aggregate_secure_batch", "blsgpu_hash_to_curve_batch", "blsgpu_recode_points",
     "blsgpu_fp_mul_batch", "blsgpu_pairing_product_is_one", "blsgpu_testdata_sign", "blsgpu_imad_peak",
@@ -190,6 +194,22 @@ def verify_batch_sharded(verify_slice, n: int, rank: int, world: int, gather=Non
     for plo, part in parts:
         out[plo:plo + part.size] = part
     return out
+
+
+def verify_batch_folded(eng, impl_id: int, scheme: int, pk: np.ndarray, sg: np.ndarray, data: np.ndarray, off: np.ndarray, rank: int,
+                        world: int, all_gather, fmt: int = 1) -> Tuple[int, np.ndarray]:
+    """ONE batch over `world` processes (one GPU each), strong scaling: this rank folds its contiguous slice
+    into one partial product of Miller values and one partial sum (blsgpu_miller_partial), the partial results (672 bytes per
+    rank) are exchanged with `all_gather` (a callable: object -> list of every rank's object, e.g. built on
+    torch.distributed.all_gather_object), every rank runs the single Miller loop + final exponentiation of the whole batch
+    (blsgpu_final_exp_is_one, redundantly: no broadcast needed) and finishes its slice.  Returns (lo, statuses of [lo, hi))."""
+    n = off.size - 1
+    lo, hi = shard_range(n, rank, world)
+    pl, sl = pk_len(impl_id), sig_len(impl_id)
+    part = eng.miller_partial(impl_id, scheme, pk[pl * lo:pl * hi], sg[sl * lo:sl * hi], data, off[lo:hi + 1], fmt)
+    parts = all_gather(part) if world > 1 else [part]
+    ok = eng.final_exp_is_one(impl_id, [p[0] for p in parts], [p[1] for p in parts])
+    return lo, eng.partial_finish(hi - lo, ok)
 
 
 def pack_messages(msgs: Sequence[bytes]) -> Tuple[np.ndarray, np.ndarray]:
@@ -281,6 +301,30 @@ class Engine:
                          fmt: int = SerializationFormat.Modern) -> None:
         rc = self._lib.blsgpu_verify_batch_dev(self._ctx, impl_id, scheme, fmt, n, pk_ptr, sig_ptr, msg_ptr, off_ptr, status_ptr)
         self._check(rc, "blsgpu_verify_batch_dev")
+
+    # ---- one batch over several GPUs / processes: slice-local partial results, fold, finish ------------
+    def miller_partial(self, impl_id, scheme, pk: np.ndarray, sg: np.ndarray, data: np.ndarray, off: np.ndarray,
+                       fmt: int = SerializationFormat.Modern) -> Tuple[bytes, bytes]:
+        """This slice's (product of Miller values as 576 bytes, sum of r_i sig_i as a compressed point)."""
+        n = off.size - 1
+        gt = np.zeros(576, dtype=np.uint8)
+        sm = np.zeros(sig_len(impl_id), dtype=np.uint8)
+        rc = self._lib.blsgpu_miller_partial(self._ctx, impl_id, scheme, fmt, n, _ptr(pk), _ptr(sg), _ptr(data), _ptr(off), _ptr(gt), _ptr(sm))
+        self._check(rc, "blsgpu_miller_partial")
+        return gt.tobytes(), sm.tobytes()
+
+    def final_exp_is_one(self, impl_id, partial_gts: Sequence[bytes], partial_sums: Sequence[bytes]) -> bool:
+        k = len(partial_gts)
+        gts = np.frombuffer(b"".join(partial_gts), dtype=np.uint8)
+        sums = np.frombuffer(b"".join(partial_sums), dtype=np.uint8)
+        res = ctypes.c_int(0)
+        self._check(self._lib.blsgpu_final_exp_is_one(self._ctx, impl_id, k, _ptr(gts), _ptr(sums), ctypes.byref(res)), "blsgpu_final_exp_is_one")
+        return bool(res.value)
+
+    def partial_finish(self, n: int, batch_ok: bool) -> np.ndarray:
+        status = np.zeros(n, dtype=np.uint8)
+        self._check(self._lib.blsgpu_partial_finish(self._ctx, 1 if batch_ok else 0, _ptr(status)), "blsgpu_partial_finish")
+        return status
 
     def pop_verify_batch(self, impl_id: int, pks, sigs, fmt: int = SerializationFormat.Modern) -> np.ndarray:
         pk = _pack_points(pks, pk_len(impl_id), "public key")
@@ -376,6 +420,26 @@ class Engine:
                                                   _ptr(off), _ptr(status))
         self._check(rc, "blsgpu_verify_secure_batch")
         return status
+
+    def aggregate_secure_batch_packed(self, impl_id: int, koff: np.ndarray, pk: np.ndarray, sg: np.ndarray,
+                                      fmt: int = SerializationFormat.Modern) -> Tuple[np.ndarray, np.ndarray]:
+        """Flat-buffer form: koff[q + 1] key offsets, pk all keys, sg one signature per key; returns (status[q], q signatures flat)."""
+        q = koff.size - 1
+        out = np.zeros(q * sig_len(impl_id), dtype=np.uint8)
+        status = np.empty(q, dtype=np.uint8)
+        rc = self._lib.blsgpu_aggregate_secure_batch(self._ctx, impl_id, fmt, q, _ptr(koff), _ptr(pk), _ptr(sg), _ptr(out), _ptr(status))
+        self._check(rc, "blsgpu_aggregate_secure_batch")
+        return status, out
+
+    def recode_points_packed(self, group: int, pts: np.ndarray, fmt_in: int, fmt_out: int) -> np.ndarray:
+        L = 48 if group == 1 else 96
+        n = pts.size // L
+        out = np.zeros(n * L, dtype=np.uint8)
+        status = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.blsgpu_recode_points(self._ctx, group, fmt_in, fmt_out, n, _ptr(pts), _ptr(out), _ptr(status)), "blsgpu_recode_points")
+        if n and int(status.max()) != 0:
+            raise BlsError(int(status.max()), "recode_points_packed")
+        return out
 
     def aggregate_secure_batch(self, impl_id: int, key_sets: Sequence[Sequence[bytes]], sig_sets: Sequence[Sequence[bytes]],
                                fmt: int = SerializationFormat.Modern) -> Tuple[np.ndarray, List[bytes]]:

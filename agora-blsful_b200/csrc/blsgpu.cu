@@ -5,9 +5,11 @@
 #include <sys/random.h>
 
 #include <algorithm>
+#include <functional>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <unordered_map>
 #include <thread>
@@ -67,8 +69,17 @@ struct Level {
 
 }  // namespace
 
+// the slice-local state blsgpu_miller_partial leaves behind for blsgpu_partial_finish (lives in the arena)
+struct PendingSlice {
+  virtual ~PendingSlice() {}
+  virtual int finish(blsgpu_ctx* ctx, bool batch_ok, uint8_t* status_out) = 0;
+};
+
 struct blsgpu_ctx {
   std::vector<int> devices;
+  std::unique_ptr<PendingSlice> pending;  // invalidated by every call that re-plans the arena
+  uint8_t* fold_scratch = nullptr;        // small device buffer of the fold (blsgpu_final_exp_is_one), apart from the arena
+  size_t fold_cap = 0;
   std::vector<blsgpu_ctx*> peers;  // one single-device context per further device (devices[1..]); see verify_host_common
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
@@ -102,6 +113,7 @@ struct blsgpu_ctx {
 namespace {
 
 int ensure_arena(blsgpu_ctx* ctx, size_t bytes) {
+  ctx->pending.reset();  // the arena is about to be handed out again
   ctx->arena.off = 0;
   ctx->arena.over = false;
   if (ctx->arena.cap >= bytes) return BLSGPU_OK;
@@ -282,25 +294,121 @@ size_t levels_total(const std::vector<Level>& lv) { return lv.back().off + lv.ba
 //   pre[i]   : status before pairing work (non-OK items are excluded from the batch equation)
 //   use_rlc  : true  -> per-item check  e(pk_i,H_i) e(-g,sig_i) == 1 for all i, decided by one random linear combination
 //                       and bisection on failure (writes INVALID_SIGNATURE into status[i] for the exact failures);
-//              false -> aggregate check prod e(pk_i,H_i) * e(-g, sig_0) == 1 (sig has ONE element), *agg_ok receives it
+//              false -> aggregate check prod e(pk_i,H_i) * e(-g, sig_0) == 1 (sig has ONE element)
+// Three phases, so that a batch cut over several devices can be folded: pipeline_partials leaves the slice's
+// product of Miller values (root of the product tree) and its sum of r_i sig_i in device memory; pipeline_check decides
+// F * e(-g, S) == 1 for this slice alone; pipeline_bisect finds the exact failures of a slice whose check failed.
 // -----------------------------------------------------------------------------------------------------------------
+constexpr size_t PROBE_SMALL = 16;  // probes the dedicated scratch holds (the root check; small batches' bisection levels)
 template <class PkA, class SigA>
-int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA* d_sig, const SigA* d_h, uint8_t* d_status,
-                         bool use_rlc, int* agg_ok) {
+struct Pipe {
   typedef typename PtInfo<SigA>::Jac SigJ;
-  // leaves of the product/sum trees are GROUPS of 6 consecutive items (the cooperative Miller kernel's unit)
-  const size_t ng = (n + M6_GROUP - 1) / M6_GROUP;
-  std::vector<Level> lv = make_levels(ng);
-  size_t total = levels_total(lv);
-  Fp12* d_F = ctx->arena.take<Fp12>(total);
-  SigJ* d_S = ctx->arena.take<SigJ>(use_rlc ? total : 1);
-  SigJ* d_Sitem = ctx->arena.take<SigJ>(use_rlc ? n : 1);
-  Digest* d_dig = ctx->arena.take<Digest>(levels_total(make_levels(n)) + 2);
-  Digest* d_root = d_dig + levels_total(make_levels(n));  // [root, salt]
-  uint8_t* d_ok = ctx->arena.take<uint8_t>(std::max<size_t>(n, 16));
-  uint32_t* d_idx = ctx->arena.take<uint32_t>(std::max<size_t>(n, 16));
+  size_t n = 0, ng = 0;
+  bool use_rlc = true, use_msm = false;
+  int rbits = 0;
+  std::vector<Level> lv;
+  const PkA* d_pk = nullptr;
+  const SigA *d_sig = nullptr, *d_h = nullptr;
+  uint8_t* d_status = nullptr;
+  Fp12* d_F = nullptr;
+  SigJ *d_S = nullptr, *d_Sitem = nullptr, *d_msm_root = nullptr;
+  Digest* d_root = nullptr;
+  uint8_t* d_ok = nullptr;
+  uint32_t* d_idx = nullptr;
+  // probe scratch: a small dedicated one, and (after the Miller stage) the first line buffer for levels with many probes
+  PkA* x_pk = nullptr;
+  SigA* x_h = nullptr;
+  uint8_t* x_pre = nullptr;
+  M6Arg* x_args = nullptr;
+  SLineRec* x_lines = nullptr;
+  Fp12* x_T = nullptr;
+  size_t x_cap = 0;            // probes per launch the point / status / T scratch holds
+  M6Arg* big_args = nullptr;   // line buffer 0 of the Miller stage, free once the stage is done
+  SLineRec* big_lines = nullptr;
+  size_t big_items = 0;
+  bool root_T_ready = false;   // T = ML(-g, S_root) already computed beside the Miller stage (x_T[0])
+  const Fp12* rootF() const { return d_F + lv.back().off; }
+  const SigJ* rootS() const { return use_msm ? d_msm_root : use_rlc ? d_S + lv.back().off : d_S; }
+};
 
-  const int rbits = use_rlc ? ctx->rlc_bits : 0;
+// T[c] = product of the Miller values of probe c's pairs, c < cnt, on `stream`; the scratch batch was filled by k_probe_fill_*
+template <class PkA, class SigA>
+int probe_miller(blsgpu_ctx* ctx, Pipe<PkA, SigA>& P, cudaStream_t stream, size_t cnt, M6Arg* args, SLineRec* lines) {
+  const size_t items = 6 * cnt;
+  ARENA_OK();
+  k_m6_prep<PkA, SigA><<<blocks_for(items), TPB, 0, stream>>>(items, 0, (const PkA*)P.x_pk, (const SigA*)P.x_h, (const uint8_t*)P.x_pre,
+                                                               (const Digest*)nullptr, 0, args);
+  CKR(check_launch(ctx, "k_m6_prep(probe)"));
+  k_m6_lines<PkA, SigA><<<blocks_for(items, M6_LINES_PAIRS), M6_LINES_TPB, M6_LINES_SMEM, stream>>>(items, 0, args, (const PkA*)P.x_pk, (const SigA*)P.x_h,
+                                                                                                       (const uint8_t*)P.x_pre, lines);
+  CKR(check_launch(ctx, "k_m6_lines(probe)"));
+  k_m6_accum<<<blocks_for(items, M6_ITEMS_PER_BLOCK), 128, M6_ACCUM_SMEM, stream>>>(items, 0, (const uint8_t*)P.x_pre, lines, P.x_T);
+  CKR(check_launch(ctx, "k_m6_accum(probe)"));
+  return BLSGPU_OK;
+}
+// ok[c] = final_exp(F[idx[c]] * T[c]) == 1 for the cnt probes whose T sits in x_T
+template <class PkA, class SigA>
+int probe_final(blsgpu_ctx* ctx, Pipe<PkA, SigA>& P, size_t cnt, const uint32_t* d_idx, const Fp12* F, uint8_t* d_ok) {
+  ARENA_OK();
+  k_final6<<<blocks_for(cnt, FE6_PER_WARP), 32, FE6_SMEM, ctx->stream>>>(cnt, d_idx, F, (const Fp12*)P.x_T, d_ok);
+  CKR(check_launch(ctx, "k_final6"));
+  return BLSGPU_OK;
+}
+// node probes over one tree level: res[c] = ( F[cand[c]] * e(-g, S[cand[c]]) == 1 )
+template <class PkA, class SigA>
+int probe_level(blsgpu_ctx* ctx, Pipe<PkA, SigA>& P, const std::vector<uint32_t>& cand, const Fp12* F, const typename Pipe<PkA, SigA>::SigJ* S,
+                std::vector<uint8_t>& res) {
+  res.resize(cand.size());
+  const bool big = cand.size() > PROBE_SMALL && P.big_items >= 6 * PROBE_SMALL;
+  const size_t per = big ? std::min(P.x_cap, P.big_items / 6) : PROBE_SMALL;
+  for (size_t lo = 0; lo < cand.size(); lo += per) {
+    const size_t cnt = std::min(per, cand.size() - lo);
+    CK(cudaMemcpyAsync(P.d_idx, cand.data() + lo, cnt * 4, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH((k_probe_fill_nodes<PkA, SigA>), blocks_for(cnt), TPB, cnt, (const uint32_t*)P.d_idx, S, P.x_pk, P.x_h, P.x_pre);
+    CKR((probe_miller<PkA, SigA>(ctx, P, ctx->stream, cnt, big ? P.big_args : P.x_args, big ? P.big_lines : P.x_lines)));
+    CKR((probe_final<PkA, SigA>(ctx, P, cnt, P.d_idx, F, P.d_ok)));
+    CK(cudaMemcpyAsync(res.data() + lo, P.d_ok, cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return BLSGPU_OK;
+}
+
+template <class PkA, class SigA>
+int pipeline_partials(blsgpu_ctx* ctx, Pipe<PkA, SigA>& P, size_t n, const PkA* d_pk, const SigA* d_sig, const SigA* d_h, uint8_t* d_status,
+                      bool use_rlc) {
+  typedef typename PtInfo<SigA>::Jac SigJ;
+  P.n = n;
+  P.use_rlc = use_rlc;
+  P.d_pk = d_pk;
+  P.d_sig = d_sig;
+  P.d_h = d_h;
+  P.d_status = d_status;
+  // leaves of the product/sum trees are GROUPS of 6 consecutive items (the cooperative Miller kernel's unit)
+  const size_t ng = P.ng = (n + M6_GROUP - 1) / M6_GROUP;
+  std::vector<Level>& lv = P.lv = make_levels(ng);
+  size_t total = levels_total(lv);
+  Fp12* d_F = P.d_F = ctx->arena.take<Fp12>(total);
+  SigJ* d_S = P.d_S = ctx->arena.take<SigJ>(use_rlc ? total : 1);
+  P.d_Sitem = ctx->arena.take<SigJ>(use_rlc ? n : 1);
+  Digest* d_dig = ctx->arena.take<Digest>(levels_total(make_levels(n)) + 2);
+  Digest* d_root = P.d_root = d_dig + levels_total(make_levels(n));  // [root, salt]
+  P.d_ok = ctx->arena.take<uint8_t>(std::max<size_t>(n, 16));
+  P.d_idx = ctx->arena.take<uint32_t>(std::max<size_t>(n, 16));
+  // probe scratch (points and statuses for as many probes as one bisection level can ask for at once: 16 per failing
+  // node, at most one node per group; the line records of big levels go through the Miller stage's buffer)
+  P.x_cap = std::max<size_t>(PROBE_SMALL, std::min<size_t>(ng, 4096) + 16);
+  P.x_pk = ctx->arena.take<PkA>(6 * P.x_cap);
+  P.x_h = ctx->arena.take<SigA>(6 * P.x_cap);
+  P.x_pre = ctx->arena.take<uint8_t>(6 * P.x_cap);
+  P.x_T = ctx->arena.take<Fp12>(P.x_cap);
+  P.x_args = ctx->arena.take<M6Arg>(6 * PROBE_SMALL);
+  P.x_lines = ctx->arena.take<SLineRec>(6 * PROBE_SMALL * M6_LINE_RECS);
+  // per device and per call (microseconds): a context per device may run this from several host threads
+  CK(cudaFuncSetAttribute(k_m6_lines<PkA, SigA>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_LINES_SMEM));
+  CK(cudaFuncSetAttribute(k_m6_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_ACCUM_SMEM));
+  CK(cudaFuncSetAttribute(k_final6, cudaFuncAttributeMaxDynamicSharedMemorySize, FE6_SMEM));
+
+  const int rbits = P.rbits = use_rlc ? ctx->rlc_bits : 0;
   if (use_rlc) {
     CKR(fresh_salt(ctx));
     std::vector<Level> ld = make_levels(n);
@@ -311,13 +419,11 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
     CK(cudaMemcpyAsync(d_root + 1, ctx->salt, 32, cudaMemcpyHostToDevice, ctx->stream));
   }
   // S = sum r_i sig_i.  Large batches: bucket multi-scalar multiplication for the total only (the per-group sums the
-  // bisection needs are computed if the batch fails) BEFORE the Miller stage, so that its Miller loop T = ML(-g, S) - one
-  // thread, pure latency - can run on the aux stream beside the Miller kernels.  Small batches: per-item scaling.
+  // bisection needs are computed if the batch fails) BEFORE the Miller stage, so that its Miller loop T = ML(-g, S) can
+  // run on the aux stream beside the Miller kernels.  Small batches: per-item scaling.
   // (Running the bucket kernels themselves beside the Miller stage was measured: they evict Miller blocks, +70 ms at 1M.)
   stage_mark(ctx, BLSGPU_STAGE_SCALE_SIG);
-  const bool use_msm = use_rlc && n >= MSM_MIN_ITEMS;
-  SigJ* d_msm_root = nullptr;
-  Fp12* d_T = ctx->arena.take<Fp12>(1);
+  const bool use_msm = P.use_msm = use_rlc && n >= MSM_MIN_ITEMS;
   if (use_msm) {
     int rc = [&]() -> int {
       const int c = msm_window_bits(n, rbits);
@@ -339,28 +445,29 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
       LAUNCH((k_msm_chunk<SigJ>), blocks_for(nchunks), TPB, nchunks, c, (const SigJ*)d_B, d_V);
       for (size_t k = 0; k + 1 < lm.size(); k++)
         LAUNCH((k_reduce_jac<SigJ>), blocks_for(lm[k + 1].cnt), TPB, lm[k].cnt, d_V + lm[k].off, lm[k + 1].cnt, d_V + lm[k + 1].off);
-      d_msm_root = d_V + lm.back().off;
+      P.d_msm_root = d_V + lm.back().off;
       return BLSGPU_OK;
     }();
     CKR(rc);
   }
   CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  P.root_T_ready = false;
   if (use_msm) {
-    // one thread's Miller loop (9 ms of latency, no throughput): on the aux stream, beside the Miller stage
+    // the signature side of the batch equation, T = ML(-g, S): one cooperative probe on the aux stream, beside the Miller stage
     CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
-    k_probe_ml<SigJ><<<1, 32, 0, ctx->aux>>>((const SigJ*)d_msm_root, d_T);
-    CKR(check_launch(ctx, "k_probe_ml"));
+    ARENA_OK();
+    k_probe_fill_nodes<PkA, SigA><<<1, TPB, 0, ctx->aux>>>((size_t)1, (const uint32_t*)nullptr, (const SigJ*)P.d_msm_root, P.x_pk, P.x_h, P.x_pre);
+    CKR(check_launch(ctx, "k_probe_fill_nodes"));
+    CKR((probe_miller<PkA, SigA>(ctx, P, ctx->aux, 1, P.x_args, P.x_lines)));
     CK(cudaEventRecord(ctx->ev_aux, ctx->aux));
+    P.root_T_ready = true;
   }
   stage_mark(ctx, BLSGPU_STAGE_MILLER);
   {
-    // per device and per call (microseconds): a context per device may run this from several host threads
-    CK(cudaFuncSetAttribute(k_m6_lines<PkA, SigA>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_LINES_SMEM));
-    CK(cudaFuncSetAttribute(k_m6_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_ACCUM_SMEM));
-    // The line stream is 39 KB per item.  Batches beyond one pass (m6_chunk) go through in chunks with two line buffers:
+    // The line stream is 39 KB per item.  Batches beyond one pass (ctx->m6_chunk) go through in chunks with two line buffers:
     // chunk c's lines are produced on side stream 0 while chunk c-1's accumulator consumes the other buffer on side stream 1.
     const size_t M6_CHUNK = ctx->m6_chunk;  // planned by the entry point together with the arena size (plan_m6_chunk)
-    const size_t chunk = std::min(n, M6_CHUNK);
+    const size_t chunk = std::max<size_t>(std::min(n, M6_CHUNK), 6 * PROBE_SMALL);
     const int nbuf = n > M6_CHUNK ? 2 : 1;
     M6Arg* d_args[2];
     SLineRec* d_lines[2];
@@ -368,6 +475,9 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
       d_args[b] = ctx->arena.take<M6Arg>(chunk);
       d_lines[b] = ctx->arena.take<SLineRec>(chunk * M6_LINE_RECS);
     }
+    P.big_args = d_args[0];
+    P.big_lines = d_lines[0];
+    P.big_items = chunk;
     ARENA_OK();
     CK(cudaStreamWaitEvent(ctx->side[0], ctx->ev_fork, 0));
     CK(cudaStreamWaitEvent(ctx->side[1], ctx->ev_fork, 0));
@@ -400,8 +510,8 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
   }
   if (use_msm) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_aux, 0));  // T = ML(-g, S) ran beside the Miller stage
   if (use_rlc && !use_msm) {
-    LAUNCH((k_scale_sig<SigA>), blocks_for(n), TPB, n, d_sig, d_status, d_root, rbits, d_Sitem);
-    LAUNCH((k_group_sum<SigJ>), blocks_for(ng), TPB, n, (const SigJ*)d_Sitem, ng, d_S);
+    LAUNCH((k_scale_sig<SigA>), blocks_for(n), TPB, n, d_sig, d_status, d_root, rbits, P.d_Sitem);
+    LAUNCH((k_group_sum<SigJ>), blocks_for(ng), TPB, n, (const SigJ*)P.d_Sitem, ng, d_S);
   }
   stage_mark(ctx, BLSGPU_STAGE_REDUCE);
   for (size_t k = 0; k + 1 < lv.size(); k++) {
@@ -409,69 +519,91 @@ int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA*
     if (use_rlc && !use_msm)
       LAUNCH((k_reduce_jac<SigJ>), blocks_for(lv[k + 1].cnt), TPB, lv[k].cnt, d_S + lv[k].off, lv[k + 1].cnt, d_S + lv[k + 1].off);
   }
-  stage_mark(ctx, BLSGPU_STAGE_FINAL);
   if (!use_rlc) LAUNCH((k_reduce_aff<SigA>), 1, 32, (size_t)1, d_sig, (size_t)1, d_S);  // S = the single aggregate signature
-  const Fp12* rootF = d_F + lv.back().off;
-  const SigJ* rootS = use_msm ? d_msm_root : use_rlc ? d_S + lv.back().off : d_S;
-  if (use_msm) LAUNCH(k_probe_fin, 1, 32, rootF, (const Fp12*)d_T, d_ok);
-  else LAUNCH((k_probe<SigJ>), 1, 64, (size_t)1, (const uint32_t*)nullptr, rootF, rootS, d_ok);
+  return BLSGPU_OK;
+}
+
+// F_root * e(-g, S_root) == 1 for this slice?  (synchronises the stream)
+template <class PkA, class SigA>
+int pipeline_check(blsgpu_ctx* ctx, Pipe<PkA, SigA>& P, bool* ok_out) {
+  typedef typename PtInfo<SigA>::Jac SigJ;
+  stage_mark(ctx, BLSGPU_STAGE_FINAL);
+  if (!P.root_T_ready) {
+    LAUNCH((k_probe_fill_nodes<PkA, SigA>), 1, TPB, (size_t)1, (const uint32_t*)nullptr, (const SigJ*)P.rootS(), P.x_pk, P.x_h, P.x_pre);
+    CKR((probe_miller<PkA, SigA>(ctx, P, ctx->stream, 1, P.x_args, P.x_lines)));
+    P.root_T_ready = true;
+  }
+  CKR((probe_final<PkA, SigA>(ctx, P, 1, nullptr, P.rootF(), P.d_ok)));
   uint8_t ok = 0;
-  CK(cudaMemcpyAsync(&ok, d_ok, 1, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(&ok, P.d_ok, 1, cudaMemcpyDeviceToHost, ctx->stream));
   stage_mark(ctx, BLSGPU_STAGE_BISECT);
   CK(cudaStreamSynchronize(ctx->stream));
-  if (!use_rlc) {
-    *agg_ok = ok;
-    stage_mark(ctx, BLSGPU_STAGE_COUNT);
-    return BLSGPU_OK;
-  }
-  if (!ok && use_msm) {
-    // the batch failed: now the bisection needs the per-group sums of r_i sig_i
-    LAUNCH((k_scale_sig<SigA>), blocks_for(n), TPB, n, d_sig, d_status, d_root, rbits, d_Sitem);
-    LAUNCH((k_group_sum<SigJ>), blocks_for(ng), TPB, n, (const SigJ*)d_Sitem, ng, d_S);
+  *ok_out = ok != 0;
+  return BLSGPU_OK;
+}
+
+// the slice's check failed: per-group sums, descent of the 16-ary tree, exact per-item checks of the failing groups
+template <class PkA, class SigA>
+int pipeline_bisect(blsgpu_ctx* ctx, Pipe<PkA, SigA>& P) {
+  typedef typename PtInfo<SigA>::Jac SigJ;
+  const size_t n = P.n, ng = P.ng;
+  const std::vector<Level>& lv = P.lv;
+  if (P.use_msm) {
+    // the bucket method gave the total only: now the bisection needs the per-group sums of r_i sig_i
+    LAUNCH((k_scale_sig<SigA>), blocks_for(n), TPB, n, P.d_sig, P.d_status, P.d_root, P.rbits, P.d_Sitem);
+    LAUNCH((k_group_sum<SigJ>), blocks_for(ng), TPB, n, (const SigJ*)P.d_Sitem, ng, P.d_S);
     for (size_t k = 0; k + 1 < lv.size(); k++)
-      LAUNCH((k_reduce_jac<SigJ>), blocks_for(lv[k + 1].cnt), TPB, lv[k].cnt, d_S + lv[k].off, lv[k + 1].cnt, d_S + lv[k + 1].off);
+      LAUNCH((k_reduce_jac<SigJ>), blocks_for(lv[k + 1].cnt), TPB, lv[k].cnt, P.d_S + lv[k].off, lv[k + 1].cnt, P.d_S + lv[k + 1].off);
   }
-  if (!ok) {
-    // walk down the 16-ary tree to the failing groups: children of node j at level k+1 are {j + m * cnt(k+1)} at level k
-    std::vector<uint32_t> bad{0};
-    for (size_t k = lv.size() - 1; k-- > 0;) {
-      std::vector<uint32_t> cand;
-      size_t cn = lv[k + 1].cnt;
-      for (uint32_t j : bad)
-        for (int m = 0; m < 16; m++) {
-          size_t idx = (size_t)j + (size_t)m * cn;
-          if (idx < lv[k].cnt) cand.push_back((uint32_t)idx);
-        }
-      if (cand.empty()) break;
-      CK(cudaMemcpyAsync(d_idx, cand.data(), cand.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-      LAUNCH((k_probe<SigJ>), blocks_for(cand.size(), 64), 64, cand.size(), (const uint32_t*)d_idx, d_F + lv[k].off, d_S + lv[k].off,
-             d_ok);
-      std::vector<uint8_t> res(cand.size());
-      CK(cudaMemcpyAsync(res.data(), d_ok, cand.size(), cudaMemcpyDeviceToHost, ctx->stream));
-      CK(cudaStreamSynchronize(ctx->stream));
-      bad.clear();
-      for (size_t c = 0; c < cand.size(); c++)
-        if (!res[c]) bad.push_back(cand[c]);
-      if (bad.empty()) break;  // cannot happen for a failing parent; defensive
-    }
-    // every item of a failing group is decided by its own exact equation e(pk_i, H_i) e(-g, sig_i) == 1
-    std::vector<uint32_t> items;
-    for (uint32_t gidx : bad)
-      for (int m = 0; m < M6_GROUP; m++) {
-        size_t i = (size_t)gidx * M6_GROUP + m;
-        if (i < n) items.push_back((uint32_t)i);
+  // walk down the 16-ary tree to the failing groups: children of node j at level k+1 are {j + m * cnt(k+1)} at level k
+  std::vector<uint32_t> bad{0};
+  std::vector<uint8_t> res;
+  for (size_t k = lv.size() - 1; k-- > 0;) {
+    std::vector<uint32_t> cand;
+    size_t cn = lv[k + 1].cnt;
+    for (uint32_t j : bad)
+      for (int m = 0; m < 16; m++) {
+        size_t idx = (size_t)j + (size_t)m * cn;
+        if (idx < lv[k].cnt) cand.push_back((uint32_t)idx);
       }
-    if (!items.empty()) {
-      CK(cudaMemcpyAsync(d_idx, items.data(), items.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-      Fp12* d_Fx = ctx->arena.take<Fp12>(items.size());
-      SigJ* d_Sx = ctx->arena.take<SigJ>(items.size());
-      LAUNCH((k_exact_leaves<PkA, SigA>), blocks_for(items.size()), TPB, items.size(), (const uint32_t*)d_idx, d_pk, d_h, d_sig,
-             (const uint8_t*)d_status, d_Fx, d_Sx);
-      LAUNCH((k_probe<SigJ>), blocks_for(items.size(), 64), 64, items.size(), (const uint32_t*)nullptr, (const Fp12*)d_Fx, (const SigJ*)d_Sx, d_ok);
-      LAUNCH(k_mark_invalid, blocks_for(items.size()), TPB, items.size(), (const uint32_t*)d_idx, (const uint8_t*)d_ok, d_status);
-      CK(cudaStreamSynchronize(ctx->stream));
-    }
+    if (cand.empty()) break;
+    CKR((probe_level<PkA, SigA>(ctx, P, cand, P.d_F + lv[k].off, P.d_S + lv[k].off, res)));
+    bad.clear();
+    for (size_t c = 0; c < cand.size(); c++)
+      if (!res[c]) bad.push_back(cand[c]);
+    if (bad.empty()) break;  // cannot happen for a failing parent; defensive
   }
+  // every item of a failing group is decided by its own exact equation e(pk_i, H_i) e(-g, sig_i) == 1
+  std::vector<uint32_t> items;
+  for (uint32_t gidx : bad)
+    for (int m = 0; m < M6_GROUP; m++) {
+      size_t i = (size_t)gidx * M6_GROUP + m;
+      if (i < n) items.push_back((uint32_t)i);
+    }
+  const bool big = items.size() > PROBE_SMALL && P.big_items >= 6 * PROBE_SMALL;
+  const size_t per = big ? std::min(P.x_cap, P.big_items / 6) : PROBE_SMALL;
+  for (size_t lo = 0; lo < items.size(); lo += per) {
+    const size_t cnt = std::min(per, items.size() - lo);
+    CK(cudaMemcpyAsync(P.d_idx, items.data() + lo, cnt * 4, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH((k_probe_fill_leaves<PkA, SigA>), blocks_for(cnt), TPB, cnt, (const uint32_t*)P.d_idx, P.d_pk, P.d_h, P.d_sig,
+           (const uint8_t*)P.d_status, P.x_pk, P.x_h, P.x_pre);
+    CKR((probe_miller<PkA, SigA>(ctx, P, ctx->stream, cnt, big ? P.big_args : P.x_args, big ? P.big_lines : P.x_lines)));
+    CKR((probe_final<PkA, SigA>(ctx, P, cnt, nullptr, nullptr, P.d_ok)));
+    LAUNCH(k_mark_invalid, blocks_for(cnt), TPB, cnt, (const uint32_t*)P.d_idx, (const uint8_t*)P.d_ok, P.d_status);
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return BLSGPU_OK;
+}
+
+template <class PkA, class SigA>
+int run_pairing_pipeline(blsgpu_ctx* ctx, size_t n, const PkA* d_pk, const SigA* d_sig, const SigA* d_h, uint8_t* d_status,
+                         bool use_rlc, int* agg_ok) {
+  Pipe<PkA, SigA> P;
+  CKR((pipeline_partials<PkA, SigA>(ctx, P, n, d_pk, d_sig, d_h, d_status, use_rlc)));
+  bool ok = false;
+  CKR((pipeline_check<PkA, SigA>(ctx, P, &ok)));
+  if (!use_rlc) *agg_ok = ok;
+  else if (!ok) CKR((pipeline_bisect<PkA, SigA>(ctx, P)));
   stage_mark(ctx, BLSGPU_STAGE_COUNT);
   return BLSGPU_OK;
 }
@@ -482,10 +614,14 @@ size_t pipeline_other_bytes(size_t n) {
   typedef typename PtInfo<SigA>::Jac SigJ;
   size_t total = levels_total(make_levels(std::max<size_t>(n, 1)));
   size_t gtotal = levels_total(make_levels((std::max<size_t>(n, 1) + M6_GROUP - 1) / M6_GROUP));
+  const size_t x_cap = std::max<size_t>(PROBE_SMALL, std::min<size_t>((n + M6_GROUP - 1) / M6_GROUP, 4096) + 16);
   return gtotal * (sizeof(Fp12) + sizeof(SigJ)) + n * (sizeof(SigJ) + sizeof(Fp12) + sizeof(SigJ)) + total * sizeof(Digest) +
-         n * (16 + 4 * 32) + ((size_t)32 << 16) * (12 + 2 * sizeof(SigJ)) + (1 << 20) + (n + 64) * 8 + 16 * 256 + 4096;
+         n * (16 + 4 * 32) + ((size_t)32 << 16) * (12 + 2 * sizeof(SigJ)) + (1 << 20) + (n + 64) * 8 + 16 * 256 + 4096 +
+         x_cap * (6 * (sizeof(PkA) + sizeof(SigA) + 1) + sizeof(Fp12)) + 6 * PROBE_SMALL * M6_ITEM_BYTES + 16 * 256;
 }
-size_t m6_line_bytes(size_t n, size_t chunk) { return (n > chunk ? 2 : 1) * std::min(std::max<size_t>(n, 1), chunk) * M6_ITEM_BYTES; }
+size_t m6_line_bytes(size_t n, size_t chunk) {
+  return (n > chunk ? 2 : 1) * std::max<size_t>(std::min(std::max<size_t>(n, 1), chunk), 6 * PROBE_SMALL) * M6_ITEM_BYTES;
+}
 // Plans the pass size of the Miller kernels for this call and sizes the arena: `head_bytes` is what the entry point takes
 // from the arena besides the pipeline's own scratch.  If the allocation fails the pass size is halved (more passes) until
 // it fits or reaches the minimum.
@@ -531,26 +667,40 @@ int hash_points(blsgpu_ctx* ctx, size_t n, const uint8_t* d_msgs, const uint64_t
 
 // verify over decoded points: per-item pre-status, hash_to_curve of the framed message, pairing pipeline
 template <int IMPL>
-int verify_points(blsgpu_ctx* ctx, int msg_mode, const DstParam& dst, size_t n, const typename ImplT<IMPL>::PkAff* d_pk,
-                  const typename ImplT<IMPL>::SigAff* d_sig, const uint8_t* d_stpk, const uint8_t* d_stsig, const uint8_t* d_msgs,
-                  const uint64_t* d_moff, uint8_t* d_status_out) {
+int verify_points_partials(blsgpu_ctx* ctx, Pipe<typename ImplT<IMPL>::PkAff, typename ImplT<IMPL>::SigAff>& P, int msg_mode, const DstParam& dst,
+                           size_t n, const typename ImplT<IMPL>::PkAff* d_pk, const typename ImplT<IMPL>::SigAff* d_sig, const uint8_t* d_stpk,
+                           const uint8_t* d_stsig, const uint8_t* d_msgs, const uint64_t* d_moff, uint8_t* d_status_out) {
   typedef typename ImplT<IMPL>::PkAff PkA;
   typedef typename ImplT<IMPL>::SigAff SigA;
   SigA* d_h = ctx->arena.take<SigA>(n);
   LAUNCH((k_prestatus<PkA, SigA>), blocks_for(n), TPB, n, d_stpk, d_stsig, d_pk, d_sig, d_status_out);
   stage_mark(ctx, BLSGPU_STAGE_HASH);
   CKR((hash_points<SigA, PkA>(ctx, n, d_msgs, d_moff, msg_mode, d_pk, (const uint8_t*)d_status_out, dst, d_h)));
-  CKR((run_pairing_pipeline<PkA, SigA>(ctx, n, d_pk, d_sig, d_h, d_status_out, true, nullptr)));
+  return pipeline_partials<PkA, SigA>(ctx, P, n, d_pk, d_sig, d_h, d_status_out, true);
+}
+template <int IMPL>
+int verify_points(blsgpu_ctx* ctx, int msg_mode, const DstParam& dst, size_t n, const typename ImplT<IMPL>::PkAff* d_pk,
+                  const typename ImplT<IMPL>::SigAff* d_sig, const uint8_t* d_stpk, const uint8_t* d_stsig, const uint8_t* d_msgs,
+                  const uint64_t* d_moff, uint8_t* d_status_out) {
+  typedef typename ImplT<IMPL>::PkAff PkA;
+  typedef typename ImplT<IMPL>::SigAff SigA;
+  Pipe<PkA, SigA> P;
+  CKR((verify_points_partials<IMPL>(ctx, P, msg_mode, dst, n, d_pk, d_sig, d_stpk, d_stsig, d_msgs, d_moff, d_status_out)));
+  bool ok = false;
+  CKR((pipeline_check<PkA, SigA>(ctx, P, &ok)));
+  if (!ok) CKR((pipeline_bisect<PkA, SigA>(ctx, P)));
+  stage_mark(ctx, BLSGPU_STAGE_COUNT);
   return BLSGPU_OK;
 }
 
-// verify over device-resident compressed inputs.  msg_mode: 0 msg, 1 pk||msg, 2 pk bytes (PoP)
+// verify over device-resident compressed inputs.  msg_mode: 0 msg, 1 pk||msg, 2 pk bytes (PoP).
+// verify_dev_partials stops after the slice's partial results (its product of Miller values and sum of r_i sig_i).
 template <int IMPL>
-int verify_dev(blsgpu_ctx* ctx, int msg_mode, const DstParam& dst, int format, size_t n, const uint8_t* d_pks, const uint8_t* d_sigs,
-               const uint8_t* d_msgs, const uint64_t* d_moff, uint8_t* d_status_out, size_t arena_reserved) {
+int verify_dev_partials(blsgpu_ctx* ctx, Pipe<typename ImplT<IMPL>::PkAff, typename ImplT<IMPL>::SigAff>& P, int msg_mode, const DstParam& dst,
+                        int format, size_t n, const uint8_t* d_pks, const uint8_t* d_sigs, const uint8_t* d_msgs, const uint64_t* d_moff,
+                        uint8_t* d_status_out) {
   typedef typename ImplT<IMPL>::PkAff PkA;
   typedef typename ImplT<IMPL>::SigAff SigA;
-  (void)arena_reserved;
   PkA* d_pk = ctx->arena.take<PkA>(n);
   SigA* d_sig = ctx->arena.take<SigA>(n);
   uint8_t* d_stpk = ctx->arena.take<uint8_t>(n);
@@ -560,10 +710,80 @@ int verify_dev(blsgpu_ctx* ctx, int msg_mode, const DstParam& dst, int format, s
   CKR((decode_points<PkA>(ctx, n, d_pks, format, d_pk, d_stpk, BLSGPU_KERNEL_DECODE_PK)));
   stage_mark(ctx, BLSGPU_STAGE_DECODE_SIG);
   CKR((decode_points<SigA>(ctx, n, d_sigs, format, d_sig, d_stsig, BLSGPU_KERNEL_DECODE_SIG)));
-  CKR((verify_points<IMPL>(ctx, msg_mode, dst, n, d_pk, d_sig, d_stpk, d_stsig, d_msgs, d_moff, d_status_out)));
+  return verify_points_partials<IMPL>(ctx, P, msg_mode, dst, n, d_pk, d_sig, d_stpk, d_stsig, d_msgs, d_moff, d_status_out);
+}
+template <int IMPL>
+int verify_dev(blsgpu_ctx* ctx, int msg_mode, const DstParam& dst, int format, size_t n, const uint8_t* d_pks, const uint8_t* d_sigs,
+               const uint8_t* d_msgs, const uint64_t* d_moff, uint8_t* d_status_out, size_t arena_reserved) {
+  typedef typename ImplT<IMPL>::PkAff PkA;
+  typedef typename ImplT<IMPL>::SigAff SigA;
+  (void)arena_reserved;
+  Pipe<PkA, SigA> P;
+  CKR((verify_dev_partials<IMPL>(ctx, P, msg_mode, dst, format, n, d_pks, d_sigs, d_msgs, d_moff, d_status_out)));
+  bool ok = false;
+  CKR((pipeline_check<PkA, SigA>(ctx, P, &ok)));
+  if (!ok) CKR((pipeline_bisect<PkA, SigA>(ctx, P)));
+  stage_mark(ctx, BLSGPU_STAGE_COUNT);
   stage_collect(ctx);
   return BLSGPU_OK;
 }
+
+// ---- the fold: partial results of several slices -> one verdict ------------------------------------------------------------
+// d_F[k], d_S[k] on this context's device: is  prod F_j * e(-g, sum S_j)  == 1 ?   One product/sum launch, one cooperative
+// probe, one six-lane final exponentiation - the "host multiplies the partials and runs a single final exponentiation" step
+// of the north star, executed on a GPU because the engine has no CPU arithmetic.
+int ensure_fold_scratch(blsgpu_ctx* ctx, size_t bytes) {
+  if (ctx->fold_cap >= bytes) return BLSGPU_OK;
+  if (ctx->fold_scratch) CK(cudaFree(ctx->fold_scratch));
+  ctx->fold_scratch = nullptr;
+  ctx->fold_cap = 0;
+  CK(cudaMalloc(&ctx->fold_scratch, bytes));
+  ctx->fold_cap = bytes;
+  return BLSGPU_OK;
+}
+template <class PkA, class SigA>
+size_t fold_bytes(size_t k) {
+  typedef typename PtInfo<SigA>::Jac SigJ;
+  return (k + 2) * (sizeof(Fp12) + sizeof(SigJ) + sizeof(SigA) + PtInfo<SigA>::LEN + 600) + 6 * (sizeof(PkA) + sizeof(SigA) + 1 + M6_ITEM_BYTES) +
+         2 * sizeof(Fp12) + 64 * 256;
+}
+template <class PkA, class SigA>
+int fold_check(blsgpu_ctx* ctx, Arena& A, size_t k, const Fp12* d_F, const typename PtInfo<SigA>::Jac* d_S, bool* ok_out) {
+  typedef typename PtInfo<SigA>::Jac SigJ;
+  Pipe<PkA, SigA> P;  // only its probe scratch is used
+  Fp12* d_Froot = A.take<Fp12>(1);
+  SigJ* d_Sroot = A.take<SigJ>(1);
+  P.x_cap = 1;
+  P.x_pk = A.take<PkA>(6);
+  P.x_h = A.take<SigA>(6);
+  P.x_pre = A.take<uint8_t>(6);
+  P.x_T = A.take<Fp12>(1);
+  P.x_args = A.take<M6Arg>(6);
+  P.x_lines = A.take<SLineRec>(6 * M6_LINE_RECS);
+  P.d_ok = A.take<uint8_t>(16);
+  if (A.over) {
+    ctx->err = "internal: fold scratch sized too small";
+    return BLSGPU_E_ALLOC;
+  }
+  CK(cudaFuncSetAttribute(k_m6_lines<PkA, SigA>, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_LINES_SMEM));
+  CK(cudaFuncSetAttribute(k_m6_accum, cudaFuncAttributeMaxDynamicSharedMemorySize, M6_ACCUM_SMEM));
+  CK(cudaFuncSetAttribute(k_final6, cudaFuncAttributeMaxDynamicSharedMemorySize, FE6_SMEM));
+  if (k > 16) {
+    ctx->err = "fold: at most 16 partial results";
+    return BLSGPU_E_ARG;
+  }
+  LAUNCH(k_reduce_fp12, 1, TPB, k, d_F, (size_t)1, d_Froot);      // 16-ary: one level covers up to 16 slices
+  LAUNCH((k_reduce_jac<SigJ>), 1, TPB, k, d_S, (size_t)1, d_Sroot);
+  LAUNCH((k_probe_fill_nodes<PkA, SigA>), 1, TPB, (size_t)1, (const uint32_t*)nullptr, (const SigJ*)d_Sroot, P.x_pk, P.x_h, P.x_pre);
+  CKR((probe_miller<PkA, SigA>(ctx, P, ctx->stream, 1, P.x_args, P.x_lines)));
+  CKR((probe_final<PkA, SigA>(ctx, P, 1, nullptr, (const Fp12*)d_Froot, P.d_ok)));
+  uint8_t ok = 0;
+  CK(cudaMemcpyAsync(&ok, P.d_ok, 1, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *ok_out = ok != 0;
+  return BLSGPU_OK;
+}
+
 // what verify_dev takes from the arena before the pipeline's own scratch
 template <int IMPL>
 size_t verify_head_bytes(size_t n) {
@@ -673,7 +893,9 @@ void blsgpu_ctx_destroy(blsgpu_ctx* ctx) {
   if (!ctx) return;
   for (blsgpu_ctx* peer : ctx->peers) blsgpu_ctx_destroy(peer);
   cudaSetDevice(ctx->devices[0]);
+  ctx->pending.reset();
   if (ctx->arena.base) cudaFree(ctx->arena.base);
+  if (ctx->fold_scratch) cudaFree(ctx->fold_scratch);
   for (int i = 0; i <= BLSGPU_STAGE_COUNT; i++) cudaEventDestroy(ctx->ev[i]);
   for (const blsgpu_ctx::KernelMark& m : ctx->kmarks) {
     cudaEventDestroy(m.begin);
@@ -757,69 +979,239 @@ int blsgpu_verify_batch_dev(blsgpu_ctx* ctx, int impl_id, int scheme, int format
   return verify_dev<1>(ctx, mode, dst, format, n, pks_dev, sigs_dev, msgs_dev, msg_off_dev, status_out_dev, 0);
 }
 
-static int verify_host_one(blsgpu_ctx* ctx, int impl_id, int msg_mode, const DstParam& dst, int format, size_t n, const uint8_t* pks,
-                           const uint8_t* sigs, const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out);
-
-// A context created on several devices shards a host-buffer batch into contiguous slices, one per device, each driven by
-// its own host thread and verified exactly like a batch of its own (own random linear combination, own bisection): the
-// per-item results are independent, so there is no collective and no combine step.  Below
-// SHARD_MIN_ITEMS per device the first device takes the whole batch.
-constexpr size_t SHARD_MIN_ITEMS = 4096;
-static int verify_host_common(blsgpu_ctx* ctx, int impl_id, int msg_mode, const DstParam& dst, int format, size_t n, const uint8_t* pks,
-                              const uint8_t* sigs, const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out) {
-  const size_t ndev = 1 + ctx->peers.size();
-  if (ndev == 1 || n < ndev * SHARD_MIN_ITEMS)
-    return verify_host_one(ctx, impl_id, msg_mode, dst, format, n, pks, sigs, msgs, msg_off, status_out);
-  const size_t pk_len = impl_id == 2 ? 48 : 96, sig_len = impl_id == 2 ? 96 : 48;
-  std::vector<int> rc(ndev, BLSGPU_OK);
-  auto slice = [&](size_t d) {
-    const size_t s = n * d / ndev, e = n * (d + 1) / ndev;
-    blsgpu_ctx* c = d == 0 ? ctx : ctx->peers[d - 1];
-    std::vector<uint64_t> off;  // the slice's offsets, rebased to its first message
-    if (msg_off) {
-      off.resize(e - s + 1);
-      for (size_t i = s; i <= e; i++) off[i - s] = msg_off[i] - msg_off[s];
-    }
-    rc[d] = verify_host_one(c, impl_id, msg_mode, dst, format, e - s, pks + s * pk_len, sigs + s * sig_len,
-                            msg_off ? msgs + msg_off[s] : nullptr, msg_off ? off.data() : nullptr, status_out + s);
-  };
-  std::vector<std::thread> workers;
-  for (size_t d = 1; d < ndev; d++) workers.emplace_back(slice, d);
-  slice(0);
-  for (std::thread& w : workers) w.join();
-  for (size_t d = 0; d < ndev; d++)
-    if (rc[d] != BLSGPU_OK) {
-      if (d) ctx->err = "device " + std::to_string(ctx->devices[d]) + ": " + ctx->peers[d - 1]->err;
-      return rc[d];
-    }
-  return BLSGPU_OK;
-}
-
-static int verify_host_one(blsgpu_ctx* ctx, int impl_id, int msg_mode, const DstParam& dst, int format, size_t n, const uint8_t* pks,
-                           const uint8_t* sigs, const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out) {
+namespace {
+// host buffers of one slice -> its partial results (state in P, statuses so far in *d_st_out); the stream is synchronised
+template <int IMPL>
+int host_partials(blsgpu_ctx* ctx, Pipe<typename ImplT<IMPL>::PkAff, typename ImplT<IMPL>::SigAff>& P, int msg_mode, const DstParam& dst, int format,
+                  size_t n, const uint8_t* pks, const uint8_t* sigs, const uint8_t* msgs, const uint64_t* msg_off, uint8_t** d_st_out) {
   CKR(set_device(ctx));
-  size_t pk_len = impl_id == 2 ? 48 : 96, sig_len = impl_id == 2 ? 96 : 48;
-  size_t msg_bytes = msg_off ? (size_t)msg_off[n] : 0;
-  size_t in_bytes = n * (pk_len + sig_len + 1) + msg_bytes + (n + 1) * 8 + 8 * 256;
-  CKR(impl_id == 2 ? ensure_verify_arena<2>(ctx, n, in_bytes) : ensure_verify_arena<1>(ctx, n, in_bytes));
-  uint8_t *d_pks, *d_sigs, *d_msgs, *d_st;
+  const size_t pk_len = IMPL == 2 ? 48 : 96, sig_len = IMPL == 2 ? 96 : 48;
+  size_t msg_bytes = msg_off ? (size_t)(msg_off[n] - msg_off[0]) : 0;
+  size_t in_bytes = n * (pk_len + sig_len + 1) + msg_bytes + (n + 1) * 8 + 16 * 256 + 8192;
+  CKR(ensure_verify_arena<IMPL>(ctx, n, in_bytes));
+  uint8_t *d_pks, *d_sigs, *d_msgs;
   uint64_t* d_off;
   CKR(upload(ctx, d_pks, pks, n * pk_len));
   CKR(upload(ctx, d_sigs, sigs, n * sig_len));
-  CKR(upload(ctx, d_msgs, msgs, msg_bytes));
-  std::vector<uint64_t> zero_off;
-  if (!msg_off) {
-    zero_off.assign(n + 1, 0);
-    msg_off = zero_off.data();
-  }
-  CKR(upload(ctx, d_off, msg_off, n + 1));
-  d_st = ctx->arena.take<uint8_t>(n);
-  int r = impl_id == 2 ? verify_dev<2>(ctx, msg_mode, dst, format, n, d_pks, d_sigs, d_msgs, d_off, d_st, 0)
-                       : verify_dev<1>(ctx, msg_mode, dst, format, n, d_pks, d_sigs, d_msgs, d_off, d_st, 0);
-  CKR(r);
-  CK(cudaMemcpyAsync(status_out, d_st, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CKR(upload(ctx, d_msgs, msg_off ? msgs + msg_off[0] : msgs, msg_bytes));
+  std::vector<uint64_t> off(n + 1, 0);  // rebased to the slice's first message (all zero without messages: PoP)
+  if (msg_off)
+    for (size_t i = 0; i <= n; i++) off[i] = msg_off[i] - msg_off[0];
+  CKR(upload(ctx, d_off, off.data(), n + 1));
+  uint8_t* d_st = ctx->arena.take<uint8_t>(n);
+  *d_st_out = d_st;
+  CKR((verify_dev_partials<IMPL>(ctx, P, msg_mode, dst, format, n, d_pks, d_sigs, d_msgs, d_off, d_st)));
   CK(cudaStreamSynchronize(ctx->stream));
   return BLSGPU_OK;
+}
+// batch_ok: the verdict of the fold over all slices.  A slice of a failed batch checks its own partial results and bisects
+// only if they fail too (only the devices holding bad items do extra work).
+template <int IMPL>
+int host_finish(blsgpu_ctx* ctx, Pipe<typename ImplT<IMPL>::PkAff, typename ImplT<IMPL>::SigAff>& P, bool batch_ok, const uint8_t* d_st, size_t n,
+                uint8_t* status_out) {
+  typedef typename ImplT<IMPL>::PkAff PkA;
+  typedef typename ImplT<IMPL>::SigAff SigA;
+  CKR(set_device(ctx));
+  if (!batch_ok) {
+    bool ok = false;
+    CKR((pipeline_check<PkA, SigA>(ctx, P, &ok)));
+    if (!ok) CKR((pipeline_bisect<PkA, SigA>(ctx, P)));
+  }
+  stage_mark(ctx, BLSGPU_STAGE_COUNT);
+  CK(cudaMemcpyAsync(status_out, d_st, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  stage_collect(ctx);
+  return BLSGPU_OK;
+}
+
+template <int IMPL>
+int verify_host_one(blsgpu_ctx* ctx, int msg_mode, const DstParam& dst, int format, size_t n, const uint8_t* pks, const uint8_t* sigs,
+                    const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out) {
+  Pipe<typename ImplT<IMPL>::PkAff, typename ImplT<IMPL>::SigAff> P;
+  uint8_t* d_st = nullptr;
+  CKR((host_partials<IMPL>(ctx, P, msg_mode, dst, format, n, pks, sigs, msgs, msg_off, &d_st)));
+  return host_finish<IMPL>(ctx, P, false, d_st, n, status_out);
+}
+
+// A context created on several devices cuts a host-buffer batch into contiguous slices, one per device, each driven by its
+// own host thread.  Every device folds its slice into ONE partial product of Miller values and ONE partial sum
+// of r_i sig_i; the partial results meet on the first device, which multiplies / adds them and runs a single Miller loop
+// and a single final exponentiation for the whole batch.  Only if that check fails does a device look at its own partial
+// results, and only a device whose slice fails bisects.  No collective: 2 x ndev small copies.
+// Below SHARD_MIN_ITEMS per device the first device takes the whole batch.
+constexpr size_t SHARD_MIN_ITEMS = 4096;
+template <int IMPL>
+int verify_host_fold(blsgpu_ctx* ctx, int msg_mode, const DstParam& dst, int format, size_t n, const uint8_t* pks, const uint8_t* sigs,
+                     const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out) {
+  typedef typename ImplT<IMPL>::PkAff PkA;
+  typedef typename ImplT<IMPL>::SigAff SigA;
+  typedef typename PtInfo<SigA>::Jac SigJ;
+  const size_t ndev = 1 + ctx->peers.size();
+  const size_t pk_len = IMPL == 2 ? 48 : 96, sig_len = IMPL == 2 ? 96 : 48;
+  std::vector<Pipe<PkA, SigA>> P(ndev);
+  std::vector<uint8_t*> d_st(ndev, nullptr);
+  std::vector<int> rc(ndev, BLSGPU_OK);
+  auto dev_ctx = [&](size_t d) { return d == 0 ? ctx : ctx->peers[d - 1]; };
+  auto lo = [&](size_t d) { return n * d / ndev; };
+  auto run_all = [&](const std::function<void(size_t)>& f) {
+    std::vector<std::thread> workers;
+    for (size_t d = 1; d < ndev; d++) workers.emplace_back(f, d);
+    f(0);
+    for (std::thread& w : workers) w.join();
+    for (size_t d = 0; d < ndev; d++)
+      if (rc[d] != BLSGPU_OK) {
+        if (d) ctx->err = "device " + std::to_string(ctx->devices[d]) + ": " + ctx->peers[d - 1]->err;
+        return rc[d];
+      }
+    return (int)BLSGPU_OK;
+  };
+  CKR(run_all([&](size_t d) {
+    const size_t s = lo(d), e = lo(d + 1);
+    rc[d] = host_partials<IMPL>(dev_ctx(d), P[d], msg_mode, dst, format, e - s, pks + s * pk_len, sigs + s * sig_len, msgs,
+                                msg_off ? msg_off + s : nullptr, &d_st[d]);
+  }));
+  // the partial results meet on the first device
+  CKR(set_device(ctx));
+  CKR(ensure_fold_scratch(ctx, fold_bytes<PkA, SigA>(ndev)));
+  Arena A;
+  A.base = ctx->fold_scratch;
+  A.cap = ctx->fold_cap;
+  Fp12* d_Fk = A.take<Fp12>(ndev);
+  SigJ* d_Sk = A.take<SigJ>(ndev);
+  for (size_t d = 0; d < ndev; d++) {
+    CK(cudaMemcpyPeerAsync(d_Fk + d, ctx->devices[0], P[d].rootF(), ctx->devices[d], sizeof(Fp12), ctx->stream));
+    CK(cudaMemcpyPeerAsync(d_Sk + d, ctx->devices[0], P[d].rootS(), ctx->devices[d], sizeof(SigJ), ctx->stream));
+  }
+  bool ok = false;
+  CKR((fold_check<PkA, SigA>(ctx, A, ndev, d_Fk, d_Sk, &ok)));
+  return run_all([&](size_t d) {
+    const size_t s = lo(d), e = lo(d + 1);
+    rc[d] = host_finish<IMPL>(dev_ctx(d), P[d], ok, d_st[d], e - s, status_out + s);
+  });
+}
+
+int verify_host_common(blsgpu_ctx* ctx, int impl_id, int msg_mode, const DstParam& dst, int format, size_t n, const uint8_t* pks,
+                       const uint8_t* sigs, const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out) {
+  const size_t ndev = 1 + ctx->peers.size();
+  if (ndev == 1 || n < ndev * SHARD_MIN_ITEMS)
+    return impl_id == 2 ? verify_host_one<2>(ctx, msg_mode, dst, format, n, pks, sigs, msgs, msg_off, status_out)
+                        : verify_host_one<1>(ctx, msg_mode, dst, format, n, pks, sigs, msgs, msg_off, status_out);
+  return impl_id == 2 ? verify_host_fold<2>(ctx, msg_mode, dst, format, n, pks, sigs, msgs, msg_off, status_out)
+                      : verify_host_fold<1>(ctx, msg_mode, dst, format, n, pks, sigs, msgs, msg_off, status_out);
+}
+
+template <int IMPL>
+struct PendingImpl : PendingSlice {
+  Pipe<typename ImplT<IMPL>::PkAff, typename ImplT<IMPL>::SigAff> P;
+  uint8_t* d_st = nullptr;
+  size_t n = 0;
+  int finish(blsgpu_ctx* ctx, bool batch_ok, uint8_t* status_out) override { return host_finish<IMPL>(ctx, P, batch_ok, d_st, n, status_out); }
+};
+template <int IMPL>
+int miller_partial_impl(blsgpu_ctx* ctx, int msg_mode, const DstParam& dst, int format, size_t n, const uint8_t* pks, const uint8_t* sigs,
+                        const uint8_t* msgs, const uint64_t* msg_off, uint8_t* gt_out, uint8_t* sum_out) {
+  typedef typename ImplT<IMPL>::SigAff SigA;
+  typedef typename PtInfo<SigA>::Jac SigJ;
+  const size_t Ls = PtInfo<SigA>::LEN;
+  std::unique_ptr<PendingImpl<IMPL>> pend(new PendingImpl<IMPL>());
+  pend->n = n;
+  CKR((host_partials<IMPL>(ctx, pend->P, msg_mode, dst, format, n, pks, sigs, msgs, msg_off, &pend->d_st)));
+  uint8_t* d_gt = ctx->arena.take<uint8_t>(576);
+  SigA* d_aff = ctx->arena.take<SigA>(1);
+  uint8_t* d_enc = ctx->arena.take<uint8_t>(Ls);
+  LAUNCH(k_fp12_to_bytes, 1, 32, (size_t)1, pend->P.rootF(), d_gt);
+  LAUNCH((k_to_affine<SigA>), 1, 32, (size_t)1, (const SigJ*)pend->P.rootS(), d_aff);
+  LAUNCH((k_encode<SigA>), 1, 32, (size_t)1, (const SigA*)d_aff, 1, d_enc);
+  CK(cudaMemcpyAsync(gt_out, d_gt, 576, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(sum_out, d_enc, Ls, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->pending = std::move(pend);
+  return BLSGPU_OK;
+}
+template <int IMPL>
+int fold_bytes_impl(blsgpu_ctx* ctx, size_t k, const uint8_t* gts, const uint8_t* sums, int* ok_out) {
+  typedef typename ImplT<IMPL>::PkAff PkA;
+  typedef typename ImplT<IMPL>::SigAff SigA;
+  typedef typename PtInfo<SigA>::Jac SigJ;
+  const size_t Ls = PtInfo<SigA>::LEN;
+  CKR(ensure_fold_scratch(ctx, fold_bytes<PkA, SigA>(k)));
+  Arena A;
+  A.base = ctx->fold_scratch;
+  A.cap = ctx->fold_cap;
+  uint8_t* d_gt = A.take<uint8_t>(576 * k);
+  uint8_t* d_sb = A.take<uint8_t>(Ls * k);
+  Fp12* d_Fk = A.take<Fp12>(k);
+  SigA* d_aff = A.take<SigA>(k);
+  SigJ* d_Sk = A.take<SigJ>(k);
+  uint8_t* d_flag = A.take<uint8_t>(2 * k);
+  if (A.over) {
+    ctx->err = "internal: fold scratch sized too small";
+    return BLSGPU_E_ALLOC;
+  }
+  CK(cudaMemcpyAsync(d_gt, gts, 576 * k, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_sb, sums, Ls * k, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(k_fp12_from_bytes, blocks_for(k), TPB, k, (const uint8_t*)d_gt, d_Fk, d_flag);
+  CKR((decode_points<SigA>(ctx, k, (const uint8_t*)d_sb, 1, d_aff, d_flag + k)));
+  LAUNCH((k_aff_to_jac<SigA>), blocks_for(k), TPB, k, (const SigA*)d_aff, d_Sk);
+  std::vector<uint8_t> flag(2 * k);
+  CK(cudaMemcpyAsync(flag.data(), d_flag, 2 * k, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (uint8_t f : flag)
+    if (f) {
+      ctx->err = "blsgpu_final_exp_is_one: a partial result is not a canonical field element / group element";
+      return BLSGPU_E_ARG;
+    }
+  bool ok = false;
+  CKR((fold_check<PkA, SigA>(ctx, A, k, d_Fk, d_Sk, &ok)));
+  *ok_out = ok ? 1 : 0;
+  return BLSGPU_OK;
+}
+}  // namespace
+
+int blsgpu_miller_partial(blsgpu_ctx* ctx, int impl_id, int scheme, int format, size_t n, const uint8_t* pks, const uint8_t* sigs,
+                          const uint8_t* msgs, const uint64_t* msg_off, uint8_t gt_out[576], uint8_t* sum_out) {
+  if (!ctx) return BLSGPU_E_ARG;
+  if (!args_ok(impl_id, scheme, format) || !gt_out || !sum_out || (n && (!pks || !sigs || !msg_off))) {
+    ctx->err = "blsgpu_miller_partial: bad arguments";
+    return BLSGPU_E_ARG;
+  }
+  const size_t Ls = impl_id == 2 ? 96 : 48;
+  if (n == 0) {  // the empty slice: (1, O)
+    ctx->pending.reset();
+    memset(gt_out, 0, 576);
+    gt_out[47] = 1;
+    memset(sum_out, 0, Ls);
+    sum_out[0] = 0xc0;
+    return BLSGPU_OK;
+  }
+  CHECK_OFFSETS(msg_off, n, "blsgpu_miller_partial");
+  DstParam dst;
+  make_dst(dst, impl_id, scheme, false);
+  const int mode = scheme == 1 ? 1 : 0;
+  return impl_id == 2 ? miller_partial_impl<2>(ctx, mode, dst, format, n, pks, sigs, msgs, msg_off, gt_out, sum_out)
+                      : miller_partial_impl<1>(ctx, mode, dst, format, n, pks, sigs, msgs, msg_off, gt_out, sum_out);
+}
+
+int blsgpu_final_exp_is_one(blsgpu_ctx* ctx, int impl_id, size_t k, const uint8_t* partial_gts, const uint8_t* partial_sums, int* is_one_out) {
+  if (!ctx) return BLSGPU_E_ARG;
+  if ((impl_id != 1 && impl_id != 2) || k == 0 || k > 16 || !partial_gts || !partial_sums || !is_one_out) {
+    ctx->err = "blsgpu_final_exp_is_one: bad arguments (1 to 16 partial results)";
+    return BLSGPU_E_ARG;
+  }
+  CKR(set_device(ctx));
+  return impl_id == 2 ? fold_bytes_impl<2>(ctx, k, partial_gts, partial_sums, is_one_out)
+                      : fold_bytes_impl<1>(ctx, k, partial_gts, partial_sums, is_one_out);
+}
+
+int blsgpu_partial_finish(blsgpu_ctx* ctx, int batch_ok, uint8_t* status_out) {
+  if (!ctx) return BLSGPU_E_ARG;
+  if (!ctx->pending) return BLSGPU_OK;  // an empty slice, or nothing pending
+  if (!status_out) {
+    ctx->err = "blsgpu_partial_finish: status_out is null";
+    return BLSGPU_E_ARG;
+  }
+  std::unique_ptr<PendingSlice> p = std::move(ctx->pending);
+  return p->finish(ctx, batch_ok != 0, status_out);
 }
 
 int blsgpu_verify_batch(blsgpu_ctx* ctx, int impl_id, int scheme, int format, size_t n, const uint8_t* pks, const uint8_t* sigs,

@@ -8,6 +8,7 @@
 #include "h2c.cuh"
 #include "pairing.cuh"
 #include "miller6.cuh"
+#include "finalexp6.cuh"
 #include "fr.cuh"
 
 namespace bls {
@@ -675,95 +676,82 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_reduce_aff(size_t n_in,
   out[j] = acc;
 }
 
-// ---- probe: is  F * e'(generator side, S)  == 1 after the final exponentiation? ----------------------------------------
-// G2Impl: F * ML(-g1, S), S in G2.   G1Impl: F * ML(S, -g2), S in G1.
-__device__ __forceinline__ bool probe_node(const Fp12& F, const G2Jac& S) {
-  Fp12 g = F;
-  if (!jac_is_inf(S)) {
-    G2Aff sa;
-    jac_to_aff(sa, S);
-    G1Aff ng;
-    pt_generator(ng);
-    fp_neg(ng.y, ng.y);
-    MillerG1 mp;
-    miller_prepare(mp, ng);
-    Fp12 t;
-    miller_loop(t, mp, sa);
-    fp12_mul(g, g, t);
-  }
-  Fp12 e;
-  final_exponentiation(e, g);
-  return fp12_is_one(e);
-}
-__device__ __forceinline__ bool probe_node(const Fp12& F, const G1Jac& S) {
-  Fp12 g = F;
-  if (!jac_is_inf(S)) {
-    G2Aff ng;
-    pt_generator(ng);
-    fneg(ng.y, ng.y);
-    MillerG1 mp;
-    miller_prepare(mp, S);
-    Fp12 t;
-    miller_loop(t, mp, ng);
-    fp12_mul(g, g, t);
-  }
-  Fp12 e;
-  final_exponentiation(e, g);
-  return fp12_is_one(e);
-}
-// The same probe in two halves, so that the signature side can run while the Miller kernels are still busy:
-//   k_probe_ml:   T = ML(-g, S)  (one if S is the identity)       k_probe_fin:  final_exponentiation(F * T) == 1 ?
-__device__ __forceinline__ void probe_ml(Fp12& t, const G2Jac& S) {
-  if (jac_is_inf(S)) {
-    fp12_one(t);
-    return;
-  }
-  G2Aff sa;
-  jac_to_aff(sa, S);
-  G1Aff ng;
-  pt_generator(ng);
-  fp_neg(ng.y, ng.y);
-  MillerG1 mp;
-  miller_prepare(mp, ng);
-  miller_loop(t, mp, sa);
-}
-__device__ __forceinline__ void probe_ml(Fp12& t, const G1Jac& S) {
-  if (jac_is_inf(S)) {
-    fp12_one(t);
-    return;
-  }
-  G2Aff ng;
-  pt_generator(ng);
-  fneg(ng.y, ng.y);
-  MillerG1 mp;
-  miller_prepare(mp, S);
-  miller_loop(t, mp, ng);
-}
-template <class J>
-__global__ void __launch_bounds__(32) k_probe_ml(const J* __restrict__ S, Fp12* __restrict__ T) {
-  if (BLS_TID() != 0) return;
-  J s = S[0];
-  Fp12 t;
-  probe_ml(t, s);
-  T[0] = t;
-}
-__global__ void __launch_bounds__(32) k_probe_fin(const Fp12* __restrict__ F, const Fp12* __restrict__ T, uint8_t* __restrict__ ok) {
-  if (BLS_TID() != 0) return;
-  Fp12 f = F[0], t = T[0], g, e;
-  fp12_mul(g, f, t);
-  final_exponentiation(e, g);
-  ok[0] = fp12_is_one(e) ? 1 : 0;
-}
-// node list: idx[c] indexes into F/S of one tree level (idx == nullptr: identity)
-template <class J>
-__global__ void __launch_bounds__(64) k_probe(size_t cnt, const uint32_t* __restrict__ idx, const Fp12* __restrict__ F,
-                                              const J* __restrict__ S, uint8_t* __restrict__ ok) {
+// ---- probes: is  F * prod_j e(P_j, Q_j)  == 1 after the final exponentiation? --------------------------------------------
+// A probe is one GROUP of the cooperative Miller kernels (up to six pairs at items 6c .. 6c + 5 of a scratch batch) followed
+// by the six-lane final exponentiation (finalexp6.cuh).  Round 1 ran every probe on ONE thread (Miller loop 9 ms + final
+// exponentiation 14 ms of latency per bisection level); the cooperative kernels bring a level to ~3 ms.
+//   node probe : F = the node's product of Miller values, one pair (-g, S_node):   e(pk-side generator negated, sum r_i sig_i)
+//   leaf probe : F = 1, two pairs (pk_i, H_i), (-g, sig_i): the exact per-item equation of core_verify (sig_core.rs:138-145)
+// k_probe_fill_* write the scratch batch (points + per-item status; everything not written stays "skip").
+constexpr uint8_t PROBE_SKIP = 0xfe;  // any status != ST_OK makes the Miller kernels skip the item
+template <class PkA, class SigA>
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_probe_fill_nodes(size_t cnt, const uint32_t* __restrict__ idx,
+                                                          const typename PtInfo<SigA>::Jac* __restrict__ S, PkA* __restrict__ xpk,
+                                                          SigA* __restrict__ xh, uint8_t* __restrict__ xpre) {
   size_t c = BLS_TID();
   if (c >= cnt) return;
-  size_t j = idx ? idx[c] : c;
-  Fp12 f = F[j];
-  J s = S[j];
-  ok[c] = probe_node(f, s) ? 1 : 0;
+  const size_t j = idx ? idx[c] : c;
+  typename PtInfo<SigA>::Jac s = S[j];
+  SigA sa;
+  jac_to_aff(sa, s);
+  PkA ng;
+  pt_generator(ng);
+  aff_neg(ng, ng);
+  xpk[6 * c] = ng;
+  xh[6 * c] = sa;
+  xpre[6 * c] = sa.inf ? PROBE_SKIP : ST_OK;  // S = O contributes e(., O) = 1
+  for (int m = 1; m < 6; m++) xpre[6 * c + m] = PROBE_SKIP;
+}
+template <class PkA, class SigA>
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_probe_fill_leaves(size_t cnt, const uint32_t* __restrict__ idx, const PkA* __restrict__ pk,
+                                                           const SigA* __restrict__ h, const SigA* __restrict__ sig,
+                                                           const uint8_t* __restrict__ status, PkA* __restrict__ xpk,
+                                                           SigA* __restrict__ xh, uint8_t* __restrict__ xpre) {
+  size_t c = BLS_TID();
+  if (c >= cnt) return;
+  const size_t i = idx[c];
+  const bool on = status[i] == ST_OK;  // anything else was decided before the pairing: its probe is the empty product
+  if (on) {
+    PkA ng;
+    pt_generator(ng);
+    aff_neg(ng, ng);
+    xpk[6 * c] = pk[i];
+    xh[6 * c] = h[i];
+    xpk[6 * c + 1] = ng;
+    xh[6 * c + 1] = sig[i];
+  }
+  xpre[6 * c] = xpre[6 * c + 1] = on ? ST_OK : PROBE_SKIP;
+  for (int m = 2; m < 6; m++) xpre[6 * c + m] = PROBE_SKIP;
+}
+// ok[c] = ( F[idx ? idx[c] : c] * T[c] )^(3 (p^12-1)/r) == 1 ; F == nullptr: F = 1.  Five probes per warp, six lanes each.
+constexpr int FE6_PER_WARP = 5;
+constexpr int FE6_SMEM = FE6_PER_WARP * (FE6_NREG * 6 * (int)sizeof(SAccRec) + (int)sizeof(Fp12));
+__global__ void __launch_bounds__(32) k_final6(size_t cnt, const uint32_t* __restrict__ idx, const Fp12* __restrict__ F,
+                                               const Fp12* __restrict__ T, uint8_t* __restrict__ ok) {
+  extern __shared__ __align__(16) uint8_t fe6_smem[];
+  const int lane = threadIdx.x, g = lane / 6, k = lane - 6 * g;
+  const size_t c = (size_t)blockIdx.x * FE6_PER_WARP + g;
+  if (g >= FE6_PER_WARP || c >= cnt) return;  // whole groups leave together: every barrier below names one group's lanes
+  Fe6 cx;
+  cx.R = reinterpret_cast<SAccRec*>(fe6_smem) + g * FE6_NREG * 6;
+  cx.scratch = reinterpret_cast<Fp12*>(fe6_smem + FE6_PER_WARP * FE6_NREG * 6 * sizeof(SAccRec)) + g;
+  cx.k = k;
+  cx.mask = 63u << (6 * g);
+  {
+    Fp12 t = T[c];
+    fe6_load_coeff(fe6_reg(cx, F ? 1 : 0)[k], *fp12_coeff(t, k));
+  }
+  if (F) {
+    Fp12 f = F[idx ? idx[c] : c];
+    fe6_load_coeff(fe6_reg(cx, 2)[k], *fp12_coeff(f, k));
+    __syncwarp(cx.mask);
+    fe6_mul(cx, 0, 1, 2);
+  } else {
+    __syncwarp(cx.mask);
+  }
+  fe6_final_exponentiation(cx);
+  const unsigned votes = __ballot_sync(cx.mask, fe6_lane_is_one(cx, k));
+  if (k == 0) ok[c] = ((votes >> (6 * g)) & 63u) == 63u ? 1 : 0;
 }
 
 // S_g = sum of the (up to) 6 consecutive per-item points of group g
@@ -780,33 +768,6 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_group_sum(size_t n, con
     }
   }
   out[g] = acc;
-}
-
-// exact per-item decision for the items of a failing group, e(pk_i, H_i) e(-g, sig_i) == 1 ?  (sig_core.rs:138-145):
-// the unscaled per-item Miller value and the signature itself, probed by k_probe like any tree node
-template <class PkA, class SigA>
-__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_exact_leaves(size_t cnt, const uint32_t* __restrict__ idx, const PkA* __restrict__ pk,
-                                                      const SigA* __restrict__ h, const SigA* __restrict__ sig,
-                                                      const uint8_t* __restrict__ status, Fp12* __restrict__ F,
-                                                      typename PtInfo<SigA>::Jac* __restrict__ S) {
-  size_t c = BLS_TID();
-  if (c >= cnt) return;
-  const size_t i = idx[c];
-  Fp12 f;
-  typename PtInfo<SigA>::Jac sj;
-  if (status[i] != ST_OK) {
-    fp12_one(f);
-    jac_set_inf(sj);
-  } else {
-    PkA p = pk[i];
-    SigA q = h[i];
-    const uint32_t one[2] = {1, 0};
-    miller_item(f, p, q, one, false);
-    SigA sa = sig[i];
-    jac_from_aff(sj, sa);
-  }
-  F[c] = f;
-  S[c] = sj;
 }
 
 // leaves that failed their exact check
@@ -995,6 +956,55 @@ __global__ void k_final_is_one(const Fp12* f, uint8_t* ok) {
   Fp12 g = f[0], e;
   final_exponentiation(e, g);
   ok[0] = fp12_is_one(e) ? 1 : 0;
+}
+
+// ---- partial results of a batch cut over several devices / processes --------------------------------
+// 576-byte form of an Fp12: the coefficients of w^0 .. w^5, each as c0 || c1 in 48-byte big-endian canonical form
+__global__ void k_fp12_to_bytes(size_t n, const Fp12* __restrict__ in, uint8_t* __restrict__ out) {
+  size_t t = BLS_TID();
+  if (t >= 6 * n) return;
+  Fp12 f = in[t / 6];
+  const Fp2 c = *fp12_coeff(f, (int)(t % 6));
+  Fp raw;
+  uint8_t b[48];
+  fp_from_mont(raw, c.c0);
+  fp_to_be48_raw(b, raw);
+  for (int k = 0; k < 48; k++) out[96 * t + k] = b[k];
+  fp_from_mont(raw, c.c1);
+  fp_to_be48_raw(b, raw);
+  for (int k = 0; k < 48; k++) out[96 * t + 48 + k] = b[k];
+}
+// bad[i] = 1 if some coefficient of value i is not a canonical field element
+__global__ void k_fp12_from_bytes(size_t n, const uint8_t* __restrict__ in, Fp12* __restrict__ out, uint8_t* __restrict__ bad) {
+  size_t i = BLS_TID();
+  if (i >= n) return;
+  Fp12 f;
+  uint8_t flag = 0;
+  for (int k = 0; k < 6; k++) {
+    Fp2 c;
+    for (int h = 0; h < 2; h++) {
+      uint8_t b[48];
+      for (int j = 0; j < 48; j++) b[j] = in[576 * i + 96 * k + 48 * h + j];
+      Fp raw;
+      if (b[0] & 0xe0) flag = 1;
+      b[0] &= 0x1f;
+      if (!fp_from_be48_raw(raw, b)) flag = 1;
+      fp_to_mont(h ? c.c1 : c.c0, raw);
+    }
+    *fp12_coeff(f, k) = c;
+  }
+  out[i] = f;
+  bad[i] = flag;
+}
+// affine -> Jacobian (the partial sums of the slices arrive as compressed points)
+template <class A>
+__global__ void k_aff_to_jac(size_t n, const A* __restrict__ in, typename PtInfo<A>::Jac* __restrict__ out) {
+  size_t i = BLS_TID();
+  if (i >= n) return;
+  A a = in[i];
+  typename PtInfo<A>::Jac j;
+  jac_from_aff(j, a);
+  out[i] = j;
 }
 
 // ---- the reference's other public 2-pairing checks ---------------------------------------------

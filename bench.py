@@ -140,6 +140,125 @@ def run_reference(args, rank, world):
     emit(line)
 
 
+def _ms(fn, reps=1):
+    """Wall time of a synchronous host call (every C-ABI entry point returns after its results are in host memory)."""
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        r = fn()
+        dt = (time.perf_counter() - t0) * 1e3
+        best = dt if best is None or dt < best else best
+    return r, best
+
+
+def other_configs(eng, B, batch, peak_mac, quorums):
+    """The other BASELINE.json configs and the failure path, once each, through the host-buffer C-ABI calls (H2D/D2H inside
+    the timed call).  Every result is checked by construction (valid data verifies, planted failures are found exactly)."""
+    pks, sigs, msgs, off = batch
+    n = off.size - 1
+    out = {}
+
+    def frac(fp_mul_per_item, items, ms):
+        return items * fp_mul_per_item * MAC_PER_FPMUL / (ms * 1e-3) / peak_mac
+
+    # cfg 1: 1,024 distinct triples (latency of a small batch)
+    m = min(1024, n)
+    sub = (pks[:48 * m], sigs[:96 * m], msgs[:int(off[m])], off[:m + 1])
+    eng.verify_batch_packed(2, 0, *sub)
+    st, ms = _ms(lambda: eng.verify_batch_packed(2, 0, *sub), 3)
+    assert int(st.max()) == 0
+    out["cfg1_verify_1024_triples"] = {"ms": ms, "items_per_s": m / (ms * 1e-3), "note": "latency-bound: 1,024 items do not fill 148 SMs"}
+    # cfg 2 failure path: 1 and 1,000 corrupted signatures (exact bad set through bisection)
+    rng = np.random.default_rng(1)
+    st, ms0 = _ms(lambda: eng.verify_batch_packed(2, 0, pks, sigs, msgs, off))
+    assert int(st.max()) == 0
+    out["cfg2_all_valid_host_call"] = {"ms": ms0, "items_per_s": n / (ms0 * 1e-3)}
+    for nbad in (1, 1000):
+        if nbad >= n:
+            continue
+        bad = np.sort(rng.choice(n, nbad, replace=False))
+        s2 = sigs.copy().reshape(n, 96)
+        s2[bad] = s2[(bad + 1) % n]
+        st, ms = _ms(lambda: eng.verify_batch_packed(2, 0, pks, s2.reshape(-1), msgs, off))
+        assert np.array_equal(np.nonzero(st)[0], bad) and set(st[bad].tolist()) == {1}
+        out[f"cfg2_{nbad}_bad"] = {"ms": ms, "items_per_s": n / (ms * 1e-3), "vs_all_valid": ms / ms0}
+    # cfg 2 with 128-bit random-linear-combination scalars
+    eng.set_rlc_bits(128)
+    st, ms = _ms(lambda: eng.verify_batch_packed(2, 0, pks, sigs, msgs, off))
+    eng.set_rlc_bits(64)
+    assert int(st.max()) == 0
+    out["cfg2_rlc_128bit"] = {"ms": ms, "items_per_s": n / (ms * 1e-3), "vs_64bit": ms / ms0}
+    # cfg 4: AggregateSignature::verify over 100k distinct messages
+    m4 = min(100_000, n)
+    agg = eng.sum_points(2, sigs[:m4 * 96])
+    msgs_list = [msgs[int(off[i]):int(off[i + 1])].tobytes() for i in range(m4)]
+    eng.aggregate_verify(2, 0, pks[:m4 * 48], msgs_list, agg)
+    _, ms = _ms(lambda: eng.aggregate_verify(2, 0, pks[:m4 * 48], msgs_list, agg))
+    out["cfg4_aggregate_verify_100k"] = {"ms": ms, "items_per_s": m4 / (ms * 1e-3), "frac": frac(11300, m4, ms),
+                                         "note": "includes packing 100k Python byte strings on the host"}
+    # Bls12381G1Impl batch verify and cfg 3 (same-message aggregation of n signers, PoP scheme), both impls
+    scal = np.zeros((n, 32), dtype=np.uint8)
+    scal[:, 8:] = rng.integers(0, 256, size=(n, 24), dtype=np.uint8)
+    scal[:, 31] |= 1
+    one_msg = np.frombuffer(b"one message for every signer....", dtype=np.uint8)
+    chunk = 1 << 18
+    for impl_id, pkg, sgg in ((2, 1, 2), (1, 2, 1)):
+        pl, sl = B.pk_len(impl_id), B.sig_len(impl_id)
+        pk3, sg3 = np.empty(n * pl, dtype=np.uint8), np.empty(n * sl, dtype=np.uint8)
+        for lo in range(0, n, chunk):
+            hi = min(n, lo + chunk)
+            o = np.arange(hi - lo + 1, dtype=np.uint64) * 32
+            p, g = eng.testdata_sign(impl_id, 2, scal[lo:hi].reshape(-1), np.tile(one_msg, hi - lo), o)
+            pk3[lo * pl:hi * pl], sg3[lo * sl:hi * sl] = p, g
+        apk, t1 = _ms(lambda: eng.sum_points(pkg, pk3))
+        asg, t2 = _ms(lambda: eng.sum_points(sgg, sg3))
+        st, t3 = _ms(lambda: eng.verify_batch(impl_id, 2, [apk], [asg], [one_msg.tobytes()]))
+        assert st.tolist() == [0]
+        name = "G2Impl" if impl_id == 2 else "G1Impl"
+        out[f"cfg3_aggregate_{n}_signers_{name}"] = {"ms": t1 + t2 + t3, "sum_pk_ms": t1, "sum_sig_ms": t2, "verify_ms": t3,
+                                                      "items_per_s": n / ((t1 + t2 + t3) * 1e-3), "frac": frac(3750, n, t1 + t2 + t3)}
+        if impl_id == 1:
+            # G1Impl distinct-message batch verify (signatures in G1, keys in G2)
+            p1, s1, m1, o1 = synth_batch(eng, n, seed=4242, impl=1)
+            eng.verify_batch_packed(1, 0, p1, s1, m1, o1)
+            st, ms = _ms(lambda: eng.verify_batch_packed(1, 0, p1, s1, m1, o1))
+            assert int(st.max()) == 0
+            out["G1Impl_batch_verify"] = {"ms": ms, "items_per_s": n / (ms * 1e-3), "n": n}
+    # cfg 5: verify_secure / aggregate_secure over quorums of 400 members, Modern and Legacy
+    q, mem = quorums, 400
+    tot = q * mem
+    sc5 = np.zeros((tot, 32), dtype=np.uint8)
+    sc5[:, 8:] = rng.integers(0, 256, size=(tot, 24), dtype=np.uint8)
+    sc5[:, 31] |= 1
+    qm = rng.integers(0, 256, size=(q, 32), dtype=np.uint8)
+    qm[:, :8] = np.arange(q, dtype=np.uint64).view(np.uint8).reshape(q, 8)
+    pk5, sg5 = np.empty(tot * 48, dtype=np.uint8), np.empty(tot * 96, dtype=np.uint8)
+    for lo in range(0, tot, chunk):
+        hi = min(tot, lo + chunk)
+        o = np.arange(hi - lo + 1, dtype=np.uint64) * 32
+        p, g = eng.testdata_sign(2, 0, sc5[lo:hi].reshape(-1), np.ascontiguousarray(qm[np.arange(lo, hi) // mem]).reshape(-1), o)
+        pk5[lo * 48:hi * 48], sg5[lo * 96:hi * 96] = p, g
+    koff = np.arange(q + 1, dtype=np.uint64) * mem
+    qoff = np.arange(q + 1, dtype=np.uint64) * 32
+    for fmt, fname in ((1, "modern"), (0, "legacy")):
+        if fmt == 0:
+            pk5 = eng.recode_points_packed(1, pk5, 1, 0)
+            sg5 = eng.recode_points_packed(2, sg5, 1, 0)
+        (stq, aggs), ta = _ms(lambda: eng.aggregate_secure_batch_packed(2, koff, pk5, sg5, fmt))
+        assert int(stq.max()) == 0
+        st, tv = _ms(lambda: eng.verify_secure_batch_packed(2, 0, koff, pk5, aggs, qm.reshape(-1), qoff, fmt))
+        assert int(st.max()) == 0
+        swapped = aggs.copy().reshape(q, 96)
+        if q > 4:
+            swapped[[3, 4]] = swapped[[4, 3]]
+            st = eng.verify_secure_batch_packed(2, 0, koff, pk5, swapped.reshape(-1), qm.reshape(-1), qoff, fmt)
+            assert np.nonzero(st)[0].tolist() == [3, 4]
+        out[f"cfg5_verify_secure_{q}x{mem}_{fname}"] = {"ms": tv, "members_per_s": tot / (tv * 1e-3), "quorums_per_s": q / (tv * 1e-3),
+                                                        "frac": frac(2400, tot, tv)}
+        out[f"cfg5_aggregate_secure_{q}x{mem}_{fname}"] = {"ms": ta, "members_per_s": tot / (ta * 1e-3)}
+    return out
+
+
 _RESULT_FD = None
 
 
@@ -171,6 +290,8 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=0, help="signatures per step for --impl reference (0 = 1,024: configs[0])")
     ap.add_argument("--cpu-sample", type=int, default=0, help="signatures for the cpu_baseline leg (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE.json configs (cfg 1, 3, 4, 5, failure path)")
+    ap.add_argument("--quorums", type=int, default=int(os.environ.get("BLSGPU_BENCH_QUORUMS", 10_000)), help="cfg 5 quorums of 400 members")
     args = ap.parse_args()
     _claim_stdout()
 
@@ -278,7 +399,8 @@ def main():
                  for k, v in stages.items()}
     traffic = None
     try:  # dram bytes per launch of the dominant kernel from the committed ncu capture of this round (profiles/)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json")))
+        tp = os.path.join(ROOT, "profiles", "traffic_r2.json")
+        tr = json.load(open(tp if os.path.exists(tp) else os.path.join(ROOT, "profiles", "traffic_r1.json")))
         traffic = tr.get(dom, {}).get("dram_bytes_per_sig", None)
         traffic = traffic * n / per_kernel[dom]["launches_per_step"] if traffic is not None else None
     except Exception:
@@ -301,11 +423,32 @@ def main():
         "config": {"workload": f"Bls12381G2Impl Basic batch verify, {n} distinct 32-byte messages per GPU, compressed inputs "
                                "(48 B pk + 96 B sig), hash_to_curve + pairing, all valid",
                    "sigs_per_gpu": n, "l2": "inputs (176 B/sig) and the 39 KB/sig Miller line records exceed L2 at 1M: everything streams through HBM",
-                   "miller_loops_per_s_per_gpu": n * args.steps / (ms_total * 1e-3)},
+                   "miller_loops_per_s_per_gpu": (n / (stages["miller"] * 1e-3)) if stages.get("miller") else None,
+                   "miller_loops_note": "n Miller loops / device time of the Miller stage (prep + lines + accumulator kernels)"},
         "roofline": roofline, "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 176 + (n + 1) * 8), "d2h_bytes_per_step": int(n)},
         "gpu_launches": int(launches),
     }
+    # strong scaling: ONE batch of n signatures cut over the ranks; every rank folds its slice into one partial product of
+    # Miller values + one partial sum, the 672-byte partial results are exchanged (NCCL all_gather), every rank runs the single
+    # Miller loop + final exponentiation of the whole batch and finishes its slice (host buffers in and out)
+    def all_gather_parts(part):
+        mine = torch.tensor(list(part[0] + part[1]), dtype=torch.uint8, device=dev)
+        outs = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(outs, mine)
+        return [(bytes(o[:576].tolist()), bytes(o[576:].tolist())) for o in outs]
+
+    def step_strong():
+        return B.verify_batch_folded(eng, impl, scheme, np_pk, np_sig, np_msg, np_off, rank, world, all_gather_parts)
+
+    lo_s, st = step_strong()
+    assert int(st.max()) == 0
+    ms_strong = timed(step_strong, e2e_steps)
+    line["strong_scaling"] = {"batch": n, "n_gpus": world, "ms_per_batch": ms_strong / e2e_steps, "value": n * e2e_steps / (ms_strong * 1e-3),
+                              "unit": UNIT, "exchange_bytes_per_rank": 672,
+                              "what": "ONE batch cut over the ranks: per-rank partial Fp12 + partial sum, all_gather, single final exponentiation"}
+    if rank == 0 and world == 1 and not args.no_configs:
+        line["configs"] = other_configs(eng, B, (pks, sigs, msgs, off), peak_mac, args.quorums)
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline((pks, sigs, msgs, off), args.cpu_sample or 256 * (os.cpu_count() or 1))
     if rank == 0:

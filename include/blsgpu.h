@@ -57,10 +57,11 @@ extern "C" {
 typedef struct blsgpu_ctx blsgpu_ctx;
 
 /* Create a context on the given CUDA devices (ndev >= 1).  With several devices, blsgpu_verify_batch and
- * blsgpu_pop_verify_batch shard a batch of at least 4096 items per device into contiguous slices, one per device, each
- * driven by its own host thread and verified as a batch of its own (per-item results are independent, so there is no
- * collective and no combine step); every other entry point, the *_dev variants and blsgpu_ctx_set_stream use the first
- * device.  One context per device in one process (or one process per device) works just as well. */
+ * blsgpu_pop_verify_batch cut a batch of at least 4096 items per device into contiguous slices, one per device, each
+ * driven by its own host thread; the slices' partial results (one Fp12 and one point each) are folded on the first device
+ * into a single Miller loop + final exponentiation for the whole batch, and only a device whose slice fails bisects (no
+ * collective: 2 x ndev copies of < 1 KB).  Every other entry point, the *_dev variants and blsgpu_ctx_set_stream use the
+ * first device.  One process per device with blsgpu_miller_partial / blsgpu_final_exp_is_one does the same across processes. */
 int blsgpu_ctx_create(const int* devices, int ndev, blsgpu_ctx** out);
 void blsgpu_ctx_destroy(blsgpu_ctx* ctx);
 /* Text of the last engine error on this context (or of the last failed blsgpu_ctx_create when ctx is NULL). */
@@ -95,6 +96,25 @@ int blsgpu_verify_batch(blsgpu_ctx* ctx, int impl_id, int scheme, int format, si
 int blsgpu_verify_batch_dev(blsgpu_ctx* ctx, int impl_id, int scheme, int format, size_t n, const uint8_t* pks_dev,
                             const uint8_t* sigs_dev, const uint8_t* msgs_dev, const uint64_t* msg_off_dev,
                             uint8_t* status_out_dev);
+
+/* ---- one batch cut over several GPUs / processes ---------------------------------------------------
+ * The random-linear-combination check of a batch factors over slices: every slice folds into ONE partial product of
+ * Miller values F_j = prod_i ML(r_i pk_i, H(m_i)) and ONE partial sum S_j = sum_i r_i sig_i; the batch is valid iff
+ * prod_j F_j * e(-g, sum_j S_j) == 1 - a single Miller loop and a single final exponentiation for the whole batch
+ * (replaces `multi_miller_loop(..).final_exponentiation()`, reference src/helpers.rs:50,62, across devices).
+ *   1. every process:  blsgpu_miller_partial on its slice -> gt_out (576 B: the coefficients of w^0..w^5 of F_j, each c0 || c1
+ *      as 48-byte big-endian canonical values) and sum_out (S_j as an IETF compressed point of the signature group, 96 | 48 B).
+ *      The slice's decode / identity statuses and its product and sum trees stay in the context.
+ *   2. any process (or all, redundantly): blsgpu_final_exp_is_one over the k <= 16 gathered partial results.
+ *   3. every process:  blsgpu_partial_finish(batch_ok, status_out[n]): if the batch check passed, the statuses are final;
+ *      otherwise the slice checks its own partial results and bisects only if they fail too.
+ * A context created on several devices does the same inside blsgpu_verify_batch with one host thread per device.
+ * Any other call on the context between steps 1 and 3 discards the pending slice. */
+int blsgpu_miller_partial(blsgpu_ctx* ctx, int impl_id, int scheme, int format, size_t n, const uint8_t* pks, const uint8_t* sigs,
+                          const uint8_t* msgs, const uint64_t* msg_off, uint8_t gt_out[576], uint8_t* sum_out);
+int blsgpu_final_exp_is_one(blsgpu_ctx* ctx, int impl_id, size_t k, const uint8_t* partial_gts, const uint8_t* partial_sums,
+                            int* is_one_out);
+int blsgpu_partial_finish(blsgpu_ctx* ctx, int batch_ok, uint8_t* status_out);
 
 /* ---- ProofOfPossession::verify over a slice:  core_verify(pk, sig, msg = pk.to_bytes(), POP_DST)
  * (reference src/proof_of_possession.rs:77-81, src/traits/sig_pop.rs:61-70) */

@@ -5,6 +5,7 @@
 #include "../../agora-blsful_b200/csrc/pairing.cuh"
 #include "../../agora-blsful_b200/csrc/h2c.cuh"
 #include "../../agora-blsful_b200/csrc/miller6.cuh"
+#include "../../agora-blsful_b200/csrc/finalexp6.cuh"
 #include "../../agora-blsful_b200/csrc/fr.cuh"
 
 using namespace bls;
@@ -246,6 +247,25 @@ int emu_miller6(int n, const uint8_t* p48, const uint8_t* q96, const uint32_t* k
   fp12_out(ml_out, f);
   final_exponentiation(g, f); fp12_out(fe_out, g);
   return 0;
+}
+// cooperative final exponentiation of finalexp6.cuh (lanes emulated one after the other): out = f^(3 (p^12-1)/r) and the
+// lane-wise "== 1" test; mul_out = f * g through the general six-lane product
+int emu_final6(const uint8_t* f576, const uint8_t* g576, uint8_t* fe_out, uint8_t* mul_out) {
+  static SAccRec R[FE6_NREG * 6];
+  Fp12 f, g, scratch, o;
+  fp12_in(f, f576); fp12_in(g, g576);
+  Fe6 cx;
+  cx.R = R; cx.scratch = &scratch; cx.k = 0; cx.mask = 0;
+  for (int k = 0; k < 6; k++) { fe6_load_coeff(fe6_reg(cx, 0)[k], *fp12_coeff(f, k)); fe6_load_coeff(fe6_reg(cx, 1)[k], *fp12_coeff(g, k)); }
+  fe6_mul(cx, 2, 0, 1);
+  for (int k = 0; k < 6; k++) fe6_store_coeff(*fp12_coeff(o, k), fe6_reg(cx, 2)[k]);
+  fp12_out(mul_out, o);
+  fe6_final_exponentiation(cx);
+  for (int k = 0; k < 6; k++) fe6_store_coeff(*fp12_coeff(o, k), fe6_reg(cx, 0)[k]);
+  fp12_out(fe_out, o);
+  int one = 1;
+  for (int k = 0; k < 6; k++) one &= fe6_lane_is_one(cx, k) ? 1 : 0;
+  return one;
 }
 // Fr: c = a*b mod r, d = a^-1 mod r (32-byte big-endian in and out), and the Lagrange coefficient at zero of share i
 int emu_fr_ops(const uint8_t* a32, const uint8_t* b32, uint8_t* mul_out, uint8_t* inv_out) {

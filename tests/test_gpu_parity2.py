@@ -417,3 +417,78 @@ def test_verify_batch_records_lengths_tags_and_formats(eng, B, impl):
     got = eng.verify_batch_records(impl, O.MODERN, -1, [r[0] for r in recs], [r[1] for r in recs], [r[2] for r in recs])
     assert got.tolist() == [0, 0, 0, 4, 4, O.verify(impl, 1, O.MODERN, pk[0], tagged[0][1:], msgs[0]), 6]
     assert got[5] == 1
+
+
+# ---- one batch cut over several slices, folded into a single Miller loop + final exponentiation ----------------
+def test_partial_results_fold_and_finish(B, cpp):
+    """blsgpu_miller_partial / blsgpu_final_exp_is_one / blsgpu_partial_finish with three contexts on one GPU standing in
+    for three devices: statuses equal blsgpu_verify_batch's; the partial results satisfy the batch equation under the
+    ORACLE's pairing as well; a tampered partial result makes the fold fail."""
+    rnd = random.Random(555)
+    n = 3 * 4200 + 5
+    k = np.frombuffer(b"".join(rnd.randrange(1, O.R).to_bytes(32, "big") for _ in range(n)), dtype=np.uint8)
+    msgs = [hashlib.sha256(b"fold%d" % i).digest()[: 1 + i % 32] for i in range(n)]
+    data, off = B.pack_messages(msgs)
+    engs = [B.Engine([0]) for _ in range(3)]
+    try:
+        pks, sigs = engs[0].testdata_sign(2, 1, k, data, off)       # MessageAugmentation: the pk prefix travels with each slice
+        sigs = sigs.copy()
+        for trial, bad in enumerate(([], [4200 + 7, 4200 + 8, 2 * 4200 - 1])):   # all valid; three bad items, all in slice 1
+            s2 = sigs.reshape(n, 96).copy()
+            for i in bad:
+                s2[i] = sigs.reshape(n, 96)[(i + 11) % n]
+            s2[3] = 0; s2[3, 0] = 0xC0                               # an identity signature in slice 0: status 2, no failure
+            flat = s2.reshape(-1)
+            want = engs[0].verify_batch_packed(2, 1, pks, flat, data, off)
+            assert [i for i in range(n) if want[i] == 1] == bad and want[3] == 2
+            parts, ranges = [], []
+            for r, e in enumerate(engs):
+                lo, hi = B.shard_range(n, r, 3)
+                ranges.append((lo, hi))
+                parts.append(e.miller_partial(2, 1, pks[48 * lo:48 * hi], flat[96 * lo:96 * hi], data, off[lo:hi + 1]))
+            ok = engs[2].final_exp_is_one(2, [p[0] for p in parts], [p[1] for p in parts])
+            assert ok == (not bad)
+            got = np.concatenate([e.partial_finish(hi - lo, ok) for e, (lo, hi) in zip(engs, ranges)])
+            assert np.array_equal(got, want)
+            if trial == 0:
+                # the oracle agrees that the folded equation holds:  prod F_j * e(-g, sum S_j) == 1
+                f = O.F12_ONE
+                s = None
+                for gt, sm in parts:
+                    f = O.f12_mul(f, tuple((int.from_bytes(gt[96 * i:96 * i + 48], "big"), int.from_bytes(gt[96 * i + 48:96 * i + 96], "big")) for i in range(6)))
+                    s = O.g2_add(s, O.g2_deserialize(sm))
+                f = O.f12_mul(f, O.miller_loop(O.g1_neg(O.G1_GEN), s))
+                assert O.final_exponentiation(f) == O.F12_ONE
+                # and that a tampered partial result breaks it
+                assert not engs[1].final_exp_is_one(2, [parts[0][0], parts[1][0], parts[1][0]], [p[1] for p in parts])
+                assert not engs[1].final_exp_is_one(2, [p[0] for p in parts], [parts[0][1], parts[0][1], parts[2][1]])
+                assert engs[1].final_exp_is_one(2, [p[0] for p in parts[::-1]], [p[1] for p in parts[::-1]])   # order-free
+        # an empty slice is (1, O)
+        gt, sm = engs[0].miller_partial(2, 0, np.zeros(0, np.uint8), np.zeros(0, np.uint8), np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+        assert gt == (1).to_bytes(48, "big") + bytes(528) and sm == ident(96)
+        assert engs[0].final_exp_is_one(2, [gt], [sm]) and engs[0].partial_finish(0, True).size == 0
+        with pytest.raises(B.EngineError):
+            engs[0].final_exp_is_one(2, [bytes([0xff]) * 576], [sm])
+    finally:
+        for e in engs:
+            e.close()
+
+
+def test_small_batches_and_probe_paths(eng, B):
+    """The cooperative probes (six-lane Miller loop + final exponentiation) on every small shape: 1, 2, 5, 6, 7, 13, 97 items,
+    each all-valid and with every second item invalid (all leaves of the tree probed), both impls."""
+    rnd = random.Random(777)
+    for impl in (2, 1):
+        sl = B.sig_len(impl)
+        nmax = 97
+        k = np.frombuffer(b"".join(rnd.randrange(1, O.R).to_bytes(32, "big") for _ in range(nmax)), dtype=np.uint8)
+        data, off = B.pack_messages([b"small-%d" % i for i in range(nmax)])
+        pks, sigs = eng.testdata_sign(impl, 0, k, data, off)
+        pl = B.pk_len(impl)
+        for n in (1, 2, 5, 6, 7, 13, 97):
+            assert eng.verify_batch_packed(impl, 0, pks[:pl * n], sigs[:sl * n], data, off[:n + 1]).tolist() == [0] * n
+            s2 = sigs[:sl * n].copy().reshape(n, sl)
+            bad = list(range(0, n, 2))
+            s2[bad] = sigs.reshape(nmax, sl)[[(b + 1) % nmax for b in bad]]
+            st = eng.verify_batch_packed(impl, 0, pks[:pl * n], s2.reshape(-1), data, off[:n + 1])
+            assert st.tolist() == [1 if i % 2 == 0 else 0 for i in range(n)], (impl, n)

@@ -275,6 +275,30 @@ def test_miller6_cooperative(L):
         assert bf12(fe.raw) == want
 
 
+def test_final6_cooperative_final_exponentiation(L):
+    """finalexp6.cuh: the six-lane final exponentiation equals the one-thread tower version (fp12.cuh), which equals the
+    big-int oracle's plain power cubed; the six-lane general product equals the oracle's Fp12 product."""
+    rnd = random.Random(66)
+    def rand12():
+        return tuple((rnd.randrange(P), rnd.randrange(P)) for _ in range(6))
+    for trial in range(2):
+        f, g = rand12(), rand12()
+        fe, mul = buf(576), buf(576)
+        one = L.emu_final6(f12b(f), f12b(g), fe, mul)
+        assert mul.raw == f12b(O.f12_mul(f, g))
+        want = buf(576)
+        L.emu_final_exp(f12b(f), want)
+        assert fe.raw == want.raw and one == 0
+        if trial == 0:
+            assert fe.raw == f12b(O.f12_pow(O.final_exponentiation(f), 3))
+    # a value whose exponentiation IS one: e(aP, Q) * e(-P, aQ)
+    a = 0xabcdef
+    m = O.f12_mul(O.miller_loop(O.g1_mul(O.G1_GEN, a), O.G2_GEN), O.miller_loop(O.g1_neg(O.G1_GEN), O.g2_mul(O.G2_GEN, a)))
+    fe, mul = buf(576), buf(576)
+    assert L.emu_final6(f12b(m), f12b(O.F12_ONE), fe, mul) == 1
+    assert fe.raw == f12b(O.F12_ONE) and mul.raw == f12b(m)
+
+
 def test_windowed_scalar_multiplication(L):
     """csrc/curve.cuh jac_mul_aff_w4_64 (the r_i * pk_i of the batch equation): zero digits, zero top window, all-ones."""
     rnd = random.Random(9)
