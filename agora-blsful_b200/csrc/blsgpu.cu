@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <thread>
@@ -885,6 +886,23 @@ int blsgpu_ctx_create(const int* devices, int ndev, blsgpu_ctx** out) {
     ctx->peers.push_back(peer);
   }
   cudaSetDevice(devices[0]);
+  // the device code vouches for itself once per process (and per first device): ~50 ms; BLSGPU_SKIP_SELFTEST=1 skips it
+  static std::mutex selftest_mutex;
+  static std::vector<int> selftested;
+  {
+    std::lock_guard<std::mutex> lock(selftest_mutex);
+    const char* skip = getenv("BLSGPU_SKIP_SELFTEST");
+    if (!(skip && skip[0] == '1') && std::find(selftested.begin(), selftested.end(), devices[0]) == selftested.end()) {
+      selftested.push_back(devices[0]);  // before the call: the self-test's own entry points do not create contexts, but stay safe
+      const int r = blsgpu_selftest(ctx);
+      if (r != BLSGPU_OK) {
+        g_create_error = ctx->err;
+        blsgpu_ctx_destroy(ctx);
+        return r;
+      }
+      ctx->launches = 0;
+    }
+  }
   *out = ctx;
   return BLSGPU_OK;
 }
@@ -1150,7 +1168,8 @@ int fold_bytes_impl(blsgpu_ctx* ctx, size_t k, const uint8_t* gts, const uint8_t
   }
   CK(cudaMemcpyAsync(d_gt, gts, 576 * k, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_sb, sums, Ls * k, cudaMemcpyHostToDevice, ctx->stream));
-  LAUNCH(k_fp12_from_bytes, blocks_for(k), TPB, k, (const uint8_t*)d_gt, d_Fk, d_flag);
+  CK(cudaMemsetAsync(d_flag, 0, 2 * k, ctx->stream));
+  LAUNCH(k_fp12_from_bytes, blocks_for(12 * k), TPB, k, (const uint8_t*)d_gt, d_Fk, d_flag);
   CKR((decode_points<SigA>(ctx, k, (const uint8_t*)d_sb, 1, d_aff, d_flag + k)));
   LAUNCH((k_aff_to_jac<SigA>), blocks_for(k), TPB, k, (const SigA*)d_aff, d_Sk);
   std::vector<uint8_t> flag(2 * k);
@@ -1616,6 +1635,9 @@ struct SecurePlan {
 
 // sorts every key set by serialized bytes (reference src/secure_aggregation.rs:42,281: sort_by on the byte strings; the
 // sort is stable, and a valid compressed encoding is canonical, so the caller's bytes are the reference's sort keys)
+// blocks of the key-set multi-scalar multiplication: four warps (= four key sets in flight) per block, a few blocks per SM
+size_t secure_msm_blocks(const blsgpu_ctx* ctx, size_t q) { return std::max<size_t>(1, std::min<size_t>((q + 3) / 4, (size_t)ctx->sm_count * 4)); }
+
 SecurePlan make_secure_plan(size_t q, const uint64_t* key_off, const uint8_t* pks, size_t L) {
   SecurePlan pl;
   pl.q = q;
@@ -1648,38 +1670,36 @@ SecurePlan make_secure_plan(size_t q, const uint64_t* key_off, const uint8_t* pk
   return pl;
 }
 
-// device part shared by verify and aggregate: out_sum[j] = sum_i t_i * points[src(i)] ; zero_out[m] flags t_m == 0
+// device part shared by verify and aggregate: out_sum[j] = sum_i t_i * points[src(i)] ; zero_out[m] flags t_m == 0.
+// One bucket multi-scalar multiplication per key set: a warp per set, a lane per 8-bit window (kernels.cuh k_secure_msm).
 template <class A>
 int secure_weighted_sums(blsgpu_ctx* ctx, const SecurePlan& pl, const uint64_t* key_off, const uint8_t* d_key_bytes, int key_len, const std::vector<uint32_t>& src,
                          const A* d_points, typename PtInfo<A>::Jac* d_sum, uint8_t* d_zero) {
   typedef typename PtInfo<A>::Jac J;
-  uint32_t *d_ord, *d_set, *d_pos, *d_src, *d_cs, *d_cc, *d_ss, *d_sc;
+  uint32_t *d_ord, *d_set, *d_pos, *d_src;
   uint64_t* d_koff;
   CKR(upload(ctx, d_koff, key_off, pl.q + 1));
   CKR(upload(ctx, d_ord, pl.ord.data(), pl.M));
   CKR(upload(ctx, d_set, pl.set_of.data(), pl.M));
   CKR(upload(ctx, d_pos, pl.pos.data(), pl.M));
   CKR(upload(ctx, d_src, src.data(), pl.M));
-  CKR(upload(ctx, d_cs, pl.c_start.data(), pl.c_start.size()));
-  CKR(upload(ctx, d_cc, pl.c_cnt.data(), pl.c_cnt.size()));
-  CKR(upload(ctx, d_ss, pl.s_start.data(), pl.q));
-  CKR(upload(ctx, d_sc, pl.s_cnt.data(), pl.q));
   Digest* d_base = ctx->arena.take<Digest>(pl.q);
-  J* d_scaled = ctx->arena.take<J>(std::max<size_t>(pl.M, 1));
-  J* d_part = ctx->arena.take<J>(std::max<size_t>(pl.c_start.size(), 1));
+  int8_t* d_digits = ctx->arena.take<int8_t>(std::max<size_t>(pl.M, 1) * SECURE_WINDOWS);
+  const size_t nblocks = secure_msm_blocks(ctx, pl.q);
+  J* d_buckets = ctx->arena.take<J>(nblocks * 128 * SECURE_BUCKETS);
+  J* d_W = ctx->arena.take<J>(pl.q * SECURE_WINDOWS);
   LAUNCH(k_secure_base, blocks_for(pl.q), TPB, pl.q, (const uint64_t*)d_koff, (const uint32_t*)d_ord, d_key_bytes, key_len, d_base);
-  if (pl.M) {
-    LAUNCH((k_secure_scale<A>), blocks_for(pl.M), TPB, pl.M, (const uint32_t*)d_set, (const uint32_t*)d_pos, (const uint32_t*)d_src,
-           (const Digest*)d_base, d_points, d_scaled, d_zero);
-    LAUNCH((k_seg_sum<J>), blocks_for(pl.c_start.size()), TPB, pl.c_start.size(), (const uint32_t*)d_cs, (const uint32_t*)d_cc,
-           (const J*)d_scaled, d_part);
-  }
-  LAUNCH((k_seg_sum<J>), blocks_for(pl.q), TPB, pl.q, (const uint32_t*)d_ss, (const uint32_t*)d_sc, (const J*)d_part, d_sum);
+  if (pl.M)
+    LAUNCH(k_secure_digits, blocks_for(pl.M), TPB, pl.M, (const uint32_t*)d_set, (const uint32_t*)d_pos, (const Digest*)d_base, d_digits, d_zero);
+  LAUNCH((k_secure_msm<A>), (unsigned)nblocks, 128, pl.q, (const uint64_t*)d_koff, (const uint32_t*)d_src, (const int8_t*)d_digits, d_points,
+         d_buckets, d_W);
+  LAUNCH((k_secure_combine<J>), blocks_for(pl.q), TPB, pl.q, (const J*)d_W, d_sum);
   return BLSGPU_OK;
 }
 
-size_t secure_plan_bytes(const SecurePlan& pl, size_t jac_size) {
-  return (pl.q + 1) * 8 + pl.M * 16 + pl.c_start.size() * 8 + pl.q * 8 + pl.q * 32 + (pl.M + pl.c_start.size() + 2) * jac_size + 24 * 256;
+size_t secure_plan_bytes(const blsgpu_ctx* ctx, const SecurePlan& pl, size_t jac_size) {
+  return (pl.q + 1) * 8 + pl.M * (16 + SECURE_WINDOWS) + pl.q * 32 + secure_msm_blocks(ctx, pl.q) * 128 * SECURE_BUCKETS * jac_size +
+         (pl.q * SECURE_WINDOWS + 2) * jac_size + 24 * 256;
 }
 
 template <int IMPL>
@@ -1692,7 +1712,7 @@ int verify_secure_impl(blsgpu_ctx* ctx, int scheme, int format, size_t q, const 
   SecurePlan pl = make_secure_plan(q, key_off, pks, Lp);
   const size_t M = pl.M, msg_bytes = (size_t)msg_off[q];
   size_t head = M * (Lp + sizeof(PkA) + 2) + q * (Ls + 2 * sizeof(SigA) + sizeof(PkA) + sizeof(PkJ) + 8) + msg_bytes + (q + 1) * 8 +
-                secure_plan_bytes(pl, sizeof(PkJ)) + 32 * 256;
+                secure_plan_bytes(ctx, pl, sizeof(PkJ)) + 32 * 256;
   CKR(ensure_verify_arena<IMPL>(ctx, q, head));
   stage_reset(ctx);
   uint8_t *d_pkb, *d_sigb, *d_msgs;
@@ -1760,7 +1780,7 @@ int aggregate_secure_impl(blsgpu_ctx* ctx, int format, size_t q, const uint64_t*
   SecurePlan pl = make_secure_plan(q, key_off, pks, Lp);
   const size_t M = pl.M;
   size_t need = M * (Lp + Ls + sizeof(PkA) + sizeof(SigA) + 3) + q * (Ls + sizeof(SigA) + sizeof(SigJ) + 8) +
-                secure_plan_bytes(pl, sizeof(SigJ)) + 32 * 256;
+                secure_plan_bytes(ctx, pl, sizeof(SigJ)) + 32 * 256;
   CKR(ensure_arena(ctx, need));
   uint8_t *d_pkb, *d_sigb;
   CKR(upload(ctx, d_pkb, pks, M * Lp));
@@ -1853,43 +1873,34 @@ static int combine_shares_impl(blsgpu_ctx* ctx, size_t q, const uint64_t* share_
   typedef typename PtInfo<A>::Jac J;
   const size_t L = PtInfo<A>::LEN, REC = 32 + L, M = (size_t)share_off[q];
   std::vector<uint8_t> ids(M * 32), pts(M * L);
-  std::vector<uint32_t> set_of(M), c_start, c_cnt, s_start, s_cnt;
-  for (size_t j = 0; j < q; j++) {
-    const size_t lo = (size_t)share_off[j], hi = (size_t)share_off[j + 1];
-    s_start.push_back((uint32_t)c_start.size());
-    for (size_t i = lo; i < hi; i++) {
+  std::vector<uint32_t> set_of(M), iota(M);
+  for (size_t j = 0; j < q; j++)
+    for (size_t i = (size_t)share_off[j]; i < (size_t)share_off[j + 1]; i++) {
       memcpy(&ids[i * 32], shares + i * REC, 32);
       memcpy(&pts[i * L], shares + i * REC + 32, L);
       set_of[i] = (uint32_t)j;
+      iota[i] = (uint32_t)i;
     }
-    for (size_t i = lo; i < hi; i += 16) {
-      c_start.push_back((uint32_t)i);
-      c_cnt.push_back((uint32_t)std::min<size_t>(16, hi - i));
-    }
-    s_cnt.push_back((uint32_t)c_start.size() - s_start.back());
-  }
-  const size_t nc = c_start.size();
-  CKR(ensure_arena(ctx, M * (32 + L + 32 + sizeof(A) + sizeof(J) + 8) + (nc + q + 2) * (sizeof(J) + 8) + q * (sizeof(A) + L + 16) +
-                            (q + 1) * 8 + 32 * 256));
+  const size_t nblocks = secure_msm_blocks(ctx, q);
+  CKR(ensure_arena(ctx, M * (32 + L + 32 + sizeof(A) + SECURE_WINDOWS + 16) + q * (SECURE_WINDOWS + 2) * sizeof(J) +
+                            nblocks * 128 * SECURE_BUCKETS * sizeof(J) + q * (sizeof(A) + L + 16) + (q + 1) * 8 + 32 * 256));
   uint8_t *d_ids, *d_pts;
-  uint32_t *d_set, *d_cs, *d_cc, *d_ss, *d_sc;
+  uint32_t *d_set, *d_iota;
   uint64_t* d_off;
   CKR(upload(ctx, d_ids, ids.data(), M * 32));
   CKR(upload(ctx, d_pts, pts.data(), M * L));
   CKR(upload(ctx, d_set, set_of.data(), M));
+  CKR(upload(ctx, d_iota, iota.data(), M));
   CKR(upload(ctx, d_off, share_off, q + 1));
-  CKR(upload(ctx, d_cs, c_start.data(), nc));
-  CKR(upload(ctx, d_cc, c_cnt.data(), nc));
-  CKR(upload(ctx, d_ss, s_start.data(), q));
-  CKR(upload(ctx, d_sc, s_cnt.data(), q));
   uint32_t* d_raw = ctx->arena.take<uint32_t>(std::max<size_t>(M, 1) * 8);
   uint8_t* d_idflag = ctx->arena.take<uint8_t>(std::max<size_t>(M, 1));
   uint8_t* d_stpt = ctx->arena.take<uint8_t>(std::max<size_t>(M, 1));
   uint8_t* d_dup = ctx->arena.take<uint8_t>(std::max<size_t>(M, 1));
   uint8_t* d_bad = ctx->arena.take<uint8_t>(q);
   A* d_p = ctx->arena.take<A>(std::max<size_t>(M, 1));
-  J* d_scaled = ctx->arena.take<J>(std::max<size_t>(M, 1));
-  J* d_part = ctx->arena.take<J>(std::max<size_t>(nc, 1));
+  int8_t* d_digits = ctx->arena.take<int8_t>(std::max<size_t>(M, 1) * SECURE_WINDOWS);
+  J* d_buckets = ctx->arena.take<J>(nblocks * 128 * SECURE_BUCKETS);
+  J* d_W = ctx->arena.take<J>(q * SECURE_WINDOWS);
   J* d_sum = ctx->arena.take<J>(q);
   A* d_res = ctx->arena.take<A>(q);
   uint8_t* d_out = ctx->arena.take<uint8_t>(q * L);
@@ -1915,12 +1926,14 @@ static int combine_shares_impl(blsgpu_ctx* ctx, size_t q, const uint64_t* share_
   }
   CK(cudaMemcpyAsync(d_bad, bad.data(), q, cudaMemcpyHostToDevice, ctx->stream));
   if (M) {
-    LAUNCH((k_share_scale<A>), blocks_for(M), TPB, M, (const uint32_t*)d_set, (const uint64_t*)d_off, (const uint8_t*)d_bad,
-           (const uint32_t*)d_raw, (const A*)d_p, d_scaled, d_dup);
-    LAUNCH((k_seg_sum<J>), blocks_for(nc), TPB, nc, (const uint32_t*)d_cs, (const uint32_t*)d_cc, (const J*)d_scaled, d_part);
+    // lambda_i as window digits, then one bucket multi-scalar multiplication per share set (a warp per set)
+    LAUNCH(k_share_digits, blocks_for(M), TPB, M, (const uint32_t*)d_set, (const uint64_t*)d_off, (const uint8_t*)d_bad, (const uint32_t*)d_raw,
+           d_digits, d_dup);
     CK(cudaMemcpyAsync(dup.data(), d_dup, M, cudaMemcpyDeviceToHost, ctx->stream));
   }
-  LAUNCH((k_seg_sum<J>), blocks_for(q), TPB, q, (const uint32_t*)d_ss, (const uint32_t*)d_sc, (const J*)d_part, d_sum);
+  LAUNCH((k_secure_msm<A>), (unsigned)nblocks, 128, q, (const uint64_t*)d_off, (const uint32_t*)d_iota, (const int8_t*)d_digits, (const A*)d_p,
+         d_buckets, d_W);
+  LAUNCH((k_secure_combine<J>), blocks_for(q), TPB, q, (const J*)d_W, d_sum);
   LAUNCH((k_to_affine<A>), blocks_for(q), TPB, q, (const J*)d_sum, d_res);
   LAUNCH((k_encode<A>), blocks_for(q), TPB, q, (const A*)d_res, 1, d_out);
   CK(cudaMemcpyAsync(out, d_out, q * L, cudaMemcpyDeviceToHost, ctx->stream));
@@ -2276,6 +2289,53 @@ int blsgpu_verify_batch_records(blsgpu_ctx* ctx, int impl_id, int format, int sc
                             st.data()));
     for (size_t k = 0; k < idx.size(); k++) status_out[idx[k]] = st[k];
   }
+  return BLSGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Known-answer self-test of the device code.  This code base has met device-only wrong results that were compiler
+// artefacts (a dropped struct copy in cicc, stack colouring): a build that miscompiles the arithmetic
+// must fail HERE, loudly, not return wrong verdicts.  Vectors: the first C++ bls-signatures triple of the reference's
+// tests/cpp_integration_test.rs:19-82 (message "hello") and H("hello") derived from it (sig = sk * H).
+int blsgpu_selftest(blsgpu_ctx* ctx) {
+  if (!ctx) return BLSGPU_E_ARG;
+  static const uint8_t PK1[48] = {0xb1, 0x45, 0xdf, 0xcb, 0x3c, 0xbd, 0xef, 0x21, 0x50, 0x2f, 0x30, 0x5d, 0x1b, 0xa1, 0xcb, 0xa5, 0x84, 0x79, 0x69, 0x18, 0x57, 0x1e, 0x8b, 0x5d, 0x85, 0xbe, 0x17, 0x6f, 0x34, 0x45, 0xac, 0x7a, 0xd9, 0x9a, 0xec, 0x19, 0xe1, 0x93, 0x1b, 0x69, 0x34, 0xd7, 0x29, 0x0b, 0x97, 0xec, 0x2d, 0x75};
+  static const uint8_t SIG1[96] = {0x82, 0xc8, 0x08, 0x03, 0xa3, 0x24, 0x6f, 0x5d, 0x10, 0xb5, 0x19, 0x23, 0xd4, 0x96, 0x7b, 0xef, 0x55, 0x7c, 0xf0, 0x41, 0x6f, 0xa3, 0x06, 0x05, 0x94, 0x9c, 0xaa, 0xc6, 0x27, 0x3b, 0x59, 0x93, 0xd2, 0x6f, 0xef, 0x27, 0x8e, 0xb4, 0x86, 0x75, 0xc6, 0x2b, 0x42, 0x26, 0x6f, 0x9b, 0x01, 0x48, 0x0a, 0x8d, 0xc0, 0x7e, 0xf1, 0x68, 0xed, 0xd3, 0xf1, 0xa9, 0xca, 0xd3, 0x63, 0x30, 0x83, 0xdc, 0xb3, 0xc2, 0xdf, 0x37, 0x27, 0x89, 0xb8, 0x78, 0x71, 0x24, 0x9d, 0xab, 0x38, 0x0b, 0x07, 0x1d, 0xd4, 0x80, 0xd7, 0x42, 0xd0, 0x27, 0xf3, 0x7c, 0x36, 0xf8, 0x9e, 0x63, 0xb5, 0xf1, 0xe0, 0x93};
+  static const uint8_t SIG2[96] = {0xb2, 0xca, 0x57, 0x80, 0x16, 0xe8, 0x96, 0x20, 0xb4, 0x94, 0x03, 0xa0, 0x29, 0xad, 0x96, 0x40, 0x27, 0x2c, 0x18, 0x45, 0x5a, 0x5f, 0xdd, 0xc4, 0x0f, 0x99, 0x9b, 0xd7, 0x5c, 0xb9, 0xda, 0xc0, 0x71, 0x61, 0x3c, 0xb5, 0xa6, 0x64, 0xe0, 0xa7, 0x19, 0xa2, 0x29, 0xff, 0x65, 0x51, 0xfd, 0x52, 0x0b, 0x6d, 0x92, 0x96, 0x75, 0x08, 0xd5, 0xf1, 0xf5, 0x8c, 0xd4, 0x14, 0xcb, 0xde, 0x44, 0xc9, 0xe3, 0x91, 0x18, 0x73, 0xb4, 0xa2, 0xe9, 0x54, 0x44, 0x29, 0xb8, 0x67, 0x6f, 0xca, 0x69, 0xcb, 0x97, 0xab, 0xc6, 0xf4, 0x99, 0x16, 0xd0, 0x8c, 0xee, 0xda, 0x42, 0xb0, 0x6b, 0xe3, 0x6f, 0xf4};
+  static const uint8_t FA[48] = {0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x01, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x30, 0x39};
+  static const uint8_t FB[48] = {0x1a, 0x01, 0x11, 0xea, 0x39, 0x7f, 0xe6, 0x9a, 0x4b, 0x1b, 0xa7, 0xb6, 0x43, 0x4b, 0xac, 0xd7, 0x64, 0x77, 0x4b, 0x84, 0xf3, 0x85, 0x12, 0xbf, 0x67, 0x30, 0xd2, 0xa0, 0xf6, 0xb0, 0xf6, 0x24, 0x1e, 0xab, 0xff, 0xfe, 0xb1, 0x53, 0xff, 0xff, 0xb9, 0xfe, 0xff, 0xff, 0xff, 0xff, 0xaa, 0xa9};
+  static const uint8_t FAB[48] = {0x1a, 0x01, 0x11, 0xea, 0x39, 0x7f, 0xe6, 0x9a, 0x4b, 0x1b, 0xa7, 0xb6, 0x43, 0x4b, 0xac, 0xd7, 0x64, 0x77, 0x4b, 0x84, 0xf3, 0x85, 0x10, 0xbf, 0x67, 0x30, 0xd2, 0xa0, 0xf6, 0xb0, 0xf6, 0x24, 0x1e, 0xab, 0xff, 0xfe, 0xb1, 0x53, 0xff, 0xff, 0xb9, 0xfe, 0xff, 0xff, 0xff, 0xff, 0x4a, 0x39};
+  static const uint8_t HHELLO[96] = {0x8d, 0xbf, 0x4d, 0x3c, 0x42, 0x6b, 0xad, 0xac, 0x1e, 0x66, 0x42, 0x1c, 0x7d, 0x65, 0xdc, 0x01, 0x7c, 0x05, 0xfb, 0x76, 0x31, 0x83, 0x3f, 0x3c, 0x9a, 0x72, 0xf5, 0x31, 0xbe, 0xdf, 0x79, 0x95, 0xf2, 0x30, 0x9d, 0x2f, 0xd6, 0x83, 0x10, 0x18, 0xc8, 0x3d, 0xe0, 0xc2, 0x7b, 0x6a, 0x10, 0xc8, 0x10, 0x94, 0x69, 0x37, 0xad, 0x15, 0x67, 0x4b, 0x2f, 0x39, 0x76, 0xd1, 0x0f, 0x50, 0xae, 0x5a, 0x66, 0xa0, 0x7f, 0x5d, 0xa2, 0x3a, 0x4f, 0x17, 0x78, 0x70, 0x70, 0x2d, 0x0d, 0xbf, 0x84, 0x63, 0x22, 0x5a, 0x49, 0x3a, 0x8c, 0x22, 0x10, 0x32, 0xe1, 0x5d, 0x44, 0x5a, 0xfe, 0xac, 0x74, 0x8a};
+  static const uint8_t MSG[5] = {'h', 'e', 'l', 'l', 'o'};
+  static const char DST[] = "BLS_SIG_BLS12381G2_XMD:SHA-256_SSWU_RO_NUL_";
+  auto fail = [&](const char* what) {
+    ctx->err = std::string("self-test failed: ") + what + " (this build of libblsgpu.so computes wrong results; do not use it)";
+    return BLSGPU_E_CUDA;
+  };
+  uint8_t out[96];
+  for (int variant = 0; variant < 2; variant++) {
+    CKR(blsgpu_fp_mul_batch(ctx, variant, 1, FA, FB, out));
+    if (memcmp(out, FAB, 48) != 0) return fail("field multiplication");
+  }
+  const uint64_t off1[2] = {0, 5};
+  CKR(blsgpu_hash_to_curve_batch(ctx, 2, 1, MSG, off1, reinterpret_cast<const uint8_t*>(DST), sizeof(DST) - 1, out));
+  if (memcmp(out, HHELLO, 96) != 0) return fail("hash_to_curve");
+  uint8_t pks[96], sigs[192], msgs[10], st[2] = {9, 9};
+  memcpy(pks, PK1, 48); memcpy(pks + 48, PK1, 48);
+  memcpy(sigs, SIG1, 96); memcpy(sigs + 96, SIG2, 96);
+  memcpy(msgs, MSG, 5); memcpy(msgs + 5, MSG, 5);
+  const uint64_t off2[3] = {0, 5, 10};
+  CKR(blsgpu_verify_batch(ctx, 2, 0, 1, 2, pks, sigs, msgs, off2, st));
+  if (st[0] != BLSGPU_ST_OK || st[1] != BLSGPU_ST_INVALID_SIGNATURE) return fail("signature verification (pairing, final exponentiation, bisection)");
+  uint8_t gt[576], sum[96];
+  int one = 0;
+  CKR(blsgpu_miller_partial(ctx, 2, 0, 1, 1, PK1, SIG1, MSG, off1, gt, sum));
+  CKR(blsgpu_final_exp_is_one(ctx, 2, 1, gt, sum, &one));
+  CKR(blsgpu_partial_finish(ctx, one, st));
+  if (!one || st[0] != BLSGPU_ST_OK) return fail("fold of partial results (byte conversions)");
+  gt[100] ^= 1;
+  CKR(blsgpu_final_exp_is_one(ctx, 2, 1, gt, sum, &one));
+  if (one) return fail("fold of a tampered partial result");
   return BLSGPU_OK;
 }
 

@@ -258,6 +258,11 @@ int blsgpu_combine_shares_batch(blsgpu_ctx* ctx, int group, size_t q, const uint
 int blsgpu_verify_share_batch(blsgpu_ctx* ctx, int impl_id, int scheme, size_t n, const uint8_t* pk_shares,
                               const uint8_t* sig_shares, const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out);
 
+/* Known-answer self-test of the device code: field multiplication, hash_to_curve, one accepted and one rejected golden
+ * signature (reference tests/cpp_integration_test.rs:19-82), the fold of partial results.  Runs automatically at the first
+ * blsgpu_ctx_create of a process on a device (a failing build refuses to create contexts); may be called again at any time. */
+int blsgpu_selftest(blsgpu_ctx* ctx);
+
 /* Host-only planning query (no device needed): the window layout the bucket multi-scalar multiplication of
  * blsgpu_verify_batch uses for a batch of n signatures with scalar_bits-bit (64 | 128) scalars. */
 int blsgpu_plan_msm(size_t n, int scalar_bits, int* window_bits_out, int* windows_out, int* top_window_bits_out);
