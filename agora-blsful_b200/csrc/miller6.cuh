@@ -73,7 +73,7 @@ BLS_HD void m6_finish_lane(Fp2& out, const SAccRec& fa, int k) {
 // enters as three Fp scalars px = Xp Zp, -py = -Yp, pz = Zp^3 (affine: x, -y, 1), so a Jacobian r_i * pk_i needs no
 // inversion.  Lines are scaled by factors in proper subfields (erased by the final exponentiation):
 //   doubling:  B = Y^2, C = Z^2, J = X^2, E = 12 xi C;   U = B - 3E, V = B + 3E
-//              X3 = 2XY U,  Y3 = V^2 - 12 E^2,  Z3 = 8 B YZ                     (4 x the textbook (X3:Y3:Z3))
+//              X3 = 2XY U,  Y3 = V^2 - 12 E^2 = V^2 - 3 F^2 (F = 2E),  Z3 = 8 B YZ     (4 x the textbook (X3:Y3:Z3))
 //              l0 = (E - B) pz,  l2 = 3J px,  l3 = 2YZ (-py)
 //   addition:  u = y2 Z - Y, v = x2 Z - X, A = u^2 Z - v^3 - 2 v^2 X
 //              X3 = v A,  Y3 = u (v^2 X - A) - v^3 Y,  Z3 = v^3 Z
@@ -96,6 +96,8 @@ struct M6Op {
 };
 #define M6_T(a, b) {a, b, 0, 0, 0, 0, 0, 0}
 #define M6_TS(a, sha, b, shb, fl) {a, b, sha, shb, fl, 0, 0, 0}
+#define M6_SQ(a) {a, a, 0, 0, SOP_SQR, 0, 0, 0}
+#define M6_SQS(a, sha, shb, fl) {a, a, sha, shb, (fl) | SOP_SQR, 0, 0, 0}
 #define M6_SOP1(dst, t0) {0, dst, 1, 0, {t0, t0, t0}, 0, 0, 0, RNONE, RNONE, RNONE, 0, 0}
 #define M6_SOP2(dst, t0, t1) {0, dst, 2, 0, {t0, t1, t1}, 0, 0, 0, RNONE, RNONE, RNONE, 0, 0}
 #define M6_SOP3(dst, t0, t1, t2) {0, dst, 3, 0, {t0, t1, t2}, 0, 0, 0, RNONE, RNONE, RNONE, 0, 0}
@@ -104,9 +106,9 @@ struct M6Op {
 #define M6_LIN(dst, x, lx, fl, y, ly, z, lz) {1, dst, 0, 0, {M6_T(RNONE, RNONE), M6_T(RNONE, RNONE), M6_T(RNONE, RNONE)}, lx, ly, lz, x, y, z, fl, 0}
 // Ten records per pair (X, Y, Z and seven temporaries) is what lets THREE blocks of the lines kernel share an SM.
 BLS_CONST M6Op K_M6_DBL[] = {
-    M6_SOP1(RT0, M6_T(RY, RY)),                                   // B
-    M6_SOP1(RT1, M6_T(RZ, RZ)),                                   // C
-    M6_SOP1(RT2, M6_T(RX, RX)),                                   // J
+    M6_SOP1(RT0, M6_SQ(RY)),                                      // B   (squares: one product per lane instead of two)
+    M6_SOP1(RT1, M6_SQ(RZ)),                                      // C
+    M6_SOP1(RT2, M6_SQ(RX)),                                      // J
     M6_SOP1(RT3, M6_T(RX, RY)),                                   // XY
     M6_SOP1(RT4, M6_T(RY, RZ)),                                   // YZ
     M6_LIN(RT1, RT1, 12, SOP_XI, RNONE, 0, RNONE, 0),             // E = 12 xi C       (in place)
@@ -114,9 +116,11 @@ BLS_CONST M6Op K_M6_DBL[] = {
     M6_LIN(RT6, RT1, 3, 0, RT0, 1, RNONE, 0),                     // V = B + 3E
     M6_LIN(RT2, RT2, 3, 0, RNONE, 0, RNONE, 0),                   // J3 = 3J           (in place)
     M6_SOP1(RX, M6_TS(RT3, 1, RT5, 0, 0)),                        // X3 = 2XY U
-    M6_SOP3(RY, M6_T(RT6, RT6), M6_TS(RT1, 2, RT1, 1, SOP_NEG), M6_TS(RT1, 2, RT1, 0, SOP_NEG)),  // Y3 = V^2 - 8E^2 - 4E^2
+    M6_LIN(RT5, RT1, 1, 0, RT0, -1, RNONE, 0),                    // E - B             (U is dead; before E is doubled)
+    M6_SOPFP(RL0, M6_T(RT5, RPZ)),                                // l0 = (E - B) pz
+    M6_LIN(RT1, RT1, 2, 0, RNONE, 0, RNONE, 0),                   // F = 2E            (in place)
+    M6_SOP3(RY, M6_SQ(RT6), M6_SQS(RT1, 1, 0, SOP_NEG), M6_SQS(RT1, 0, 0, SOP_NEG)),  // Y3 = V^2 - 2F^2 - F^2 = V^2 - 12E^2
     M6_SOP1(RZ, M6_TS(RT0, 2, RT4, 1, 0)),                        // Z3 = 4B 2YZ
-    M6_SOPFP2(RL0, M6_T(RT1, RPZ), M6_TS(RT0, 0, RPZ, 0, SOP_NEG)),  // l0 = (E - B) pz
     M6_SOPFP(RL2, M6_T(RT2, RPX)),                                // l2 = 3J px
     M6_SOPFP(RL3, M6_TS(RT4, 1, RNPY, 0, 0)),                     // l3 = 2YZ (-py)
 };
@@ -125,14 +129,14 @@ BLS_CONST M6Op K_M6_ADD[] = {
     M6_SOP1(RT1, M6_TS(RNQX, 0, RZ, 0, SOP_NEG)),                 // x2 Z
     M6_LIN(RT0, RT0, 1, 0, RY, -1, RNONE, 0),                     // u
     M6_LIN(RT1, RT1, 1, 0, RX, -1, RNONE, 0),                     // v
-    M6_SOP1(RT2, M6_T(RT1, RT1)),                                 // vv
+    M6_SOP1(RT2, M6_SQ(RT1)),                                     // vv
     M6_SOP1(RT3, M6_T(RT1, RT2)),                                 // vvv
     M6_SOP1(RT4, M6_T(RT2, RX)),                                  // Rr = vv X
     M6_SOP2(RT2, M6_T(RT1, RQY), M6_T(RT0, RNQX)),                // v y2 - u x2       (vv is dead)
     M6_SOPFP(RL0, M6_T(RT2, RPZ)),                                // l0
     M6_SOPFP(RL2, M6_T(RT0, RPX)),                                // l2 = u px
     M6_SOPFP(RL3, M6_T(RT1, RNPY)),                               // l3 = v (-py)
-    M6_SOP1(RT2, M6_T(RT0, RT0)),                                 // uu
+    M6_SOP1(RT2, M6_SQ(RT0)),                                     // uu
     M6_SOP1(RT2, M6_T(RT2, RZ)),                                  // uu Z
     M6_LIN(RT2, RT2, 1, 0, RT3, -1, RT4, -2),                     // A = uu Z - vvv - 2 Rr
     M6_SOP1(RX, M6_T(RT1, RT2)),                                  // X3 = v A
@@ -141,6 +145,8 @@ BLS_CONST M6Op K_M6_ADD[] = {
 };
 #undef M6_T
 #undef M6_TS
+#undef M6_SQ
+#undef M6_SQS
 #undef M6_SOP1
 #undef M6_SOP2
 #undef M6_SOP3

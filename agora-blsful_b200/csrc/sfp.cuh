@@ -73,6 +73,8 @@ enum : uint32_t {
   SOP_NEG = 2u,       // A operand negated
   SOP_XI_LT2 = 8u,    // A operand times xi when the lane's coefficient index k < 2   (Fp12 wrap-around, miller6.cuh)
   SOP_XI_LT3 = 16u,   //                                                      k < 3
+  SOP_SQR = 32u,      // a and b name the SAME record (a square, up to the shifts): the two-lane unit sop1 then needs ONE
+                      // product per lane - (a0 + a1)(a0 - a1) | 2 a0 a1 - instead of two; other units may ignore the flag
 };
 constexpr int SOP_MAX_TERMS = 8;
 
@@ -418,6 +420,25 @@ BLS_HD SopPrep sop1_prep_b(int idx, int sh) {
 // res[14] = lane h's coefficient (balanced limbs).  Returns the value bound of the result under BLS_TRACK (else 0).
 // (inlined into its single call site: the result stays in registers; at most three terms: all are read up front so that no
 // product waits for a table load)
+// operand preparation of a SQUARE term: lane 0 multiplies (a0 + a1) by (a0 - a1), lane 1 multiplies 2 a0 by a1
+BLS_HD SopPrep sop1_prep_sqr_x(int h, int neg, int sh) {
+  SopPrep p;
+  p.m0 = -1;
+  p.m1 = -(h ^ 1);
+  p.n1 = 0;
+  p.ng = -neg;
+  p.sh = sh + h;
+  return p;
+}
+BLS_HD SopPrep sop1_prep_sqr_y(int h, int sh) {
+  SopPrep p;
+  p.m0 = -(h ^ 1);
+  p.m1 = -1;
+  p.n1 = -(h ^ 1);
+  p.ng = 0;
+  p.sh = sh;
+  return p;
+}
 BLS_HD double sop1_compute(int32_t* res, const SopTerm* t, int nt, int fp_mode, const SopSpaces& cx_, int h) {
   const SopSpaces cx = cx_;  // into registers once: the caller's copy lives in local memory
   const int lane_k = cx.k;
@@ -433,9 +454,12 @@ BLS_HD double sop1_compute(int32_t* res, const SopTerm* t, int nt, int fp_mode, 
     const SopTerm m = t[k];
     const SFp2 *pa = sop_rec(cx, m.a), *pb = sop_rec(cx, m.b);
     const double xi = sop_term_xi(m.fl, lane_k) ? 2.0 : 1.0;
+    const double sq = (m.fl & SOP_SQR) ? 2.0 : 1.0;  // (a0 + a1)(a0 - a1): both factors carry twice the limb / value bound
     const double la = pa->lb * (double)(1 << m.sha) * xi, lb = pb->lb * (double)(1 << m.shb);
-    BLS_REQ(la < 1073741824.0 && lb < 1073741824.0 && m.sha < 4 && m.shb < 4, "sop1 operand limb overflow");
-    col += 14.0 * 2.0 * la * lb;
+    BLS_REQ(la * sq < 1073741824.0 && lb * sq < 1073741824.0 && m.sha < 4 && m.shb < 4, "sop1 operand limb overflow");
+    BLS_REQ(!(m.fl & SOP_SQR) || (m.a == m.b && !fp_mode && xi == 1.0), "sop1 square term");
+    col += 14.0 * 2.0 * sq * la * lb;
+    // value: (a0 + a1)(a0 - a1) = a0^2 - a1^2 and 2 a0 a1 are the parts of the true square: no larger than a general product's
     vsum += 2.0 * pa->vb * (double)(1 << m.sha) * xi * pb->vb * (double)(1 << m.shb);
   }
   {
@@ -452,24 +476,37 @@ BLS_HD double sop1_compute(int32_t* res, const SopTerm* t, int nt, int fp_mode, 
     const SopTerm m = tm0;
     sop_fetch(ra, sop_rec(cx, m.a));
     sop_fetch(rb, sop_rec(cx, m.b));
-    sop_prep_apply(x, ra, sop1_prep_a(fp_mode ? h : 0, sop_term_xi(m.fl, lane_k), (m.fl & SOP_NEG) != 0, m.sha));
-    sop_prep_apply(y, rb, sop1_prep_b(fp_mode ? 0 : h, m.shb));
+    if (m.fl & SOP_SQR) {
+      sop_prep_apply(x, ra, sop1_prep_sqr_x(h, (m.fl & SOP_NEG) != 0, m.sha));
+      sop_prep_apply(y, rb, sop1_prep_sqr_y(h, m.shb));
+    } else {
+      sop_prep_apply(x, ra, sop1_prep_a(fp_mode ? h : 0, sop_term_xi(m.fl, lane_k), (m.fl & SOP_NEG) != 0, m.sha));
+      sop_prep_apply(y, rb, sop1_prep_b(fp_mode ? 0 : h, m.shb));
+    }
   }
   int k = 0, q = 0;
-  const int nsteps = per * nt;
+  int nsteps = 0;
+  nsteps += (tm0.fl & SOP_SQR) ? 1 : per;
+  if (nt > 1) nsteps += (tm1.fl & SOP_SQR) ? 1 : per;
+  if (nt > 2) nsteps += (tm2.fl & SOP_SQR) ? 1 : per;
 #pragma unroll 1
   for (int s = 0; s < nsteps; s++) {
-    const int qw = (q + 1 == per);
+    const SopTerm cur = k == 0 ? tm0 : k == 1 ? tm1 : tm2;
+    const int perk = (cur.fl & SOP_SQR) ? 1 : per;
+    const int qw = (q + 1 == perk);
     const int q1 = qw ? 0 : q + 1;
     const int k1 = qw ? (k + 1 == nt ? 0 : k + 1) : k;  // after the last step: a harmless refetch of term 0
     const SopTerm m = k1 == 0 ? tm0 : k1 == 1 ? tm1 : tm2;
     sop_fetch(ra, sop_rec(cx, m.a));
     sop_fetch(rb, sop_rec(cx, m.b));
     sop_acc(T, x, y);
+    const int sqr = (m.fl & SOP_SQR) != 0;
     const int sel = fp_mode ? h : q1;
-    const int neg = (int)((m.fl & SOP_NEG) != 0) ^ (fp_mode ? 0 : (q1 & (h ^ 1)));
-    sop_prep_apply(x, ra, sop1_prep_a(sel, sop_term_xi(m.fl, lane_k), neg, m.sha));
-    sop_prep_apply(y, rb, sop1_prep_b(fp_mode ? 0 : (q1 ^ h), m.shb));
+    const int neg = (int)((m.fl & SOP_NEG) != 0) ^ ((fp_mode | sqr) ? 0 : (q1 & (h ^ 1)));
+    const SopPrep pa = sqr ? sop1_prep_sqr_x(h, neg, m.sha) : sop1_prep_a(sel, sop_term_xi(m.fl, lane_k), neg, m.sha);
+    const SopPrep pb = sqr ? sop1_prep_sqr_y(h, m.shb) : sop1_prep_b(fp_mode ? 0 : (q1 ^ h), m.shb);
+    sop_prep_apply(x, ra, pa);
+    sop_prep_apply(y, rb, pb);
     k = k1;
     q = q1;
   }
