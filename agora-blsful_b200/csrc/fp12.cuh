@@ -219,7 +219,8 @@ BLS_FN void fp12_mul(Fp12& r, const Fp12& a, const Fp12& b) {
   fp6_mul_lazy(t1, a.c1, b.c1);
   fp6_add(s, a.c0, a.c1);
   fp6_add(u, b.c0, b.c1);
-  fp6_norm(u, u);  // second operands must stay normalised: their Karatsuba sums meet the 2^30 limbs of the first
+  fp6_norm(s, s);  // both operands normalised: the fused Fp2 product sums the halves of BOTH operands once more
+  fp6_norm(u, u);
   fp6_mul_lazy(x, s, u);
   fp6_sub_k<128>(x, x, t0);
   fp6_sub_k<128>(x, x, t1);
@@ -233,6 +234,7 @@ BLS_FN void fp12_sqr(Fp12& r, const Fp12& a) {
   Fp6 t, s, u, x;
   fp6_mul_lazy(t, a.c0, a.c1);
   fp6_add(s, a.c0, a.c1);
+  fp6_norm(s, s);
   fp6_mul_by_v_k<4>(u, a.c1);
   fp6_add(u, u, a.c0);
   fp6_norm(u, u);
@@ -256,6 +258,7 @@ BLS_FN void fp12_mul_by_014(Fp12& f, const Fp2& c0, const Fp2& c1, const Fp2& c4
   fadd(c14, c1, c4);
   fnorm(c14, c14);
   fp6_add(s, f.c0, f.c1);
+  fp6_norm(s, s);
   fp6_mul_by_01_lazy(x, s, c0, c14);
   fp6_sub_k<64>(x, x, aa);
   fp6_sub_k<32>(x, x, bb);

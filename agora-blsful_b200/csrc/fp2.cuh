@@ -98,8 +98,202 @@ BLS_HD void fselect(Fp2& r, bool c, const Fp2& a, const Fp2& b) {
   fp_select(r.c1, c, a.c1, b.c1);
 }
 
-// Karatsuba: 3 Fp products (calls of the one resident fp_mul instance: the hot instruction footprint of every kernel is
-// fp_mul + fp_sqr, ~12 KB, which is what keeps the SM's instruction cache from thrashing).
+// ---- fused Fp2 products --------------------------------------------------------------------------------------------------
+// Round 1 built an Fp2 product from three calls of fp_mul plus five additive steps, every operand and every partial result
+// travelling through local memory (64 local loads + 32 local stores of 16 bytes per product: k_clear_cofactor moved 424 KB
+// of DRAM traffic per signature).  Now the three integer products (Karatsuba over Fp2, and one Karatsuba level over the limbs
+// inside each: 3 x 147 multiplies) accumulate in 64-bit columns, and each output half gets ONE Montgomery reduction
+// (2 x 210): 861 multiply-accumulates instead of 1,071, 16 local loads + 8 stores, no glue.
+//   c1 = a0 b1 + a1 b0 = (a0 + a1)(b0 + b1) - a0 b0 - a1 b1          (a non-negative integer)
+//   c0 = a0 b0 - a1 b1 + R p                                          (R p = p in columns 14..27: keeps the integer >= 0)
+// Columns may wrap modulo 2^64 while they are being combined; the TRUE column values fit a signed 64-bit word, which is what
+// the BLS_TRACK build checks for every call site.
+// MEASURED (B200, 1M signatures, profiles/fp2_fused_r2.txt): correct and bound-checked, but SLOWER than three fp_mul calls in
+// every register configuration tried - k_clear_cofactor 159 ms unfused vs 168 (246 registers, 2 blocks/SM), 174 (168 registers),
+// 169 (128 registers); k_hash 93 vs 99.  The fused body needs ~190 live registers (27 + 27 columns, operands, limb-Karatsuba
+// temporaries): under the kernels' caps it spills, and with the cap lifted it loses the warps the multiplier needs.  Off by default.
+#if !defined(FP2_FUSED)
+#define FP2_FUSED 0
+#endif
+
+// t[i + j] += a[i] * b[j], i, j < 14 (unsigned limbs < 2^31; one Karatsuba level over the limbs; columns modulo 2^64)
+BLS_HD void fp_cols_acc(uint64_t* t, const uint32_t* a, const uint32_t* b) {
+  constexpr int HL = NL / 2;
+  uint64_t C[2 * HL - 1];
+#pragma unroll
+  for (int part = 0; part < 2; part++) {
+#pragma unroll
+    for (int i = 0; i < 2 * HL - 1; i++) C[i] = 0;
+#pragma unroll
+    for (int i = 0; i < HL; i++) {
+#pragma unroll
+      for (int j = 0; j < HL; j++) C[i + j] += (uint64_t)a[part * HL + i] * b[part * HL + j];
+    }
+#pragma unroll
+    for (int i = 0; i < 2 * HL - 1; i++) {
+      t[2 * part * HL + i] += C[i];
+      t[HL + i] -= C[i];
+    }
+  }
+  uint32_t sa[HL], sb[HL];
+#pragma unroll
+  for (int i = 0; i < HL; i++) {
+    sa[i] = a[i] + a[HL + i];
+    sb[i] = b[i] + b[HL + i];
+  }
+#pragma unroll
+  for (int i = 0; i < HL; i++) {
+#pragma unroll
+    for (int j = 0; j < HL; j++) t[HL + i + j] += (uint64_t)sa[i] * sb[j];
+  }
+}
+// Montgomery reduction of 27 SIGNED columns whose total is a non-negative integer below R * 2^388 -> 14 limbs < 2^28 (+ top)
+BLS_HD void fp_cols_redc(uint32_t* rl, uint64_t* t) {
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+    const uint32_t m = opaque32(((uint32_t)t[i] * K_PINV28) & M28);
+#pragma unroll
+    for (int j = 0; j < NL; j++) t[i + j] += (uint64_t)m * p28(j);
+    t[i + 1] += (uint64_t)((int64_t)t[i] >> 28);  // exact (the low 28 bits are zero now); arithmetic: a column may be negative
+  }
+  int64_t c = 0;
+#pragma unroll
+  for (int j = 0; j < NL - 1; j++) {
+    c += (int64_t)t[NL + j];
+    rl[j] = (uint32_t)c & M28;
+    c >>= 28;
+  }
+  rl[NL - 1] = (uint32_t)(c + (int64_t)t[2 * NL - 1]);
+}
+// 28 x u64 parked in local memory with 128-bit accesses (kept out of the register file while the next product runs)
+struct alignas(16) Fp2Keep {
+  uint64_t v[2 * NL];
+};
+BLS_HD void fp2_keep_st(Fp2Keep& k, int i, uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("st.local.v2.u64 [%0], {%1, %2};" ::"l"(__cvta_generic_to_local(&k.v[2 * i])), "l"(a), "l"(b) : "memory");
+#else
+  k.v[2 * i] = a;
+  k.v[2 * i + 1] = b;
+#endif
+}
+BLS_HD void fp2_keep_ld(const Fp2Keep& k, int i, uint64_t& a, uint64_t& b) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("ld.local.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(__cvta_generic_to_local(&k.v[2 * i])) : "memory");
+#else
+  a = k.v[2 * i];
+  b = k.v[2 * i + 1];
+#endif
+}
+
+#if FP2_FUSED
+// Inputs: limbs <= 2^29+64, value bounds with (vb(a0)+vb(a1)) * (vb(b0)+vb(b1)) <= 2000.  Output: limbs < 2^28, values <= 3.
+BLS_FN void fp2_mul(Fp2& r, const Fp2& a, const Fp2& b) {
+#if defined(BLS_TRACK)
+  {
+    const double la = (double)(a.c0.lb > a.c1.lb ? a.c0.lb : a.c1.lb), lb = (double)(b.c0.lb > b.c1.lb ? b.c0.lb : b.c1.lb);
+    BLS_REQ(2.0 * 14.0 * la * lb + 15.0 * 72057594037927936.0 < 9223372036854775808.0, "fp2_mul column overflow");
+    BLS_REQ(la < 1073741824.0 + 256.0 && lb < 1073741824.0 + 256.0, "fp2_mul operand half sums");
+    BLS_REQ((a.c0.vb + a.c1.vb) * (b.c0.vb + b.c1.vb) <= 2000.0, "fp2_mul value bound");
+  }
+#endif
+  uint64_t T[2 * NL];
+  Fp2Keep keep;
+  uint32_t x[NL], y[NL], rl[NL];
+#pragma unroll
+  for (int i = 0; i < 2 * NL; i++) T[i] = 0;
+  fp_ld(x, a.c0);
+  fp_ld(y, b.c0);
+  fp_cols_acc(T, x, y);  // P0
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+    fp2_keep_st(keep, i, T[2 * i], T[2 * i + 1]);
+    T[2 * i] = T[2 * i + 1] = 0;
+  }
+  fp_ld(x, a.c1);
+  fp_ld(y, b.c1);
+  fp_cols_acc(T, x, y);  // P1
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+    uint64_t u0, u1;
+    fp2_keep_ld(keep, i, u0, u1);
+    const uint64_t v0 = T[2 * i], v1 = T[2 * i + 1];
+    fp2_keep_st(keep, i, u0 + v0, u1 + v1);  // P0 + P1
+    T[2 * i] = u0 - v0;                      // P0 - P1
+    T[2 * i + 1] = u1 - v1;
+  }
+#pragma unroll
+  for (int j = 0; j < NL; j++) T[NL + j] += p28(j);  // + R p
+  T[2 * NL - 1] = p28(NL - 1);                       // (column 27 carries nothing else)
+  fp_cols_redc(rl, T);
+  // the operand sums of the third product while c0 is still in registers: r may alias a or b
+  {
+    uint32_t x1[NL], y1[NL];
+    fp_ld(x, a.c0);
+    fp_ld(x1, a.c1);
+    fp_ld(y, b.c0);
+    fp_ld(y1, b.c1);
+#pragma unroll
+    for (int i = 0; i < NL; i++) {
+      x[i] += x1[i];
+      y[i] += y1[i];
+    }
+  }
+  fp_st(r.c0, rl);
+  TRK(r.c0, 3.0, M28);
+#pragma unroll
+  for (int i = 0; i < 2 * NL; i++) T[i] = 0;
+  fp_cols_acc(T, x, y);  // P2
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+    uint64_t u0, u1;
+    fp2_keep_ld(keep, i, u0, u1);
+    T[2 * i] -= u0;
+    T[2 * i + 1] -= u1;
+  }
+  T[2 * NL - 1] = 0;
+  fp_cols_redc(rl, T);
+  fp_st(r.c1, rl);
+  TRK(r.c1, 2.0, M28);
+}
+// c0 = (a0 + a1)(a0 - a1 + 32 p), c1 = a0 * 2 a1: two products, two reductions.  Input value bounds <= 22 each, limbs <= 2^29+64;
+// output limbs < 2^28, values <= 2.
+BLS_FN void fp2_sqr(Fp2& r, const Fp2& a) {
+  Fp s, d;
+  fp_add(s, a.c0, a.c1);
+  fp_sub_k<32>(d, a.c0, a.c1);
+  fp_norm(s, s);
+  fp_norm(d, d);
+#if defined(BLS_TRACK)
+  BLS_REQ(14.0 * (double)s.lb * (double)d.lb + 15.0 * 72057594037927936.0 < 9223372036854775808.0, "fp2_sqr column overflow");
+  BLS_REQ(14.0 * 2.0 * (double)a.c0.lb * (double)a.c1.lb + 15.0 * 72057594037927936.0 < 9223372036854775808.0, "fp2_sqr column overflow");
+  BLS_REQ(s.vb * d.vb <= 2000.0 && 2.0 * a.c0.vb * a.c1.vb <= 2000.0, "fp2_sqr value bound");
+#endif
+  uint64_t T[2 * NL];
+  uint32_t x[NL], y[NL], r0[NL], r1[NL];
+#pragma unroll
+  for (int i = 0; i < 2 * NL; i++) T[i] = 0;
+  fp_ld(x, a.c0);
+  fp_ld(y, a.c1);
+#pragma unroll
+  for (int i = 0; i < NL; i++) y[i] <<= 1;
+  fp_cols_acc(T, x, y);
+  T[2 * NL - 1] = 0;
+  fp_cols_redc(r1, T);
+#pragma unroll
+  for (int i = 0; i < 2 * NL; i++) T[i] = 0;
+  fp_ld(x, s);
+  fp_ld(y, d);
+  fp_cols_acc(T, x, y);
+  T[2 * NL - 1] = 0;
+  fp_cols_redc(r0, T);
+  fp_st(r.c0, r0);
+  fp_st(r.c1, r1);
+  TRK(r.c0, 2.0, M28);
+  TRK(r.c1, 2.0, M28);
+}
+#else
+// Karatsuba: 3 Fp products (calls of the one resident fp_mul instance).
 // Inputs: limbs <= 2^29+64 (a sum of two normalised values), value bounds with (vb(a0)+vb(a1)) * (vb(b0)+vb(b1)) <= 2000.
 // Output: limbs <= 2^28+11, value bounds c0 <= 6, c1 <= 10.
 BLS_FN void fp2_mul(Fp2& r, const Fp2& a, const Fp2& b) {
@@ -128,6 +322,7 @@ BLS_FN void fp2_sqr(Fp2& r, const Fp2& a) {
   fp_mul(r.c0, s, d);
   fp_add(r.c1, m, m);
 }
+#endif
 BLS_HD void fmul(Fp2& r, const Fp2& a, const Fp2& b) { fp2_mul(r, a, b); }
 BLS_HD void fsqr(Fp2& r, const Fp2& a) { fp2_sqr(r, a); }
 
