@@ -2,6 +2,7 @@
 // No CPU arithmetic lives here: every field/curve/pairing operation runs on the device; the host only stages buffers,
 // launches kernels, walks the bisection tree and applies the reference's host-side rules (duplicate messages, sorting).
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges cost nothing unless a profiler is attached (tracing)
 #include <sys/random.h>
 
 #include <algorithm>
@@ -24,6 +25,15 @@ using namespace bls;
 namespace {
 
 thread_local std::string g_create_error;
+
+// NVTX range over a C-ABI call or a pipeline stage (visible in Nsight Systems / ncu --nvtx)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define NVTX_RANGE(name) NvtxRange nvtx_range_(name)
 
 #define CK(expr)                                                                                   \
   do {                                                                                             \
@@ -207,6 +217,9 @@ size_t kernel_begin(blsgpu_ctx* ctx, int id, cudaStream_t stream);
 void kernel_end(blsgpu_ctx* ctx, size_t k, cudaStream_t stream);
 
 void stage_mark(blsgpu_ctx* ctx, int idx) {
+  static const char* const names[BLSGPU_STAGE_COUNT + 1] = {"stage:decode_pk", "stage:decode_sig", "stage:hash_to_curve", "stage:scale_sig",
+                                                            "stage:miller", "stage:reduce", "stage:final", "stage:bisect", "stage:done"};
+  nvtxMarkA(names[idx]);  // host-side marker of the stage's launches (the device times are the CUDA events below)
   cudaEventRecord(ctx->ev[idx], ctx->stream);
   ctx->ev_valid[idx] = true;
 }
@@ -300,6 +313,8 @@ size_t levels_total(const std::vector<Level>& lv) { return lv.back().off + lv.ba
 // product of Miller values (root of the product tree) and its sum of r_i sig_i in device memory; pipeline_check decides
 // F * e(-g, S) == 1 for this slice alone; pipeline_bisect finds the exact failures of a slice whose check failed.
 // -----------------------------------------------------------------------------------------------------------------
+// blocks of the node-level bucket method of the failure path (a warp per level-1 node, four per block)
+size_t node_msm_blocks(const blsgpu_ctx* ctx, size_t n1) { return std::max<size_t>(1, std::min<size_t>((n1 + 3) / 4, (size_t)ctx->sm_count * 4)); }
 constexpr size_t PROBE_SMALL = 16;  // probes the dedicated scratch holds (the root check; small batches' bisection levels)
 template <class PkA, class SigA>
 struct Pipe {
@@ -313,6 +328,7 @@ struct Pipe {
   uint8_t* d_status = nullptr;
   Fp12* d_F = nullptr;
   SigJ *d_S = nullptr, *d_Sitem = nullptr, *d_msm_root = nullptr;
+  RlcScalar* d_r = nullptr;  // the scalars of the bucket path (use_msm)
   Digest* d_root = nullptr;
   uint8_t* d_ok = nullptr;
   uint32_t* d_idx = nullptr;
@@ -430,7 +446,7 @@ int pipeline_partials(blsgpu_ctx* ctx, Pipe<PkA, SigA>& P, size_t n, const PkA* 
       const int c = msm_window_bits(n, rbits);
       const int nwin = (rbits + c - 1) / c;
       const size_t nb = (size_t)1 << c, nbuckets = nb * nwin, nchunks = nbuckets / MSM_CHUNK;
-      RlcScalar* d_r = ctx->arena.take<RlcScalar>(n);
+      RlcScalar* d_r = P.d_r = ctx->arena.take<RlcScalar>(n);
       uint32_t* d_cnt = ctx->arena.take<uint32_t>(3 * nbuckets);
       uint32_t *d_off = d_cnt + nbuckets, *d_cur = d_off + nbuckets;
       uint32_t* d_sorted = ctx->arena.take<uint32_t>((size_t)nwin * n);
@@ -549,11 +565,23 @@ int pipeline_bisect(blsgpu_ctx* ctx, Pipe<PkA, SigA>& P) {
   typedef typename PtInfo<SigA>::Jac SigJ;
   const size_t n = P.n, ng = P.ng;
   const std::vector<Level>& lv = P.lv;
-  if (P.use_msm) {
-    // the bucket method gave the total only: now the bisection needs the per-group sums of r_i sig_i
+  // The bucket method gave the total only.  64-bit scalars: the sums of the LEVEL-1 nodes come from a small bucket method per
+  // node (k_node_msm: ~21 point operations per item), the levels above from the tree, and only the groups of level-1 nodes
+  // that FAIL get per-item scalar multiplications.  Otherwise (128-bit scalars): per-item scaling of the whole batch.
+  const bool by_nodes = P.use_msm && P.rbits == 64 && lv.size() >= 3;
+  if (P.use_msm && !by_nodes) {
     LAUNCH((k_scale_sig<SigA>), blocks_for(n), TPB, n, P.d_sig, P.d_status, P.d_root, P.rbits, P.d_Sitem);
     LAUNCH((k_group_sum<SigJ>), blocks_for(ng), TPB, n, (const SigJ*)P.d_Sitem, ng, P.d_S);
     for (size_t k = 0; k + 1 < lv.size(); k++)
+      LAUNCH((k_reduce_jac<SigJ>), blocks_for(lv[k + 1].cnt), TPB, lv[k].cnt, P.d_S + lv[k].off, lv[k + 1].cnt, P.d_S + lv[k + 1].off);
+  }
+  if (by_nodes) {
+    const size_t n1 = lv[1].cnt, nblocks = node_msm_blocks(ctx, n1);
+    SigJ* d_buckets = ctx->arena.take<SigJ>(nblocks * 128 * NODE_BUCKETS);
+    SigJ* d_W = ctx->arena.take<SigJ>(n1 * 32);
+    LAUNCH((k_node_msm<SigA>), (unsigned)nblocks, 128, n, n1, ng, P.d_sig, (const uint8_t*)P.d_status, (const RlcScalar*)P.d_r, d_buckets, d_W);
+    LAUNCH((k_node_combine<SigJ>), blocks_for(n1), TPB, n1, (const SigJ*)d_W, P.d_S + lv[1].off);
+    for (size_t k = 1; k + 1 < lv.size(); k++)
       LAUNCH((k_reduce_jac<SigJ>), blocks_for(lv[k + 1].cnt), TPB, lv[k].cnt, P.d_S + lv[k].off, lv[k + 1].cnt, P.d_S + lv[k + 1].off);
   }
   // walk down the 16-ary tree to the failing groups: children of node j at level k+1 are {j + m * cnt(k+1)} at level k
@@ -568,6 +596,22 @@ int pipeline_bisect(blsgpu_ctx* ctx, Pipe<PkA, SigA>& P) {
         if (idx < lv[k].cnt) cand.push_back((uint32_t)idx);
       }
     if (cand.empty()) break;
+    if (k == 0 && by_nodes) {
+      // the candidate groups (children of failing level-1 nodes) get their sums now: r_i sig_i for their items only
+      std::vector<uint32_t> its;
+      for (uint32_t g : cand)
+        for (int m = 0; m < M6_GROUP; m++)
+          if ((size_t)g * M6_GROUP + m < n) its.push_back(g * M6_GROUP + m);
+      uint32_t* d_list = ctx->arena.take<uint32_t>(its.size() + cand.size());
+      ARENA_OK();
+      CK(cudaMemcpyAsync(d_list, its.data(), its.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(d_list + its.size(), cand.data(), cand.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+      LAUNCH((k_scale_sig_list<SigA>), blocks_for(its.size()), TPB, its.size(), (const uint32_t*)d_list, P.d_sig, (const uint8_t*)P.d_status,
+             (const Digest*)P.d_root, P.rbits, P.d_Sitem);
+      LAUNCH((k_group_sum_list<SigJ>), blocks_for(cand.size()), TPB, cand.size(), (const uint32_t*)(d_list + its.size()), n, (const SigJ*)P.d_Sitem,
+             P.d_S + lv[0].off);
+      CK(cudaStreamSynchronize(ctx->stream));  // the host vectors go out of scope
+    }
     CKR((probe_level<PkA, SigA>(ctx, P, cand, P.d_F + lv[k].off, P.d_S + lv[k].off, res)));
     bad.clear();
     for (size_t c = 0; c < cand.size(); c++)
@@ -618,7 +662,9 @@ size_t pipeline_other_bytes(size_t n) {
   const size_t x_cap = std::max<size_t>(PROBE_SMALL, std::min<size_t>((n + M6_GROUP - 1) / M6_GROUP, 4096) + 16);
   return gtotal * (sizeof(Fp12) + sizeof(SigJ)) + n * (sizeof(SigJ) + sizeof(Fp12) + sizeof(SigJ)) + total * sizeof(Digest) +
          n * (16 + 4 * 32) + ((size_t)32 << 16) * (12 + 2 * sizeof(SigJ)) + (1 << 20) + (n + 64) * 8 + 16 * 256 + 4096 +
-         x_cap * (6 * (sizeof(PkA) + sizeof(SigA) + 1) + sizeof(Fp12)) + 6 * PROBE_SMALL * M6_ITEM_BYTES + 16 * 256;
+         x_cap * (6 * (sizeof(PkA) + sizeof(SigA) + 1) + sizeof(Fp12)) + 6 * PROBE_SMALL * M6_ITEM_BYTES + 16 * 256 +
+         // failure path of the bucket route: window sums of the level-1 nodes, bucket scratch of 592 x 4 warps at most, item / group lists
+         (n >= MSM_MIN_ITEMS ? (n / 96 + 2) * 32 * sizeof(SigJ) + std::min<size_t>(n / 384 + 1, 592) * 128 * NODE_BUCKETS * sizeof(SigJ) + n * 5 + 8 * 256 : 0);
 }
 size_t m6_line_bytes(size_t n, size_t chunk) {
   return (n > chunk ? 2 : 1) * std::max<size_t>(std::min(std::max<size_t>(n, 1), chunk), 6 * PROBE_SMALL) * M6_ITEM_BYTES;
@@ -835,6 +881,7 @@ int set_device(blsgpu_ctx* ctx) {
 // (C linkage comes from the declarations in include/blsgpu.h)
 
 int blsgpu_ctx_create(const int* devices, int ndev, blsgpu_ctx** out) {
+  NVTX_RANGE("blsgpu_ctx_create");
   if (!out || ndev < 1 || !devices) {
     g_create_error = "blsgpu_ctx_create: bad arguments";
     return BLSGPU_E_ARG;
@@ -908,6 +955,7 @@ int blsgpu_ctx_create(const int* devices, int ndev, blsgpu_ctx** out) {
 }
 
 void blsgpu_ctx_destroy(blsgpu_ctx* ctx) {
+  NVTX_RANGE("blsgpu_ctx_destroy");
   if (!ctx) return;
   for (blsgpu_ctx* peer : ctx->peers) blsgpu_ctx_destroy(peer);
   cudaSetDevice(ctx->devices[0]);
@@ -979,6 +1027,7 @@ uint64_t blsgpu_launch_count(const blsgpu_ctx* ctx) {
 
 int blsgpu_verify_batch_dev(blsgpu_ctx* ctx, int impl_id, int scheme, int format, size_t n, const uint8_t* pks_dev,
                             const uint8_t* sigs_dev, const uint8_t* msgs_dev, const uint64_t* msg_off_dev, uint8_t* status_out_dev) {
+  NVTX_RANGE("blsgpu_verify_batch_dev");
   if (!ctx) return BLSGPU_E_ARG;
   if (!args_ok(impl_id, scheme, format) || (n && (!pks_dev || !sigs_dev || !msg_off_dev || !status_out_dev))) {
     ctx->err = "blsgpu_verify_batch_dev: bad arguments";
@@ -1189,6 +1238,7 @@ int fold_bytes_impl(blsgpu_ctx* ctx, size_t k, const uint8_t* gts, const uint8_t
 
 int blsgpu_miller_partial(blsgpu_ctx* ctx, int impl_id, int scheme, int format, size_t n, const uint8_t* pks, const uint8_t* sigs,
                           const uint8_t* msgs, const uint64_t* msg_off, uint8_t gt_out[576], uint8_t* sum_out) {
+  NVTX_RANGE("blsgpu_miller_partial");
   if (!ctx) return BLSGPU_E_ARG;
   if (!args_ok(impl_id, scheme, format) || !gt_out || !sum_out || (n && (!pks || !sigs || !msg_off))) {
     ctx->err = "blsgpu_miller_partial: bad arguments";
@@ -1212,6 +1262,7 @@ int blsgpu_miller_partial(blsgpu_ctx* ctx, int impl_id, int scheme, int format, 
 }
 
 int blsgpu_final_exp_is_one(blsgpu_ctx* ctx, int impl_id, size_t k, const uint8_t* partial_gts, const uint8_t* partial_sums, int* is_one_out) {
+  NVTX_RANGE("blsgpu_final_exp_is_one");
   if (!ctx) return BLSGPU_E_ARG;
   if ((impl_id != 1 && impl_id != 2) || k == 0 || k > 16 || !partial_gts || !partial_sums || !is_one_out) {
     ctx->err = "blsgpu_final_exp_is_one: bad arguments (1 to 16 partial results)";
@@ -1223,6 +1274,7 @@ int blsgpu_final_exp_is_one(blsgpu_ctx* ctx, int impl_id, size_t k, const uint8_
 }
 
 int blsgpu_partial_finish(blsgpu_ctx* ctx, int batch_ok, uint8_t* status_out) {
+  NVTX_RANGE("blsgpu_partial_finish");
   if (!ctx) return BLSGPU_E_ARG;
   if (!ctx->pending) return BLSGPU_OK;  // an empty slice, or nothing pending
   if (!status_out) {
@@ -1235,6 +1287,7 @@ int blsgpu_partial_finish(blsgpu_ctx* ctx, int batch_ok, uint8_t* status_out) {
 
 int blsgpu_verify_batch(blsgpu_ctx* ctx, int impl_id, int scheme, int format, size_t n, const uint8_t* pks, const uint8_t* sigs,
                         const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out) {
+  NVTX_RANGE("blsgpu_verify_batch");
   if (!ctx) return BLSGPU_E_ARG;
   if (!args_ok(impl_id, scheme, format) || (n && (!pks || !sigs || !msg_off || !status_out))) {
     ctx->err = "blsgpu_verify_batch: bad arguments";
@@ -1253,6 +1306,7 @@ int blsgpu_verify_batch(blsgpu_ctx* ctx, int impl_id, int scheme, int format, si
 
 int blsgpu_pop_verify_batch(blsgpu_ctx* ctx, int impl_id, int format, size_t n, const uint8_t* pks, const uint8_t* sigs,
                             uint8_t* status_out) {
+  NVTX_RANGE("blsgpu_pop_verify_batch");
   if (!ctx) return BLSGPU_E_ARG;
   if (!args_ok(impl_id, 2, format) || (n && (!pks || !sigs || !status_out))) {
     ctx->err = "blsgpu_pop_verify_batch: bad arguments";
@@ -1353,6 +1407,7 @@ static int aggregate_verify_impl(blsgpu_ctx* ctx, int scheme, int format, size_t
 
 int blsgpu_aggregate_verify(blsgpu_ctx* ctx, int impl_id, int scheme, int format, size_t n, const uint8_t* pks, const uint8_t* msgs,
                             const uint64_t* msg_off, const uint8_t* sig, uint8_t* status_out, int64_t index_out[2]) {
+  NVTX_RANGE("blsgpu_aggregate_verify");
   if (!ctx) return BLSGPU_E_ARG;
   int64_t dummy[2];
   if (!index_out) index_out = dummy;
@@ -1416,6 +1471,7 @@ static int sum_points_impl(blsgpu_ctx* ctx, int format, size_t n, const uint8_t*
 
 int blsgpu_sum_points(blsgpu_ctx* ctx, int group, int format, size_t n, const uint8_t* points, uint8_t* out, uint8_t* status_out,
                       int64_t* bad_index_out) {
+  NVTX_RANGE("blsgpu_sum_points");
   if (!ctx) return BLSGPU_E_ARG;
   int64_t dummy;
   if (!bad_index_out) bad_index_out = &dummy;
@@ -1450,6 +1506,7 @@ static int hash_batch_impl(blsgpu_ctx* ctx, size_t n, const uint8_t* msgs, const
 
 int blsgpu_hash_to_curve_batch(blsgpu_ctx* ctx, int group, size_t n, const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* dst,
                                size_t dst_len, uint8_t* out) {
+  NVTX_RANGE("blsgpu_hash_to_curve_batch");
   if (!ctx) return BLSGPU_E_ARG;
   if ((group != 1 && group != 2) || !msg_off || !dst || dst_len == 0 || dst_len > 63 || (n && !out)) {
     ctx->err = "blsgpu_hash_to_curve_batch: bad arguments (dst_len must be 1..63)";
@@ -1484,6 +1541,7 @@ static int recode_impl(blsgpu_ctx* ctx, int fin, int fout, size_t n, const uint8
 
 int blsgpu_recode_points(blsgpu_ctx* ctx, int group, int format_in, int format_out, size_t n, const uint8_t* in, uint8_t* out,
                          uint8_t* status_out) {
+  NVTX_RANGE("blsgpu_recode_points");
   if (!ctx) return BLSGPU_E_ARG;
   if ((group != 1 && group != 2) || (format_in | format_out) & ~1 || (n && (!in || !out || !status_out))) {
     ctx->err = "blsgpu_recode_points: bad arguments";
@@ -1496,6 +1554,7 @@ int blsgpu_recode_points(blsgpu_ctx* ctx, int group, int format_in, int format_o
 }
 
 int blsgpu_fp_mul_batch(blsgpu_ctx* ctx, int variant, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+  NVTX_RANGE("blsgpu_fp_mul_batch");
   if (!ctx) return BLSGPU_E_ARG;
   if ((variant != 0 && variant != 1) || (n && (!a || !b || !out))) {
     ctx->err = "blsgpu_fp_mul_batch: bad arguments";
@@ -1515,6 +1574,7 @@ int blsgpu_fp_mul_batch(blsgpu_ctx* ctx, int variant, size_t n, const uint8_t* a
 }
 
 int blsgpu_pairing_product_is_one(blsgpu_ctx* ctx, size_t n, const uint8_t* g1_points, const uint8_t* g2_points, int* is_one_out) {
+  NVTX_RANGE("blsgpu_pairing_product_is_one");
   if (!ctx) return BLSGPU_E_ARG;
   if (!is_one_out || (n && (!g1_points || !g2_points))) {
     ctx->err = "blsgpu_pairing_product_is_one: bad arguments";
@@ -1558,6 +1618,7 @@ int blsgpu_pairing_product_is_one(blsgpu_ctx* ctx, size_t n, const uint8_t* g1_p
 
 int blsgpu_testdata_sign(blsgpu_ctx* ctx, int impl_id, int scheme, size_t n, const uint8_t* scalars32, const uint8_t* msgs,
                          const uint64_t* msg_off, uint8_t* out_pks, uint8_t* out_sigs) {
+  NVTX_RANGE("blsgpu_testdata_sign");
   if (!ctx) return BLSGPU_E_ARG;
   const bool pop_proof = scheme == 3;  // proof of possession: message = the key's own bytes, BLS_POP_ DST
   if (!args_ok(impl_id, pop_proof ? 2 : scheme, 1) || (n && (!scalars32 || !msg_off || !out_pks || !out_sigs))) {
@@ -1593,6 +1654,7 @@ int blsgpu_testdata_sign(blsgpu_ctx* ctx, int impl_id, int scheme, size_t n, con
 }
 
 int blsgpu_imad_peak(blsgpu_ctx* ctx, double* mac_per_s_out) {
+  NVTX_RANGE("blsgpu_imad_peak");
   if (!ctx || !mac_per_s_out) return BLSGPU_E_ARG;
   CKR(set_device(ctx));
   CKR(ensure_arena(ctx, 4096));
@@ -1827,6 +1889,7 @@ int aggregate_secure_impl(blsgpu_ctx* ctx, int format, size_t q, const uint64_t*
 
 int blsgpu_verify_secure_batch(blsgpu_ctx* ctx, int impl_id, int scheme, int format, size_t q, const uint64_t* key_off, const uint8_t* pks,
                                const uint8_t* sigs, const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out) {
+  NVTX_RANGE("blsgpu_verify_secure_batch");
   if (!ctx) return BLSGPU_E_ARG;
   if (!args_ok(impl_id, scheme, format) || (q && (!key_off || !sigs || !msg_off || !status_out)) || (q && key_off[q] && !pks) ||
       (impl_id == 1 && format == 0)) {
@@ -1847,6 +1910,7 @@ int blsgpu_verify_secure_batch(blsgpu_ctx* ctx, int impl_id, int scheme, int for
 
 int blsgpu_aggregate_secure_batch(blsgpu_ctx* ctx, int impl_id, int format, size_t q, const uint64_t* key_off, const uint8_t* pks,
                                   const uint8_t* member_sigs, uint8_t* out_sigs, uint8_t* status_out) {
+  NVTX_RANGE("blsgpu_aggregate_secure_batch");
   if (!ctx) return BLSGPU_E_ARG;
   if (!args_ok(impl_id, 0, format) || (q && (!key_off || !out_sigs || !status_out)) || (q && key_off[q] && (!pks || !member_sigs)) ||
       (impl_id == 1 && format == 0)) {
@@ -1949,6 +2013,7 @@ static int combine_shares_impl(blsgpu_ctx* ctx, size_t q, const uint64_t* share_
 
 int blsgpu_combine_shares_batch(blsgpu_ctx* ctx, int group, size_t q, const uint64_t* share_off, const uint8_t* shares, uint8_t* out,
                                 uint8_t* status_out) {
+  NVTX_RANGE("blsgpu_combine_shares_batch");
   if (!ctx) return BLSGPU_E_ARG;
   if ((group != 1 && group != 2) || (q && (!share_off || !out || !status_out)) || (q && share_off[q] && !shares)) {
     ctx->err = "blsgpu_combine_shares_batch: bad arguments";
@@ -1965,6 +2030,7 @@ int blsgpu_combine_shares_batch(blsgpu_ctx* ctx, int group, size_t q, const uint
 // Wire-format front end: tagged signatures, schemes mixed in one call.  The host only regroups bytes by tag.
 int blsgpu_verify_batch_wire(blsgpu_ctx* ctx, int impl_id, size_t n, const uint8_t* pks, const uint8_t* tagged_sigs, const uint8_t* msgs,
                              const uint64_t* msg_off, uint8_t* status_out) {
+  NVTX_RANGE("blsgpu_verify_batch_wire");
   if (!ctx) return BLSGPU_E_ARG;
   if ((impl_id != 1 && impl_id != 2) || (n && (!pks || !tagged_sigs || !msg_off || !status_out))) {
     ctx->err = "blsgpu_verify_batch_wire: bad arguments";
@@ -1998,6 +2064,7 @@ int blsgpu_verify_batch_wire(blsgpu_ctx* ctx, int impl_id, size_t n, const uint8
 // Share verification on raw share records: strip (and validate) the identifiers on the host, verify the values.
 int blsgpu_verify_share_batch(blsgpu_ctx* ctx, int impl_id, int scheme, size_t n, const uint8_t* pk_shares, const uint8_t* sig_shares,
                               const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out) {
+  NVTX_RANGE("blsgpu_verify_share_batch");
   if (!ctx) return BLSGPU_E_ARG;
   if (!args_ok(impl_id, scheme, 1) || (n && (!pk_shares || !sig_shares || !msg_off || !status_out))) {
     ctx->err = "blsgpu_verify_share_batch: bad arguments";
@@ -2024,6 +2091,7 @@ int blsgpu_verify_share_batch(blsgpu_ctx* ctx, int impl_id, int scheme, size_t n
 // ---------------------------------------------------------------------------------------------------------------------
 int blsgpu_pairing_check_batch(blsgpu_ctx* ctx, size_t q, const uint64_t* pair_off, const uint8_t* g1_points, const uint8_t* g2_points,
                                uint8_t* ok_out, uint8_t* status_out) {
+  NVTX_RANGE("blsgpu_pairing_check_batch");
   if (!ctx) return BLSGPU_E_ARG;
   if (q && (!pair_off || !ok_out || !status_out || (pair_off[q] && (!g1_points || !g2_points)))) {
     ctx->err = "blsgpu_pairing_check_batch: bad arguments";
@@ -2070,6 +2138,7 @@ int blsgpu_pairing_check_batch(blsgpu_ctx* ctx, size_t q, const uint64_t* pair_o
 // as a boolean: both check  pairing([(w, -g), (hash_to_point(u_bytes || v), u)]) == 1  and reject identity u / w.
 int blsgpu_signcrypt_valid_batch(blsgpu_ctx* ctx, int impl_id, int scheme, size_t n, const uint8_t* u_points, const uint8_t* w_points,
                                  const uint8_t* v_bytes, const uint64_t* v_off, uint8_t* ok_out, uint8_t* status_out) {
+  NVTX_RANGE("blsgpu_signcrypt_valid_batch");
   if (!ctx) return BLSGPU_E_ARG;
   if (!args_ok(impl_id, scheme, 1) || (n && (!u_points || !w_points || !v_off || !ok_out || !status_out))) {
     ctx->err = "blsgpu_signcrypt_valid_batch: bad arguments";
@@ -2207,6 +2276,7 @@ int signcrypt_share_impl(blsgpu_ctx* ctx, int scheme, size_t n, const uint8_t* s
 
 int blsgpu_pok_verify_batch(blsgpu_ctx* ctx, int impl_id, int scheme, size_t n, const uint8_t* commitments, const uint8_t* proofs,
                             const uint8_t* pks, const uint8_t* challenges32, const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status_out) {
+  NVTX_RANGE("blsgpu_pok_verify_batch");
   if (!ctx) return BLSGPU_E_ARG;
   if (!args_ok(impl_id, scheme, 1) || (n && (!commitments || !proofs || !pks || !challenges32 || !msg_off || !status_out))) {
     ctx->err = "blsgpu_pok_verify_batch: bad arguments";
@@ -2222,6 +2292,7 @@ int blsgpu_pok_verify_batch(blsgpu_ctx* ctx, int impl_id, int scheme, size_t n, 
 int blsgpu_signcrypt_verify_share_batch(blsgpu_ctx* ctx, int impl_id, int scheme, size_t n, const uint8_t* shares, const uint8_t* pk_shares,
                                         const uint8_t* u_points, const uint8_t* w_points, const uint8_t* v_bytes, const uint64_t* v_off,
                                         uint8_t* ok_out, uint8_t* status_out) {
+  NVTX_RANGE("blsgpu_signcrypt_verify_share_batch");
   if (!ctx) return BLSGPU_E_ARG;
   if (!args_ok(impl_id, scheme, 1) || (n && (!shares || !pk_shares || !u_points || !w_points || !v_off || !ok_out || !status_out))) {
     ctx->err = "blsgpu_signcrypt_verify_share_batch: bad arguments";
@@ -2240,6 +2311,7 @@ int blsgpu_signcrypt_verify_share_batch(blsgpu_ctx* ctx, int impl_id, int scheme
 int blsgpu_verify_batch_records(blsgpu_ctx* ctx, int impl_id, int format, int scheme_or_tagged, size_t n, const uint8_t* pk_bytes,
                                 const uint64_t* pk_off, const uint8_t* sig_bytes, const uint64_t* sig_off, const uint8_t* msgs,
                                 const uint64_t* msg_off, uint8_t* status_out) {
+  NVTX_RANGE("blsgpu_verify_batch_records");
   if (!ctx) return BLSGPU_E_ARG;
   const bool tagged = scheme_or_tagged < 0;
   if ((impl_id != 1 && impl_id != 2) || (format != 0 && format != 1) || scheme_or_tagged > 2 ||
@@ -2298,6 +2370,7 @@ int blsgpu_verify_batch_records(blsgpu_ctx* ctx, int impl_id, int format, int sc
 // must fail HERE, loudly, not return wrong verdicts.  Vectors: the first C++ bls-signatures triple of the reference's
 // tests/cpp_integration_test.rs:19-82 (message "hello") and H("hello") derived from it (sig = sk * H).
 int blsgpu_selftest(blsgpu_ctx* ctx) {
+  NVTX_RANGE("blsgpu_selftest");
   if (!ctx) return BLSGPU_E_ARG;
   static const uint8_t PK1[48] = {0xb1, 0x45, 0xdf, 0xcb, 0x3c, 0xbd, 0xef, 0x21, 0x50, 0x2f, 0x30, 0x5d, 0x1b, 0xa1, 0xcb, 0xa5, 0x84, 0x79, 0x69, 0x18, 0x57, 0x1e, 0x8b, 0x5d, 0x85, 0xbe, 0x17, 0x6f, 0x34, 0x45, 0xac, 0x7a, 0xd9, 0x9a, 0xec, 0x19, 0xe1, 0x93, 0x1b, 0x69, 0x34, 0xd7, 0x29, 0x0b, 0x97, 0xec, 0x2d, 0x75};
   static const uint8_t SIG1[96] = {0x82, 0xc8, 0x08, 0x03, 0xa3, 0x24, 0x6f, 0x5d, 0x10, 0xb5, 0x19, 0x23, 0xd4, 0x96, 0x7b, 0xef, 0x55, 0x7c, 0xf0, 0x41, 0x6f, 0xa3, 0x06, 0x05, 0x94, 0x9c, 0xaa, 0xc6, 0x27, 0x3b, 0x59, 0x93, 0xd2, 0x6f, 0xef, 0x27, 0x8e, 0xb4, 0x86, 0x75, 0xc6, 0x2b, 0x42, 0x26, 0x6f, 0x9b, 0x01, 0x48, 0x0a, 0x8d, 0xc0, 0x7e, 0xf1, 0x68, 0xed, 0xd3, 0xf1, 0xa9, 0xca, 0xd3, 0x63, 0x30, 0x83, 0xdc, 0xb3, 0xc2, 0xdf, 0x37, 0x27, 0x89, 0xb8, 0x78, 0x71, 0x24, 0x9d, 0xab, 0x38, 0x0b, 0x07, 0x1d, 0xd4, 0x80, 0xd7, 0x42, 0xd0, 0x27, 0xf3, 0x7c, 0x36, 0xf8, 0x9e, 0x63, 0xb5, 0xf1, 0xe0, 0x93};

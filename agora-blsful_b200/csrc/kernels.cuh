@@ -106,6 +106,10 @@ struct Digest {
 #if !defined(BLS_SPLIT_MIN_BLOCKS)
 #define BLS_SPLIT_MIN_BLOCKS 4
 #endif
+// the per-key-set bucket kernel k_secure_msm: pure curve arithmetic as well (cfg 5 verify_secure 809 -> 784 ms at 10,000 x 400)
+#if !defined(BLS_MSM_MIN_BLOCKS)
+#define BLS_MSM_MIN_BLOCKS 4
+#endif
 // ---- decode: compressed bytes -> affine Montgomery points, curve + subgroup check --------------------------------
 // Input staging: the block's 128 records (48 | 96 bytes each, contiguous) are fetched with coalesced 16-byte loads into
 // shared memory and every thread then picks up its own record; a base pointer that is not 16-byte aligned (possible only
@@ -630,6 +634,115 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_msm_chunk(size_t nchunk
   V[t] = res;
 }
 
+// ---- failure path: S of every LEVEL-1 node of the product tree, without per-item scalar multiplications -----------------
+// A failed batch needs sum r_i sig_i per tree node.  Round 1 multiplied every signature by its 64-bit scalar (64 doublings +
+// ~32 additions per item: +370 ms at 1M).  A level-1 node covers 16 groups of 6 items (groups j + m * n1, m < 16): one warp
+// per node runs a small bucket method over its 96 signatures - lane = (4-bit window w = lane & 15, half = lane >> 4 of the
+// node's groups): 48 mixed additions into 15 buckets + 30 additions of the running-sum reduction per lane, then the halves
+// are added and the 16 window sums folded by k_node_combine.  ~21 point operations per item instead of ~96; the levels above
+// come from the usual tree sums, and per-item work is left for the (few) level-1 nodes that fail.
+constexpr int NODE_BUCKETS = 15;
+// (no register cap here: measured at 1M with one bad signature, the G2 instance under a 128-register cap made the failure
+// path 60 ms slower - 204 registers and 2 blocks per SM is its better point, unlike k_secure_msm below)
+template <class SigA>
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_node_msm(size_t n, size_t n1, size_t ng, const SigA* __restrict__ sig, const uint8_t* __restrict__ pre,
+                                                  const RlcScalar* __restrict__ r, typename PtInfo<SigA>::Jac* __restrict__ buckets,
+                                                  typename PtInfo<SigA>::Jac* __restrict__ W) {
+  typedef typename PtInfo<SigA>::Jac J;
+  const int lane = threadIdx.x & 31, w = lane & 15, half = lane >> 4;
+  const size_t warp = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = (size_t)gridDim.x * (blockDim.x >> 5);
+  J* mine = buckets + (warp * 32 + lane) * NODE_BUCKETS;
+  for (size_t node = warp; node < n1; node += nwarps) {
+    uint32_t full = 0;
+    for (int m = 8 * half; m < 8 * half + 8; m++) {
+      const size_t g = node + (size_t)m * n1;
+      if (g >= ng) break;
+      for (int t = 0; t < M6_GROUP; t++) {
+        const size_t i = g * M6_GROUP + t;
+        if (i >= n || pre[i] != ST_OK) continue;
+        const RlcScalar k = r[i];
+        const uint32_t d = (uint32_t)(k.lo >> (4 * w)) & 15u;  // 64-bit scalars: 16 windows of 4 bits
+        if (d == 0) continue;
+        SigA p = sig[i];
+        J acc;
+        if ((full >> (d - 1)) & 1u) {
+          acc = mine[d - 1];
+          jac_add_mixed(acc, acc, p);
+        } else {
+          jac_from_aff(acc, p);
+          full |= 1u << (d - 1);
+        }
+        mine[d - 1] = acc;
+      }
+    }
+    J run, tot;
+    jac_set_inf(run);
+    jac_set_inf(tot);
+    bool any = false;
+    for (int b = NODE_BUCKETS - 1; b >= 0; b--) {
+      if ((full >> b) & 1u) {
+        J t = mine[b];
+        jac_add(run, run, t);
+        any = true;
+      }
+      if (any) jac_add(tot, tot, run);
+    }
+    W[node * 32 + lane] = tot;
+  }
+}
+// S[node] = sum_w 16^w (W[node][w] + W[node][16 + w])
+template <class J>
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_node_combine(size_t n1, const J* __restrict__ W, J* __restrict__ S) {
+  size_t node = BLS_TID();
+  if (node >= n1) return;
+  J acc;
+  jac_set_inf(acc);
+  for (int w = 15; w >= 0; w--) {
+    if (!jac_is_inf(acc))
+      for (int k = 0; k < 4; k++) jac_dbl(acc, acc);
+    J a = W[node * 32 + w], b = W[node * 32 + 16 + w];
+    jac_add(acc, acc, a);
+    jac_add(acc, acc, b);
+  }
+  S[node] = acc;
+}
+// S_i = r_i * sig_i for the listed items only
+template <class SigA>
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_scale_sig_list(size_t cnt, const uint32_t* __restrict__ idx, const SigA* __restrict__ sig,
+                                                        const uint8_t* __restrict__ pre, const Digest* __restrict__ root, int rbits,
+                                                        typename PtInfo<SigA>::Jac* __restrict__ out) {
+  size_t c = BLS_TID();
+  if (c >= cnt) return;
+  const size_t i = idx[c];
+  typename PtInfo<SigA>::Jac s;
+  if (pre[i] != ST_OK) {
+    jac_set_inf(s);
+  } else {
+    uint32_t k[RLC_MAX_WORDS];
+    rlc_scalar(k, root, i, rbits);
+    SigA a = sig[i];
+    jac_mul_aff(s, a, k, rbits / 32);
+  }
+  out[i] = s;
+}
+// S_g for the listed groups
+template <class J>
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_group_sum_list(size_t cnt, const uint32_t* __restrict__ groups, size_t n, const J* __restrict__ in,
+                                                        J* __restrict__ out) {
+  size_t c = BLS_TID();
+  if (c >= cnt) return;
+  const size_t g = groups[c];
+  J acc = in[g * M6_GROUP];
+  for (int m = 1; m < M6_GROUP; m++) {
+    size_t i = g * M6_GROUP + m;
+    if (i < n) {
+      J t = in[i];
+      jac_add(acc, acc, t);
+    }
+  }
+  out[g] = acc;
+}
+
 // ---- 16-ary strided reduction trees: out[j] = op over in[j + m*n_out], m = 0..15 -------------------------------------
 __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_reduce_fp12(size_t n_in, const Fp12* __restrict__ in, size_t n_out, Fp12* __restrict__ out) {
   size_t j = BLS_TID();
@@ -857,7 +970,7 @@ __global__ void __launch_bounds__(128) k_secure_digits(size_t M, const uint32_t*
 // one warp per key set (warp-stride loop), lane = window.  src[m] = index of member m's point (sorted position -> point);
 // buckets: scratch of SECURE_BUCKETS Jacobian points per resident lane; W[set * 32 + lane] = the window's sum.
 template <class A>
-__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_secure_msm(size_t q, const uint64_t* __restrict__ key_off, const uint32_t* __restrict__ src,
+__global__ void __launch_bounds__(128, BLS_MSM_MIN_BLOCKS) k_secure_msm(size_t q, const uint64_t* __restrict__ key_off, const uint32_t* __restrict__ src,
                                                     const int8_t* __restrict__ digits, const A* __restrict__ points,
                                                     typename PtInfo<A>::Jac* __restrict__ buckets, typename PtInfo<A>::Jac* __restrict__ W) {
   typedef typename PtInfo<A>::Jac J;
