@@ -54,3 +54,25 @@ def test_msm_window_plan_never_has_a_narrow_top_window():
         assert (w - 1) * c + top == bits and 0 < top <= c
         assert n >> c >= 8 or c == 4          # enough signatures per bucket to amortise the bucket reduction
         assert (n >> top) <= 16 * max(1, n >> c) or n < (1 << 16), (n, c, top)   # top-window buckets at most 16x larger
+
+
+def test_rust_sys_crate_declares_the_whole_header():
+    """rust/blsful-gpu-sys/src/lib.rs is source only (no cargo here): at least keep it in step with include/blsgpu.h -
+    the same functions with the same number of arguments, and the same status constants."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "blsgpu.h")).read()
+    h = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    h = re.sub(r"//[^\n]*", "", h)
+    c_fns = {m.group(1): len([a for a in m.group(2).split(",") if a.strip() and a.strip() != "void"])
+             for m in re.finditer(r"\b(blsgpu_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", h, flags=re.S)}
+    rs = open(os.path.join(root, "rust", "blsful-gpu-sys", "src", "lib.rs")).read()
+    r = re.sub(r"/\*.*?\*/", "", rs, flags=re.S)
+    r = re.sub(r"//[^\n]*", "", r)
+    rs_fns = {m.group(1): len([a for a in m.group(2).split(",") if a.strip()])
+              for m in re.finditer(r"pub fn (blsgpu_[a-z0-9_]+)\(([^)]*)\)", r, flags=re.S)}
+    assert c_fns and set(c_fns) == set(rs_fns), (set(c_fns) ^ set(rs_fns))
+    assert c_fns == rs_fns, {k: (c_fns[k], rs_fns[k]) for k in c_fns if c_fns[k] != rs_fns[k]}
+    c_consts = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define (BLSGPU_(?:ST|E)_[A-Z_]+|BLSGPU_OK|BLSGPU_STAGE_COUNT|BLSGPU_KERNEL_COUNT) \(?(-?\d+)\)?", hdr)}
+    rs_consts = {m.group(1): int(m.group(2)) for m in re.finditer(r"pub const (BLSGPU_[A-Z_]+): \w+ = (-?\d+);", rs)}
+    assert c_consts == rs_consts, set(c_consts.items()) ^ set(rs_consts.items())
