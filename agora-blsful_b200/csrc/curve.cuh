@@ -76,37 +76,48 @@ BLS_HD void fmul8(F& r, const F& a) {
   fdbl(r, r);
 }
 
-// doubling (a = 0): X3 = E^2 - 8XB, Y3 = E(4XB - X3) - 8C, Z3 = 2YZ with B = Y^2, C = B^2, E = 3X^2  (4S + 3M)
+// Working-set note (round 2): the compiler gives every named temporary of these functions its own stack slot (stack
+// colouring is off, __graft_entry__.py), and with 128 registers per thread all of them live in local memory.  At ~75,000
+// resident threads each extra Fp2 temporary is 9.7 MB of L2; the round-1 versions (12 / 13 / 15 temporaries) pushed the
+// per-thread hot set of a doubling loop past what the 126 MB L2 holds and the kernels streamed ~400 KB per point through
+// HBM.  The versions below do the same arithmetic in 4 / 8 / 9 temporaries.
+
+// doubling (a = 0), dbl-2009-l shape: A = X^2, B = Y^2, C = B^2, D = 2((X+B)^2 - A - C) = 4XB, E = 3A,
+// X3 = E^2 - 2D, Y3 = E(D - X3) - 8C, Z3 = 2YZ   (5S + 2M).  r may alias p.
 template <class F>
 BLS_HD void jac_dbl_impl(Jac<F>& r, const Jac<F>& p) {
-  F A, B, C, XB, E, Fq, D, D2, T, X3, Y3, YZ;
-  fsqr(A, p.X);
-  fsqr(B, p.Y);
-  fsqr(C, B);
-  fmul(XB, p.X, B);
-  fmul(YZ, p.Y, p.Z);  // before X/Y are overwritten (r may alias p)
-  fdbl(E, A);
-  fadd(E, E, A);
-  fnorm(E, E);  // 3A, value <= 6
-  fsqr(Fq, E);
-  fmul8(D2, XB);
-  fnorm(D2, D2);  // value <= 16 (Fp) / 80 (Fp2)
-  fsub_k<128>(X3, Fq, D2);
-  fred(X3, X3);
-  fmul4(D, XB);  // value <= 8
-  fsub_k<4>(T, D, X3);
-  fnorm(T, T);
-  fmul(Y3, E, T);
-  fmul8(C, C);
-  fnorm(C, C);  // value <= 16 (Fp) / 32 (Fp2)
-  fsub_k<64>(Y3, Y3, C);
-  fred(r.Y, Y3);
-  r.X = X3;
-  fdbl(YZ, YZ);
-  fred(r.Z, YZ);
+  F t0, t1, t2, t3;
+  fmul(t0, p.Y, p.Z);  // YZ
+  fsqr(t1, p.Y);       // B            value <= 2 (Fp) / (2,4) (Fp2)
+  fadd(t2, p.X, t1);
+  fnorm(t2, t2);
+  fsqr(t2, t2);        // (X+B)^2
+  fsqr(t3, p.X);       // A            -- p is not read below this line
+  fsqr(t1, t1);        // C
+  fsub_k<8>(t2, t2, t3);
+  fsub_k<8>(t2, t2, t1);
+  fnorm(t2, t2);       // 2XB          value <= 18 (Fp) / 20 (Fp2)
+  fdbl(t0, t0);
+  fred(r.Z, t0);       // Z3
+  fdbl(t0, t3);
+  fadd(t0, t0, t3);
+  fnorm(t0, t0);       // E = 3A       value <= 6 (Fp) / 12 (Fp2)
+  fsqr(t3, t0);        // E^2
+  fmul4(r.X, t2);
+  fnorm(r.X, r.X);     // 8XB          value <= 80
+  fsub_k<128>(t3, t3, r.X);
+  fred(r.X, t3);       // X3
+  fdbl(t2, t2);        // D = 4XB      value <= 40
+  fsub_k<4>(t2, t2, r.X);
+  fnorm(t2, t2);
+  fmul(t3, t0, t2);    // E (D - X3)
+  fmul8(t1, t1);
+  fnorm(t1, t1);       // 8C           value <= 16 (Fp) / 32 (Fp2)
+  fsub_k<64>(t3, t3, t1);
+  fred(r.Y, t3);
 }
 
-// madd-2007-bl: 7M + 4S, with the exceptional cases handled (public data, variable time)
+// madd-2007-bl: 7M + 4S, with the exceptional cases handled (public data, variable time).  r may alias p.
 template <class F>
 BLS_HD void jac_add_mixed_impl(Jac<F>& r, const Jac<F>& p, const Aff<F>& q) {
   if (q.inf) {
@@ -117,50 +128,50 @@ BLS_HD void jac_add_mixed_impl(Jac<F>& r, const Jac<F>& p, const Aff<F>& q) {
     jac_from_aff(r, q);
     return;
   }
-  F Z1Z1, U2, S2, H, HH, I, J, rr, V, t, X3, Y3, Z3;
-  fsqr(Z1Z1, p.Z);
-  fmul(U2, q.x, Z1Z1);
-  fmul(S2, q.y, p.Z);
-  fmul(S2, S2, Z1Z1);
-  fsub_k<16>(H, U2, p.X);
-  fsub_k<16>(rr, S2, p.Y);
-  fred(H, H);
-  fred(rr, rr);
-  if (fis_zero(H)) {
-    if (fis_zero(rr)) {
+  F a, b, c, d, e, f, g, h;
+  fsqr(a, p.Z);       // Z1Z1
+  fmul(b, q.x, a);    // U2
+  fmul(c, q.y, p.Z);
+  fmul(c, c, a);      // S2
+  fsub_k<16>(b, b, p.X);
+  fsub_k<16>(c, c, p.Y);
+  fred(b, b);         // H
+  fred(c, c);         // r/2
+  if (fis_zero(b)) {
+    if (fis_zero(c)) {
       jac_dbl_impl(r, p);
     } else {
       jac_set_inf(r);
     }
     return;
   }
-  fdbl(rr, rr);
-  fsqr(HH, H);
-  fmul4(I, HH);  // value <= 8, limbs < 2^30
-  fmul(J, H, I);
-  fmul(V, p.X, I);
-  fsqr(X3, rr);
-  fdbl(t, V);
-  fadd(t, t, J);  // J + 2V, value <= 6 (Fp) / 30 (Fp2)
-  fsub_k<32>(X3, X3, t);
-  fred(X3, X3);
-  fsub_k<4>(Y3, V, X3);
-  fnorm(Y3, Y3);
-  fmul(Y3, rr, Y3);
-  fmul(t, p.Y, J);
-  fdbl(t, t);  // value <= 4 (Fp) / 20 (Fp2)
-  fsub_k<32>(Y3, Y3, t);
-  fadd(Z3, p.Z, H);
-  fnorm(Z3, Z3);
-  fsqr(Z3, Z3);
-  fadd(t, Z1Z1, HH);
-  fsub_k<16>(Z3, Z3, t);
-  fred(r.Y, Y3);
-  r.X = X3;
-  fred(r.Z, Z3);
+  fdbl(c, c);         // rr
+  fsqr(d, b);         // HH
+  fmul4(e, d);        // I, value <= 8, limbs < 2^30
+  fmul(f, b, e);      // J
+  fmul(e, p.X, e);    // V
+  fsqr(g, c);
+  fdbl(h, e);
+  fadd(h, h, f);      // J + 2V, value <= 6 (Fp) / 30 (Fp2)
+  fsub_k<32>(g, g, h);
+  fred(g, g);         // X3
+  fsub_k<4>(e, e, g);
+  fnorm(e, e);
+  fmul(e, c, e);      // rr (V - X3)
+  fmul(f, p.Y, f);
+  fdbl(f, f);         // 2 Y1 J, value <= 4 (Fp) / 20 (Fp2)
+  fsub_k<32>(e, e, f);
+  fadd(h, p.Z, b);
+  fnorm(h, h);
+  fsqr(h, h);         // (Z1 + H)^2
+  fadd(a, a, d);
+  fsub_k<16>(h, h, a);
+  fred(r.Y, e);
+  r.X = g;
+  fred(r.Z, h);
 }
 
-// add-2007-bl: 11M + 5S
+// add-2007-bl: 11M + 5S.  r may alias p or q.
 template <class F>
 BLS_HD void jac_add_impl(Jac<F>& r, const Jac<F>& p, const Jac<F>& q) {
   if (jac_is_inf(q)) {
@@ -171,53 +182,53 @@ BLS_HD void jac_add_impl(Jac<F>& r, const Jac<F>& p, const Jac<F>& q) {
     r = q;
     return;
   }
-  F Z1Z1, Z2Z2, U1, U2, S1, S2, H, I, J, rr, V, t, X3, Y3, Z3;
-  fsqr(Z1Z1, p.Z);
-  fsqr(Z2Z2, q.Z);
-  fmul(U1, p.X, Z2Z2);
-  fmul(U2, q.X, Z1Z1);
-  fmul(S1, p.Y, q.Z);
-  fmul(S1, S1, Z2Z2);
-  fmul(S2, q.Y, p.Z);
-  fmul(S2, S2, Z1Z1);
-  fsub_k<16>(H, U2, U1);
-  fsub_k<16>(rr, S2, S1);
-  fred(H, H);
-  fred(rr, rr);
-  if (fis_zero(H)) {
-    if (fis_zero(rr)) {
+  F a, b, c, d, e, f, g, h, i;
+  fsqr(a, p.Z);       // Z1Z1
+  fsqr(b, q.Z);       // Z2Z2
+  fmul(c, p.X, b);    // U1
+  fmul(d, q.X, a);    // U2
+  fmul(e, p.Y, q.Z);
+  fmul(e, e, b);      // S1
+  fmul(f, q.Y, p.Z);
+  fmul(f, f, a);      // S2
+  fsub_k<16>(d, d, c);
+  fsub_k<16>(f, f, e);
+  fred(d, d);         // H
+  fred(f, f);         // r/2
+  if (fis_zero(d)) {
+    if (fis_zero(f)) {
       jac_dbl_impl(r, p);
     } else {
       jac_set_inf(r);
     }
     return;
   }
-  fdbl(rr, rr);
-  fdbl(I, H);
-  fsqr(I, I);
-  fmul(J, H, I);
-  fmul(V, U1, I);
-  fsqr(X3, rr);
-  fdbl(t, V);
-  fadd(t, t, J);
-  fsub_k<32>(X3, X3, t);
-  fred(X3, X3);
-  fsub_k<4>(Y3, V, X3);
-  fnorm(Y3, Y3);
-  fmul(Y3, rr, Y3);
-  fmul(t, S1, J);
-  fdbl(t, t);
-  fsub_k<32>(Y3, Y3, t);
-  fadd(Z3, p.Z, q.Z);
-  fnorm(Z3, Z3);
-  fsqr(Z3, Z3);
-  fadd(t, Z1Z1, Z2Z2);
-  fsub_k<16>(Z3, Z3, t);
-  fnorm(Z3, Z3);
-  fmul(Z3, Z3, H);
-  fred(r.Y, Y3);
-  r.X = X3;
-  fred(r.Z, Z3);
+  fdbl(f, f);         // rr
+  fdbl(g, d);
+  fsqr(g, g);         // I
+  fmul(h, d, g);      // J
+  fmul(c, c, g);      // V
+  fsqr(g, f);
+  fdbl(i, c);
+  fadd(i, i, h);
+  fsub_k<32>(g, g, i);
+  fred(g, g);         // X3
+  fsub_k<4>(c, c, g);
+  fnorm(c, c);
+  fmul(c, f, c);      // rr (V - X3)
+  fmul(e, e, h);
+  fdbl(e, e);         // 2 S1 J
+  fsub_k<32>(c, c, e);
+  fadd(i, p.Z, q.Z);
+  fnorm(i, i);
+  fsqr(i, i);
+  fadd(a, a, b);
+  fsub_k<16>(i, i, a);
+  fnorm(i, i);
+  fmul(i, i, d);
+  fred(r.Y, c);
+  r.X = g;
+  fred(r.Z, i);
 }
 
 // out-of-line instances (code size: one copy of each per group)
@@ -340,36 +351,34 @@ BLS_HD void jac_mul_aff_w4_64(Jac<F>& r, const Aff<F>& p, uint64_t k) {
   const uint32_t w[2] = {(uint32_t)k, (uint32_t)(k >> 32)};
   jac_mul_aff_w4(r, p, w, 16);
 }
-// [|x|]P, |x| = 0xd201000000010000 (Hamming weight 6), Jacobian base
+// [|x|]P, |x| = 0xd201000000010000 (Hamming weight 6), Jacobian base.  r must not alias p (the running point lives in r:
+// no second copy on the stack).
 template <class F>
 BLS_HD void jac_mul_xabs(Jac<F>& r, const Jac<F>& p) {
-  Jac<F> acc = p;
+  r = p;
   const uint64_t e = K_X_ABS;
   for (int i = 62; i >= 0; i--) {
-    jac_dbl(acc, acc);
-    if ((e >> i) & 1) jac_add(acc, acc, p);
+    jac_dbl(r, r);
+    if ((e >> i) & 1) jac_add(r, r, p);
   }
-  r = acc;
 }
 template <class F>
 BLS_HD void jac_mul_xabs_aff(Jac<F>& r, const Aff<F>& p) {
-  Jac<F> acc;
-  jac_from_aff(acc, p);
+  jac_from_aff(r, p);
   const uint64_t e = K_X_ABS;
   for (int i = 62; i >= 0; i--) {
-    jac_dbl(acc, acc);
-    if ((e >> i) & 1) jac_add_mixed(acc, acc, p);
+    jac_dbl(r, r);
+    if ((e >> i) & 1) jac_add_mixed(r, r, p);
   }
-  r = acc;
 }
 
 // ---- endomorphisms and subgroup checks -----------------------------------------------------------------
 // G1: phi(x,y) = (beta x, y) acts as [-x^2] on G1; P in G1  <=>  phi(P) + [x^2]P = O   (Scott, eprint 2021/1130)
 BLS_FN bool g1_in_subgroup(const G1Aff& p) {
   if (p.inf) return true;
-  G1Jac t;
-  jac_mul_xabs_aff(t, p);
-  jac_mul_xabs(t, t);  // [x^2]P  (sign of x cancels)
+  G1Jac t, t1;
+  jac_mul_xabs_aff(t1, p);
+  jac_mul_xabs(t, t1);  // [x^2]P  (sign of x cancels)
   G1Aff phi;
   Fp beta;
   fp_set(beta, K_BETA);

@@ -297,19 +297,19 @@ BLS_FN void fp2_sqr(Fp2& r, const Fp2& a) {
 // Inputs: limbs <= 2^29+64 (a sum of two normalised values), value bounds with (vb(a0)+vb(a1)) * (vb(b0)+vb(b1)) <= 2000.
 // Output: limbs <= 2^28+11, value bounds c0 <= 6, c1 <= 10.
 BLS_FN void fp2_mul(Fp2& r, const Fp2& a, const Fp2& b) {
-  Fp t0, t1, sa, sb, t2;
+  Fp sa, sb, t2;  // three stack slots (they are the hot working set of every G2 kernel): the sums are dead after the first product
   fp_add(sa, a.c0, a.c1);
   fp_add(sb, b.c0, b.c1);
   fp_norm(sa, sa);
   fp_norm(sb, sb);
-  fp_mul(t0, a.c0, b.c0);
-  fp_mul(t1, a.c1, b.c1);
   fp_mul(t2, sa, sb);
-  fp_sub_k<4>(t2, t2, t0);
-  fp_sub_k<4>(t2, t2, t1);
-  fp_sub_k<4>(t0, t0, t1);
+  fp_mul(sa, a.c0, b.c0);
+  fp_mul(sb, a.c1, b.c1);
+  fp_sub_k<4>(t2, t2, sa);
+  fp_sub_k<4>(t2, t2, sb);
+  fp_sub_k<4>(sa, sa, sb);
   fp_norm(r.c1, t2);
-  fp_norm(r.c0, t0);
+  fp_norm(r.c0, sa);
 }
 // (a0+a1)(a0-a1), 2 a0 a1: 2 Fp products.  Input value bounds <= 22 each; output c0 <= 2, c1 <= 4.
 BLS_FN void fp2_sqr(Fp2& r, const Fp2& a) {

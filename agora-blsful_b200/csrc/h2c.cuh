@@ -262,9 +262,9 @@ BLS_FN void g2_clear_cofactor(G2Jac& r, const G2Jac& p) {
   jac_neg(n, t2);
   jac_add(t3, t3, n);  // psi^2(2P) - psi(P)
   jac_add(t2, t1, t2);  // xP + psi(P)
-  jac_mul_xabs(t2, t2);
-  jac_neg(t2, t2);  // x (xP + psi(P))
-  jac_add(t3, t3, t2);
+  jac_mul_xabs(n, t2);
+  jac_neg(n, n);  // x (xP + psi(P))
+  jac_add(t3, t3, n);
   jac_neg(n, t1);
   jac_add(t3, t3, n);  // - xP
   jac_neg(n, p);

@@ -106,6 +106,13 @@ struct Digest {
 #if !defined(BLS_SPLIT_MIN_BLOCKS)
 #define BLS_SPLIT_MIN_BLOCKS 4
 #endif
+#if !defined(BLS_SPLIT2_MIN_BLOCKS)  // the same two kernels over Fp2 points
+#define BLS_SPLIT2_MIN_BLOCKS 4
+#endif
+template <class A>
+struct SplitBlocks {
+  static constexpr int value = sizeof(A) > 2 * sizeof(Fp) + 16 ? BLS_SPLIT2_MIN_BLOCKS : BLS_SPLIT_MIN_BLOCKS;
+};
 // the per-key-set bucket kernel k_secure_msm: pure curve arithmetic as well (cfg 5 verify_secure 809 -> 784 ms at 10,000 x 400)
 #if !defined(BLS_MSM_MIN_BLOCKS)
 #define BLS_MSM_MIN_BLOCKS 4
@@ -157,7 +164,7 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_decode(size_t n, const 
 __device__ __forceinline__ bool pt_in_subgroup(const G1Aff& p) { return g1_in_subgroup(p); }
 __device__ __forceinline__ bool pt_in_subgroup(const G2Aff& p) { return g2_in_subgroup(p); }
 template <class A>
-__global__ void __launch_bounds__(128, BLS_SPLIT_MIN_BLOCKS) k_subgroup_check(size_t n, A* __restrict__ pts, uint8_t* __restrict__ st) {
+__global__ void __launch_bounds__(128, SplitBlocks<A>::value) k_subgroup_check(size_t n, A* __restrict__ pts, uint8_t* __restrict__ st) {
   size_t i = BLS_TID();
   if (i >= n || st[i] != ST_OK) return;
   A p = pts[i];
@@ -252,7 +259,7 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_hash(size_t n, const ui
 // 276 ms at 1M; as two: 267 ms.  A third launch for hash_to_field, with map_to_curve per field element, gained nothing.)
 // The result stays Jacobian: k_to_affine_batch normalises TO_AFFINE_BATCH points per field inversion.
 template <class HA>
-__global__ void __launch_bounds__(128, BLS_SPLIT_MIN_BLOCKS) k_clear_cofactor(size_t n, typename PtInfo<HA>::Jac* __restrict__ pts) {
+__global__ void __launch_bounds__(128, SplitBlocks<HA>::value) k_clear_cofactor(size_t n, typename PtInfo<HA>::Jac* __restrict__ pts) {
   size_t i = BLS_TID();
   if (i >= n) return;
   typename PtInfo<HA>::Jac q = pts[i], r;
