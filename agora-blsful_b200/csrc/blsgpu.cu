@@ -1061,10 +1061,15 @@ int host_partials(blsgpu_ctx* ctx, Pipe<typename ImplT<IMPL>::PkAff, typename Im
   CKR(upload(ctx, d_pks, pks, n * pk_len));
   CKR(upload(ctx, d_sigs, sigs, n * sig_len));
   CKR(upload(ctx, d_msgs, msg_off ? msgs + msg_off[0] : msgs, msg_bytes));
-  std::vector<uint64_t> off(n + 1, 0);  // rebased to the slice's first message (all zero without messages: PoP)
-  if (msg_off)
-    for (size_t i = 0; i <= n; i++) off[i] = msg_off[i] - msg_off[0];
-  CKR(upload(ctx, d_off, off.data(), n + 1));
+  std::vector<uint64_t> off;  // rebased to the slice's first message (all zero without messages: PoP)
+  if (msg_off && msg_off[0] == 0) {
+    CKR(upload(ctx, d_off, msg_off, n + 1));  // the usual case: the caller's offsets go up as they are (no 8n-byte host copy)
+  } else {
+    off.assign(n + 1, 0);
+    if (msg_off)
+      for (size_t i = 0; i <= n; i++) off[i] = msg_off[i] - msg_off[0];
+    CKR(upload(ctx, d_off, off.data(), n + 1));
+  }
   uint8_t* d_st = ctx->arena.take<uint8_t>(n);
   *d_st_out = d_st;
   CKR((verify_dev_partials<IMPL>(ctx, P, msg_mode, dst, format, n, d_pks, d_sigs, d_msgs, d_off, d_st)));

@@ -16,6 +16,7 @@ no data-path collective, weak scaling): every rank verifies its own batch.
 `--impl reference` times the reference's CPU path (oracle restatement: blsful itself needs cargo + un-vendored crates).
 """
 import argparse
+import gc
 import json
 import os
 import sys
@@ -337,8 +338,13 @@ def main():
 
     np_pk, np_sig, np_msg, np_off = h_pk.numpy(), h_sig.numpy(), h_msg.numpy(), h_off.numpy().view(np.uint64)
 
+    host_ms = []
+
     def step_host():
-        return eng.verify_batch_packed(impl, scheme, np_pk, np_sig, np_msg, np_off)
+        t0 = time.perf_counter()
+        st = eng.verify_batch_packed(impl, scheme, np_pk, np_sig, np_msg, np_off)
+        host_ms.append((time.perf_counter() - t0) * 1e3)
+        return st
 
     def barrier():
         if world > 1:
@@ -346,6 +352,14 @@ def main():
         torch.cuda.synchronize()
 
     def timed(fn, steps):
+        gc.collect()
+        gc.disable()  # a collection inside the host-buffer call showed up as a 25 ms outlier in one of three steps
+        try:
+            return _timed(fn, steps)
+        finally:
+            gc.enable()
+
+    def _timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -426,7 +440,8 @@ def main():
                    "miller_loops_per_s_per_gpu": (n / (stages["miller"] * 1e-3)) if stages.get("miller") else None,
                    "miller_loops_note": "n Miller loops / device time of the Miller stage (prep + lines + accumulator kernels)"},
         "roofline": roofline, "clocks": sampler.summary(),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 176 + (n + 1) * 8), "d2h_bytes_per_step": int(n)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 176 + (n + 1) * 8), "d2h_bytes_per_step": int(n),
+                "host_call_ms": [round(x, 1) for x in host_ms[-e2e_steps:]]},
         "gpu_launches": int(launches),
     }
     # strong scaling: ONE batch of n signatures cut over the ranks; every rank folds its slice into one partial product of
@@ -438,8 +453,13 @@ def main():
         dist.all_gather(outs, mine)
         return [(bytes(o[:576].tolist()), bytes(o[576:].tolist())) for o in outs]
 
+    if rank == 0 or world == 1:
+        s_pk, s_sig, s_msg, s_off = np_pk, np_sig, np_msg, np_off
+    else:  # the SAME batch on every rank (rank 0's): each rank verifies its slice of it
+        s_pk, s_sig, s_msg, s_off = synth_batch(eng, n, seed=1000)
+
     def step_strong():
-        return B.verify_batch_folded(eng, impl, scheme, np_pk, np_sig, np_msg, np_off, rank, world, all_gather_parts)
+        return B.verify_batch_folded(eng, impl, scheme, s_pk, s_sig, s_msg, s_off, rank, world, all_gather_parts)
 
     lo_s, st = step_strong()
     assert int(st.max()) == 0
