@@ -106,6 +106,12 @@ struct Digest {
 #if !defined(BLS_SPLIT_MIN_BLOCKS)
 #define BLS_SPLIT_MIN_BLOCKS 4
 #endif
+// k_hash: three blocks per SM (170 registers).  Left to itself the G2 instance compiles to 164-176 registers depending on
+// unrelated inlining decisions, and at 176 it drops to two blocks per SM: 93 -> 100 ms at 1M (seen when the point
+// additions were rewritten in round 2).
+#if !defined(BLS_HASH_MIN_BLOCKS)
+#define BLS_HASH_MIN_BLOCKS 3
+#endif
 #if !defined(BLS_SPLIT2_MIN_BLOCKS)  // the same two kernels over Fp2 points
 #define BLS_SPLIT2_MIN_BLOCKS 4
 #endif
@@ -225,7 +231,7 @@ __global__ void k_prestatus(size_t n, const uint8_t* st_pk, const uint8_t* st_si
 // ---- hash_to_curve of the framed message ---------------------------------------------------------------------------
 // msg_mode 0: msg ; 1: pk.to_bytes() || msg (MessageAugmentation, sig_aug.rs:20-24) ; 2: pk.to_bytes() (PoP, sig_pop.rs:66-69)
 template <class HA, class PkA>
-__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_hash(size_t n, const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ msg_off,
+__global__ void __launch_bounds__(128, BLS_HASH_MIN_BLOCKS) k_hash(size_t n, const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ msg_off,
                                               int msg_mode, const PkA* __restrict__ pk, const uint8_t* __restrict__ pre,
                                               DstParam dst, typename PtInfo<HA>::Jac* __restrict__ out) {
   size_t i = BLS_TID();
