@@ -279,14 +279,17 @@ bool make_dst(DstParam& d, int impl_id, int scheme, bool pop_proof) {
   return true;
 }
 
-// Window width of the bucket multi-scalar multiplication over rbits-bit scalars: >= ~16 signatures per bucket, and only
+// Window width of the bucket multi-scalar multiplication over rbits-bit scalars: >= 4 signatures per bucket, and only
 // widths whose TOP window (rbits - (nwin - 1) c bits) is not much narrower than the others - a 4-bit top window would put
 // n/16 signatures into each of 16 buckets, one thread each (measured: 1.5 s at n = 500,000 with c = 15).
+// A bucket is summed by ONE thread, ~70 us per addition: what a slice of a batch cut over several GPUs pays is the LENGTH of
+// the buckets, not the number of additions (round 2, measured with >= 16 per bucket: 21 ms at n = 125,000 with c = 11 and 61
+// signatures per bucket, against 13 ms at n = 250,000 with c = 13 and 30 per bucket) - hence the wider windows.
 int msm_window_bits(size_t n, int rbits = 64) {
   static const int widths64[] = {16, 13, 11, 8, 5, 4};    // top windows of 16, 12, 9, 8, 4, 4 bits
   static const int widths128[] = {16, 13, 10, 8, 5, 4};   // top windows of 16, 11, 8, 8, 3, 4 bits
   for (int w : (rbits == 128 ? widths128 : widths64))
-    if (((size_t)1 << (w + 4)) <= n) return w;
+    if (((size_t)1 << (w + 2)) <= n) return w;
   return 4;
 }
 

@@ -609,9 +609,13 @@ template <class J>
 __device__ __forceinline__ void jac_mul_small(J& r, const J& p, uint32_t k) {
   J acc;
   jac_set_inf(acc);
+  bool started = false;  // doubling the identity costs as much as doubling a point
   for (int b = 31; b >= 0; b--) {
-    jac_dbl(acc, acc);
-    if ((k >> b) & 1u) jac_add(acc, acc, p);
+    if (started) jac_dbl(acc, acc);
+    if ((k >> b) & 1u) {
+      jac_add(acc, acc, p);
+      started = true;
+    }
   }
   r = acc;
 }

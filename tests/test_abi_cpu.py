@@ -52,7 +52,7 @@ def test_msm_window_plan_never_has_a_narrow_top_window():
         assert lib.blsgpu_plan_msm(n, bits, ctypes.byref(c), ctypes.byref(w), ctypes.byref(top)) == 0
         c, w, top = c.value, w.value, top.value
         assert (w - 1) * c + top == bits and 0 < top <= c
-        assert n >> c >= 8 or c == 4          # enough signatures per bucket to amortise the bucket reduction
+        assert n >> c >= 4 or c == 4          # enough signatures per bucket to amortise the bucket reduction
         assert (n >> top) <= 16 * max(1, n >> c) or n < (1 << 16), (n, c, top)   # top-window buckets at most 16x larger
 
 
