@@ -1477,6 +1477,43 @@ static int sum_points_impl(blsgpu_ctx* ctx, int format, size_t n, const uint8_t*
   return BLSGPU_OK;
 }
 
+// A context on several devices: independent work (point sums of slices, key sets, quorums) goes to the devices in contiguous
+// runs, one host thread per device on the device's own child context - the same sharding blsgpu_verify_batch does, minus the
+// fold (nothing is shared between the runs).  cut[d] .. cut[d + 1] is device d's run; f(device context, d) returns a BLSGPU_* code.
+static int run_on_devices(blsgpu_ctx* ctx, const std::function<int(blsgpu_ctx*, size_t)>& f) {
+  const size_t ndev = 1 + ctx->peers.size();
+  std::vector<int> rc(ndev, BLSGPU_OK);
+  auto body = [&](size_t d) {
+    blsgpu_ctx* c = d == 0 ? ctx : ctx->peers[d - 1];
+    rc[d] = set_device(c);
+    if (rc[d] == BLSGPU_OK) rc[d] = f(c, d);
+  };
+  std::vector<std::thread> workers;
+  for (size_t d = 1; d < ndev; d++) workers.emplace_back(body, d);
+  body(0);
+  for (std::thread& w : workers) w.join();
+  for (size_t d = 0; d < ndev; d++)
+    if (rc[d] != BLSGPU_OK) {
+      if (d) ctx->err = "device " + std::to_string(ctx->devices[d]) + ": " + ctx->peers[d - 1]->err;
+      return rc[d];
+    }
+  return set_device(ctx);
+}
+// cut points of `sets` sets with cumulative weights off[0..sets] into ndev runs of about equal weight
+static std::vector<size_t> balanced_cuts(size_t sets, const uint64_t* off, size_t ndev) {
+  std::vector<size_t> cut(ndev + 1, sets);
+  cut[0] = 0;
+  const uint64_t total = off[sets] - off[0];
+  size_t j = 0;
+  for (size_t d = 1; d < ndev; d++) {
+    const uint64_t want = off[0] + total * d / ndev;
+    while (j < sets && off[j] < want) j++;
+    cut[d] = j;
+  }
+  return cut;
+}
+constexpr size_t SHARD_MIN_POINTS = 65536;  // per device, for the entry points without pairing work
+
 int blsgpu_sum_points(blsgpu_ctx* ctx, int group, int format, size_t n, const uint8_t* points, uint8_t* out, uint8_t* status_out,
                       int64_t* bad_index_out) {
   NVTX_RANGE("blsgpu_sum_points");
@@ -1488,8 +1525,25 @@ int blsgpu_sum_points(blsgpu_ctx* ctx, int group, int format, size_t n, const ui
     return BLSGPU_E_ARG;
   }
   CKR(set_device(ctx));
-  return group == 1 ? sum_points_impl<G1Aff>(ctx, format, n, points, out, status_out, bad_index_out)
-                    : sum_points_impl<G2Aff>(ctx, format, n, points, out, status_out, bad_index_out);
+  auto one = [&](blsgpu_ctx* c, size_t cnt, const uint8_t* pts, uint8_t* o, uint8_t* st, int64_t* bad) {
+    return group == 1 ? sum_points_impl<G1Aff>(c, format, cnt, pts, o, st, bad) : sum_points_impl<G2Aff>(c, format, cnt, pts, o, st, bad);
+  };
+  const size_t ndev = 1 + ctx->peers.size(), L = group == 1 ? 48 : 96;
+  if (ndev == 1 || n < SHARD_MIN_POINTS * ndev) return one(ctx, n, points, out, status_out, bad_index_out);
+  // per-device partial sums of contiguous slices (cfg 3), then the sum of the ndev partial results on the first device
+  std::vector<uint8_t> part(ndev * L), st(ndev, BLSGPU_ST_OK);
+  std::vector<int64_t> bad(ndev, -1);
+  CKR(run_on_devices(ctx, [&](blsgpu_ctx* c, size_t d) {
+    const size_t lo = n * d / ndev, hi = n * (d + 1) / ndev;
+    return one(c, hi - lo, points + lo * L, &part[d * L], &st[d], &bad[d]);
+  }));
+  for (size_t d = 0; d < ndev; d++)
+    if (st[d] != BLSGPU_ST_OK) {  // the first bad element of the whole input is in the first slice that has one
+      *status_out = st[d];
+      *bad_index_out = (int64_t)(n * d / ndev) + bad[d];
+      return BLSGPU_OK;
+    }
+  return one(ctx, ndev, part.data(), out, status_out, bad_index_out);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1912,8 +1966,27 @@ int blsgpu_verify_secure_batch(blsgpu_ctx* ctx, int impl_id, int scheme, int for
     }
   CHECK_OFFSETS(msg_off, q, "blsgpu_verify_secure_batch");
   CKR(set_device(ctx));
-  return impl_id == 2 ? verify_secure_impl<2>(ctx, scheme, format, q, key_off, pks, sigs, msgs, msg_off, status_out)
-                      : verify_secure_impl<1>(ctx, scheme, format, q, key_off, pks, sigs, msgs, msg_off, status_out);
+  auto one = [&](blsgpu_ctx* c, size_t cnt, const uint64_t* ko, const uint8_t* pk, const uint8_t* sg, const uint8_t* ms, const uint64_t* mo,
+                 uint8_t* st) {
+    return impl_id == 2 ? verify_secure_impl<2>(c, scheme, format, cnt, ko, pk, sg, ms, mo, st)
+                        : verify_secure_impl<1>(c, scheme, format, cnt, ko, pk, sg, ms, mo, st);
+  };
+  const size_t ndev = 1 + ctx->peers.size();
+  if (ndev == 1 || q < 2 * ndev || key_off[q] - key_off[0] < SHARD_MIN_ITEMS * ndev) return one(ctx, q, key_off, pks, sigs, msgs, msg_off, status_out);
+  // quorums are independent (cfg 5): contiguous runs of quorums per device, balanced by member count
+  const size_t pk_len = impl_id == 2 ? 48 : 96, sig_len = impl_id == 2 ? 96 : 48;
+  const std::vector<size_t> cut = balanced_cuts(q, key_off, ndev);
+  return run_on_devices(ctx, [&](blsgpu_ctx* c, size_t d) {
+    const size_t lo = cut[d], hi = cut[d + 1];
+    if (hi == lo) return (int)BLSGPU_OK;
+    std::vector<uint64_t> ko(hi - lo + 1), mo(hi - lo + 1);
+    for (size_t j = lo; j <= hi; j++) {
+      ko[j - lo] = key_off[j] - key_off[lo];
+      mo[j - lo] = msg_off[j] - msg_off[lo];
+    }
+    return one(c, hi - lo, ko.data(), pks ? pks + key_off[lo] * pk_len : nullptr, sigs + lo * sig_len, msgs ? msgs + msg_off[lo] : nullptr,
+               mo.data(), status_out + lo);
+  });
 }
 
 int blsgpu_aggregate_secure_batch(blsgpu_ctx* ctx, int impl_id, int format, size_t q, const uint64_t* key_off, const uint8_t* pks,
@@ -1932,8 +2005,20 @@ int blsgpu_aggregate_secure_batch(blsgpu_ctx* ctx, int impl_id, int format, size
       return BLSGPU_E_ARG;
     }
   CKR(set_device(ctx));
-  return impl_id == 2 ? aggregate_secure_impl<2>(ctx, format, q, key_off, pks, member_sigs, out_sigs, status_out)
-                      : aggregate_secure_impl<1>(ctx, format, q, key_off, pks, member_sigs, out_sigs, status_out);
+  auto one = [&](blsgpu_ctx* c, size_t cnt, const uint64_t* ko, const uint8_t* pk, const uint8_t* ms, uint8_t* o, uint8_t* st) {
+    return impl_id == 2 ? aggregate_secure_impl<2>(c, format, cnt, ko, pk, ms, o, st) : aggregate_secure_impl<1>(c, format, cnt, ko, pk, ms, o, st);
+  };
+  const size_t ndev = 1 + ctx->peers.size();
+  if (ndev == 1 || q < 2 * ndev || key_off[q] - key_off[0] < SHARD_MIN_ITEMS * ndev) return one(ctx, q, key_off, pks, member_sigs, out_sigs, status_out);
+  const size_t pk_len = impl_id == 2 ? 48 : 96, sig_len = impl_id == 2 ? 96 : 48;
+  const std::vector<size_t> cut = balanced_cuts(q, key_off, ndev);
+  return run_on_devices(ctx, [&](blsgpu_ctx* c, size_t d) {
+    const size_t lo = cut[d], hi = cut[d + 1];
+    if (hi == lo) return (int)BLSGPU_OK;
+    std::vector<uint64_t> ko(hi - lo + 1);
+    for (size_t j = lo; j <= hi; j++) ko[j - lo] = key_off[j] - key_off[lo];
+    return one(c, hi - lo, ko.data(), pks + key_off[lo] * pk_len, member_sigs + key_off[lo] * sig_len, out_sigs + lo * sig_len, status_out + lo);
+  });
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

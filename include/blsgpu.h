@@ -60,8 +60,11 @@ typedef struct blsgpu_ctx blsgpu_ctx;
  * blsgpu_pop_verify_batch cut a batch of at least 4096 items per device into contiguous slices, one per device, each
  * driven by its own host thread; the slices' partial results (one Fp12 and one point each) are folded on the first device
  * into a single Miller loop + final exponentiation for the whole batch, and only a device whose slice fails bisects (no
- * collective: 2 x ndev copies of < 1 KB).  Every other entry point, the *_dev variants and blsgpu_ctx_set_stream use the
- * first device.  One process per device with blsgpu_miller_partial / blsgpu_final_exp_is_one does the same across processes. */
+ * collective: 2 x ndev copies of < 1 KB).  Entry points whose units are independent are cut the same way without a fold:
+ * blsgpu_sum_points (per-device partial sums of contiguous slices, from 65,536 points per device, then the sum of the partial
+ * results) and blsgpu_verify_secure_batch / blsgpu_aggregate_secure_batch (contiguous runs of key sets, balanced by member
+ * count).  Every other entry point, the *_dev variants and blsgpu_ctx_set_stream use the first device.  One process per
+ * device with blsgpu_miller_partial / blsgpu_final_exp_is_one does the same across processes. */
 int blsgpu_ctx_create(const int* devices, int ndev, blsgpu_ctx** out);
 void blsgpu_ctx_destroy(blsgpu_ctx* ctx);
 /* Text of the last engine error on this context (or of the last failed blsgpu_ctx_create when ctx is NULL). */

@@ -492,3 +492,62 @@ def test_small_batches_and_probe_paths(eng, B):
             s2[bad] = sigs.reshape(nmax, sl)[[(b + 1) % nmax for b in bad]]
             st = eng.verify_batch_packed(impl, 0, pks[:pl * n], s2.reshape(-1), data, off[:n + 1])
             assert st.tolist() == [1 if i % 2 == 0 else 0 for i in range(n)], (impl, n)
+
+
+def test_context_on_two_devices_shards_sums_and_quorums(eng, B):
+    """A context on several devices cuts blsgpu_sum_points (cfg 3: per-device partial sums, then the sum of the partial results)
+    and blsgpu_verify_secure_batch / blsgpu_aggregate_secure_batch (cfg 5: quorums are independent) over its devices
+    (SURVEY 8e).  Results must equal the single-device ones, including the index of the first bad element and the statuses of
+    bad quorums on either side of the cut."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rnd = random.Random(91)
+    e2 = B.Engine([0, 1])
+    try:
+        # point sums, both groups
+        n = 2 * 65536 + 11
+        k = np.zeros((n, 32), dtype=np.uint8)
+        k[:, 24:] = np.frombuffer(rnd.randbytes(8 * n), dtype=np.uint8).reshape(n, 8)
+        k[:, 31] |= 1
+        msg = np.frombuffer(b"same message", dtype=np.uint8)
+        off = np.arange(n + 1, dtype=np.uint64) * msg.size
+        pks, sigs = eng.testdata_sign(2, 2, k.reshape(-1), np.tile(msg, n), off)
+        for group, pts, L in ((1, pks, 48), (2, sigs, 96)):
+            before = e2.launch_count()
+            assert e2.sum_points(group, pts) == eng.sum_points(group, pts)
+            assert e2.launch_count() - before >= 2 * 4                      # both devices decoded and summed
+            bad = pts.copy()
+            bad[(n - 5) * L:(n - 4) * L] = 0xFF                              # undecodable, in the second slice
+            bad[(70000) * L + 1] ^= 0x55                                     # earlier one (second slice as well)
+            for e in (eng, e2):
+                with pytest.raises(B.BlsError) as err:
+                    e.sum_points(group, bad)
+                assert err.value.status == B.ST_DESERIALIZE and "element 70000" in str(err.value)
+        # quorums: 40 key sets of ragged sizes, bad aggregates on both sides of the cut, one Legacy pass
+        q = 40
+        sizes = [150 + 23 * (j % 7) for j in range(q)]
+        tot = sum(sizes)
+        kk = np.zeros((tot, 32), dtype=np.uint8)
+        kk[:, 20:] = np.frombuffer(rnd.randbytes(12 * tot), dtype=np.uint8).reshape(tot, 12)
+        kk[:, 31] |= 1
+        qmsgs = [(b"quorum %d" % j) * (1 + j % 3) for j in range(q)]
+        m5, o5 = B.pack_messages([qmsgs[j] for j in range(q) for _ in range(sizes[j])])
+        pk5, sg5 = eng.testdata_sign(2, 0, kk.reshape(-1), m5, o5)
+        koff = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+        qm, qoff = B.pack_messages(qmsgs)
+        for fmt in (1, 0):
+            if fmt == 0:
+                pk5, sg5 = eng.recode_points_packed(1, pk5, 1, 0), eng.recode_points_packed(2, sg5, 1, 0)
+            st1, agg1 = eng.aggregate_secure_batch_packed(2, koff, pk5, sg5, fmt)
+            before = e2.launch_count()
+            st2, agg2 = e2.aggregate_secure_batch_packed(2, koff, pk5, sg5, fmt)
+            assert e2.launch_count() - before >= 2 * 4
+            assert st1.tolist() == st2.tolist() == [0] * q and np.array_equal(agg1, agg2)
+            wrong = agg1.copy().reshape(q, 96)
+            wrong[[2, 3, q - 2]] = wrong[[3, 2, 5]]
+            want = eng.verify_secure_batch_packed(2, 0, koff, pk5, wrong.reshape(-1), qm, qoff, fmt)
+            assert np.nonzero(want)[0].tolist() == [2, 3, q - 2]
+            assert e2.verify_secure_batch_packed(2, 0, koff, pk5, wrong.reshape(-1), qm, qoff, fmt).tolist() == want.tolist()
+    finally:
+        e2.close()

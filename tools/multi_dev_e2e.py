@@ -26,4 +26,37 @@ for name, cnt in (("1 device", per), (f"{G} devices", n)):
         best = dt if best is None else min(best, dt)
     res[name] = {"n": cnt, "seconds": round(best, 4), "sigs_per_s": round(cnt / best)}
     eng.close()
+# cfg 3 (point sums) and cfg 5 (quorums) through the same multi-device context: G x the single-device work
+one = B.Engine([0])
+many = B.Engine(list(range(G)))
+q1, mem = 2500, 400
+rng = np.random.default_rng(5)
+tot = q1 * mem
+sc = np.zeros((tot, 32), dtype=np.uint8)
+sc[:, 8:] = rng.integers(0, 256, size=(tot, 24), dtype=np.uint8)
+sc[:, 31] |= 1
+qm = rng.integers(0, 256, size=(q1, 32), dtype=np.uint8)
+qm[:, :8] = np.arange(q1, dtype=np.uint64).view(np.uint8).reshape(q1, 8)
+pk5, sg5 = np.empty(tot * 48, dtype=np.uint8), np.empty(tot * 96, dtype=np.uint8)
+for lo in range(0, tot, 1 << 18):
+    hi = min(tot, lo + (1 << 18))
+    p, g = one.testdata_sign(2, 0, sc[lo:hi].reshape(-1), np.ascontiguousarray(qm[np.arange(lo, hi) // mem]).reshape(-1), np.arange(hi - lo + 1, dtype=np.uint64) * 32)
+    pk5[lo * 48:hi * 48], sg5[lo * 96:hi * 96] = p, g
+_, agg = one.aggregate_secure_batch_packed(2, np.arange(q1 + 1, dtype=np.uint64) * mem, pk5, sg5, 1)
+def best_of(f, reps=3):
+    b = None
+    for _ in range(reps):
+        t0 = time.perf_counter(); r = f(); dt = time.perf_counter() - t0
+        b = dt if b is None else min(b, dt)
+    return b, r
+for name, eng, rep in (("1 device", one, 1), (f"{G} devices", many, G)):
+    pts = np.tile(sigs[:96 * per], rep)
+    t, _ = best_of(lambda: eng.sum_points(2, pts))
+    res[name]["cfg3_sum_g2_points"] = {"n": per * rep, "seconds": round(t, 4), "points_per_s": round(per * rep / t)}
+    q = q1 * rep
+    koff = np.arange(q + 1, dtype=np.uint64) * mem
+    a = [np.tile(pk5, rep), np.tile(agg, rep), np.tile(qm.reshape(-1), rep), np.arange(q + 1, dtype=np.uint64) * 32]
+    t, st = best_of(lambda: eng.verify_secure_batch_packed(2, 0, koff, a[0], a[1], a[2], a[3], 1))
+    assert int(st.max()) == 0
+    res[name]["cfg5_verify_secure"] = {"quorums": q, "members": q * mem, "seconds": round(t, 4), "members_per_s": round(q * mem / t)}
 print(json.dumps(res))
