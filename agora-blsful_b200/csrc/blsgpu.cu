@@ -1327,48 +1327,114 @@ int blsgpu_pop_verify_batch(blsgpu_ctx* ctx, int impl_id, int format, size_t n, 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// A context on several devices: independent work (point sums of slices, key sets, quorums) goes to the devices in contiguous
+// runs, one host thread per device on the device's own child context - the same sharding blsgpu_verify_batch does, minus the
+// fold (nothing is shared between the runs).  cut[d] .. cut[d + 1] is device d's run; f(device context, d) returns a BLSGPU_* code.
+static int run_on_devices(blsgpu_ctx* ctx, const std::function<int(blsgpu_ctx*, size_t)>& f) {
+  const size_t ndev = 1 + ctx->peers.size();
+  std::vector<int> rc(ndev, BLSGPU_OK);
+  auto body = [&](size_t d) {
+    blsgpu_ctx* c = d == 0 ? ctx : ctx->peers[d - 1];
+    rc[d] = set_device(c);
+    if (rc[d] == BLSGPU_OK) rc[d] = f(c, d);
+  };
+  std::vector<std::thread> workers;
+  for (size_t d = 1; d < ndev; d++) workers.emplace_back(body, d);
+  body(0);
+  for (std::thread& w : workers) w.join();
+  for (size_t d = 0; d < ndev; d++)
+    if (rc[d] != BLSGPU_OK) {
+      if (d) ctx->err = "device " + std::to_string(ctx->devices[d]) + ": " + ctx->peers[d - 1]->err;
+      return rc[d];
+    }
+  return set_device(ctx);
+}
+// cut points of `sets` sets with cumulative weights off[0..sets] into ndev runs of about equal weight
+static std::vector<size_t> balanced_cuts(size_t sets, const uint64_t* off, size_t ndev) {
+  std::vector<size_t> cut(ndev + 1, sets);
+  cut[0] = 0;
+  const uint64_t total = off[sets] - off[0];
+  size_t j = 0;
+  for (size_t d = 1; d < ndev; d++) {
+    const uint64_t want = off[0] + total * d / ndev;
+    while (j < sets && off[j] < want) j++;
+    cut[d] = j;
+  }
+  return cut;
+}
+// AggregateSignature::verify in phases, so that a context on several devices can cut the pairs over its devices (SURVEY 8e,
+// cfg 4): (1) every device decodes its slice of the keys (the first one also the signature), (2) the host applies the
+// reference's checks in the reference's order over the whole input, (3) every device hashes its messages and folds its pairs
+// into one product of Miller values, (4) the products meet on the first device: one Miller loop against -g, one final
+// exponentiation.
 template <int IMPL>
-static int aggregate_verify_impl(blsgpu_ctx* ctx, int scheme, int format, size_t n, const uint8_t* pks, const uint8_t* msgs,
-                                 const uint64_t* msg_off, const uint8_t* sig, uint8_t* status_out, int64_t index_out[2]) {
+struct AggSlice {
+  typedef typename ImplT<IMPL>::PkAff PkA;
+  typedef typename ImplT<IMPL>::SigAff SigA;
+  size_t n = 0;
+  PkA* d_pk = nullptr;
+  SigA *d_sig = nullptr, *d_h = nullptr;
+  uint8_t *d_msgs = nullptr, *d_status = nullptr;
+  uint64_t* d_off = nullptr;
+  Pipe<PkA, SigA> P;
+};
+// (1) st_out[n] and inf_out[n] get the slice's decode statuses and identity flags; with `sig` also st_out[n] / inf_out[n]
+// (the signature's); without it the slice's signature slot holds the identity (it adds nothing to the fold).
+// msg_off is the slice's own (starting at 0).
+template <int IMPL>
+static int agg_decode(blsgpu_ctx* ctx, AggSlice<IMPL>& S, int format, size_t n, const uint8_t* pks, const uint8_t* msgs, const uint64_t* msg_off,
+                      const uint8_t* sig, uint8_t* st_out, uint32_t* inf_out) {
   typedef typename ImplT<IMPL>::PkAff PkA;
   typedef typename ImplT<IMPL>::SigAff SigA;
   const size_t pk_len = PtInfo<PkA>::LEN, sig_len = PtInfo<SigA>::LEN;
+  S.n = n;
   size_t msg_bytes = (size_t)msg_off[n];
   size_t head = n * (pk_len + sizeof(PkA) + sizeof(SigA) + 2) + msg_bytes + (n + 1) * 8 + sig_len + sizeof(SigA) + 16 * 256 +
                 std::max<size_t>(n, 1) * sizeof(typename PtInfo<SigA>::Jac);
   CKR((ensure_pipeline_arena<PkA, SigA>(ctx, std::max<size_t>(n, 1), head)));
-  uint8_t *d_pks, *d_msgs, *d_sigb;
-  uint64_t* d_off;
+  uint8_t *d_pks, *d_sigb;
   CKR(upload(ctx, d_pks, pks, n * pk_len));
-  CKR(upload(ctx, d_msgs, msgs, msg_bytes));
-  CKR(upload(ctx, d_off, msg_off, n + 1));
-  CKR(upload(ctx, d_sigb, sig, sig_len));
-  PkA* d_pk = ctx->arena.take<PkA>(std::max<size_t>(n, 1));
-  SigA* d_sig = ctx->arena.take<SigA>(1);
-  SigA* d_h = ctx->arena.take<SigA>(std::max<size_t>(n, 1));
+  CKR(upload(ctx, S.d_msgs, msgs, msg_bytes));
+  CKR(upload(ctx, S.d_off, msg_off, n + 1));
+  d_sigb = ctx->arena.take<uint8_t>(sig_len);
+  S.d_pk = ctx->arena.take<PkA>(std::max<size_t>(n, 1));
+  S.d_sig = ctx->arena.take<SigA>(1);
+  S.d_h = ctx->arena.take<SigA>(std::max<size_t>(n, 1));
   uint8_t* d_stpk = ctx->arena.take<uint8_t>(n + 1);
-  uint8_t* d_stsig = d_stpk + n;
+  S.d_status = ctx->arena.take<uint8_t>(std::max<size_t>(n, 1));
+  ARENA_OK();
   stage_reset(ctx);
-  if (n) CKR((decode_points<PkA>(ctx, n, (const uint8_t*)d_pks, format, d_pk, d_stpk)));
-  CKR((decode_points<SigA>(ctx, (size_t)1, (const uint8_t*)d_sigb, format, d_sig, d_stsig)));
-  std::vector<uint8_t> st(n + 1);
-  CK(cudaMemcpyAsync(st.data(), d_stpk, n + 1, cudaMemcpyDeviceToHost, ctx->stream));
-  std::vector<uint32_t> inf(n + 1, 0);
+  if (n) CKR((decode_points<PkA>(ctx, n, (const uint8_t*)d_pks, format, S.d_pk, d_stpk)));
+  if (sig) {
+    CK(cudaMemcpyAsync(d_sigb, sig, sig_len, cudaMemcpyHostToDevice, ctx->stream));
+    CKR((decode_points<SigA>(ctx, (size_t)1, (const uint8_t*)d_sigb, format, S.d_sig, d_stpk + n)));
+  } else {
+    SigA ident;
+    memset(&ident, 0, sizeof(ident));
+    ident.inf = 1;
+    CK(cudaMemcpyAsync(S.d_sig, &ident, sizeof(ident), cudaMemcpyHostToDevice, ctx->stream));  // pageable source: staged before the call returns
+  }
+  CK(cudaMemcpyAsync(st_out, d_stpk, n + (sig ? 1 : 0), cudaMemcpyDeviceToHost, ctx->stream));
   // identity flags: read the `inf` words back (strided copy)
-  if (n) CK(cudaMemcpy2DAsync(inf.data(), 4, reinterpret_cast<const uint8_t*>(d_pk) + offsetof(PkA, inf), sizeof(PkA), 4, n,
-                              cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(&inf[n], reinterpret_cast<const uint8_t*>(d_sig) + offsetof(SigA, inf), 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (n) CK(cudaMemcpy2DAsync(inf_out, 4, reinterpret_cast<const uint8_t*>(S.d_pk) + offsetof(PkA, inf), sizeof(PkA), 4, n, cudaMemcpyDeviceToHost,
+                              ctx->stream));
+  if (sig) CK(cudaMemcpyAsync(inf_out + n, reinterpret_cast<const uint8_t*>(S.d_sig) + offsetof(SigA, inf), 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  return BLSGPU_OK;
+}
+// (2) the reference's checks before any pairing work, in its order (sig_core.rs:149-178, sig_basic.rs:46-58); true = decided
+static bool agg_host_checks(int scheme, size_t n, const uint8_t* st, const uint32_t* inf, const uint8_t* msgs, const uint64_t* msg_off,
+                            uint8_t* status_out, int64_t index_out[2]) {
   index_out[0] = index_out[1] = -1;
   for (size_t i = 0; i < n; i++)
     if (st[i] != BLSGPU_ST_OK) {
       *status_out = st[i];
       index_out[0] = (int64_t)i;
-      return BLSGPU_OK;
+      return true;
     }
   if (st[n] != BLSGPU_ST_OK) {
     *status_out = st[n];
-    return BLSGPU_OK;
+    return true;
   }
   if (scheme == 0) {
     // Basic: duplicate messages are rejected before any curve work (reference src/traits/sig_basic.rs:46-58)
@@ -1381,34 +1447,106 @@ static int aggregate_verify_impl(blsgpu_ctx* ctx, int scheme, int format, size_t
         *status_out = BLSGPU_ST_DUPLICATE_MESSAGES;
         index_out[0] = (int64_t)it->second;
         index_out[1] = (int64_t)i;
-        return BLSGPU_OK;
+        return true;
       }
       seen.emplace(std::move(m), i);
     }
   }
   if (inf[n]) {
     *status_out = BLSGPU_ST_SIG_IDENTITY;
-    return BLSGPU_OK;
+    return true;
   }
   for (size_t i = 0; i < n; i++)
     if (inf[i]) {
       *status_out = BLSGPU_ST_PK_IDENTITY;
       index_out[0] = (int64_t)i + 1;  // the reference reports i+1 (sig_core.rs:162-167)
-      return BLSGPU_OK;
+      return true;
     }
-  int ok = 0;
   if (n == 0) {
     // only the (sig, -g) pair remains and sig != identity: never the Gt identity
     *status_out = BLSGPU_ST_INVALID_SIGNATURE;
-    return BLSGPU_OK;
+    return true;
   }
+  return false;
+}
+// (3) hash the slice's messages, Miller loops of its pairs, product tree: S.P.rootF() / S.P.rootS() (the stream is NOT synchronised)
+template <int IMPL>
+static int agg_partials(blsgpu_ctx* ctx, AggSlice<IMPL>& S, int scheme) {
+  typedef typename ImplT<IMPL>::PkAff PkA;
+  typedef typename ImplT<IMPL>::SigAff SigA;
   DstParam dst;
   make_dst(dst, IMPL, scheme, false);
-  uint8_t* d_status = ctx->arena.take<uint8_t>(n);
-  CK(cudaMemsetAsync(d_status, 0, n, ctx->stream));
-  CKR((hash_points<SigA, PkA>(ctx, n, (const uint8_t*)d_msgs, (const uint64_t*)d_off, scheme == 1 ? 1 : 0, (const PkA*)d_pk,
-                              (const uint8_t*)nullptr, dst, d_h)));
-  CKR((run_pairing_pipeline<PkA, SigA>(ctx, n, d_pk, d_sig, d_h, d_status, false, &ok)));
+  CK(cudaMemsetAsync(S.d_status, 0, S.n, ctx->stream));
+  CKR((hash_points<SigA, PkA>(ctx, S.n, (const uint8_t*)S.d_msgs, (const uint64_t*)S.d_off, scheme == 1 ? 1 : 0, (const PkA*)S.d_pk,
+                              (const uint8_t*)nullptr, dst, S.d_h)));
+  return pipeline_partials<PkA, SigA>(ctx, S.P, S.n, S.d_pk, S.d_sig, S.d_h, S.d_status, false);
+}
+template <int IMPL>
+static int aggregate_verify_impl(blsgpu_ctx* ctx, int scheme, int format, size_t n, const uint8_t* pks, const uint8_t* msgs,
+                                 const uint64_t* msg_off, const uint8_t* sig, uint8_t* status_out, int64_t index_out[2]) {
+  typedef typename ImplT<IMPL>::PkAff PkA;
+  typedef typename ImplT<IMPL>::SigAff SigA;
+  AggSlice<IMPL> S;
+  std::vector<uint8_t> st(n + 1);
+  std::vector<uint32_t> inf(n + 1, 0);
+  CKR((agg_decode<IMPL>(ctx, S, format, n, pks, msgs, msg_off, sig, st.data(), inf.data())));
+  if (agg_host_checks(scheme, n, st.data(), inf.data(), msgs, msg_off, status_out, index_out)) return BLSGPU_OK;
+  CKR((agg_partials<IMPL>(ctx, S, scheme)));
+  bool ok = false;
+  CKR((pipeline_check<PkA, SigA>(ctx, S.P, &ok)));
+  stage_mark(ctx, BLSGPU_STAGE_COUNT);
+  *status_out = ok ? BLSGPU_ST_OK : BLSGPU_ST_INVALID_SIGNATURE;
+  return BLSGPU_OK;
+}
+// the same over the devices of a context: contiguous slices of the pairs, the signature travels with the first slice
+template <int IMPL>
+static int aggregate_verify_multi(blsgpu_ctx* ctx, int scheme, int format, size_t n, const uint8_t* pks, const uint8_t* msgs,
+                                  const uint64_t* msg_off, const uint8_t* sig, uint8_t* status_out, int64_t index_out[2]) {
+  typedef typename ImplT<IMPL>::PkAff PkA;
+  typedef typename ImplT<IMPL>::SigAff SigA;
+  typedef typename PtInfo<SigA>::Jac SigJ;
+  const size_t ndev = 1 + ctx->peers.size(), pk_len = PtInfo<PkA>::LEN;
+  std::vector<AggSlice<IMPL>> S(ndev);
+  std::vector<uint8_t> st(n + 1);
+  std::vector<uint32_t> inf(n + 1, 0);
+  std::vector<std::vector<uint64_t>> off(ndev);
+  auto lo = [&](size_t d) { return n * d / ndev; };
+  // the signature's status and identity flag come back at the END of slice 0's arrays: stage them, then move them to [n]
+  std::vector<uint8_t> st0(lo(1) + 1);
+  std::vector<uint32_t> inf0(lo(1) + 1, 0);
+  CKR(run_on_devices(ctx, [&](blsgpu_ctx* c, size_t d) {
+    const size_t s0 = lo(d), cnt = lo(d + 1) - s0;
+    off[d].resize(cnt + 1);
+    for (size_t i = 0; i <= cnt; i++) off[d][i] = msg_off[s0 + i] - msg_off[s0];
+    return agg_decode<IMPL>(c, S[d], format, cnt, pks + s0 * pk_len, msgs + msg_off[s0], off[d].data(), d == 0 ? sig : nullptr,
+                            d == 0 ? st0.data() : st.data() + s0, d == 0 ? inf0.data() : inf.data() + s0);
+  }));
+  std::copy(st0.begin(), st0.end() - 1, st.begin());
+  std::copy(inf0.begin(), inf0.end() - 1, inf.begin());
+  st[n] = st0.back();
+  inf[n] = inf0.back();
+  if (agg_host_checks(scheme, n, st.data(), inf.data(), msgs, msg_off, status_out, index_out)) return BLSGPU_OK;
+  CKR(run_on_devices(ctx, [&](blsgpu_ctx* c, size_t d) {
+    int rc = agg_partials<IMPL>(c, S[d], scheme);
+    if (rc != BLSGPU_OK) return rc;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
+      c->err = "aggregate_verify: device synchronisation failed";
+      return (int)BLSGPU_E_CUDA;
+    }
+    return (int)BLSGPU_OK;
+  }));
+  CKR(ensure_fold_scratch(ctx, fold_bytes<PkA, SigA>(ndev)));
+  Arena A;
+  A.base = ctx->fold_scratch;
+  A.cap = ctx->fold_cap;
+  Fp12* d_Fk = A.take<Fp12>(ndev);
+  SigJ* d_Sk = A.take<SigJ>(ndev);
+  for (size_t d = 0; d < ndev; d++) {
+    CK(cudaMemcpyPeerAsync(d_Fk + d, ctx->devices[0], S[d].P.rootF(), ctx->devices[d], sizeof(Fp12), ctx->stream));
+    CK(cudaMemcpyPeerAsync(d_Sk + d, ctx->devices[0], S[d].P.rootS(), ctx->devices[d], sizeof(SigJ), ctx->stream));
+  }
+  bool ok = false;
+  CKR((fold_check<PkA, SigA>(ctx, A, ndev, d_Fk, d_Sk, &ok)));
   *status_out = ok ? BLSGPU_ST_OK : BLSGPU_ST_INVALID_SIGNATURE;
   return BLSGPU_OK;
 }
@@ -1425,6 +1563,9 @@ int blsgpu_aggregate_verify(blsgpu_ctx* ctx, int impl_id, int scheme, int format
   }
   CHECK_OFFSETS(msg_off, n, "blsgpu_aggregate_verify");
   CKR(set_device(ctx));
+  if (!ctx->peers.empty() && n >= (1 + ctx->peers.size()) * SHARD_MIN_ITEMS)
+    return impl_id == 2 ? aggregate_verify_multi<2>(ctx, scheme, format, n, pks, msgs, msg_off, sig, status_out, index_out)
+                        : aggregate_verify_multi<1>(ctx, scheme, format, n, pks, msgs, msg_off, sig, status_out, index_out);
   return impl_id == 2 ? aggregate_verify_impl<2>(ctx, scheme, format, n, pks, msgs, msg_off, sig, status_out, index_out)
                       : aggregate_verify_impl<1>(ctx, scheme, format, n, pks, msgs, msg_off, sig, status_out, index_out);
 }
@@ -1477,41 +1618,6 @@ static int sum_points_impl(blsgpu_ctx* ctx, int format, size_t n, const uint8_t*
   return BLSGPU_OK;
 }
 
-// A context on several devices: independent work (point sums of slices, key sets, quorums) goes to the devices in contiguous
-// runs, one host thread per device on the device's own child context - the same sharding blsgpu_verify_batch does, minus the
-// fold (nothing is shared between the runs).  cut[d] .. cut[d + 1] is device d's run; f(device context, d) returns a BLSGPU_* code.
-static int run_on_devices(blsgpu_ctx* ctx, const std::function<int(blsgpu_ctx*, size_t)>& f) {
-  const size_t ndev = 1 + ctx->peers.size();
-  std::vector<int> rc(ndev, BLSGPU_OK);
-  auto body = [&](size_t d) {
-    blsgpu_ctx* c = d == 0 ? ctx : ctx->peers[d - 1];
-    rc[d] = set_device(c);
-    if (rc[d] == BLSGPU_OK) rc[d] = f(c, d);
-  };
-  std::vector<std::thread> workers;
-  for (size_t d = 1; d < ndev; d++) workers.emplace_back(body, d);
-  body(0);
-  for (std::thread& w : workers) w.join();
-  for (size_t d = 0; d < ndev; d++)
-    if (rc[d] != BLSGPU_OK) {
-      if (d) ctx->err = "device " + std::to_string(ctx->devices[d]) + ": " + ctx->peers[d - 1]->err;
-      return rc[d];
-    }
-  return set_device(ctx);
-}
-// cut points of `sets` sets with cumulative weights off[0..sets] into ndev runs of about equal weight
-static std::vector<size_t> balanced_cuts(size_t sets, const uint64_t* off, size_t ndev) {
-  std::vector<size_t> cut(ndev + 1, sets);
-  cut[0] = 0;
-  const uint64_t total = off[sets] - off[0];
-  size_t j = 0;
-  for (size_t d = 1; d < ndev; d++) {
-    const uint64_t want = off[0] + total * d / ndev;
-    while (j < sets && off[j] < want) j++;
-    cut[d] = j;
-  }
-  return cut;
-}
 constexpr size_t SHARD_MIN_POINTS = 65536;  // per device, for the entry points without pairing work
 
 int blsgpu_sum_points(blsgpu_ctx* ctx, int group, int format, size_t n, const uint8_t* points, uint8_t* out, uint8_t* status_out,

@@ -63,7 +63,8 @@ typedef struct blsgpu_ctx blsgpu_ctx;
  * collective: 2 x ndev copies of < 1 KB).  Entry points whose units are independent are cut the same way without a fold:
  * blsgpu_sum_points (per-device partial sums of contiguous slices, from 65,536 points per device, then the sum of the partial
  * results) and blsgpu_verify_secure_batch / blsgpu_aggregate_secure_batch (contiguous runs of key sets, balanced by member
- * count).  Every other entry point, the *_dev variants and blsgpu_ctx_set_stream use the first device.  One process per
+ * count); blsgpu_aggregate_verify cuts its pairs over the devices (from 4096 per device) and folds the partial products of
+ * Miller values on the first device.  Every other entry point, the *_dev variants and blsgpu_ctx_set_stream use the first device.  One process per
  * device with blsgpu_miller_partial / blsgpu_final_exp_is_one does the same across processes. */
 int blsgpu_ctx_create(const int* devices, int ndev, blsgpu_ctx** out);
 void blsgpu_ctx_destroy(blsgpu_ctx* ctx);

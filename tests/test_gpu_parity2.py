@@ -551,3 +551,56 @@ def test_context_on_two_devices_shards_sums_and_quorums(eng, B):
             assert e2.verify_secure_batch_packed(2, 0, koff, pk5, wrong.reshape(-1), qm, qoff, fmt).tolist() == want.tolist()
     finally:
         e2.close()
+
+
+@pytest.mark.parametrize("impl,scheme", [(2, 0), (2, 1), (1, 2)])
+def test_context_on_two_devices_shards_aggregate_verify(eng, B, impl, scheme):
+    """cfg 4 on several devices: the pairs of AggregateSignature::verify are cut over the devices, the partial products of Miller
+    values are folded on the first device.  Status and reported indices must equal the single-device ones for a valid aggregate,
+    a wrong one, and every rule the reference applies before the pairing (first decode error, duplicate messages, identity key)
+    when the offending element lies in the second slice."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n = 2 * 4096 + 5
+    rnd = random.Random(17 + scheme)
+    pl, sl = B.pk_len(impl), B.sig_len(impl)
+    k = np.frombuffer(b"".join(rnd.randrange(1, O.R).to_bytes(32, "big") for _ in range(n)), dtype=np.uint8)
+    msgs = [hashlib.sha256(b"agg%d" % i).digest()[:1 + i % 32] + bytes([i & 255, i >> 8 & 255]) for i in range(n)]
+    data, off = B.pack_messages(msgs)
+    pks, sigs = eng.testdata_sign(impl, scheme, k, data, off)
+    agg = eng.sum_points(2 if impl == 2 else 1, sigs)
+    pk_rows = pks.reshape(n, pl)
+    ident = bytes([0xC0]) + bytes(pl - 1)
+    e2 = B.Engine([0, 1])
+    try:
+        def both(pk_arr, ms, sg):
+            a = eng.aggregate_verify_status(impl, scheme, pk_arr, ms, sg)
+            before = e2.launch_count()
+            b = e2.aggregate_verify_status(impl, scheme, pk_arr, ms, sg)
+            assert a == b, (a, b)
+            return a, e2.launch_count() - before
+        (st, _), launched = both(pks, msgs, agg)
+        assert st == 0 and launched > 2 * 12                       # both devices ran their own pipeline
+        wrong = eng.sum_points(2 if impl == 2 else 1, sigs[sl:])
+        assert both(pks, msgs, wrong)[0][0] == B.ST_INVALID_SIGNATURE
+        swapped = list(msgs)
+        swapped[6000], swapped[6001] = swapped[6001], swapped[6000]   # same multiset of pairs? no: keys stay - must fail
+        assert both(pks, swapped, agg)[0][0] == B.ST_INVALID_SIGNATURE
+        bad = pk_rows.copy()
+        bad[7000] = 0xFF                                           # undecodable key in the second slice
+        bad[8000] = np.frombuffer(ident, dtype=np.uint8)           # identity key later on
+        assert both(bad.reshape(-1), msgs, agg)[0] == (B.ST_DESERIALIZE, (7000, -1))
+        bad[7000] = pk_rows[7000]
+        assert both(bad.reshape(-1), msgs, agg)[0] == (B.ST_PK_IDENTITY, (8001, -1))
+        if scheme == 0:
+            dup = list(msgs)
+            dup[8100] = dup[3]
+            assert both(pks, dup, agg)[0] == (B.ST_DUPLICATE_MESSAGES, (3, 8100))
+        assert both(pks, msgs, bytes([0xC0]) + bytes(sl - 1))[0][0] == B.ST_SIG_IDENTITY
+        # a batch too small to shard stays on the first device
+        small = eng.sum_points(2 if impl == 2 else 1, sigs[:64 * sl])
+        (st, _), launched = both(pks[:64 * pl], msgs[:64], small)
+        assert st == 0 and launched < 2 * 12 + 40
+    finally:
+        e2.close()

@@ -53,6 +53,14 @@ for name, eng, rep in (("1 device", one, 1), (f"{G} devices", many, G)):
     pts = np.tile(sigs[:96 * per], rep)
     t, _ = best_of(lambda: eng.sum_points(2, pts))
     res[name]["cfg3_sum_g2_points"] = {"n": per * rep, "seconds": round(t, 4), "points_per_s": round(per * rep / t)}
+    # cfg 4: AggregateSignature::verify over rep x 100,000 distinct messages (pairs cut over the devices, fold on the first)
+    m4 = 100000 * rep
+    if m4 <= n:
+        agg4 = one.sum_points(2, sigs[:96 * m4])
+        ml = [msgs[32 * i:32 * i + 32].tobytes() for i in range(m4)]
+        t, r4 = best_of(lambda: eng.aggregate_verify_status(2, 0, pks[:48 * m4], ml, agg4), 2)
+        assert r4[0] == 0
+        res[name]["cfg4_aggregate_verify"] = {"pairs": m4, "seconds": round(t, 4), "pairs_per_s": round(m4 / t)}
     q = q1 * rep
     koff = np.arange(q + 1, dtype=np.uint64) * mem
     a = [np.tile(pk5, rep), np.tile(agg, rep), np.tile(qm.reshape(-1), rep), np.arange(q + 1, dtype=np.uint64) * 32]
