@@ -588,16 +588,30 @@ int pipeline_bisect(blsgpu_ctx* ctx, Pipe<PkA, SigA>& P) {
       LAUNCH((k_reduce_jac<SigJ>), blocks_for(lv[k + 1].cnt), TPB, lv[k].cnt, P.d_S + lv[k].off, lv[k + 1].cnt, P.d_S + lv[k + 1].off);
   }
   // walk down the 16-ary tree to the failing groups: children of node j at level k+1 are {j + m * cnt(k+1)} at level k
-  std::vector<uint32_t> bad{0};
-  std::vector<uint8_t> res;
-  for (size_t k = lv.size() - 1; k-- > 0;) {
-    std::vector<uint32_t> cand;
-    size_t cn = lv[k + 1].cnt;
-    for (uint32_t j : bad)
+  // A round of probes costs ~9 ms whatever its size (one cooperative Miller pass + one final-exponentiation launch, both
+  // latency), so a round goes down as many levels as it can while the candidates stay below BISECT_FANOUT: one bad signature
+  // in 1M is found in 3 rounds instead of 6.
+  const size_t one_round = P.big_items >= 6 * PROBE_SMALL ? std::min(P.x_cap, P.big_items / 6) : PROBE_SMALL;  // what probe_level takes at once
+  const size_t BISECT_FANOUT = std::min<size_t>(1024, one_round);
+  auto children = [&](const std::vector<uint32_t>& nodes, size_t level) {  // nodes at `level` -> their children at level - 1
+    std::vector<uint32_t> out;
+    const size_t cn = lv[level].cnt;
+    for (uint32_t j : nodes)
       for (int m = 0; m < 16; m++) {
         size_t idx = (size_t)j + (size_t)m * cn;
-        if (idx < lv[k].cnt) cand.push_back((uint32_t)idx);
+        if (idx < lv[level - 1].cnt) out.push_back((uint32_t)idx);
       }
+    return out;
+  };
+  std::vector<uint32_t> bad{0};
+  std::vector<uint8_t> res;
+  for (size_t k = lv.size() - 1; k > 0;) {
+    std::vector<uint32_t> cand = children(bad, k);
+    k--;
+    while (k > 0 && cand.size() * 16 <= BISECT_FANOUT) {
+      cand = children(cand, k);
+      k--;
+    }
     if (cand.empty()) break;
     if (k == 0 && by_nodes) {
       // the candidate groups (children of failing level-1 nodes) get their sums now: r_i sig_i for their items only
