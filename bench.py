@@ -338,12 +338,13 @@ def main():
 
     np_pk, np_sig, np_msg, np_off = h_pk.numpy(), h_sig.numpy(), h_msg.numpy(), h_off.numpy().view(np.uint64)
 
-    host_ms = []
+    host_ms, host_dev_ms = [], []
 
     def step_host():
         t0 = time.perf_counter()
         st = eng.verify_batch_packed(impl, scheme, np_pk, np_sig, np_msg, np_off)
         host_ms.append((time.perf_counter() - t0) * 1e3)
+        host_dev_ms.append(sum(eng.last_stage_ms().values()))
         return st
 
     def barrier():
@@ -442,7 +443,8 @@ def main():
                    "miller_loops_note": "n Miller loops / device time of the Miller stage (prep + lines + accumulator kernels)"},
         "roofline": roofline, "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 176 + (n + 1) * 8), "d2h_bytes_per_step": int(n),
-                "host_call_ms": [round(x, 1) for x in host_ms[-e2e_steps:]]},
+                "host_call_ms": [round(x, 1) for x in host_ms[-e2e_steps:]],
+                "host_call_device_ms": [round(x, 1) for x in host_dev_ms[-e2e_steps:]]},
         "gpu_launches": int(launches),
     }
     # strong scaling: ONE batch of n signatures cut over the ranks; every rank folds its slice into one partial product of
