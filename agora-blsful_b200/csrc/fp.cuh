@@ -129,6 +129,29 @@ BLS_HD void fp_st(Fp& r, const uint32_t* v) {
 }
 
 // ---- lazy additive operations --------------------------------------------------------------------------------------
+// a + b issued on the ALU pipe.  ptxas is free to emit a 32-bit addition as IMAD.IADD on the multiplier pipe, and in these
+// kernels it does so for the operand sums of the Karatsuba products - where the multiplier is the one pipe that has no time to
+// spare.  VIADDMNMX (max(a + b, c)) exists only on the ALU pipe: with c = the smallest value it IS the sum.
+// Measured at 1M (round 2): the Karatsuba operand sums this way: 776 -> 768 ms over the step.  NOT for everything: the same
+// trick on fp_add cost 3.6 ms and on fp_norm 7 ms (they break ptxas's three-input IADD3 fusions), and on the operand preparation of the
+// lines kernel 13 ms (that kernel is bound by issue slots and the ALU pipe, not by the multiplier alone).
+#if !defined(BLS_ALU_ADD)
+#define BLS_ALU_ADD 1
+#endif
+BLS_HD uint32_t alu_add_u32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__) && BLS_ALU_ADD
+  return __viaddmax_u32(a, b, 0u);
+#else
+  return a + b;
+#endif
+}
+BLS_HD int32_t alu_add_s32(int32_t a, int32_t b) {
+#if defined(__CUDA_ARCH__) && BLS_ALU_ADD
+  return __viaddmax_s32(a, b, (int32_t)0x80000000);
+#else
+  return a + b;
+#endif
+}
 BLS_HD void fp_add(Fp& r, const Fp& a, const Fp& b) {
 #if defined(BLS_TRACK)
   BLS_REQ(a.lb + b.lb < (1ull << 32), "fp_add limb overflow");
@@ -228,8 +251,8 @@ BLS_HD void fp_mul_inl(Fp& r, const Fp& a, const Fp& b) {
   fp_ld(bl, b);
 #pragma unroll
   for (int i = 0; i < HL; i++) {
-    sa[i] = al[i] + al[HL + i];
-    sb[i] = bl[i] + bl[HL + i];
+    sa[i] = alu_add_u32(al[i], al[HL + i]);
+    sb[i] = alu_add_u32(bl[i], bl[HL + i]);
   }
 #pragma unroll
   for (int i = 0; i < 2 * HL - 1; i++) L[i] = H[i] = M[i] = 0;
@@ -299,7 +322,7 @@ BLS_HD void fp_sqr_inl(Fp& r, const Fp& a) {
   uint32_t al[NL], sa[HL], rl[NL];
   fp_ld(al, a);
 #pragma unroll
-  for (int i = 0; i < HL; i++) sa[i] = al[i] + al[HL + i];
+  for (int i = 0; i < HL; i++) sa[i] = alu_add_u32(al[i], al[HL + i]);
   fp_sqr_half(L, al);
   fp_sqr_half(H, al + HL);
   fp_sqr_half(M, sa);

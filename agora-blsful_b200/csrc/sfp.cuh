@@ -159,8 +159,8 @@ BLS_HD void sop_acc(uint64_t* T, const int32_t* a, const int32_t* b) {
   int32_t sa[H], sb[H];
 #pragma unroll
   for (int i = 0; i < H; i++) {
-    sa[i] = a[i] + a[H + i];
-    sb[i] = b[i] + b[H + i];
+    sa[i] = alu_add_s32(a[i], a[H + i]);
+    sb[i] = alu_add_s32(b[i], b[H + i]);
   }
 #pragma unroll
   for (int i = 0; i < H; i++) {
