@@ -58,6 +58,22 @@ constexpr size_t MSM_MIN_ITEMS = 4096;  // below this the per-item scaling is as
 constexpr size_t M6_CHUNK_MAX = (size_t)8736 * 120;  // 1,048,320 items = 41 GB of line records: a 1M batch in one pass
 constexpr size_t M6_CHUNK_MIN = 120;
 inline unsigned blocks_for(size_t n, int tpb = TPB) { return (unsigned)((n + tpb - 1) / tpb); }
+// one level of a 16-ary product / sum tree: levels with few output nodes take the 16-lanes-per-node kernels (kernels.cuh)
+constexpr size_t REDUCE_WIDE_MAX = 4096;
+#define REDUCE_FP12(n_in, in, n_out, out)                                                                       \
+  do {                                                                                                          \
+    if ((size_t)(n_out) <= REDUCE_WIDE_MAX)                                                                     \
+      LAUNCH(k_reduce_fp12_w, blocks_for((size_t)(n_out) * 16), TPB, (size_t)(n_in), in, (size_t)(n_out), out); \
+    else                                                                                                        \
+      LAUNCH(k_reduce_fp12, blocks_for(n_out), TPB, (size_t)(n_in), in, (size_t)(n_out), out);                  \
+  } while (0)
+#define REDUCE_JAC(J, n_in, in, n_out, out)                                                                          \
+  do {                                                                                                               \
+    if ((size_t)(n_out) <= REDUCE_WIDE_MAX)                                                                          \
+      LAUNCH((k_reduce_jac_w<J>), blocks_for((size_t)(n_out) * 16), TPB, (size_t)(n_in), in, (size_t)(n_out), out);  \
+    else                                                                                                             \
+      LAUNCH((k_reduce_jac<J>), blocks_for(n_out), TPB, (size_t)(n_in), in, (size_t)(n_out), out);                   \
+  } while (0)
 
 // bump allocator over one device buffer, regrown between calls
 struct Arena {
@@ -464,7 +480,7 @@ int pipeline_partials(blsgpu_ctx* ctx, Pipe<PkA, SigA>& P, size_t n, const PkA* 
              (const uint32_t*)d_sorted, d_B);
       LAUNCH((k_msm_chunk<SigJ>), blocks_for(nchunks), TPB, nchunks, c, (const SigJ*)d_B, d_V);
       for (size_t k = 0; k + 1 < lm.size(); k++)
-        LAUNCH((k_reduce_jac<SigJ>), blocks_for(lm[k + 1].cnt), TPB, lm[k].cnt, d_V + lm[k].off, lm[k + 1].cnt, d_V + lm[k + 1].off);
+        REDUCE_JAC(SigJ, lm[k].cnt, (const SigJ*)(d_V + lm[k].off), lm[k + 1].cnt, d_V + lm[k + 1].off);
       P.d_msm_root = d_V + lm.back().off;
       return BLSGPU_OK;
     }();
@@ -535,9 +551,9 @@ int pipeline_partials(blsgpu_ctx* ctx, Pipe<PkA, SigA>& P, size_t n, const PkA* 
   }
   stage_mark(ctx, BLSGPU_STAGE_REDUCE);
   for (size_t k = 0; k + 1 < lv.size(); k++) {
-    LAUNCH(k_reduce_fp12, blocks_for(lv[k + 1].cnt), TPB, lv[k].cnt, d_F + lv[k].off, lv[k + 1].cnt, d_F + lv[k + 1].off);
+    REDUCE_FP12(lv[k].cnt, (const Fp12*)(d_F + lv[k].off), lv[k + 1].cnt, d_F + lv[k + 1].off);
     if (use_rlc && !use_msm)
-      LAUNCH((k_reduce_jac<SigJ>), blocks_for(lv[k + 1].cnt), TPB, lv[k].cnt, d_S + lv[k].off, lv[k + 1].cnt, d_S + lv[k + 1].off);
+      REDUCE_JAC(SigJ, lv[k].cnt, (const SigJ*)(d_S + lv[k].off), lv[k + 1].cnt, d_S + lv[k + 1].off);
   }
   if (!use_rlc) LAUNCH((k_reduce_aff<SigA>), 1, 32, (size_t)1, d_sig, (size_t)1, d_S);  // S = the single aggregate signature
   return BLSGPU_OK;
@@ -576,7 +592,7 @@ int pipeline_bisect(blsgpu_ctx* ctx, Pipe<PkA, SigA>& P) {
     LAUNCH((k_scale_sig<SigA>), blocks_for(n), TPB, n, P.d_sig, P.d_status, P.d_root, P.rbits, P.d_Sitem);
     LAUNCH((k_group_sum<SigJ>), blocks_for(ng), TPB, n, (const SigJ*)P.d_Sitem, ng, P.d_S);
     for (size_t k = 0; k + 1 < lv.size(); k++)
-      LAUNCH((k_reduce_jac<SigJ>), blocks_for(lv[k + 1].cnt), TPB, lv[k].cnt, P.d_S + lv[k].off, lv[k + 1].cnt, P.d_S + lv[k + 1].off);
+      REDUCE_JAC(SigJ, lv[k].cnt, (const SigJ*)(P.d_S + lv[k].off), lv[k + 1].cnt, P.d_S + lv[k + 1].off);
   }
   if (by_nodes) {
     const size_t n1 = lv[1].cnt, nblocks = node_msm_blocks(ctx, n1);
@@ -585,7 +601,7 @@ int pipeline_bisect(blsgpu_ctx* ctx, Pipe<PkA, SigA>& P) {
     LAUNCH((k_node_msm<SigA>), (unsigned)nblocks, 128, n, n1, ng, P.d_sig, (const uint8_t*)P.d_status, (const RlcScalar*)P.d_r, d_buckets, d_W);
     LAUNCH((k_node_combine<SigJ>), blocks_for(n1), TPB, n1, (const SigJ*)d_W, P.d_S + lv[1].off);
     for (size_t k = 1; k + 1 < lv.size(); k++)
-      LAUNCH((k_reduce_jac<SigJ>), blocks_for(lv[k + 1].cnt), TPB, lv[k].cnt, P.d_S + lv[k].off, lv[k + 1].cnt, P.d_S + lv[k + 1].off);
+      REDUCE_JAC(SigJ, lv[k].cnt, (const SigJ*)(P.d_S + lv[k].off), lv[k + 1].cnt, P.d_S + lv[k + 1].off);
   }
   // walk down the 16-ary tree to the failing groups: children of node j at level k+1 are {j + m * cnt(k+1)} at level k
   // A round of probes costs ~9 ms whatever its size (one cooperative Miller pass + one final-exponentiation launch, both
@@ -836,8 +852,8 @@ int fold_check(blsgpu_ctx* ctx, Arena& A, size_t k, const Fp12* d_F, const typen
     ctx->err = "fold: at most 16 partial results";
     return BLSGPU_E_ARG;
   }
-  LAUNCH(k_reduce_fp12, 1, TPB, k, d_F, (size_t)1, d_Froot);      // 16-ary: one level covers up to 16 slices
-  LAUNCH((k_reduce_jac<SigJ>), 1, TPB, k, d_S, (size_t)1, d_Sroot);
+  REDUCE_FP12(k, d_F, 1, d_Froot);  // 16-ary: one level covers up to 16 slices
+  REDUCE_JAC(SigJ, k, d_S, 1, d_Sroot);
   LAUNCH((k_probe_fill_nodes<PkA, SigA>), 1, TPB, (size_t)1, (const uint32_t*)nullptr, (const SigJ*)d_Sroot, P.x_pk, P.x_h, P.x_pre);
   CKR((probe_miller<PkA, SigA>(ctx, P, ctx->stream, 1, P.x_args, P.x_lines)));
   CKR((probe_final<PkA, SigA>(ctx, P, 1, nullptr, (const Fp12*)d_Froot, P.d_ok)));
@@ -1620,7 +1636,7 @@ static int sum_points_impl(blsgpu_ctx* ctx, int format, size_t n, const uint8_t*
   J* src = d_tree;
   while (cur > 1) {
     size_t nxt = (cur + 15) / 16;
-    LAUNCH((k_reduce_jac<J>), blocks_for(nxt), TPB, cur, (const J*)src, nxt, src + cur);
+    REDUCE_JAC(J, cur, (const J*)src, nxt, src + cur);
     src += cur;
     cur = nxt;
   }
@@ -1789,7 +1805,7 @@ int blsgpu_pairing_product_is_one(blsgpu_ctx* ctx, size_t n, const uint8_t* g1_p
     }
   LAUNCH(k_miller_pairs, blocks_for(n), TPB, n, (const G1Aff*)d_p, (const G2Aff*)d_q, d_F);
   for (size_t k = 0; k + 1 < lv.size(); k++)
-    LAUNCH(k_reduce_fp12, blocks_for(lv[k + 1].cnt), TPB, lv[k].cnt, (const Fp12*)(d_F + lv[k].off), lv[k + 1].cnt, d_F + lv[k + 1].off);
+    REDUCE_FP12(lv[k].cnt, (const Fp12*)(d_F + lv[k].off), lv[k + 1].cnt, d_F + lv[k + 1].off);
   LAUNCH(k_final_is_one, 1, 32, (const Fp12*)(d_F + lv.back().off), d_ok);
   uint8_t ok = 0;
   CK(cudaMemcpyAsync(&ok, d_ok, 1, cudaMemcpyDeviceToHost, ctx->stream));

@@ -788,6 +788,47 @@ __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_reduce_jac(size_t n_in,
   }
   out[j] = acc;
 }
+// The same levels with SIXTEEN lanes per output node (lane m loads child m, four shuffle-and-multiply steps): a level with
+// few nodes is pure latency - 15 dependent Fp12 products (~100 us each) or point additions (~70 us) per thread - and this
+// form has 4 on its critical path.  It spends 4 x 16 lane-operations per node instead of 15, so it is only used where the
+// narrow form cannot fill the GPU anyway (REDUCE_WIDE_MAX output nodes; blsgpu.cu REDUCE_FP12 / REDUCE_JAC).
+template <class T>
+__device__ __forceinline__ void words_shfl_xor(T& r, const T& p, int mask) {
+  static_assert(sizeof(T) % 4 == 0, "records are whole words");
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(&p);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll 8
+  for (size_t i = 0; i < sizeof(T) / 4; i++) dst[i] = __shfl_xor_sync(0xffffffffu, src[i], mask);
+}
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_reduce_fp12_w(size_t n_in, const Fp12* __restrict__ in, size_t n_out, Fp12* __restrict__ out) {
+  const size_t t = BLS_TID(), j = t >> 4;
+  const int m = (int)(t & 15);
+  const size_t idx = j + (size_t)m * n_out;
+  Fp12 acc;
+  if (j < n_out && idx < n_in) acc = in[idx]; else fp12_one(acc);
+#pragma unroll 1
+  for (int s = 1; s < 16; s <<= 1) {
+    Fp12 other;
+    words_shfl_xor(other, acc, s);
+    if ((m & (2 * s - 1)) == 0) fp12_mul(acc, acc, other);
+  }
+  if (j < n_out && m == 0) out[j] = acc;
+}
+template <class J>
+__global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_reduce_jac_w(size_t n_in, const J* __restrict__ in, size_t n_out, J* __restrict__ out) {
+  const size_t t = BLS_TID(), j = t >> 4;
+  const int m = (int)(t & 15);
+  const size_t idx = j + (size_t)m * n_out;
+  J acc;
+  if (j < n_out && idx < n_in) acc = in[idx]; else jac_set_inf(acc);
+#pragma unroll 1
+  for (int s = 1; s < 16; s <<= 1) {
+    J other;
+    words_shfl_xor(other, acc, s);
+    if ((m & (2 * s - 1)) == 0) jac_add(acc, acc, other);
+  }
+  if (j < n_out && m == 0) out[j] = acc;
+}
 // same for affine inputs (first level of a plain point sum)
 template <class A>
 __global__ void __launch_bounds__(128, BLS_MIN_BLOCKS) k_reduce_aff(size_t n_in, const A* __restrict__ in, size_t n_out,
