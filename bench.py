@@ -105,7 +105,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.5)  # a few samples per second are enough for a median; NVML queries contend with kernel launches
 
     def summary(self):
         if not self.samples:
