@@ -132,6 +132,7 @@ def load_library() -> ctypes.CDLL:
         "blsgpu_verify_batch_records": (c.c_int, [vp, c.c_int, c.c_int, c.c_int, c.c_size_t, u8p, u64p, u8p, u64p, u8p, u64p, u8p]),
         "blsgpu_selftest": (c.c_int, [vp]),
         "blsgpu_plan_msm": (c.c_int, [c.c_size_t, c.c_int, c.POINTER(c.c_int), c.POINTER(c.c_int), c.POINTER(c.c_int)]),
+        "blsgpu_plan_shards": (c.c_int, [c.c_size_t, c.c_void_p, c.c_int, c.c_void_p]),
         "blsgpu_imad_peak": (c.c_int, [vp, c.POINTER(c.c_double)]),
         "blsgpu_verify_share_batch": (c.c_int, [vp, c.c_int, c.c_int, c.c_size_t, vp, vp, vp, vp, vp]),
         "blsgpu_last_stage_ms": (c.c_int, [vp, c.POINTER(c.c_float)]),
@@ -154,7 +155,7 @@ EXPORTED_SYMBOLS = [
     "blsgpu_verify_secure_batch", "blsgpu_aggregate_secure_batch", "blsgpu_hash_to_curve_batch", "blsgpu_recode_points",
     "blsgpu_fp_mul_batch", "blsgpu_pairing_product_is_one", "blsgpu_testdata_sign", "blsgpu_imad_peak",
     "blsgpu_combine_shares_batch", "blsgpu_verify_batch_wire", "blsgpu_pairing_check_batch",
-    "blsgpu_signcrypt_valid_batch", "blsgpu_signcrypt_verify_share_batch", "blsgpu_pok_verify_batch", "blsgpu_verify_batch_records", "blsgpu_selftest", "blsgpu_plan_msm", "blsgpu_verify_share_batch", "blsgpu_last_stage_ms", "blsgpu_last_kernel_ms", "blsgpu_launch_count",
+    "blsgpu_signcrypt_valid_batch", "blsgpu_signcrypt_verify_share_batch", "blsgpu_pok_verify_batch", "blsgpu_verify_batch_records", "blsgpu_selftest", "blsgpu_plan_msm", "blsgpu_plan_shards", "blsgpu_verify_share_batch", "blsgpu_last_stage_ms", "blsgpu_last_kernel_ms", "blsgpu_launch_count",
 ]
 
 

@@ -2649,3 +2649,12 @@ int blsgpu_plan_msm(size_t n, int scalar_bits, int* window_bits_out, int* window
   *top_window_bits_out = scalar_bits - (nwin - 1) * c;
   return BLSGPU_OK;
 }
+
+int blsgpu_plan_shards(size_t sets, const uint64_t* set_off, int ndev, uint64_t* cut_out) {
+  if (!set_off || !cut_out || ndev < 1) return BLSGPU_E_ARG;
+  for (size_t j = 0; j < sets; j++)
+    if (set_off[j + 1] < set_off[j]) return BLSGPU_E_ARG;
+  const std::vector<size_t> cut = balanced_cuts(sets, set_off, (size_t)ndev);
+  for (int d = 0; d <= ndev; d++) cut_out[d] = cut[d];
+  return BLSGPU_OK;
+}

@@ -271,6 +271,12 @@ int blsgpu_selftest(blsgpu_ctx* ctx);
  * blsgpu_verify_batch uses for a batch of n signatures with scalar_bits-bit (64 | 128) scalars. */
 int blsgpu_plan_msm(size_t n, int scalar_bits, int* window_bits_out, int* windows_out, int* top_window_bits_out);
 
+/* Host-only planning query: how a context on ndev devices cuts `sets` independent sets (key sets of
+ * blsgpu_verify_secure_batch / blsgpu_aggregate_secure_batch; set_off = their sets + 1 cumulative member offsets) into
+ * contiguous runs of about equal member count: device d takes sets cut_out[d] .. cut_out[d + 1] - 1 (cut_out has ndev + 1
+ * entries, cut_out[0] = 0, cut_out[ndev] = sets; runs may be empty). */
+int blsgpu_plan_shards(size_t sets, const uint64_t* set_off, int ndev, uint64_t* cut_out);
+
 /* ---- metrics ---------------------------------------------------------------------------------------------------
  * Per-stage device times (CUDA events on the engine's stream) of the LAST verify call on the first device. */
 #define BLSGPU_STAGE_DECODE_PK 0

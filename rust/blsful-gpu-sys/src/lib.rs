@@ -121,6 +121,7 @@ extern "C" {
     pub fn blsgpu_imad_peak(ctx: *mut blsgpu_ctx, mac_per_s_out: *mut f64) -> c_int;
     pub fn blsgpu_plan_msm(n: usize, scalar_bits: c_int, window_bits_out: *mut c_int, windows_out: *mut c_int,
         top_window_bits_out: *mut c_int) -> c_int;
+    pub fn blsgpu_plan_shards(sets: usize, set_off: *const u64, ndev: c_int, cut_out: *mut u64) -> c_int;
 
     // ---- metrics -------------------------------------------------------------------------------------------------------------
     pub fn blsgpu_last_stage_ms(ctx: *const blsgpu_ctx, ms_out: *mut f32 /* [BLSGPU_STAGE_COUNT] */) -> c_int;

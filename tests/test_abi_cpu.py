@@ -76,3 +76,29 @@ def test_rust_sys_crate_declares_the_whole_header():
     c_consts = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define (BLSGPU_(?:ST|E)_[A-Z_]+|BLSGPU_OK|BLSGPU_STAGE_COUNT|BLSGPU_KERNEL_COUNT) \(?(-?\d+)\)?", hdr)}
     rs_consts = {m.group(1): int(m.group(2)) for m in re.finditer(r"pub const (BLSGPU_[A-Z_]+): \w+ = (-?\d+);", rs)}
     assert c_consts == rs_consts, set(c_consts.items()) ^ set(rs_consts.items())
+
+
+def test_shard_plan_of_a_multi_device_context():
+    """blsgpu_plan_shards (host-only): contiguous runs of key sets per device, balanced by member count, covering every set
+    exactly once, for ragged, empty and very uneven inputs (what blsgpu_verify_secure_batch does on a context with several
+    devices)."""
+    import numpy as np
+    import blsful_b200 as B
+    lib = B.load_library()
+    rng = np.random.default_rng(11)
+    cases = [[400] * 10000, [1], [], [0, 0, 0], [5, 0, 0, 0, 1000000, 3], [1] * 7, list(rng.integers(0, 900, size=997))]
+    for sizes in cases:
+        off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64) + np.uint64(17)   # offsets need not start at zero
+        for ndev in (1, 2, 3, 8):
+            cut = np.zeros(ndev + 1, dtype=np.uint64)
+            assert lib.blsgpu_plan_shards(len(sizes), off.ctypes.data, ndev, cut.ctypes.data) == 0
+            cut = cut.tolist()
+            assert cut[0] == 0 and cut[-1] == len(sizes) and all(a <= b for a, b in zip(cut, cut[1:]))
+            total = int(off[-1] - off[0])
+            loads = [int(off[cut[d + 1]] - off[cut[d]]) for d in range(ndev)]
+            assert sum(loads) == total
+            if sizes:   # no run exceeds its fair share by more than one set
+                assert max(loads) <= total / ndev + max(sizes) + 1e-9, (sizes[:8], ndev, loads)
+    bad = np.array([0, 5, 3], dtype=np.uint64)
+    cut = np.zeros(3, dtype=np.uint64)
+    assert lib.blsgpu_plan_shards(2, bad.ctypes.data, 2, cut.ctypes.data) == -1   # BLSGPU_E_ARG: offsets must not decrease
